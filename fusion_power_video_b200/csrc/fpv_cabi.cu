@@ -1,0 +1,503 @@
+// fpv_cabi.cu -- implementation of the C ABI declared in include/fpv_b200.h.
+//
+// Owns: the CUDA context state for one device + one frame geometry, the
+// resident delta frame (image form), per-slot device staging and streams for
+// the host-buffer entry points, and the scratch the encode kernels need.
+// There is deliberately NO CPU fallback here: every entry point either runs
+// the CUDA kernels or returns an error code with a message.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <mutex>
+#include <new>
+#include <string>
+
+#include "../../include/fpv_b200.h"
+#include "fpv_internal.h"
+
+using namespace fpv;
+
+namespace {
+
+constexpr int kNumSlots = 2;       // host-pipeline slots
+constexpr int kDeviceScratch = 2;  // scratch index used by the *_device entry points
+
+std::mutex g_err_mutex;
+std::string g_create_error = "no error";
+
+struct Slot {
+  cudaStream_t stream = nullptr;
+  uint16_t* d_frames = nullptr;  // raw frames in / decoded images out
+  uint8_t* d_high = nullptr;
+  uint8_t* d_low = nullptr;
+  uint8_t* d_preview = nullptr;
+  uint8_t* d_flags = nullptr;
+  bool allocated = false;
+};
+
+}  // namespace
+
+struct fpv_ctx {
+  int device = 0;
+  Geom g;
+  EncodeTuning tune;
+  uint32_t max_batch = 0;
+  bool encode_ok = false;        // W % 4 == 0 && H % 4 == 0
+  uint16_t* d_delta = nullptr;   // image form, P pixels
+  bool has_delta = false;
+  EncodeScratch scratch[kNumSlots + 1];
+  Slot slots[kNumSlots];
+  uint8_t* d_serial_scratch = nullptr;
+  size_t serial_scratch_bytes = 0;
+  cudaStream_t aux_stream = nullptr;
+  uint64_t launches = 0;
+  bool force_generic = false;
+  std::string err = "no error";
+};
+
+namespace {
+
+int fail(fpv_ctx* c, int code, const std::string& msg) {
+  if (c) c->err = msg;
+  else {
+    std::lock_guard<std::mutex> l(g_err_mutex);
+    g_create_error = msg;
+  }
+  return code;
+}
+
+int cuda_fail(fpv_ctx* c, cudaError_t e, const char* what) {
+  return fail(c, FPV_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+#define FPV_CUDA(call)                                          \
+  do {                                                          \
+    cudaError_t e__ = (call);                                   \
+    if (e__ != cudaSuccess) return cuda_fail(c, e__, #call);    \
+  } while (0)
+
+int ensure_scratch(fpv_ctx* c, int idx) {
+  EncodeScratch& s = c->scratch[idx];
+  if (s.stats) return FPV_OK;
+  uint32_t cap = c->max_batch;
+  FPV_CUDA(cudaMalloc(&s.stats, sizeof(FrameStat) * (size_t)cap));
+  FPV_CUDA(cudaMalloc(&s.lists, sizeof(uint32_t) * 3 * (size_t)cap));
+  FPV_CUDA(cudaMalloc(&s.counts, sizeof(uint32_t) * 4));
+  FPV_CUDA(cudaMalloc(&s.preview_raw, (size_t)cap * (c->g.PP ? c->g.PP : 1)));
+  uint32_t init[4] = {0, 0, 0, 3};  // first guess: USE_DELTA | USE_CG
+  FPV_CUDA(cudaMemcpy(s.counts, init, sizeof init, cudaMemcpyHostToDevice));
+  s.cap = cap;
+  return FPV_OK;
+}
+
+int ensure_slot(fpv_ctx* c, int idx) {
+  Slot& s = c->slots[idx];
+  if (s.allocated) return FPV_OK;
+  size_t B = c->max_batch, P = c->g.P, PP = c->g.PP ? c->g.PP : 1;
+  FPV_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+  FPV_CUDA(cudaMalloc(&s.d_frames, B * P * 2));
+  FPV_CUDA(cudaMalloc(&s.d_high, B * P));
+  FPV_CUDA(cudaMalloc(&s.d_low, B * P));
+  FPV_CUDA(cudaMalloc(&s.d_preview, B * PP));
+  FPV_CUDA(cudaMalloc(&s.d_flags, B));
+  s.allocated = true;
+  return FPV_OK;
+}
+
+int encode_device_chunked(fpv_ctx* c, int scratch_idx, const uint16_t* frames, uint32_t n,
+                          uint32_t options, uint8_t* flags, uint8_t* high, uint8_t* low,
+                          uint8_t* preview, cudaStream_t stream) {
+  if (!c->encode_ok)
+    return fail(c, FPV_ERR_UNSUPPORTED,
+                "encode requires xsize % 4 == 0 and ysize % 4 == 0 (the reference reads out of "
+                "bounds otherwise, fusion_power_video.cc:577-578)");
+  if (mode_has_low(c->g.mode) && !low) return fail(c, FPV_ERR_INVALID_ARG, "low plane buffer is NULL");
+  int rc = ensure_scratch(c, scratch_idx);
+  if (rc != FPV_OK) return rc;
+  const uint16_t* delta = (c->has_delta && !(options & FPV_ENC_NO_DELTA)) ? c->d_delta : nullptr;
+  const bool generic = c->force_generic || (options & FPV_ENC_GENERIC);
+  const uint64_t P = c->g.P, PP = c->g.PP;
+  for (uint32_t off = 0; off < n; off += c->max_batch) {
+    uint32_t m = n - off < c->max_batch ? n - off : c->max_batch;
+    cudaError_t e = cudaSuccess;
+    int l = enqueue_encode(c->g, c->tune, c->scratch[scratch_idx], frames + (uint64_t)off * P, delta, m,
+                           generic, flags + off, high + (uint64_t)off * P,
+                           low ? low + (uint64_t)off * P : nullptr, preview + (uint64_t)off * PP, stream, &e);
+    if (l < 0) return cuda_fail(c, e, "encode kernel launch");
+    c->launches += (uint64_t)l;
+  }
+  return FPV_OK;
+}
+
+int decode_device_impl(fpv_ctx* c, const uint8_t* high, const uint8_t* low, const uint8_t* flags,
+                       uint32_t n, uint32_t options, uint16_t* out, cudaStream_t stream,
+                       bool high_is_scratch) {
+  cudaError_t e = cudaSuccess;
+  const uint16_t* delta = c->has_delta ? c->d_delta : nullptr;
+  const bool unextract = (options & FPV_DEC_UNEXTRACT) != 0;
+  int l = -1;
+  if (!getenv("FPV_DECODE_SERIAL"))
+    l = enqueue_decode(c->g, c->tune.num_sms, high, low, flags, delta, n, unextract, out, stream, &e);
+  if (l < 0) {
+    // rows too wide for the shared-memory row pipeline (or forced): serial chain
+    uint8_t* scratch = const_cast<uint8_t*>(high);
+    if (!high_is_scratch) {
+      size_t need = (size_t)n * c->g.P;
+      if (need > c->serial_scratch_bytes) {
+        if (c->d_serial_scratch) cudaFree(c->d_serial_scratch);
+        c->d_serial_scratch = nullptr;
+        c->serial_scratch_bytes = 0;
+        FPV_CUDA(cudaMalloc(&c->d_serial_scratch, need));
+        c->serial_scratch_bytes = need;
+      }
+      FPV_CUDA(cudaMemcpyAsync(c->d_serial_scratch, high, need, cudaMemcpyDeviceToDevice, stream));
+      scratch = c->d_serial_scratch;
+    }
+    l = enqueue_decode_serial(c->g, scratch, low, flags, delta, n, unextract, out, stream, &e);
+    if (l < 0) return cuda_fail(c, e, "decode kernel launch");
+  }
+  c->launches += (uint64_t)l;
+  return FPV_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* fpv_version(void) { return "fpv_b200 0.1 (sm_100a)"; }
+
+int fpv_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+int fpv_create(fpv_ctx** out, int device, uint32_t xsize, uint32_t ysize, int shift, int big_endian,
+               uint32_t max_batch) {
+  fpv_ctx* c = nullptr;  // for the FPV_CUDA macro: errors before allocation go to the global slot
+  if (!out) return fail(nullptr, FPV_ERR_INVALID_ARG, "ctx out pointer is NULL");
+  *out = nullptr;
+  if (xsize == 0 || ysize == 0 || xsize > 65536 || ysize > 65536 ||
+      (uint64_t)xsize * ysize > 1000000000ull)
+    return fail(nullptr, FPV_ERR_INVALID_ARG, "invalid image dimensions");  // .cc:891-895
+  int mode = pick_split_mode(shift, big_endian);
+  if (mode < 0)
+    return fail(nullptr, FPV_ERR_UNSUPPORTED,
+                "shift must be 0..16 (0..8 for big-endian data: the reference shifts by 8 - shift)");
+  if (max_batch == 0) return fail(nullptr, FPV_ERR_INVALID_ARG, "max_batch must be >= 1");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(nullptr, FPV_ERR_NO_DEVICE,
+                std::string("no CUDA device available: ") + cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return fail(nullptr, FPV_ERR_INVALID_ARG, "device index out of range");
+  FPV_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  FPV_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10)
+    return fail(nullptr, FPV_ERR_NO_DEVICE, "device is not sm_100-class (kernels are built for sm_100a only)");
+
+  c = new (std::nothrow) fpv_ctx();
+  if (!c) return fail(nullptr, FPV_ERR_INVALID_ARG, "out of host memory");
+  c->device = device;
+  c->g.W = xsize; c->g.H = ysize; c->g.P = (uint64_t)xsize * ysize;
+  c->g.PW = xsize / 4; c->g.PP = (uint64_t)(xsize / 4) * (ysize / 4);
+  c->g.shift = shift; c->g.big_endian = big_endian ? 1 : 0; c->g.mode = mode;
+  c->max_batch = max_batch;
+  c->encode_ok = (xsize % 4 == 0) && (ysize % 4 == 0);
+  c->tune.num_sms = prop.multiProcessorCount;
+  c->tune.max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+  if (const char* v = getenv("FPV_STAGES")) c->tune.stages = atoi(v);
+  if (const char* v = getenv("FPV_BAND_ROWS")) c->tune.band_rows = atoi(v);
+  if (c->tune.stages < 2) c->tune.stages = 2;
+  if (c->tune.stages > 8) c->tune.stages = 8;
+  if (c->tune.band_rows < 4) c->tune.band_rows = 4;
+  c->force_generic = getenv("FPV_FORCE_GENERIC") != nullptr;
+  cudaError_t e2 = cudaMalloc(&c->d_delta, c->g.P * 2);
+  if (e2 == cudaSuccess) e2 = cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking);
+  if (e2 != cudaSuccess) {
+    int rc = cuda_fail(nullptr, e2, "fpv_create allocation");
+    fpv_destroy(c);
+    return rc;
+  }
+  *out = c;
+  return FPV_OK;
+}
+
+void fpv_destroy(fpv_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  for (auto& s : c->scratch) {
+    if (s.stats) cudaFree(s.stats);
+    if (s.lists) cudaFree(s.lists);
+    if (s.counts) cudaFree(s.counts);
+    if (s.preview_raw) cudaFree(s.preview_raw);
+  }
+  for (auto& s : c->slots) {
+    if (s.d_frames) cudaFree(s.d_frames);
+    if (s.d_high) cudaFree(s.d_high);
+    if (s.d_low) cudaFree(s.d_low);
+    if (s.d_preview) cudaFree(s.d_preview);
+    if (s.d_flags) cudaFree(s.d_flags);
+    if (s.stream) cudaStreamDestroy(s.stream);
+  }
+  if (c->d_serial_scratch) cudaFree(c->d_serial_scratch);
+  if (c->d_delta) cudaFree(c->d_delta);
+  if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
+  delete c;
+}
+
+const char* fpv_last_error(const fpv_ctx* c) {
+  if (c) return c->err.c_str();
+  std::lock_guard<std::mutex> l(g_err_mutex);
+  static thread_local std::string copy;
+  copy = g_create_error;
+  return copy.c_str();
+}
+
+size_t fpv_plane_bytes(const fpv_ctx* c) { return c ? (size_t)c->g.P : 0; }
+size_t fpv_preview_bytes(const fpv_ctx* c) { return c ? (size_t)c->g.PP : 0; }
+uint64_t fpv_kernel_launches(const fpv_ctx* c) { return c ? c->launches : 0; }
+
+void* fpv_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr;
+  return p;
+}
+void fpv_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+// ---- delta frame ------------------------------------------------------------
+
+int fpv_set_delta_raw_device(fpv_ctx* c, const void* raw_dev, void* stream) {
+  if (!c) return FPV_ERR_INVALID_ARG;
+  FPV_CUDA(cudaSetDevice(c->device));
+  if (!raw_dev) { c->has_delta = false; return FPV_OK; }
+  cudaError_t e = cudaSuccess;
+  int l = enqueue_delta_from_raw(c->g, static_cast<const uint16_t*>(raw_dev), c->d_delta,
+                                 static_cast<cudaStream_t>(stream), &e);
+  if (l < 0) return cuda_fail(c, e, "delta split kernel launch");
+  c->launches += (uint64_t)l;
+  c->has_delta = true;
+  return FPV_OK;
+}
+
+int fpv_set_delta_raw(fpv_ctx* c, const uint16_t* raw_host) {
+  if (!c) return FPV_ERR_INVALID_ARG;
+  FPV_CUDA(cudaSetDevice(c->device));
+  if (!raw_host) { c->has_delta = false; return FPV_OK; }
+  uint16_t* tmp = nullptr;
+  FPV_CUDA(cudaMalloc(&tmp, c->g.P * 2));
+  cudaError_t e = cudaMemcpyAsync(tmp, raw_host, c->g.P * 2, cudaMemcpyHostToDevice, c->aux_stream);
+  int rc = FPV_OK;
+  if (e != cudaSuccess) rc = cuda_fail(c, e, "delta H2D copy");
+  if (rc == FPV_OK) rc = fpv_set_delta_raw_device(c, tmp, c->aux_stream);
+  cudaError_t es = cudaStreamSynchronize(c->aux_stream);
+  cudaFree(tmp);
+  if (rc == FPV_OK && es != cudaSuccess) rc = cuda_fail(c, es, "delta split");
+  return rc;
+}
+
+int fpv_set_delta_image_device(fpv_ctx* c, const void* image_dev, void* stream) {
+  if (!c) return FPV_ERR_INVALID_ARG;
+  FPV_CUDA(cudaSetDevice(c->device));
+  if (!image_dev) { c->has_delta = false; return FPV_OK; }
+  FPV_CUDA(cudaMemcpyAsync(c->d_delta, image_dev, c->g.P * 2, cudaMemcpyDeviceToDevice,
+                           static_cast<cudaStream_t>(stream)));
+  c->has_delta = true;
+  return FPV_OK;
+}
+
+int fpv_set_delta_image(fpv_ctx* c, const uint16_t* image_host) {
+  if (!c) return FPV_ERR_INVALID_ARG;
+  FPV_CUDA(cudaSetDevice(c->device));
+  if (!image_host) { c->has_delta = false; return FPV_OK; }
+  FPV_CUDA(cudaMemcpy(c->d_delta, image_host, c->g.P * 2, cudaMemcpyHostToDevice));
+  c->has_delta = true;
+  return FPV_OK;
+}
+
+int fpv_copy_delta_peer(fpv_ctx* dst, const fpv_ctx* src) {
+  fpv_ctx* c = dst;
+  if (!dst || !src) return FPV_ERR_INVALID_ARG;
+  if (dst->g.P != src->g.P) return fail(dst, FPV_ERR_INVALID_ARG, "geometry mismatch between contexts");
+  if (!src->has_delta) { dst->has_delta = false; return FPV_OK; }
+  FPV_CUDA(cudaSetDevice(dst->device));
+  FPV_CUDA(cudaMemcpyPeerAsync(dst->d_delta, dst->device, src->d_delta, src->device, dst->g.P * 2,
+                               dst->aux_stream));
+  FPV_CUDA(cudaStreamSynchronize(dst->aux_stream));
+  dst->has_delta = true;
+  return FPV_OK;
+}
+
+// ---- encode -------------------------------------------------------------------
+
+int fpv_encode_device(fpv_ctx* c, const void* frames_dev, uint32_t n, uint32_t options, void* flags_dev,
+                      void* high_dev, void* low_dev, void* preview_dev, void* stream) {
+  if (!c) return FPV_ERR_INVALID_ARG;
+  if (n == 0) return FPV_OK;
+  if (!frames_dev || !flags_dev || !high_dev || !preview_dev)
+    return fail(c, FPV_ERR_INVALID_ARG, "NULL device buffer");
+  if ((reinterpret_cast<uintptr_t>(frames_dev) & 15) || (reinterpret_cast<uintptr_t>(high_dev) & 15) ||
+      (reinterpret_cast<uintptr_t>(low_dev) & 15) || (reinterpret_cast<uintptr_t>(preview_dev) & 15))
+    return fail(c, FPV_ERR_INVALID_ARG, "device buffers must be 16-byte aligned");
+  FPV_CUDA(cudaSetDevice(c->device));
+  return encode_device_chunked(c, kDeviceScratch, static_cast<const uint16_t*>(frames_dev), n, options,
+                               static_cast<uint8_t*>(flags_dev), static_cast<uint8_t*>(high_dev),
+                               static_cast<uint8_t*>(low_dev), static_cast<uint8_t*>(preview_dev),
+                               static_cast<cudaStream_t>(stream));
+}
+
+int fpv_encode_submit(fpv_ctx* c, uint32_t slot, const uint16_t* frames_host, uint32_t n, uint32_t options,
+                      uint8_t* flags_host, uint8_t* high_host, uint8_t* low_host, uint8_t* preview_host) {
+  if (!c) return FPV_ERR_INVALID_ARG;
+  if (slot >= kNumSlots) return fail(c, FPV_ERR_INVALID_ARG, "slot out of range");
+  if (n == 0) return FPV_OK;
+  if (n > c->max_batch) return fail(c, FPV_ERR_INVALID_ARG, "n exceeds max_batch");
+  if (!frames_host || !flags_host || !high_host || !preview_host)
+    return fail(c, FPV_ERR_INVALID_ARG, "NULL host buffer");
+  const bool has_low = mode_has_low(c->g.mode);
+  if (has_low && !low_host) return fail(c, FPV_ERR_INVALID_ARG, "low plane buffer is NULL");
+  FPV_CUDA(cudaSetDevice(c->device));
+  int rc = ensure_slot(c, (int)slot);
+  if (rc != FPV_OK) return rc;
+  Slot& s = c->slots[slot];
+  const size_t P = c->g.P, PP = c->g.PP;
+  FPV_CUDA(cudaMemcpyAsync(s.d_frames, frames_host, (size_t)n * P * 2, cudaMemcpyHostToDevice, s.stream));
+  rc = encode_device_chunked(c, (int)slot, s.d_frames, n, options, s.d_flags, s.d_high, s.d_low,
+                             s.d_preview, s.stream);
+  if (rc != FPV_OK) return rc;
+  FPV_CUDA(cudaMemcpyAsync(high_host, s.d_high, (size_t)n * P, cudaMemcpyDeviceToHost, s.stream));
+  if (has_low)
+    FPV_CUDA(cudaMemcpyAsync(low_host, s.d_low, (size_t)n * P, cudaMemcpyDeviceToHost, s.stream));
+  FPV_CUDA(cudaMemcpyAsync(preview_host, s.d_preview, (size_t)n * PP, cudaMemcpyDeviceToHost, s.stream));
+  FPV_CUDA(cudaMemcpyAsync(flags_host, s.d_flags, (size_t)n, cudaMemcpyDeviceToHost, s.stream));
+  return FPV_OK;
+}
+
+int fpv_wait(fpv_ctx* c, uint32_t slot) {
+  if (!c) return FPV_ERR_INVALID_ARG;
+  if (slot >= kNumSlots) return fail(c, FPV_ERR_INVALID_ARG, "slot out of range");
+  if (!c->slots[slot].allocated) return FPV_OK;
+  FPV_CUDA(cudaSetDevice(c->device));
+  FPV_CUDA(cudaStreamSynchronize(c->slots[slot].stream));
+  return FPV_OK;
+}
+
+int fpv_encode(fpv_ctx* c, const uint16_t* frames_host, uint32_t n, uint32_t options, uint8_t* flags_host,
+               uint8_t* high_host, uint8_t* low_host, uint8_t* preview_host) {
+  if (!c) return FPV_ERR_INVALID_ARG;
+  const size_t P = c->g.P, PP = c->g.PP;
+  for (uint32_t off = 0; off < n; off += c->max_batch) {
+    uint32_t m = n - off < c->max_batch ? n - off : c->max_batch;
+    int rc = fpv_encode_submit(c, 0, frames_host + (size_t)off * P, m, options, flags_host + off,
+                               high_host + (size_t)off * P, low_host ? low_host + (size_t)off * P : nullptr,
+                               preview_host + (size_t)off * PP);
+    if (rc != FPV_OK) return rc;
+    rc = fpv_wait(c, 0);
+    if (rc != FPV_OK) return rc;
+  }
+  return FPV_OK;
+}
+
+// ---- decode -------------------------------------------------------------------
+
+int fpv_decode_device(fpv_ctx* c, const void* high_dev, const void* low_dev, const void* flags_dev,
+                      uint32_t n, uint32_t options, void* out_dev, void* stream) {
+  if (!c) return FPV_ERR_INVALID_ARG;
+  if (n == 0) return FPV_OK;
+  if (!high_dev || !flags_dev || !out_dev) return fail(c, FPV_ERR_INVALID_ARG, "NULL device buffer");
+  if ((reinterpret_cast<uintptr_t>(high_dev) & 15) || (reinterpret_cast<uintptr_t>(low_dev) & 15) ||
+      (reinterpret_cast<uintptr_t>(out_dev) & 15))
+    return fail(c, FPV_ERR_INVALID_ARG, "device buffers must be 16-byte aligned");
+  FPV_CUDA(cudaSetDevice(c->device));
+  return decode_device_impl(c, static_cast<const uint8_t*>(high_dev), static_cast<const uint8_t*>(low_dev),
+                            static_cast<const uint8_t*>(flags_dev), n, options,
+                            static_cast<uint16_t*>(out_dev), static_cast<cudaStream_t>(stream), false);
+}
+
+int fpv_decode_submit(fpv_ctx* c, uint32_t slot, const uint8_t* high_host, const uint8_t* low_host,
+                      const uint8_t* flags_host, uint32_t n, uint32_t options, void* out_host) {
+  if (!c) return FPV_ERR_INVALID_ARG;
+  if (slot >= kNumSlots) return fail(c, FPV_ERR_INVALID_ARG, "slot out of range");
+  if (n == 0) return FPV_OK;
+  if (n > c->max_batch) return fail(c, FPV_ERR_INVALID_ARG, "n exceeds max_batch");
+  if (!high_host || !flags_host || !out_host) return fail(c, FPV_ERR_INVALID_ARG, "NULL host buffer");
+  bool any_delta = false, any_low = false;
+  for (uint32_t i = 0; i < n; i++) {
+    if (flags_host[i] & FPV_FLAG_USE_DELTA) any_delta = true;
+    if (!(flags_host[i] & FPV_FLAG_NO_LOW_BYTES)) any_low = true;
+  }
+  if (any_delta && !c->has_delta)
+    return fail(c, FPV_ERR_NO_DELTA, "delta frame not given");  // .cc:310
+  if (any_low && !low_host) return fail(c, FPV_ERR_INVALID_ARG, "low plane buffer is NULL");
+  FPV_CUDA(cudaSetDevice(c->device));
+  int rc = ensure_slot(c, (int)slot);
+  if (rc != FPV_OK) return rc;
+  Slot& s = c->slots[slot];
+  const size_t P = c->g.P;
+  FPV_CUDA(cudaMemcpyAsync(s.d_high, high_host, (size_t)n * P, cudaMemcpyHostToDevice, s.stream));
+  if (low_host)
+    FPV_CUDA(cudaMemcpyAsync(s.d_low, low_host, (size_t)n * P, cudaMemcpyHostToDevice, s.stream));
+  FPV_CUDA(cudaMemcpyAsync(s.d_flags, flags_host, (size_t)n, cudaMemcpyHostToDevice, s.stream));
+  rc = decode_device_impl(c, s.d_high, low_host ? s.d_low : nullptr, s.d_flags, n, options, s.d_frames,
+                          s.stream, true);
+  if (rc != FPV_OK) return rc;
+  FPV_CUDA(cudaMemcpyAsync(out_host, s.d_frames, (size_t)n * P * 2, cudaMemcpyDeviceToHost, s.stream));
+  return FPV_OK;
+}
+
+int fpv_decode(fpv_ctx* c, const uint8_t* high_host, const uint8_t* low_host, const uint8_t* flags_host,
+               uint32_t n, uint32_t options, void* out_host) {
+  if (!c) return FPV_ERR_INVALID_ARG;
+  const size_t P = c->g.P;
+  for (uint32_t off = 0; off < n; off += c->max_batch) {
+    uint32_t m = n - off < c->max_batch ? n - off : c->max_batch;
+    int rc = fpv_decode_submit(c, 0, high_host + (size_t)off * P, low_host ? low_host + (size_t)off * P : nullptr,
+                               flags_host + off, m, options, static_cast<uint8_t*>(out_host) + (size_t)off * P * 2);
+    if (rc != FPV_OK) return rc;
+    rc = fpv_wait(c, 0);
+    if (rc != FPV_OK) return rc;
+  }
+  return FPV_OK;
+}
+
+int fpv_unpredict_planes(fpv_ctx* c, uint8_t* high_host, uint8_t* low_host, uint8_t* preview_host,
+                         const uint8_t* flags_host, uint32_t n) {
+  if (!c) return FPV_ERR_INVALID_ARG;
+  if (n == 0) return FPV_OK;
+  if (!high_host || !flags_host) return fail(c, FPV_ERR_INVALID_ARG, "NULL host buffer");
+  FPV_CUDA(cudaSetDevice(c->device));
+  int rc = ensure_slot(c, 0);
+  if (rc != FPV_OK) return rc;
+  Slot& s = c->slots[0];
+  const size_t P = c->g.P, PP = c->g.PP;
+  for (uint32_t off = 0; off < n; off += c->max_batch) {
+    uint32_t m = n - off < c->max_batch ? n - off : c->max_batch;
+    FPV_CUDA(cudaMemcpyAsync(s.d_high, high_host + (size_t)off * P, (size_t)m * P, cudaMemcpyHostToDevice, s.stream));
+    if (low_host)
+      FPV_CUDA(cudaMemcpyAsync(s.d_low, low_host + (size_t)off * P, (size_t)m * P, cudaMemcpyHostToDevice, s.stream));
+    if (preview_host)
+      FPV_CUDA(cudaMemcpyAsync(s.d_preview, preview_host + (size_t)off * PP, (size_t)m * PP, cudaMemcpyHostToDevice, s.stream));
+    FPV_CUDA(cudaMemcpyAsync(s.d_flags, flags_host + off, (size_t)m, cudaMemcpyHostToDevice, s.stream));
+    cudaError_t e = cudaSuccess;
+    int l = enqueue_unpredict_planes(c->g, c->tune.num_sms, s.d_high, low_host ? s.d_low : nullptr,
+                                     preview_host ? s.d_preview : nullptr, s.d_flags,
+                                     c->has_delta ? c->d_delta : nullptr, m, s.stream, &e);
+    if (l < 0) return cuda_fail(c, e, "unpredict kernel launch");
+    c->launches += (uint64_t)l;
+    FPV_CUDA(cudaMemcpyAsync(high_host + (size_t)off * P, s.d_high, (size_t)m * P, cudaMemcpyDeviceToHost, s.stream));
+    if (low_host)
+      FPV_CUDA(cudaMemcpyAsync(low_host + (size_t)off * P, s.d_low, (size_t)m * P, cudaMemcpyDeviceToHost, s.stream));
+    if (preview_host)
+      FPV_CUDA(cudaMemcpyAsync(preview_host + (size_t)off * PP, s.d_preview, (size_t)m * PP, cudaMemcpyDeviceToHost, s.stream));
+    FPV_CUDA(cudaStreamSynchronize(s.stream));
+  }
+  return FPV_OK;
+}
+
+}  // extern "C"

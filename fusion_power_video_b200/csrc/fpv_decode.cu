@@ -1,0 +1,402 @@
+// fpv_decode.cu -- decode-side kernels: the post-brotli part of DecompressImage
+// (fusion_power_video.cc:326-344), UnextractFrame (.cc:850-862) and the
+// plane-level undo of Frame::Uncompress (.cc:595-641).
+//
+// The inverse ClampedGradient is a strict serial chain in flat pixel order
+// (.cc:327-332): h[i] += CG(h[i-W], h[i-1], h[i-W-1]) uses the just-written
+// west neighbour, and the flat index wraps across row ends, so the exact
+// dependency DAG has critical path W*H per frame.  What is exploited here:
+//
+//  * frames are independent                      -> one warp per frame;
+//  * within a row (row y-1 final), x_i = f_i(x_{i-1}) with
+//        f_i(w) = r_i + n_i + w - clamp(w, min(n_i,nw_i), max(n_i,nw_i))
+//    (== r_i + CG(n_i, w, nw_i)), which is CONSTANT in w whenever w lies in
+//    [min(n,nw), max(n,nw)].  Each of the 32 lanes owns a contiguous segment
+//    of the row and runs its chain from a guessed incoming west value; lanes
+//    then exchange their last pixel (shuffle) and re-run only until the new
+//    values meet the old ones.  Lane 0's input is exact, so the fixed point is
+//    the serial answer (induction over lanes); worst case 32 rounds.
+//
+// Rows are staged with cp.async (residual row, low row, delta row) a few rows
+// ahead so that the chain never waits on HBM; the delta add, the high/low
+// recombination and UnextractFrame are fused into the row write-out.
+#include "fpv_internal.h"
+
+namespace fpv {
+
+namespace {
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void cp_async4(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_addr(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// byte b of word v, moved to bits 24..31 (the chain runs on values scaled by
+// 2^24 so that 32-bit wrap-around IS the mod-256 wrap and unsigned compares
+// order bytes correctly).
+__device__ __forceinline__ uint32_t byte_hi(uint32_t v, int b) {
+  switch (b) {
+    case 0: return __byte_perm(v, 0u, 0x0444);
+    case 1: return __byte_perm(v, 0u, 0x1444);
+    case 2: return __byte_perm(v, 0u, 0x2444);
+    default: return v & 0xff000000u;
+  }
+}
+
+struct DecodeParams {
+  const uint8_t* high;
+  const uint8_t* low;      // may be nullptr (all frames flags & 4)
+  const uint8_t* flags;
+  const uint16_t* delta;   // image form, may be nullptr
+  uint16_t* out;
+  uint32_t W, H;
+  uint64_t P;
+  int shift, big_endian, unextract;
+  uint32_t n;
+  uint32_t L;              // segment length in pixels (multiple of 4), 32*L >= W
+  uint32_t Lw;             // L / 4
+  uint32_t SW;             // slot stride in words (odd -> conflict-free)
+  uint32_t Wp;             // W rounded up to 16
+  uint32_t nst;            // staged rows in flight (1..3)
+  uint32_t div_magic;      // ceil(2^32 / L) for col / L
+  uint32_t warp_smem_words;
+};
+
+// ALIGN: 16 -> W % 16 == 0 (16-byte cp.async for low/delta), 4 -> W % 4 == 0,
+//        1  -> anything (synchronous byte staging, scalar stores).
+template <int ALIGN>
+__global__ void __launch_bounds__(128) k_decode_spec(const DecodeParams p) {
+  extern __shared__ __align__(16) uint32_t dsm[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const uint32_t W = p.W, H = p.H, L = p.L, Lw = p.Lw, SW = p.SW, Wp = p.Wp, NST = p.nst;
+  uint32_t* wsm = dsm + (size_t)wib * p.warp_smem_words;
+  // per-warp layout (words): hbuf[2][32*SW] | stage[NST] x { r[32*SW] | low[Wp/4] | delta[Wp/2] }
+  const uint32_t slot_words = 32 * SW;
+  const uint32_t stage_words = slot_words + Wp / 4 + Wp / 2;
+  uint32_t* hbuf0 = wsm;
+  uint32_t* hbuf1 = wsm + slot_words;
+  uint32_t* stage0 = wsm + 2 * slot_words;
+
+  const uint32_t cs = (uint32_t)lane * L;                 // first column of this lane's segment
+  const bool lane_active = cs < W;
+  const uint32_t seg_px = lane_active ? min(L, W - cs) : 0;
+  const uint32_t seg_words = (seg_px + 3) / 4;
+  const uint32_t last_seg = (W - 1) / L, last_off = (W - 1) - last_seg * L;
+
+  const uint32_t warps_total = gridDim.x * (blockDim.x >> 5);
+  for (uint32_t f = blockIdx.x * (blockDim.x >> 5) + wib; f < p.n; f += warps_total) {
+    const uint32_t fl = p.flags[f];
+    const bool use_delta = (fl & kFlagDelta) && p.delta != nullptr;
+    const bool use_cg = (fl & kFlagCG) != 0;
+    const bool has_low = !(fl & kFlagNoLow) && p.low != nullptr;
+    const uint8_t* fh = p.high + (uint64_t)f * p.P;
+    const uint8_t* flow = has_low ? p.low + (uint64_t)f * p.P : nullptr;
+    uint16_t* fout = p.out + (uint64_t)f * p.P;
+
+    // ---- row staging -------------------------------------------------------
+    auto issue_row = [&](uint32_t y) {
+      if (y < H) {
+        uint32_t* st = stage0 + (size_t)(y % NST) * stage_words;
+        uint32_t* rb = st;
+        uint8_t* lb = reinterpret_cast<uint8_t*>(st + slot_words);
+        uint8_t* db = reinterpret_cast<uint8_t*>(st + slot_words + Wp / 4);
+        const uint8_t* src = fh + (uint64_t)y * W;
+        if (ALIGN >= 4) {
+          for (uint32_t k = 0; k < seg_words; k++) cp_async4(rb + lane * SW + k, src + cs + 4 * k);
+          if (ALIGN == 16) {
+            if (has_low)
+              for (uint32_t q = lane; q < W / 16; q += 32) cp_async16(lb + 16 * q, flow + (uint64_t)y * W + 16 * q);
+            if (use_delta)
+              for (uint32_t q = lane; q < W / 8; q += 32)
+                cp_async16(db + 16 * q, reinterpret_cast<const uint8_t*>(p.delta + (uint64_t)y * W) + 16 * q);
+          } else {
+            if (has_low)
+              for (uint32_t q = lane; q < W / 4; q += 32) cp_async4(lb + 4 * q, flow + (uint64_t)y * W + 4 * q);
+            if (use_delta)
+              for (uint32_t q = lane; q < W / 2; q += 32)
+                cp_async4(db + 4 * q, reinterpret_cast<const uint8_t*>(p.delta + (uint64_t)y * W) + 4 * q);
+          }
+        } else {
+          uint8_t* rb8 = reinterpret_cast<uint8_t*>(rb);
+          for (uint32_t c = lane; c < W; c += 32) {
+            uint32_t sg = c / L, off = c - sg * L;
+            rb8[(size_t)sg * SW * 4 + off] = src[c];
+            if (has_low) lb[c] = flow[(uint64_t)y * W + c];
+            if (use_delta) reinterpret_cast<uint16_t*>(db)[c] = p.delta[(uint64_t)y * W + c];
+          }
+        }
+      }
+      cp_async_commit();  // one group per row, empty groups keep the count uniform
+    };
+
+    __syncwarp();
+    for (uint32_t y = 0; y + 1 < NST; y++) issue_row(y);
+
+    uint32_t last_prev = 0, last_prev2 = 0;  // h[y-1][W-1], h[y-2][W-1], scaled by 2^24
+
+    for (uint32_t y = 0; y < H; y++) {
+      // keep NST-1 rows in flight beyond the one being processed
+      issue_row(y + NST - 1);
+      if (NST == 1) cp_async_wait<0>();
+      else if (NST == 2) cp_async_wait<1>();
+      else cp_async_wait<2>();
+      __syncwarp();
+
+      uint32_t* st = stage0 + (size_t)(y % NST) * stage_words;
+      const uint32_t* rb = st + lane * SW;
+      uint32_t* hcur = (y & 1) ? hbuf1 : hbuf0;
+      const uint32_t* hprev = (y & 1) ? hbuf0 : hbuf1;
+      uint32_t* myh = hcur + lane * SW;
+      const uint32_t* myn = hprev + lane * SW;
+
+      if (!use_cg || y == 0) {
+        for (uint32_t k = 0; k < seg_words; k++) myh[k] = rb[k];
+      } else {
+        // incoming west / north-west values for the first pixel of the segment
+        uint32_t w_in, nw_in;
+        if (lane == 0) {
+          w_in = last_prev;
+          nw_in = last_prev2;
+        } else {
+          // pixel above-left of my first pixel: last pixel of the previous lane's
+          // segment in row y-1.  It is also the guess for the incoming west value.
+          uint32_t v = lane_active ? hprev[(lane - 1) * SW + Lw - 1] : 0;
+          nw_in = v & 0xff000000u;
+          w_in = nw_in;
+        }
+        uint32_t out_px = 0;
+        bool need = lane_active, first = true;
+        for (;;) {
+          if (need) {
+            uint32_t x = w_in, nwv = nw_in;
+            bool ran_to_end = true;
+            for (uint32_t k = 0; k < seg_words; k++) {
+              const uint32_t rw = rb[k], nd = myn[k], old = myh[k];
+              uint32_t xs[4];
+#pragma unroll
+              for (int b = 0; b < 4; b++) {
+                uint32_t r = byte_hi(rw, b), nn = byte_hi(nd, b);
+                uint32_t lo = min(nn, nwv), hi = max(nn, nwv);
+                uint32_t t = min(max(x, lo), hi);
+                uint32_t xn = r + nn + x - t;
+                // flat index W (row 1, column 0) is not predicted (.cc:327 starts at W+1)
+                if (y == 1 && lane == 0 && k == 0 && b == 0) xn = r;
+                nwv = nn;
+                x = xn;
+                xs[b] = xn;
+              }
+              uint32_t word = __byte_perm(__byte_perm(xs[0], xs[1], 0x0073),
+                                          __byte_perm(xs[2], xs[3], 0x0073), 0x5410);
+              myh[k] = word;
+              // pixels past the end of the row inside the last word are scratch
+              if (!first && k + 1 < seg_words && (word >> 24) == (old >> 24)) {
+                ran_to_end = false;  // met the previous values: the rest is unchanged
+                break;
+              }
+            }
+            if (ran_to_end) {
+              // last valid pixel of the segment
+              uint32_t lastw = myh[seg_words - 1];
+              out_px = byte_hi(lastw, (int)((seg_px - 1) & 3u));
+            }
+          }
+          first = false;
+          uint32_t prev_out = __shfl_up_sync(0xffffffffu, out_px, 1);
+          bool changed = lane > 0 && lane_active && prev_out != w_in;
+          if (!__any_sync(0xffffffffu, changed)) break;
+          need = changed;
+          if (changed) w_in = prev_out;
+        }
+      }
+      __syncwarp();
+      last_prev2 = last_prev;
+      last_prev = byte_hi(hcur[last_seg * SW + (last_off >> 2)], (int)(last_off & 3u));
+
+      // ---- write-out: delta add (bytes wrap independently, .cc:337-338),
+      //      recombination, optional UnextractFrame ---------------------------
+      const uint32_t* lb = st + slot_words;
+      const uint32_t* db = st + slot_words + Wp / 4;
+      uint16_t* orow = fout + (uint64_t)y * W;
+      for (uint32_t q = lane; q < (W + 3) / 4; q += 32) {
+        uint32_t col = 4 * q;
+        uint32_t sg = __umulhi(col, p.div_magic);
+        if ((sg + 1) * L <= col) sg++;            // magic is exact up to one step
+        else if (sg * L > col) sg--;
+        uint32_t off = col - sg * L;
+        uint32_t hw = hcur[sg * SW + (off >> 2)];
+        uint32_t lw = has_low ? lb[q] : 0u;
+        uint32_t v01 = __byte_perm(lw, hw, 0x5140);   // (h0<<8|l0) | (h1<<8|l1)<<16
+        uint32_t v23 = __byte_perm(lw, hw, 0x7362);
+        if (use_delta) {
+          v01 = __vadd4(v01, db[2 * q]);
+          v23 = __vadd4(v23, db[2 * q + 1]);
+        }
+        if (p.unextract) {
+          uint32_t m = (0xffffu >> p.shift) * 0x00010001u;
+          v01 = (v01 >> p.shift) & m;
+          v23 = (v23 >> p.shift) & m;
+          if (p.big_endian) {
+            v01 = __byte_perm(v01, 0u, 0x2301);
+            v23 = __byte_perm(v23, 0u, 0x2301);
+          }
+        }
+        if (ALIGN >= 4) {
+          *reinterpret_cast<uint2*>(orow + col) = make_uint2(v01, v23);
+        } else {
+          if (col + 0 < W) orow[col + 0] = (uint16_t)(v01 & 0xffffu);
+          if (col + 1 < W) orow[col + 1] = (uint16_t)(v01 >> 16);
+          if (col + 2 < W) orow[col + 2] = (uint16_t)(v23 & 0xffffu);
+          if (col + 3 < W) orow[col + 3] = (uint16_t)(v23 >> 16);
+        }
+      }
+      __syncwarp();  // stage (y % NST) and hprev may be overwritten from here on
+    }
+    cp_async_wait<0>();
+    __syncwarp();
+  }
+}
+
+// ---- trivially serial fallback -------------------------------------------------
+// One thread per frame runs .cc:327-332 literally on a scratch copy of the high
+// plane; a second, fully parallel kernel does .cc:335-344 (+ .cc:850-862).
+__global__ void k_cg_inverse_serial(uint8_t* planes, const uint8_t* flags, uint32_t W, uint64_t n_px,
+                                    uint32_t n) {
+  uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= n || !(flags[f] & kFlagCG)) return;
+  uint8_t* h = planes + (uint64_t)f * n_px;
+  for (uint64_t i = (uint64_t)W + 1; i < n_px; i++)
+    h[i] = (uint8_t)(h[i] + cg1(h[i - W], h[i - 1], h[i - W - 1]));
+}
+
+__global__ void k_combine(const uint8_t* high, const uint8_t* low, const uint8_t* flags,
+                          const uint16_t* delta, uint16_t* out, uint64_t P, int shift, int big_endian,
+                          int unextract) {
+  uint32_t f = blockIdx.y;
+  uint32_t fl = flags[f];
+  bool use_delta = (fl & kFlagDelta) && delta != nullptr;
+  bool has_low = !(fl & kFlagNoLow) && low != nullptr;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    uint32_t h = high[(uint64_t)f * P + i];
+    uint32_t l = has_low ? low[(uint64_t)f * P + i] : 0u;
+    if (use_delta) {
+      uint32_t d = delta[i];
+      h = (h + (d >> 8)) & 0xffu;
+      l = (l + (d & 0xffu)) & 0xffu;
+    }
+    uint32_t v = (h << 8) | l;
+    if (unextract) {
+      v >>= shift;
+      if (big_endian) v = ((v & 0xffu) << 8) | (v >> 8);
+    }
+    out[(uint64_t)f * P + i] = (uint16_t)v;
+  }
+}
+
+// high/low planes += delta planes, for frames with flags & 1 (.cc:600-603).
+__global__ void k_planes_add_delta(uint8_t* high, uint8_t* low, const uint8_t* flags,
+                                   const uint16_t* delta, uint64_t P) {
+  uint32_t f = blockIdx.y;
+  if (!(flags[f] & kFlagDelta)) return;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    uint32_t d = delta[i];
+    high[(uint64_t)f * P + i] = (uint8_t)(high[(uint64_t)f * P + i] + (d >> 8));
+    if (low) low[(uint64_t)f * P + i] = (uint8_t)(low[(uint64_t)f * P + i] + (d & 0xffu));
+  }
+}
+
+}  // namespace
+
+int enqueue_decode(const Geom& g, int num_sms, const uint8_t* high, const uint8_t* low,
+                   const uint8_t* flags, const uint16_t* delta, uint32_t n, bool unextract,
+                   uint16_t* out, cudaStream_t stream, cudaError_t* err) {
+  DecodeParams p;
+  p.high = high; p.low = low; p.flags = flags; p.delta = delta; p.out = out;
+  p.W = g.W; p.H = g.H; p.P = g.P; p.shift = g.shift; p.big_endian = g.big_endian;
+  p.unextract = unextract ? 1 : 0; p.n = n;
+  uint32_t L = (g.W + 31) / 32;
+  L = (L + 3) / 4 * 4;
+  p.L = L; p.Lw = L / 4; p.SW = p.Lw | 1u;
+  p.Wp = (g.W + 15) / 16 * 16;
+  p.div_magic = (uint32_t)((0x100000000ull + L - 1) / L);
+  const uint32_t slot_words = 32 * p.SW;
+  const uint32_t stage_words = slot_words + p.Wp / 4 + p.Wp / 2;
+  const int warps_per_block = 4;
+  const size_t limit = 200 * 1024;
+  int nst = 3;
+  while (nst > 1 && (size_t)(2 * slot_words + nst * stage_words) * 4 * warps_per_block > limit) nst--;
+  int wpb = warps_per_block;
+  while (wpb > 1 && (size_t)(2 * slot_words + nst * stage_words) * 4 * wpb > limit) wpb--;
+  p.nst = nst;
+  p.warp_smem_words = 2 * slot_words + nst * stage_words;
+  size_t smem = (size_t)p.warp_smem_words * 4 * wpb;
+  if (smem > limit) {
+    *err = cudaErrorInvalidConfiguration;  // caller falls back to enqueue_decode_serial
+    return -1;
+  }
+  int blocks = (int)((n + wpb - 1) / wpb);
+  int max_blocks = num_sms * 16;
+  if (blocks > max_blocks) blocks = max_blocks;
+  int align = (g.W % 16 == 0) ? 16 : (g.W % 4 == 0 ? 4 : 1);
+  cudaError_t e = cudaSuccess;
+  if (align == 16) {
+    e = cudaFuncSetAttribute(k_decode_spec<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit);
+    if (e == cudaSuccess) k_decode_spec<16><<<blocks, wpb * 32, smem, stream>>>(p);
+  } else if (align == 4) {
+    e = cudaFuncSetAttribute(k_decode_spec<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit);
+    if (e == cudaSuccess) k_decode_spec<4><<<blocks, wpb * 32, smem, stream>>>(p);
+  } else {
+    e = cudaFuncSetAttribute(k_decode_spec<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit);
+    if (e == cudaSuccess) k_decode_spec<1><<<blocks, wpb * 32, smem, stream>>>(p);
+  }
+  if (e == cudaSuccess) e = cudaGetLastError();
+  *err = e;
+  return e == cudaSuccess ? 1 : -1;
+}
+
+// Serial fallback: `scratch_high` must hold a writable copy of the high planes.
+int enqueue_decode_serial(const Geom& g, uint8_t* scratch_high, const uint8_t* low,
+                          const uint8_t* flags, const uint16_t* delta, uint32_t n, bool unextract,
+                          uint16_t* out, cudaStream_t stream, cudaError_t* err) {
+  k_cg_inverse_serial<<<(n + 31) / 32, 32, 0, stream>>>(scratch_high, flags, g.W, g.P, n);
+  *err = cudaGetLastError();
+  if (*err != cudaSuccess) return -1;
+  unsigned gx = (unsigned)((g.P + 255) / 256); if (gx > 2048) gx = 2048; if (gx < 1) gx = 1;
+  k_combine<<<dim3(gx, n), 256, 0, stream>>>(scratch_high, low, flags, delta, out, g.P, g.shift,
+                                             g.big_endian, unextract ? 1 : 0);
+  *err = cudaGetLastError();
+  return *err == cudaSuccess ? 2 : -1;
+}
+
+int enqueue_unpredict_planes(const Geom& g, int num_sms, uint8_t* high, uint8_t* low,
+                             uint8_t* preview, const uint8_t* flags, const uint16_t* delta,
+                             uint32_t n, cudaStream_t stream, cudaError_t* err) {
+  (void)num_sms;
+  int launches = 0;
+  k_cg_inverse_serial<<<(n + 31) / 32, 32, 0, stream>>>(high, flags, g.W, g.P, n);
+  launches++;
+  if (preview) {
+    k_cg_inverse_serial<<<(n + 31) / 32, 32, 0, stream>>>(preview, flags, g.PW, g.PP, n);
+    launches++;
+  }
+  if (delta) {
+    unsigned gx = (unsigned)((g.P + 255) / 256); if (gx > 2048) gx = 2048; if (gx < 1) gx = 1;
+    k_planes_add_delta<<<dim3(gx, n), 256, 0, stream>>>(high, low, flags, delta, g.P);
+    launches++;
+  }
+  *err = cudaGetLastError();
+  return *err == cudaSuccess ? launches : -1;
+}
+
+}  // namespace fpv

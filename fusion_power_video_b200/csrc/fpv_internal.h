@@ -1,0 +1,76 @@
+// fpv_internal.h -- launcher interface between the C ABI (fpv_cabi.cu) and the
+// kernels (fpv_encode.cu, fpv_decode.cu).  Not installed; not part of the ABI.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "fpv_common.cuh"
+
+namespace fpv {
+
+struct Geom {
+  uint32_t W = 0, H = 0;
+  uint64_t P = 0;        // W * H
+  uint32_t PW = 0;       // W / 4
+  uint64_t PP = 0;       // (W/4) * (H/4)
+  int shift = 0;
+  int big_endian = 0;
+  int mode = 0;          // SplitMode
+};
+
+// Device scratch for one encode pass over up to `cap` frames.
+struct EncodeScratch {
+  FrameStat* stats = nullptr;     // [cap]
+  uint32_t* lists = nullptr;      // [3][cap] frame indices for pass 0,1,2
+  uint32_t* counts = nullptr;     // [4]: list counts 0..2, [3] = flags guess for the next batch
+  uint8_t* preview_raw = nullptr; // [cap][PP]
+  uint32_t cap = 0;
+};
+
+struct EncodeTuning {
+  int num_sms = 148;
+  int stages = 3;          // smem ring depth of the fast kernel
+  int band_rows = 64;      // rows per task (multiple of 4)
+  int max_smem_optin = 0;  // bytes
+};
+
+// True if the TMA fast path supports this geometry.
+bool encode_fast_supported(const Geom& g, const EncodeTuning& t);
+
+// Enqueues the whole encode transform for n <= scratch.cap frames on `stream`.
+// frames: uint16[n][P] device; delta: uint16[P] image-form device or nullptr.
+// Outputs: flags[n], high[n][P], low[n][P] (nullptr iff mode has no low
+// plane), preview[n][PP].  Returns the number of kernels launched, or -1 with
+// *err set.
+int enqueue_encode(const Geom& g, const EncodeTuning& t, const EncodeScratch& s,
+                   const uint16_t* frames, const uint16_t* delta, uint32_t n, bool force_generic,
+                   uint8_t* flags, uint8_t* high, uint8_t* low, uint8_t* preview,
+                   cudaStream_t stream, cudaError_t* err);
+
+// Splits a raw delta frame into image form ((high << 8) | low per pixel).
+int enqueue_delta_from_raw(const Geom& g, const uint16_t* raw, uint16_t* delta_image,
+                           cudaStream_t stream, cudaError_t* err);
+
+// Inverse transform for n frames (any n).  out: uint16[n][P] images, or raw
+// file bytes when `unextract`.
+int enqueue_decode(const Geom& g, int num_sms, const uint8_t* high, const uint8_t* low,
+                   const uint8_t* flags, const uint16_t* delta, uint32_t n, bool unextract,
+                   uint16_t* out, cudaStream_t stream, cudaError_t* err);
+
+// Serial fallback (one thread per frame runs the chain literally); used for
+// rows too wide for the shared-memory row pipeline and as a cross-check.
+// `scratch_high` is a WRITABLE copy of the high planes (inverse CG is applied
+// in place).
+int enqueue_decode_serial(const Geom& g, uint8_t* scratch_high, const uint8_t* low,
+                          const uint8_t* flags, const uint16_t* delta, uint32_t n, bool unextract,
+                          uint16_t* out, cudaStream_t stream, cudaError_t* err);
+
+// Plane-level inverse (Frame::Uncompress): inverse CG in place on a plane of
+// row pitch W and n_px bytes per frame, for frames with flags & 2; then
+// (optionally) delta add on high/low planes.
+int enqueue_unpredict_planes(const Geom& g, int num_sms, uint8_t* high, uint8_t* low,
+                             uint8_t* preview, const uint8_t* flags, const uint16_t* delta,
+                             uint32_t n, cudaStream_t stream, cudaError_t* err);
+
+}  // namespace fpv

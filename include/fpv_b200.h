@@ -1,0 +1,176 @@
+/*
+ * fpv_b200.h -- C ABI of the B200 (sm_100a) pre-entropy transform for
+ * fusion-power-video streams.
+ *
+ * The reference (google/fusion-power-video) has no plugin/FFI interface: its
+ * boundary is the C++ API in fusion_power_video.h.  This header is the thin
+ * layer that API is re-plumbed onto.  Every entry point below replaces a
+ * specific span of the reference's CPU code; citations are file:line into the
+ * reference's fusion_power_video.cc (".cc") and fusion_power_video.h (".h").
+ *
+ * Conventions: extern "C", opaque handle, plain pointers and sizes, int status
+ * (0 = FPV_OK).  No C++ types, no exceptions, no torch types cross this
+ * boundary.  A context is bound to one CUDA device and one frame geometry;
+ * calls on one context must be serialised by the caller (one context per
+ * worker / per GPU), different contexts are independent.
+ *
+ * Layout of all buffers: frames are dense, frame-major.
+ *   raw frames   uint16[n][ysize*xsize]   as read from the raw file (native
+ *                                         little-endian load; big_endian says
+ *                                         the file data is byte-swapped)
+ *   high / low   uint8 [n][ysize*xsize]   byte planes, exactly the bytes
+ *                                         Frame::high()/low() hold after
+ *                                         Frame::Predict()
+ *   preview      uint8 [n][(ysize/4)*(xsize/4)]
+ *   flags        uint8 [n]                FrameFlags (.h:68-73): 1 USE_DELTA,
+ *                                         2 USE_CG, 4 NO_LOW_BYTES
+ *   images       uint16[n][ysize*xsize]   decoded 16-bit frames, as
+ *                                         DecompressImage writes them
+ */
+#ifndef FPV_B200_H_
+#define FPV_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FPV_OK 0
+#define FPV_ERR_INVALID_ARG 1   /* null pointer, zero size, n > max_batch ...   */
+#define FPV_ERR_CUDA 2          /* a CUDA runtime call failed; see last_error   */
+#define FPV_ERR_UNSUPPORTED 3   /* geometry the reference itself mishandles     */
+#define FPV_ERR_NO_DELTA 4      /* USE_DELTA frame but no delta frame was set   */
+#define FPV_ERR_NO_DEVICE 5     /* no CUDA device / driver                      */
+
+/* FrameFlags, .h:68-73 */
+#define FPV_FLAG_USE_DELTA 1
+#define FPV_FLAG_USE_CG 2
+#define FPV_FLAG_NO_LOW_BYTES 4
+
+/* encode options */
+#define FPV_ENC_DEFAULT 0u
+#define FPV_ENC_NO_DELTA 1u     /* predict with Frame::EMPTY (the delta frame's
+                                   own header encoding, .cc:1099-1100)          */
+#define FPV_ENC_GENERIC 2u      /* force the generic (non-TMA) kernels          */
+
+/* decode options */
+#define FPV_DEC_DEFAULT 0u
+#define FPV_DEC_UNEXTRACT 1u    /* also apply UnextractFrame (.cc:850-862):
+                                   output is the raw file bytes, not images     */
+
+typedef struct fpv_ctx fpv_ctx;
+
+/* ---- lifetime ---------------------------------------------------------- */
+
+/* Creates a context on CUDA device `device` for xsize*ysize frames.
+ * shift_to_left_align / big_endian: as Encoder's constructor (.h:179,
+ * .cc:1076-1079) and UnextractFrame (.h:32-34).  max_batch bounds `n` of the
+ * host-buffer calls (device staging is sized for it); device-pointer calls
+ * accept any n. */
+int fpv_create(fpv_ctx** ctx, int device, uint32_t xsize, uint32_t ysize,
+               int shift_to_left_align, int big_endian, uint32_t max_batch);
+void fpv_destroy(fpv_ctx* ctx);
+
+/* Human-readable description of the last failure on this context (or of the
+ * last failed fpv_create when ctx is NULL).  Never NULL. */
+const char* fpv_last_error(const fpv_ctx* ctx);
+
+/* Library / device introspection. */
+int fpv_device_count(void);
+const char* fpv_version(void);
+size_t fpv_plane_bytes(const fpv_ctx* ctx);    /* xsize*ysize            */
+size_t fpv_preview_bytes(const fpv_ctx* ctx);  /* (xsize/4)*(ysize/4)    */
+/* Number of kernels launched by this context so far (bench.py's
+ * gpu_launches counts the difference across the timed region). */
+uint64_t fpv_kernel_launches(const fpv_ctx* ctx);
+
+/* Pinned host memory for the overlapped host<->device pipeline. */
+void* fpv_host_alloc(size_t bytes);
+void fpv_host_free(void* p);
+
+/* ---- delta frame -------------------------------------------------------- */
+
+/* Encoder side.  Replaces `delta_frame_ = Frame(xsize, ysize, delta_frame,
+ * shift, big_endian)` in Encoder::Init (.cc:1097): splits the raw delta frame
+ * on the device and keeps its high/low planes resident.  raw == NULL clears
+ * the delta frame (Frame::EMPTY, .cc:780). */
+int fpv_set_delta_raw(fpv_ctx* ctx, const uint16_t* raw_host);
+int fpv_set_delta_raw_device(fpv_ctx* ctx, const void* raw_dev, void* stream);
+
+/* Decoder side.  The delta frame as the decoded 16-bit image that
+ * DecompressImage receives as `delta_frame` (.cc:296, filled at .cc:902-906 /
+ * :983-987). */
+int fpv_set_delta_image(fpv_ctx* ctx, const uint16_t* image_host);
+int fpv_set_delta_image_device(fpv_ctx* ctx, const void* image_dev, void* stream);
+
+/* Multi-GPU: copies the resident delta planes of `src` (another device) into
+ * `dst` by peer copy -- the only inter-GPU traffic of the path (frames are
+ * independent given the delta frame, .cc:36-38). */
+int fpv_copy_delta_peer(fpv_ctx* dst, const fpv_ctx* src);
+
+/* ---- encode transform --------------------------------------------------- */
+
+/* Replaces, for n frames at once, `Frame(xsize, ysize, img, shift,
+ * big_endian)` + `Frame::Predict(delta_frame_)` as called from
+ * Encoder::RunTask (.cc:1162-1164 -> :370-451, :777-785): split, preview,
+ * optional delta prediction, optional ClampedGradient prediction (high plane
+ * and preview), including the reference's integer heuristics (.cc:517-564)
+ * bit for bit.  Outputs are exactly the bytes the Frame holds after Predict().
+ * `low` may be NULL when shift_to_left_align == 8 (no low plane exists).
+ * Requires xsize % 4 == 0 and ysize % 4 == 0 (the reference reads out of
+ * bounds otherwise, .cc:577-578): FPV_ERR_UNSUPPORTED.
+ *
+ * Host-buffer form: synchronous; copies in, transforms, copies out. */
+int fpv_encode(fpv_ctx* ctx, const uint16_t* frames_host, uint32_t n, uint32_t options,
+               uint8_t* flags_host, uint8_t* high_host, uint8_t* low_host,
+               uint8_t* preview_host);
+
+/* Device-pointer form: all pointers are device memory on the context's
+ * device; work is enqueued on `stream` (a cudaStream_t; NULL = the legacy
+ * default stream) and not synchronised. */
+int fpv_encode_device(fpv_ctx* ctx, const void* frames_dev, uint32_t n, uint32_t options,
+                      void* flags_dev, void* high_dev, void* low_dev, void* preview_dev,
+                      void* stream);
+
+/* Overlapped form for the Encoder pipeline: `slot` (0 or 1) selects one of
+ * two staging sets with its own stream; submit returns after enqueueing
+ * H2D copy + kernels + D2H copies, wait blocks until that slot's outputs
+ * have landed in the (pinned) host buffers. */
+int fpv_encode_submit(fpv_ctx* ctx, uint32_t slot, const uint16_t* frames_host, uint32_t n,
+                      uint32_t options, uint8_t* flags_host, uint8_t* high_host,
+                      uint8_t* low_host, uint8_t* preview_host);
+int fpv_wait(fpv_ctx* ctx, uint32_t slot);
+
+/* ---- decode (inverse) transform ---------------------------------------- */
+
+/* Replaces the post-brotli part of DecompressImage (.cc:326-344) for n frames
+ * at once: inverse ClampedGradient on the high plane (flags & 2), delta add
+ * with independent byte wrap (flags & 1), recombination to uint16; low bytes
+ * are taken as zero for frames with flags & 4 (their `low` slot is not read;
+ * `low` may be NULL if every frame has flags & 4).  With FPV_DEC_UNEXTRACT the
+ * output is additionally passed through UnextractFrame (.cc:850-862) with the
+ * context's shift/big_endian, i.e. `out` receives the raw file bytes.
+ * Any xsize, ysize >= 1. */
+int fpv_decode(fpv_ctx* ctx, const uint8_t* high_host, const uint8_t* low_host,
+               const uint8_t* flags_host, uint32_t n, uint32_t options, void* out_host);
+int fpv_decode_device(fpv_ctx* ctx, const void* high_dev, const void* low_dev,
+                      const void* flags_dev, uint32_t n, uint32_t options, void* out_dev,
+                      void* stream);
+int fpv_decode_submit(fpv_ctx* ctx, uint32_t slot, const uint8_t* high_host,
+                      const uint8_t* low_host, const uint8_t* flags_host, uint32_t n,
+                      uint32_t options, void* out_host);
+
+/* Plane-level inverse, replacing Frame::Uncompress's prediction undo
+ * (.cc:773-774 -> :612-641, :595-610): inverse CG on high and preview, delta
+ * add on both byte planes; planes are rewritten in place (host buffers).
+ * preview may be NULL. */
+int fpv_unpredict_planes(fpv_ctx* ctx, uint8_t* high_host, uint8_t* low_host,
+                         uint8_t* preview_host, const uint8_t* flags_host, uint32_t n);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif  /* FPV_B200_H_ */
