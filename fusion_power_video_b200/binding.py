@@ -58,6 +58,10 @@ def lib() -> C.CDLL:
     L.fpv_preview_bytes.restype = sz
     L.fpv_kernel_launches.argtypes = [vp]
     L.fpv_kernel_launches.restype = u64
+    L.fpv_enable_kernel_timing.argtypes = [vp, i32]
+    L.fpv_enable_kernel_timing.restype = i32
+    L.fpv_read_kernel_timing.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(u32)]
+    L.fpv_read_kernel_timing.restype = i32
     L.fpv_host_alloc.argtypes = [sz]
     L.fpv_host_alloc.restype = vp
     L.fpv_host_free.argtypes = [vp]
@@ -171,6 +175,15 @@ class Context:
     @property
     def kernel_launches(self) -> int:
         return int(self._L.fpv_kernel_launches(self._h))
+
+    def enable_kernel_timing(self, on=True):
+        self._check(self._L.fpv_enable_kernel_timing(self._h, int(on)))
+
+    def read_kernel_timing(self):
+        """(total device ms of the dominant kernel, number of launches) since the last read."""
+        ms, cnt = C.c_double(0), C.c_uint32(0)
+        self._check(self._L.fpv_read_kernel_timing(self._h, C.byref(ms), C.byref(cnt)))
+        return ms.value, cnt.value
 
     # -- delta frame --------------------------------------------------------
     def set_delta_raw(self, raw):

@@ -13,6 +13,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <vector>
 
 #include "../../include/fpv_b200.h"
 #include "fpv_internal.h"
@@ -54,6 +55,9 @@ struct fpv_ctx {
   cudaStream_t aux_stream = nullptr;
   uint64_t launches = 0;
   bool force_generic = false;
+  bool timing_on = false;
+  std::vector<TimingHook> timing;   // event pairs, reused
+  size_t timing_used = 0;
   std::string err = "no error";
 };
 
@@ -77,6 +81,17 @@ int cuda_fail(fpv_ctx* c, cudaError_t e, const char* what) {
     cudaError_t e__ = (call);                                   \
     if (e__ != cudaSuccess) return cuda_fail(c, e__, #call);    \
   } while (0)
+
+// Next event pair for the dominant kernel, or nullptr when timing is off.
+const TimingHook* next_hook(fpv_ctx* c) {
+  if (!c->timing_on) return nullptr;
+  if (c->timing_used == c->timing.size()) {
+    TimingHook h;
+    if (cudaEventCreate(&h.start) != cudaSuccess || cudaEventCreate(&h.stop) != cudaSuccess) return nullptr;
+    c->timing.push_back(h);
+  }
+  return &c->timing[c->timing_used++];
+}
 
 int ensure_scratch(fpv_ctx* c, int idx) {
   EncodeScratch& s = c->scratch[idx];
@@ -124,7 +139,8 @@ int encode_device_chunked(fpv_ctx* c, int scratch_idx, const uint16_t* frames, u
     cudaError_t e = cudaSuccess;
     int l = enqueue_encode(c->g, c->tune, c->scratch[scratch_idx], frames + (uint64_t)off * P, delta, m,
                            generic, flags + off, high + (uint64_t)off * P,
-                           low ? low + (uint64_t)off * P : nullptr, preview + (uint64_t)off * PP, stream, &e);
+                           low ? low + (uint64_t)off * P : nullptr, preview + (uint64_t)off * PP, stream, &e,
+                           next_hook(c));
     if (l < 0) return cuda_fail(c, e, "encode kernel launch");
     c->launches += (uint64_t)l;
   }
@@ -139,7 +155,8 @@ int decode_device_impl(fpv_ctx* c, const uint8_t* high, const uint8_t* low, cons
   const bool unextract = (options & FPV_DEC_UNEXTRACT) != 0;
   int l = -1;
   if (!getenv("FPV_DECODE_SERIAL"))
-    l = enqueue_decode(c->g, c->tune.num_sms, high, low, flags, delta, n, unextract, out, stream, &e);
+    l = enqueue_decode(c->g, c->tune.num_sms, high, low, flags, delta, n, unextract, out, stream, &e,
+                       next_hook(c));
   if (l < 0) {
     // rows too wide for the shared-memory row pipeline (or forced): serial chain
     uint8_t* scratch = const_cast<uint8_t*>(high);
@@ -244,6 +261,10 @@ void fpv_destroy(fpv_ctx* c) {
     if (s.d_flags) cudaFree(s.d_flags);
     if (s.stream) cudaStreamDestroy(s.stream);
   }
+  for (auto& h : c->timing) {
+    if (h.start) cudaEventDestroy(h.start);
+    if (h.stop) cudaEventDestroy(h.stop);
+  }
   if (c->d_serial_scratch) cudaFree(c->d_serial_scratch);
   if (c->d_delta) cudaFree(c->d_delta);
   if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
@@ -261,6 +282,29 @@ const char* fpv_last_error(const fpv_ctx* c) {
 size_t fpv_plane_bytes(const fpv_ctx* c) { return c ? (size_t)c->g.P : 0; }
 size_t fpv_preview_bytes(const fpv_ctx* c) { return c ? (size_t)c->g.PP : 0; }
 uint64_t fpv_kernel_launches(const fpv_ctx* c) { return c ? c->launches : 0; }
+
+int fpv_enable_kernel_timing(fpv_ctx* c, int on) {
+  if (!c) return FPV_ERR_INVALID_ARG;
+  c->timing_on = on != 0;
+  c->timing_used = 0;
+  return FPV_OK;
+}
+
+int fpv_read_kernel_timing(fpv_ctx* c, double* total_ms, uint32_t* launches) {
+  if (!c || !total_ms || !launches) return FPV_ERR_INVALID_ARG;
+  FPV_CUDA(cudaSetDevice(c->device));
+  double total = 0;
+  for (size_t i = 0; i < c->timing_used; i++) {
+    FPV_CUDA(cudaEventSynchronize(c->timing[i].stop));
+    float ms = 0;
+    FPV_CUDA(cudaEventElapsedTime(&ms, c->timing[i].start, c->timing[i].stop));
+    total += ms;
+  }
+  *total_ms = total;
+  *launches = (uint32_t)c->timing_used;
+  c->timing_used = 0;
+  return FPV_OK;
+}
 
 void* fpv_host_alloc(size_t bytes) {
   void* p = nullptr;

@@ -320,7 +320,7 @@ __global__ void k_planes_add_delta(uint8_t* high, uint8_t* low, const uint8_t* f
 
 int enqueue_decode(const Geom& g, int num_sms, const uint8_t* high, const uint8_t* low,
                    const uint8_t* flags, const uint16_t* delta, uint32_t n, bool unextract,
-                   uint16_t* out, cudaStream_t stream, cudaError_t* err) {
+                   uint16_t* out, cudaStream_t stream, cudaError_t* err, const TimingHook* hook) {
   DecodeParams p;
   p.high = high; p.low = low; p.flags = flags; p.delta = delta; p.out = out;
   p.W = g.W; p.H = g.H; p.P = g.P; p.shift = g.shift; p.big_endian = g.big_endian;
@@ -350,6 +350,7 @@ int enqueue_decode(const Geom& g, int num_sms, const uint8_t* high, const uint8_
   if (blocks > max_blocks) blocks = max_blocks;
   int align = (g.W % 16 == 0) ? 16 : (g.W % 4 == 0 ? 4 : 1);
   cudaError_t e = cudaSuccess;
+  if (hook) cudaEventRecord(hook->start, stream);
   if (align == 16) {
     e = cudaFuncSetAttribute(k_decode_spec<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit);
     if (e == cudaSuccess) k_decode_spec<16><<<blocks, wpb * 32, smem, stream>>>(p);
@@ -361,6 +362,7 @@ int enqueue_decode(const Geom& g, int num_sms, const uint8_t* high, const uint8_
     if (e == cudaSuccess) k_decode_spec<1><<<blocks, wpb * 32, smem, stream>>>(p);
   }
   if (e == cudaSuccess) e = cudaGetLastError();
+  if (hook) cudaEventRecord(hook->stop, stream);
   *err = e;
   return e == cudaSuccess ? 1 : -1;
 }

@@ -631,7 +631,7 @@ int enqueue_delta_from_raw(const Geom& g, const uint16_t* raw, uint16_t* delta_i
 int enqueue_encode(const Geom& g, const EncodeTuning& t, const EncodeScratch& s,
                    const uint16_t* frames, const uint16_t* delta, uint32_t n, bool force_generic,
                    uint8_t* flags, uint8_t* high, uint8_t* low, uint8_t* preview,
-                   cudaStream_t stream, cudaError_t* err) {
+                   cudaStream_t stream, cudaError_t* err, const TimingHook* hook) {
   int launches = 0;
   const int has_delta = delta != nullptr;
   const int has_low = mode_has_low(g.mode);
@@ -677,7 +677,9 @@ int enqueue_encode(const Geom& g, const EncodeTuning& t, const EncodeScratch& s,
       // redo passes are almost always empty: a small grid is enough
       int gpass = pass == 0 ? grid : (grid < t.num_sms ? grid : t.num_sms);
       cudaError_t e = cudaSuccess;
+      if (hook && pass == 0) cudaEventRecord(hook->start, stream);
       FPV_DISPATCH_MODE(g.mode, (e = launch_fast<M>(fp, gpass, threads, smem, stream)));
+      if (hook && pass == 0) cudaEventRecord(hook->stop, stream);
       launches++;
       if (e != cudaSuccess) { *err = e; return -1; }
       if (pass < 2) {
@@ -702,7 +704,9 @@ int enqueue_encode(const Geom& g, const EncodeTuning& t, const EncodeScratch& s,
     FPV_CHECK_LAUNCH();
     unsigned gtx = (unsigned)((g.P / 4 + 255) / 256); if (gtx < 1) gtx = 1; if (gtx > 4096) gtx = 4096;
     dim3 gT(gtx, n);
+    if (hook) cudaEventRecord(hook->start, stream);
     FPV_DISPATCH_MODE(g.mode, (k_gen_transform<M><<<gT, 256, 0, stream>>>(frames, delta, s.stats, high, low, g.W, g.P, g.shift)));
+    if (hook) cudaEventRecord(hook->stop, stream);
     FPV_CHECK_LAUNCH();
     unsigned gpx = (unsigned)((g.PP + 255) / 256); if (gpx < 1) gpx = 1; if (gpx > 1024) gpx = 1024;
     dim3 gP(gpx, n);

@@ -35,6 +35,12 @@ struct EncodeTuning {
   int max_smem_optin = 0;  // bytes
 };
 
+// Optional pair of events recorded around the dominant kernel of a call.
+struct TimingHook {
+  cudaEvent_t start = nullptr;
+  cudaEvent_t stop = nullptr;
+};
+
 // True if the TMA fast path supports this geometry.
 bool encode_fast_supported(const Geom& g, const EncodeTuning& t);
 
@@ -46,7 +52,7 @@ bool encode_fast_supported(const Geom& g, const EncodeTuning& t);
 int enqueue_encode(const Geom& g, const EncodeTuning& t, const EncodeScratch& s,
                    const uint16_t* frames, const uint16_t* delta, uint32_t n, bool force_generic,
                    uint8_t* flags, uint8_t* high, uint8_t* low, uint8_t* preview,
-                   cudaStream_t stream, cudaError_t* err);
+                   cudaStream_t stream, cudaError_t* err, const TimingHook* hook = nullptr);
 
 // Splits a raw delta frame into image form ((high << 8) | low per pixel).
 int enqueue_delta_from_raw(const Geom& g, const uint16_t* raw, uint16_t* delta_image,
@@ -56,7 +62,8 @@ int enqueue_delta_from_raw(const Geom& g, const uint16_t* raw, uint16_t* delta_i
 // file bytes when `unextract`.
 int enqueue_decode(const Geom& g, int num_sms, const uint8_t* high, const uint8_t* low,
                    const uint8_t* flags, const uint16_t* delta, uint32_t n, bool unextract,
-                   uint16_t* out, cudaStream_t stream, cudaError_t* err);
+                   uint16_t* out, cudaStream_t stream, cudaError_t* err,
+                   const TimingHook* hook = nullptr);
 
 // Serial fallback (one thread per frame runs the chain literally); used for
 // rows too wide for the shared-memory row pipeline and as a cross-check.

@@ -86,6 +86,14 @@ size_t fpv_preview_bytes(const fpv_ctx* ctx);  /* (xsize/4)*(ysize/4)    */
  * gpu_launches counts the difference across the timed region). */
 uint64_t fpv_kernel_launches(const fpv_ctx* ctx);
 
+/* Live roofline measurement (bench.py): when enabled, every launch of the
+ * dominant kernel of a call (the fused encode kernel / the inverse kernel) is
+ * bracketed by CUDA events on the launching stream.  fpv_read_kernel_timing
+ * synchronises those events, returns the summed device time in milliseconds
+ * and the number of launches it covers, and clears the record. */
+int fpv_enable_kernel_timing(fpv_ctx* ctx, int on);
+int fpv_read_kernel_timing(fpv_ctx* ctx, double* total_ms, uint32_t* launches);
+
 /* Pinned host memory for the overlapped host<->device pipeline. */
 void* fpv_host_alloc(size_t bytes);
 void fpv_host_free(void* p);

@@ -1,0 +1,145 @@
+"""GPU parity tests for the inverse transform (DecompressImage's post-brotli
+part, UnextractFrame, Frame::Uncompress's plane undo) through the C ABI."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import fusion_power_video_b200 as fpv
+from fusion_power_video_b200 import synth
+from oracle_binding import Oracle
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+CASES = [p for p in sorted(glob.glob(os.path.join(GOLDEN, "case_*.npz"))) if "decoded" in np.load(p).files]
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    return Oracle()
+
+
+@pytest.mark.parametrize("serial", [False, True], ids=["spec", "serial"])
+@pytest.mark.parametrize("path", CASES, ids=[os.path.basename(p)[5:-4] for p in CASES])
+def test_golden_case(path, serial, monkeypatch):
+    if serial:
+        monkeypatch.setenv("FPV_DECODE_SERIAL", "1")
+    g = np.load(path)
+    W, H, shift, be = int(g["W"]), int(g["H"]), int(g["shift"]), int(g["be"])
+    low = g["low"] if shift != 8 else None
+    with fpv.Context(W, H, shift, be, max_batch=8) as ctx:
+        ctx.set_delta_image(g["delta_image"])
+        img = ctx.decode(g["high"], low, g["flags"])
+        assert np.array_equal(img, g["decoded"])
+        raw = ctx.decode(g["high"], low, g["flags"], fpv.DEC_UNEXTRACT)
+        assert np.array_equal(raw.view(np.uint8).reshape(raw.shape[0], -1), g["unextracted"])
+        # the encoder-side delta entry point yields the same resident delta frame
+        ctx.set_delta_raw(g["delta"])
+        assert np.array_equal(ctx.decode(g["high"], low, g["flags"]), g["decoded"])
+
+
+@pytest.mark.parametrize(
+    "W,H",
+    [(1, 1), (1, 9), (7, 1), (2, 2), (3, 5), (13, 7), (31, 4), (32, 3), (33, 6), (64, 5), (100, 10), (129, 3), (250, 9), (516, 4), (1000, 3)],
+)
+def test_arbitrary_geometry_random_planes(oracle, W, H):
+    """The inverse is defined for ANY residual planes and any W, H >= 1 (no % 4 requirement)."""
+    rng = np.random.default_rng(W * 1000 + H)
+    n = 8
+    high = rng.integers(0, 256, (n, W * H), dtype=np.uint8)
+    high[1] = 0
+    high[2] = rng.integers(0, 3, W * H)
+    low = rng.integers(0, 256, (n, W * H), dtype=np.uint8)
+    delta = rng.integers(0, 65536, W * H, dtype=np.uint16)
+    flags = np.array([0, 1, 2, 3, 4, 5, 6, 7], np.uint8)
+    with fpv.Context(W, H, 3, 0, max_batch=4) as ctx:
+        ctx.set_delta_image(delta)
+        img = ctx.decode(high, low, flags)
+        raw = ctx.decode(high, low, flags, fpv.DEC_UNEXTRACT)
+        for i in range(n):
+            exp = oracle.inverse(high[i], None if flags[i] & 4 else low[i], delta, W, H, int(flags[i]))
+            assert np.array_equal(img[i], exp), f"frame {i} flags {flags[i]}: first diff at {np.flatnonzero(img[i] != exp)[:8]}"
+            assert np.array_equal(raw[i].view(np.uint8), oracle.unextract(exp, 3, 0))
+
+
+@pytest.mark.parametrize("kind", ["random", "smooth", "sparse", "sawtooth"])
+@pytest.mark.parametrize("W,H", [(1280, 40), (1024, 64), (2048, 16), (4096, 8)])
+def test_speculation_adversarial(oracle, W, H, kind):
+    """Residual planes chosen to make the incoming-west guess wrong as often as possible."""
+    rng = np.random.default_rng(7)
+    n = 3
+    if kind == "random":
+        high = rng.integers(0, 256, (n, W * H), dtype=np.uint8)
+    elif kind == "smooth":
+        img = synth.plasma_frames(n, W, H, bits=16, seed=4).reshape(n, -1)
+        high = np.stack([oracle.cg_forward((f >> 8).astype(np.uint8), W) for f in img])
+    elif kind == "sparse":
+        high = (rng.random((n, W * H)) < 0.01).astype(np.uint8) * rng.integers(1, 256, (n, W * H), dtype=np.uint8)
+    else:
+        high = np.tile((np.arange(W * H) % 7 == 0).astype(np.uint8) * 200, (n, 1)).astype(np.uint8)
+        high[:, ::2] += 1
+    flags = np.full(n, 2 | 4, np.uint8)
+    with fpv.Context(W, H, 0, 0, max_batch=4) as ctx:
+        img = ctx.decode(high, None, flags)
+        for i in range(n):
+            exp = oracle.inverse(high[i], None, None, W, H, 6)
+            assert np.array_equal(img[i], exp), f"frame {i}: first diff at {np.flatnonzero(img[i] != exp)[:8]}"
+
+
+def test_big_endian_unextract(oracle):
+    W, H, n = 64, 16, 2
+    rng = np.random.default_rng(3)
+    high = rng.integers(0, 256, (n, W * H), dtype=np.uint8)
+    low = rng.integers(0, 256, (n, W * H), dtype=np.uint8)
+    flags = np.array([2, 0], np.uint8)
+    with fpv.Context(W, H, 4, 1, max_batch=4) as ctx:
+        raw = ctx.decode(high, low, flags, fpv.DEC_UNEXTRACT)
+        for i in range(n):
+            exp = oracle.unextract(oracle.inverse(high[i], low[i], None, W, H, int(flags[i])), 4, 1)
+            assert np.array_equal(raw[i].view(np.uint8), exp)
+
+
+def test_use_delta_without_delta_frame_is_an_error():
+    with fpv.Context(16, 16, 0, 0, max_batch=1) as ctx:
+        with pytest.raises(fpv.FpvError) as e:
+            ctx.decode(np.zeros((1, 256), np.uint8), np.zeros((1, 256), np.uint8), np.array([1], np.uint8))
+        assert e.value.code == 4  # "delta frame not given", .cc:310
+
+
+def test_unpredict_planes_vs_oracle(oracle):
+    W, H, n = 128, 32, 4
+    frames = synth.plasma_frames(n, W, H, bits=16, seed=31).reshape(n, -1)
+    yy, xx = np.meshgrid(np.arange(H), np.arange(W), indexing="ij")
+    frames[2] = ((xx * 300 + yy * 500) & 0xFFFF).astype(np.uint16).reshape(-1)
+    dh, dl = oracle.delta_planes(frames[0], 0, 0)
+    with fpv.Context(W, H, 0, 0, max_batch=2) as ctx:
+        ctx.set_delta_raw(frames[0])
+        flags, high, low, preview = ctx.encode(frames)
+        h2, l2, p2 = ctx.unpredict_planes(high, low, preview, flags)
+        for i in range(n):
+            eh, el, ep = oracle.unpredict_planes(high[i], low[i], preview[i], dh, dl, W, H, int(flags[i]))
+            assert np.array_equal(h2[i], eh) and np.array_equal(l2[i], el) and np.array_equal(p2[i], ep)
+            # and it really undoes the prediction
+            assert np.array_equal((h2[i].astype(np.uint16) << 8) | l2[i], frames[i])
+
+
+def test_device_pointer_decode(oracle):
+    import torch
+
+    W, H, n = 1024, 256, 6
+    frames = synth.plasma_frames(n, W, H, bits=16, seed=13).reshape(n, -1)
+    dev = torch.device("cuda:0")
+    with fpv.Context(W, H, 0, 0, max_batch=8) as ctx:
+        ctx.set_delta_raw(frames[0])
+        flags, high, low, preview = ctx.encode(frames)
+        d_high = torch.from_numpy(high).to(dev)
+        d_low = torch.from_numpy(low).to(dev)
+        d_flags = torch.from_numpy(flags).to(dev)
+        d_out = torch.zeros((n, W * H), dtype=torch.int16, device=dev)
+        s = torch.cuda.Stream()
+        with torch.cuda.stream(s):
+            ctx.decode_device(d_high.data_ptr(), d_low.data_ptr(), d_flags.data_ptr(), n, d_out.data_ptr(), stream=s.cuda_stream)
+        s.synchronize()
+        assert np.array_equal(d_out.cpu().numpy().view(np.uint16), frames)
