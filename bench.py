@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 pre-entropy transform.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1]): 12-bit 1280x800 high-speed-camera frames
+stored as uint16 (shift 4), static delta frame = frame 0, one GPU holding a
+contiguous range of the sequence resident in HBM.  A *step* is one pass of the
+encode transform (Frame ctor + Frame::Predict of the reference) over that
+range.  With N GPUs every rank owns its own contiguous frame range (weak
+scaling, no data-path collective; the delta frame is uploaded to each GPU).
+
+Prints ONE JSON line (rank 0).  `value` is device-resident raw-pixel GB/s
+(2 bytes x pixels / s) over all GPUs; `e2e` is the same metric through the
+host-buffer C-ABI calls (pinned H2D + kernels + D2H inside the timed region);
+`roofline` is the fused encode kernel against the measured HBM peak;
+`cpu_baseline` is the reference's own CPU code (oracle/_ref) on this box's
+host cores.  `--impl reference` times only that CPU code.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # name: (xsize, ysize, bits, shift, description)
+    "c2": (1280, 800, 12, 4, "12-bit 1280x800 camera stream, static delta frame, device-resident (BASELINE configs[1])"),
+    "c1": (1024, 1024, 16, 0, "16-bit 1024x1024 (BASELINE configs[0] geometry)"),
+    "c3": (2048, 2048, 16, 0, "16-bit 2048x2048, sharded by frame range (BASELINE configs[2] geometry)"),
+}
+ENC_BYTES_PER_PX = 2 + 1 + 1 + 1.0 / 16  # raw in, high out, low out, preview out
+DEC_BYTES_PER_PX = 1 + 1 + 2             # planes in, uint16 out
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed regions run."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc, self.thread = index, [], None, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(self.index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, windows):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        time.sleep(0.12)
+        self.proc.terminate()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for t, line in self.rows:
+            if not any(a <= t <= b + 0.06 for a, b in windows):
+                continue
+            p = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(p[0])); mx.append(float(p[1])); power.append(float(p[2]))
+            except Exception:
+                continue
+            for nm, v in zip(names, p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_rate(frames_np, W, H, shift, delta_np, budget_s, threads=None):
+    """raw-pixel GB/s of the reference's CPU transform (Frame ctor + Predict) on `threads` host threads."""
+    from oracle_binding import Oracle, Ref, ref_available
+
+    threads = threads or os.cpu_count() or 1
+    n = frames_np.shape[0]
+    if ref_available():
+        ref = Ref()
+        best, t_used, reps = None, 0.0, 0
+        while t_used < budget_s or reps < 1:
+            t = ref.time_transform(frames_np, W, H, shift, 0, delta_np, threads)
+            best = t if best is None else min(best, t)
+            t_used += t
+            reps += 1
+            if reps >= 50:
+                break
+        return n * W * H * 2 / best / 1e9, "reference", threads, reps
+    oracle = Oracle()
+    t0 = time.perf_counter()
+    for i in range(n):
+        oracle.predict(frames_np[i], W, H, shift, 0, delta_np)
+    t = time.perf_counter() - t0
+    return n * W * H * 2 / t / 1e9, "port", 1, 1
+
+
+def run_reference_arm(args, W, H, bits, shift, desc):
+    """--impl reference: the reference's own CPU implementation of the path, all host threads."""
+    from fusion_power_video_b200 import synth
+    from oracle_binding import Ref, ref_available
+
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    per_step = max(threads, min(8 * threads, 64))
+    frames = synth.plasma_frames(per_step, W, H, bits=bits, seed=1).reshape(per_step, -1)
+    delta = frames[0].copy()
+    if not ref_available():
+        rate, kind, cores, _ = cpu_reference_rate(frames[:4], W, H, shift, delta, 1.0)
+        ms = 4 * W * H * 2 / rate / 1e6
+    else:
+        ref = Ref()
+        # keep (steps + warmup) bounded to a few minutes: shrink the per-step sample if needed
+        t_probe = ref.time_transform(frames, W, H, shift, 0, delta, threads)
+        budget = 150.0
+        while per_step > threads and t_probe * (args.steps + args.warmup) > budget:
+            per_step = max(threads, per_step // 2)
+            frames = frames[:per_step]
+            t_probe = ref.time_transform(frames, W, H, shift, 0, delta, threads)
+        for _ in range(args.warmup):
+            ref.time_transform(frames, W, H, shift, 0, delta, threads)
+        total = 0.0
+        for _ in range(args.steps):
+            total += ref.time_transform(frames, W, H, shift, 0, delta, threads)
+        ms = total / args.steps * 1e3
+        rate = per_step * W * H * 2 / (ms * 1e-3) / 1e9
+        kind, cores = "reference", threads
+    sample = f"{per_step} frames {W}x{H} per step, Frame ctor + Frame::Predict, {cores} host threads over frames"
+    line = {
+        "impl": "reference", "metric": "encode_transform_raw_pixel_throughput", "value": rate, "unit": "GB/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "frames_per_s": per_step / (ms * 1e-3),
+        "config": {"workload": desc, "xsize": W, "ysize": H, "bits": bits, "shift": shift, "frames_per_step": per_step},
+        "cpu_baseline": {"value": rate, "unit": "GB/s", "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": rate, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--frames", type=int, default=1024, help="frames per GPU per step (device-resident)")
+    ap.add_argument("--e2e-frames", type=int, default=256, help="frames per step of the host-buffer (e2e) leg")
+    ap.add_argument("--e2e-batch", type=int, default=32)
+    ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--no-decode", action="store_true")
+    args = ap.parse_args()
+    W, H, bits, shift, desc = WORKLOADS[args.workload]
+    P = W * H
+
+    if args.impl == "reference":
+        run_reference_arm(args, W, H, bits, shift, desc)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import fusion_power_video_b200 as fpv
+    from fusion_power_video_b200 import synth
+    from fusion_power_video_b200.binding import PinnedArray
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if fpv.device_count() < 1:
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    F = args.frames
+    # rank r owns frames [r*F, (r+1)*F) of the sequence; the delta frame is frame 0 (encode.cc:87-90)
+    frames = synth.plasma_frames_torch(F, W, H, bits=bits, seed=1, first=rank * F, device=dev).reshape(F, P)
+    delta = synth.plasma_frames_torch(1, W, H, bits=bits, seed=1, first=0, device=dev).reshape(P)
+    d_high = torch.empty((F, P), dtype=torch.uint8, device=dev)
+    d_low = torch.empty((F, P), dtype=torch.uint8, device=dev)
+    d_prev = torch.empty((F, P // 16), dtype=torch.uint8, device=dev)
+    d_flags = torch.empty(F, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream()
+    sp = stream.cuda_stream
+
+    ctx = fpv.Context(W, H, shift, False, max_batch=F, device=local)
+    ctx.set_delta_raw_device(delta.data_ptr(), sp)
+
+    def step():
+        ctx.encode_device(frames.data_ptr(), F, d_flags.data_ptr(), d_high.data_ptr(), d_low.data_ptr(),
+                          d_prev.data_ptr(), stream=sp)
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    windows = []
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ctx.enable_kernel_timing(True)
+    l0 = ctx.kernel_launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    t_a = time.perf_counter()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    t_b = time.perf_counter()
+    windows.append((t_a, t_b))
+    if world > 1:
+        dist.barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = ctx.kernel_launches - l0
+    kms, kcnt = ctx.read_kernel_timing()
+    ctx.enable_kernel_timing(False)
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    value = world * F * P * 2 / (ms_step * 1e-3) / 1e9
+    flags_host = d_flags.cpu().numpy()
+
+    peak, peak_src = measured_peak()
+    k_avg_ms = kms / max(kcnt, 1)
+    achieved = ENC_BYTES_PER_PX * F * P / (k_avg_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "k_encode_fast", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": ENC_BYTES_PER_PX * F * P, "kernel_ms": k_avg_ms,
+                "kernel_share_of_step": k_avg_ms / ms_step if world == 1 else None}
+
+    # ---- decode (inverse transform) on the planes just produced: extra, device-resident -------------
+    decode = None
+    if not args.no_decode:
+        d_out = torch.empty((F, P), dtype=torch.int16, device=dev)
+        dsteps = max(3, min(args.steps, 20))
+        for _ in range(2):
+            ctx.decode_device(d_high.data_ptr(), d_low.data_ptr(), d_flags.data_ptr(), F, d_out.data_ptr(),
+                              options=fpv.DEC_UNEXTRACT, stream=sp)
+        torch.cuda.synchronize()
+        ok = bool(torch.equal(d_out.view(torch.uint16), frames))
+        ctx.enable_kernel_timing(True)
+        t_a = time.perf_counter()
+        e0.record(stream)
+        for _ in range(dsteps):
+            ctx.decode_device(d_high.data_ptr(), d_low.data_ptr(), d_flags.data_ptr(), F, d_out.data_ptr(),
+                              options=fpv.DEC_UNEXTRACT, stream=sp)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        windows.append((t_a, time.perf_counter()))
+        dms = e0.elapsed_time(e1) / dsteps
+        dk, dc = ctx.read_kernel_timing()
+        ctx.enable_kernel_timing(False)
+        td = torch.tensor([dms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(td, op=dist.ReduceOp.MAX)
+        dms = float(td.item())
+        dach = DEC_BYTES_PER_PX * F * P / (dk / max(dc, 1) * 1e-3) / 1e9
+        decode = {"metric": "decode_transform_raw_pixel_throughput", "value": world * F * P * 2 / (dms * 1e-3) / 1e9,
+                  "unit": "GB/s", "frames_per_s": world * F / (dms * 1e-3), "ms_per_step": dms, "steps": dsteps,
+                  "round_trip_exact": ok,
+                  "roofline": {"bound": "hbm (chain-latency limited, see DESIGN.md)", "kernel": "k_decode_spec",
+                               "achieved": dach, "peak": peak, "unit": "GB/s", "frac": dach / peak}}
+        del d_out
+
+    # ---- e2e: host buffers through the C ABI, copies inside the timed region -----------------------
+    Fe, B = min(args.e2e_frames, F), args.e2e_batch
+    Fe = (Fe // B) * B or B
+    ectx = fpv.Context(W, H, shift, False, max_batch=B, device=local)
+    ectx.set_delta_raw_device(delta.data_ptr(), sp)
+    torch.cuda.synchronize()
+    hin = PinnedArray((Fe, P), np.uint16)
+    hh = PinnedArray((Fe, P), np.uint8)
+    hl = PinnedArray((Fe, P), np.uint8)
+    hp = PinnedArray((Fe, P // 16), np.uint8)
+    hf = PinnedArray((Fe,), np.uint8)
+    hin.array[:] = frames[:Fe].cpu().numpy()
+
+    def e2e_pass():
+        nb = Fe // B
+        for b in range(nb):
+            slot = b & 1
+            ectx.wait(slot)
+            o = b * B
+            ectx.encode_submit(slot, hin.array[o:o + B], B, hf.array[o:o + B], hh.array[o:o + B], hl.array[o:o + B],
+                               hp.array[o:o + B])
+        ectx.wait(0)
+        ectx.wait(1)
+
+    esteps = max(3, min(args.steps, 20))
+    for _ in range(2):
+        e2e_pass()
+    if world > 1:
+        dist.barrier()
+    t_a = time.perf_counter()
+    for _ in range(esteps):
+        e2e_pass()
+    t_b = time.perf_counter()
+    windows.append((t_a, t_b))
+    te = torch.tensor([(t_b - t_a) / esteps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s = float(te.item())
+    e2e_ok = bool(np.array_equal(hh.array, d_high[:Fe].cpu().numpy()) and np.array_equal(hf.array, flags_host[:Fe]))
+    e2e = {"value": world * Fe * P * 2 / e2e_s / 1e9, "unit": "GB/s", "h2d_bytes_per_step": Fe * P * 2,
+           "d2h_bytes_per_step": Fe * (2 * P + P // 16 + 1), "frames_per_step": Fe, "batch": B,
+           "frames_per_s": world * Fe / e2e_s, "matches_device_path": e2e_ok,
+           "what": "fpv_encode_submit/fpv_wait on pinned host buffers, two slots overlapped (no brotli)"}
+
+    clocks = sampler.stop(windows) if rank == 0 else None
+
+    # ---- CPU baseline: the reference's own code on this box's host cores (rank 0, N == 1 only) -----
+    cpu_baseline = None
+    if rank == 0 and world == 1:
+        ncpu = os.cpu_count() or 1
+        ns = min(F, 4 * ncpu)
+        fr = frames[:ns].cpu().numpy()
+        dl = delta.cpu().numpy()
+        rate, kind, cores, reps = cpu_reference_rate(fr, W, H, shift, dl, args.cpu_seconds)
+        cpu_baseline = {"value": rate, "unit": "GB/s", "cores": cores, "kind": kind,
+                        "sample": f"{ns} frames {W}x{H}, Frame ctor + Frame::Predict, best of {reps} passes"}
+
+    for a in (hin, hh, hl, hp, hf):
+        a.free()
+    if rank == 0:
+        uniq, cnt = np.unique(flags_host, return_counts=True)
+        line = {
+            "metric": "encode_transform_raw_pixel_throughput", "value": value, "unit": "GB/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "frames_per_s": world * F / (ms_step * 1e-3),
+            "config": {"workload": desc, "xsize": W, "ysize": H, "bits": bits, "shift": shift,
+                       "frames_per_gpu_per_step": F, "parallelism": f"frame-range x{world}, no collective",
+                       "l2": f"inputs larger than L2: {F * P * 2 / 1e6:.0f} MB raw + {F * P * 2.0625 / 1e6:.0f} MB out per step vs 126 MB L2",
+                       "flags_histogram": {int(u): int(c) for u, c in zip(uniq, cnt)}},
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clocks, "decode": decode,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
