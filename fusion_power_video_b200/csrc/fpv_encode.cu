@@ -23,50 +23,9 @@
 #include <stdio.h>
 
 #include "fpv_internal.h"
+#include "fpv_encode_fast.cuh"
 
 namespace fpv {
-
-// =====================================================================================
-// Small PTX wrappers (mbarrier + bulk async copy)
-// =====================================================================================
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra WAIT_DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "WAIT_DONE:\n"
-      "}\n" ::"r"(bar),
-      "r"(parity)
-      : "memory");
-}
-// 1-D TMA bulk copy global -> shared, completion counted in bytes on `bar`.
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes,
-                                         uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
-          "r"(dst),
-      "l"(src), "r"(bytes), "r"(bar)
-      : "memory");
-}
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
 
 // =====================================================================================
 // Per-batch bookkeeping kernels
@@ -171,11 +130,39 @@ __global__ void k_finalize(const FrameStat* stats, const uint8_t* preview_raw, u
                  (has_low ? (st.low_or == 0 ? kFlagNoLow : 0) : kFlagNoLow);
   const uint8_t* pr = preview_raw + (uint64_t)f * PP;
   uint8_t* po = preview + (uint64_t)f * PP;
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < PP;
-       i += (uint64_t)gridDim.x * blockDim.x) {
-    uint32_t v = pr[i];
-    if ((fin & kFlagCG) && i > PW) v = (v - cg1(pr[i - PW], pr[i - 1], pr[i - PW - 1])) & 0xffu;
-    po[i] = (uint8_t)v;
+  if ((PP & 3) == 0 && (PW & 3) == 0) {
+    // 4 preview pixels per thread: word loads, ClampedGradient in lane form.
+    const uint32_t* pr32 = reinterpret_cast<const uint32_t*>(pr);
+    uint32_t* po32 = reinterpret_cast<uint32_t*>(po);
+    const uint64_t words = PP / 4, pww = PW / 4;
+    for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < words;
+         q += (uint64_t)gridDim.x * blockDim.x) {
+      uint32_t c = pr32[q];
+      uint32_t outw = c;
+      if ((fin & kFlagCG) && q >= pww) {          // rows >= 1; pixel PW itself is patched below
+        uint32_t cm = pr32[q - 1];                // 4 pixels to the west (flat order)
+        uint32_t n = pr32[q - pww];
+        uint32_t nm = q > pww ? pr32[q - pww - 1] : 0u;
+        uint32_t wv = __funnelshift_l(cm, c, 8);  // bytes i-1 .. i+2
+        uint32_t nwv = __funnelshift_l(nm, n, 8);
+        // lane form: pixels (0,1) and (2,3)
+        uint32_t c01 = __byte_perm(c, 0u, 0x4140), c23 = __byte_perm(c, 0u, 0x4342);
+        uint32_t n01 = __byte_perm(n, 0u, 0x4140), n23 = __byte_perm(n, 0u, 0x4342);
+        uint32_t w01 = __byte_perm(wv, 0u, 0x4140), w23 = __byte_perm(wv, 0u, 0x4342);
+        uint32_t q01 = __byte_perm(nwv, 0u, 0x4140), q23 = __byte_perm(nwv, 0u, 0x4342);
+        uint32_t r01 = sub2(c01, cg2(n01, w01, q01)), r23 = sub2(c23, cg2(n23, w23, q23));
+        outw = __byte_perm(r01, r23, 0x6420);
+        if (q == pww) outw = (outw & 0xffffff00u) | (c & 0xffu);  // index PW is copied (.cc:578, :584)
+      }
+      po32[q] = outw;
+    }
+  } else {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < PP;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+      uint32_t v = pr[i];
+      if ((fin & kFlagCG) && i > PW) v = (v - cg1(pr[i - PW], pr[i - 1], pr[i - PW - 1])) & 0xffu;
+      po[i] = (uint8_t)v;
+    }
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     flags[f] = (uint8_t)fin;
@@ -338,251 +325,8 @@ k_delta_from_raw(const uint16_t* __restrict__ raw, uint16_t* __restrict__ image,
 }
 
 // =====================================================================================
-// FAST path
-// =====================================================================================
-
-constexpr int kStripPx = 256;       // columns per warp (8 pixels per lane)
-constexpr int kRowsPerStage = 4;    // one preview row group
-constexpr int kHaloPx = 8;          // pixels copied before a stage's first pixel (16 B)
-
-// v[j] for a run-time j without spilling the array to local memory.
-__device__ __forceinline__ uint32_t sel4(const uint32_t (&v)[4], uint32_t j) {
-  uint32_t a = (j & 1u) ? v[1] : v[0];
-  uint32_t b = (j & 1u) ? v[3] : v[2];
-  return (j & 2u) ? b : a;
-}
-
-struct FastParams {
-  const uint16_t* frames;
-  const uint16_t* delta;        // nullptr: no delta frame
-  FrameStat* stats;
-  const uint32_t* list;
-  const uint32_t* count;
-  uint8_t* high;
-  uint8_t* low;
-  uint8_t* preview_raw;
-  uint32_t W, H;
-  uint64_t P, PP;
-  uint32_t PW;
-  int shift;
-  uint32_t band_rows;           // multiple of 4
-  uint32_t bands;               // bands per frame
-  uint32_t stages;              // ring depth
-  uint32_t stage_bytes;         // bytes of one plane of one stage: (4W + 8) * 2
-  uint32_t compute_warps;       // ceil(W / 256)
-};
-
-// Shared memory: [ring: stages x {raw stage, delta stage}] [hist 3x256 u32]
-// [full barriers] [empty barriers]
-template <int MODE>
-__global__ void __launch_bounds__(544) k_encode_fast(const FastParams p) {
-  extern __shared__ __align__(128) uint8_t smem[];
-  const uint32_t S = p.stages;
-  const uint32_t slot_bytes = 2 * p.stage_bytes;
-  uint32_t* hist = reinterpret_cast<uint32_t*>(smem + (size_t)S * slot_bytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(hist + 768);
-  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + S);
-  const uint32_t ring0 = smem_u32(smem);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int NW = (int)p.compute_warps;
-  const uint32_t W = p.W;
-
-  for (uint32_t i = threadIdx.x; i < 768; i += blockDim.x) hist[i] = 0;
-  if (threadIdx.x == 0) {
-    for (uint32_t i = 0; i < S; i++) {
-      mbar_init(full0 + 8 * i, 1);
-      mbar_init(empty0 + 8 * i, NW);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-
-  const uint32_t total_tasks = (*p.count) * p.bands;
-  uint32_t seq = 0;  // running stage number (same sequence in producer and consumers)
-
-  if (warp == NW) {
-    // ------------------------------ producer ------------------------------------
-    if (lane == 0) {
-      for (uint32_t t = blockIdx.x; t < total_tasks; t += gridDim.x) {
-        uint32_t f = p.list[t / p.bands], b = t % p.bands;
-        uint32_t y0 = b * p.band_rows;
-        uint32_t y1 = min(p.H, y0 + p.band_rows);
-        bool use_delta = p.delta != nullptr && (p.stats[f].assumed & 1u);
-        const uint16_t* img = p.frames + (uint64_t)f * p.P;
-        // stage list: optional 1-row halo stage (row y0-1), then 4-row stages
-        uint32_t ys = y0 > 0 ? y0 - 1 : 0;
-        while (ys < y1) {
-          uint32_t nrows = (ys < y0) ? 1 : min((uint32_t)kRowsPerStage, y1 - ys);
-          uint32_t slot = seq % S, ph = (seq / S) & 1u;
-          mbar_wait(empty0 + 8 * slot, ph ^ 1u);
-          // contiguous flat range [ys*W - 8, (ys+nrows)*W); the 8-pixel lead-in
-          // holds the west neighbours of column 0 (flat indexing, .cc:556-558).
-          uint64_t px0 = (uint64_t)ys * W;
-          uint32_t lead = ys > 0 ? kHaloPx : 0;
-          uint32_t bytes = (nrows * W + lead) * 2;
-          uint32_t dst = ring0 + slot * slot_bytes + (kHaloPx - lead) * 2;
-          mbar_arrive_expect_tx(full0 + 8 * slot, use_delta ? 2 * bytes : bytes);
-          bulk_g2s(dst, img + px0 - lead, bytes, full0 + 8 * slot);
-          if (use_delta) bulk_g2s(dst + p.stage_bytes, p.delta + px0 - lead, bytes, full0 + 8 * slot);
-          seq++;
-          ys += nrows;
-        }
-      }
-    }
-    return;
-  }
-
-  // -------------------------------- consumers -----------------------------------
-  const uint32_t c0 = (uint32_t)warp * kStripPx + (uint32_t)lane * 8;
-  const bool active = c0 < W;
-  const uint32_t w15 = W % 15, w31 = W % 31;
-  const int s = p.shift;
-
-  for (uint32_t t = blockIdx.x; t < total_tasks; t += gridDim.x) {
-    const uint32_t f = p.list[t / p.bands], b = t % p.bands;
-    const uint32_t y0 = b * p.band_rows;
-    const uint32_t y1 = min(p.H, y0 + p.band_rows);
-    const uint32_t assumed = p.stats[f].assumed;
-    const bool use_delta = p.delta != nullptr && (assumed & 1u);
-    const bool use_cg = (assumed & 2u) != 0;
-    uint8_t* out_high = p.high + (uint64_t)f * p.P;
-    uint8_t* out_low = mode_has_low(MODE) ? p.low + (uint64_t)f * p.P : nullptr;
-    uint8_t* out_prev = p.preview_raw + (uint64_t)f * p.PP;
-
-    uint32_t ph[4] = {0, 0, 0, 0}, pw[4] = {0, 0, 0, 0};  // previous row: high, west-shifted high
-    uint32_t acc0 = 0, acc1 = 0, orl = 0;
-    // running residues of the flat index of this lane's first pixel in row y
-    uint32_t ystart = y0 > 0 ? y0 - 1 : 0;
-    uint64_t i0 = (uint64_t)ystart * W + c0;
-    uint32_t m15 = (uint32_t)(i0 % 15);
-    // (i0 - (W+1)) mod 31, kept non-negative by adding a multiple of 31
-    uint32_t m31 = (uint32_t)((i0 + 31ull * (W / 31 + 2) - (W + 1)) % 31);
-
-    uint32_t y = ystart;
-    while (y < y1) {
-      const uint32_t nrows = (y < y0) ? 1 : min((uint32_t)kRowsPerStage, y1 - y);
-      const uint32_t slot = seq % S, phs = (seq / S) & 1u;
-      mbar_wait(full0 + 8 * slot, phs);
-      const uint8_t* raw_s = smem + (size_t)slot * slot_bytes + kHaloPx * 2;  // pixel (y, 0)
-      const uint8_t* del_s = raw_s + p.stage_bytes;
-
-      for (uint32_t r = 0; r < nrows; r++, y++) {
-        const bool own = y >= y0;
-        const uint32_t roff = (r * W + c0) * 2;
-        uint32_t xh[4], xl[4], h[4], l[4];
-        {
-          uint4 x = make_uint4(0, 0, 0, 0);
-          if (active) x = *reinterpret_cast<const uint4*>(raw_s + roff);
-          split2<MODE>(x.x, s, xh[0], xl[0]);
-          split2<MODE>(x.y, s, xh[1], xl[1]);
-          split2<MODE>(x.z, s, xh[2], xl[2]);
-          split2<MODE>(x.w, s, xh[3], xl[3]);
-        }
-        if (use_delta) {
-          uint4 d = make_uint4(0, 0, 0, 0);
-          if (active) d = *reinterpret_cast<const uint4*>(del_s + roff);
-          uint32_t dh, dl;
-          split2_delta(d.x, dh, dl); h[0] = sub2(xh[0], dh); l[0] = xl[0] + kLaneBias - dl;
-          split2_delta(d.y, dh, dl); h[1] = sub2(xh[1], dh); l[1] = xl[1] + kLaneBias - dl;
-          split2_delta(d.z, dh, dl); h[2] = sub2(xh[2], dh); l[2] = xl[2] + kLaneBias - dl;
-          split2_delta(d.w, dh, dl); h[3] = sub2(xh[3], dh); l[3] = xl[3] + kLaneBias - dl;
-        } else {
-#pragma unroll
-          for (int j = 0; j < 4; j++) { h[j] = xh[j]; l[j] = xl[j]; }
-        }
-        // west neighbour of this lane's first pixel: previous lane's last pixel,
-        // or (lane 0) the pixel before it in flat order, read from the stage.
-        uint32_t left = __shfl_up_sync(0xffffffffu, h[3] >> 16, 1);
-        if (lane == 0) {
-          uint32_t hp, lp;
-          split1<MODE>(*reinterpret_cast<const uint16_t*>(raw_s + roff - 2), s, hp, lp);
-          if (use_delta)
-            hp = (hp - (uint32_t)(*reinterpret_cast<const uint16_t*>(del_s + roff - 2) >> 8)) & 0xffu;
-          left = hp;
-        }
-        uint32_t w[4];
-        w[0] = (h[0] << 16) | left;
-        w[1] = __funnelshift_l(h[0], h[1], 16);
-        w[2] = __funnelshift_l(h[1], h[2], 16);
-        w[3] = __funnelshift_l(h[2], h[3], 16);
-
-        if (own) {
-          uint32_t res[4];
-          if (y == 0) {
-#pragma unroll
-            for (int j = 0; j < 4; j++) res[j] = h[j];
-          } else {
-#pragma unroll
-            for (int j = 0; j < 4; j++) res[j] = sub2(h[j], cg2(ph[j], w[j], pw[j]));
-            // flat index W (row 1, column 0) is copied, not predicted (.cc:566, :572)
-            if (y == 1 && c0 == 0) res[0] = (res[0] & 0xffff0000u) | (h[0] & 0x0000ffffu);
-          }
-          if (active) {
-            uint64_t o = (uint64_t)y * W + c0;
-            uint2 hv = use_cg ? pack8(res[0], res[1], res[2], res[3]) : pack8(h[0], h[1], h[2], h[3]);
-            *reinterpret_cast<uint2*>(out_high + o) = hv;
-            if (mode_has_low(MODE))
-              *reinterpret_cast<uint2*>(out_low + o) = pack8(l[0], l[1], l[2], l[3]);
-            orl |= xl[0] | xl[1] | xl[2] | xl[3];
-            acc0 += xh[0] + xh[1];
-            acc1 += xh[2] + xh[3];
-            // delta-decision sample: flat index % 15 == 0 (.cc:526-531), RAW high byte
-            uint32_t od = m15 ? 15 - m15 : 0;
-            if (od < 8) {
-              uint32_t v = sel4(xh, od >> 1);
-              v = (od & 1) ? (v >> 16) : (v & 0xffffu);
-              atomicAdd(&hist[v], 1u);
-            }
-            // CG-decision sample: flat index == W+1 (mod 31), >= W+1 (.cc:554-562)
-            uint32_t oc = m31 ? 31 - m31 : 0;
-            if (oc < 8 && y >= 1 && !(y == 1 && c0 == 0 && oc == 0)) {
-              uint32_t a = sel4(h, oc >> 1), bb = sel4(res, oc >> 1);
-              if (oc & 1) { a >>= 16; bb >>= 16; } else { a &= 0xffffu; bb &= 0xffffu; }
-              atomicAdd(&hist[256 + a], 1u);
-              atomicAdd(&hist[512 + bb], 1u);
-            }
-            if ((y & 3u) == 3u) {
-              uint32_t s0 = (acc0 & 0xffffu) + (acc0 >> 16);
-              uint32_t s1 = (acc1 & 0xffffu) + (acc1 >> 16);
-              uint32_t pv = ((s0 >> 4) & 0xfeu) | (((s1 >> 4) & 0xfeu) << 8);
-              *reinterpret_cast<uint16_t*>(out_prev + (uint64_t)(y >> 2) * p.PW + (c0 >> 2)) = (uint16_t)pv;
-              acc0 = 0; acc1 = 0;
-            }
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < 4; j++) { ph[j] = h[j]; pw[j] = w[j]; }
-        m15 += w15; if (m15 >= 15) m15 -= 15;
-        m31 += w31; if (m31 >= 31) m31 -= 31;
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(empty0 + 8 * slot);
-      seq++;
-    }
-
-    // ---- end of task: publish low-OR and the three histograms -----------------
-#pragma unroll
-    for (int o = 16; o; o >>= 1) orl |= __shfl_xor_sync(0xffffffffu, orl, o);
-    if (lane == 0 && (orl & kLaneMask)) atomicOr(&p.stats[f].low_or, orl & kLaneMask);
-    named_bar_sync(1, NW * 32);
-    uint32_t* gh = p.stats[f].hist_d;  // hist_d, hist_a, hist_b are contiguous
-    for (uint32_t i = threadIdx.x; i < 768; i += NW * 32) {
-      uint32_t v = hist[i];
-      if (v) { atomicAdd(&gh[i], v); hist[i] = 0; }
-    }
-    named_bar_sync(1, NW * 32);
-  }
-}
-
-// =====================================================================================
 // Host-side launch logic
 // =====================================================================================
-
-static size_t fast_smem_bytes(uint32_t W, int stages) {
-  size_t stage_bytes = ((size_t)kRowsPerStage * W + kHaloPx) * 2;
-  return (size_t)stages * 2 * stage_bytes + 768 * 4 + 2 * (size_t)stages * 8;
-}
 
 bool encode_fast_supported(const Geom& g, const EncodeTuning& t) {
   if (g.W % 8 != 0 || g.W < 8) return false;
@@ -658,6 +402,7 @@ int enqueue_encode(const Geom& g, const EncodeTuning& t, const EncodeScratch& s,
     // there are at least ~4 tasks per SM.
     uint32_t band = (uint32_t)t.band_rows;
     band = (band / 4) * 4; if (band < 4) band = 4;
+    if (band > 1024) band = 1024;  // warp-private histogram counters are 16 bit
     while (band > 8 && (uint64_t)n * ((g.H + band - 1) / band) < (uint64_t)t.num_sms * 4) band = ((band / 2) / 4) * 4;
     if (band > g.H) band = g.H;
     fp.band_rows = band;
@@ -714,7 +459,7 @@ int enqueue_encode(const Geom& g, const EncodeTuning& t, const EncodeScratch& s,
     FPV_CHECK_LAUNCH();
   }
 
-  unsigned gfx = (unsigned)((g.PP + 255) / 256); if (gfx < 1) gfx = 1; if (gfx > 256) gfx = 256;
+  unsigned gfx = (unsigned)((g.PP / 4 + 255) / 256); if (gfx < 1) gfx = 1; if (gfx > 64) gfx = 64;
   dim3 gF(gfx, n);
   k_finalize<<<gF, 256, 0, stream>>>(s.stats, s.preview_raw, preview, flags, s.counts, n, g.PW, g.PP, has_low);
   FPV_CHECK_LAUNCH();
