@@ -183,6 +183,8 @@ def main():
     ap.add_argument("--e2e-batch", type=int, default=32)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-decode", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg (profiling runs)")
     args = ap.parse_args()
     W, H, bits, shift, desc = WORKLOADS[args.workload]
     P = W * H
@@ -304,54 +306,57 @@ def main():
         del d_out
 
     # ---- e2e: host buffers through the C ABI, copies inside the timed region -----------------------
-    Fe, B = min(args.e2e_frames, F), args.e2e_batch
-    Fe = (Fe // B) * B or B
-    ectx = fpv.Context(W, H, shift, False, max_batch=B, device=local)
-    ectx.set_delta_raw_device(delta.data_ptr(), sp)
-    torch.cuda.synchronize()
-    hin = PinnedArray((Fe, P), np.uint16)
-    hh = PinnedArray((Fe, P), np.uint8)
-    hl = PinnedArray((Fe, P), np.uint8)
-    hp = PinnedArray((Fe, P // 16), np.uint8)
-    hf = PinnedArray((Fe,), np.uint8)
-    hin.array[:] = frames[:Fe].cpu().numpy()
+    e2e, e2e_bufs = None, ()
+    if not args.no_e2e:
+        Fe, B = min(args.e2e_frames, F), args.e2e_batch
+        Fe = (Fe // B) * B or B
+        ectx = fpv.Context(W, H, shift, False, max_batch=B, device=local)
+        ectx.set_delta_raw_device(delta.data_ptr(), sp)
+        torch.cuda.synchronize()
+        hin = PinnedArray((Fe, P), np.uint16)
+        hh = PinnedArray((Fe, P), np.uint8)
+        hl = PinnedArray((Fe, P), np.uint8)
+        hp = PinnedArray((Fe, P // 16), np.uint8)
+        hf = PinnedArray((Fe,), np.uint8)
+        hin.array[:] = frames[:Fe].cpu().numpy()
+        e2e_bufs = (hin, hh, hl, hp, hf)
 
-    def e2e_pass():
-        nb = Fe // B
-        for b in range(nb):
-            slot = b & 1
-            ectx.wait(slot)
-            o = b * B
-            ectx.encode_submit(slot, hin.array[o:o + B], B, hf.array[o:o + B], hh.array[o:o + B], hl.array[o:o + B],
-                               hp.array[o:o + B])
-        ectx.wait(0)
-        ectx.wait(1)
+        def e2e_pass():
+            nb = Fe // B
+            for b in range(nb):
+                slot = b & 1
+                ectx.wait(slot)
+                o = b * B
+                ectx.encode_submit(slot, hin.array[o:o + B], B, hf.array[o:o + B], hh.array[o:o + B], hl.array[o:o + B],
+                                   hp.array[o:o + B])
+            ectx.wait(0)
+            ectx.wait(1)
 
-    esteps = max(3, min(args.steps, 20))
-    for _ in range(2):
-        e2e_pass()
-    if world > 1:
-        dist.barrier()
-    t_a = time.perf_counter()
-    for _ in range(esteps):
-        e2e_pass()
-    t_b = time.perf_counter()
-    windows.append((t_a, t_b))
-    te = torch.tensor([(t_b - t_a) / esteps], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_s = float(te.item())
-    e2e_ok = bool(np.array_equal(hh.array, d_high[:Fe].cpu().numpy()) and np.array_equal(hf.array, flags_host[:Fe]))
-    e2e = {"value": world * Fe * P * 2 / e2e_s / 1e9, "unit": "GB/s", "h2d_bytes_per_step": Fe * P * 2,
-           "d2h_bytes_per_step": Fe * (2 * P + P // 16 + 1), "frames_per_step": Fe, "batch": B,
-           "frames_per_s": world * Fe / e2e_s, "matches_device_path": e2e_ok,
-           "what": "fpv_encode_submit/fpv_wait on pinned host buffers, two slots overlapped (no brotli)"}
+        esteps = max(3, min(args.steps, 20))
+        for _ in range(2):
+            e2e_pass()
+        if world > 1:
+            dist.barrier()
+        t_a = time.perf_counter()
+        for _ in range(esteps):
+            e2e_pass()
+        t_b = time.perf_counter()
+        windows.append((t_a, t_b))
+        te = torch.tensor([(t_b - t_a) / esteps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_s = float(te.item())
+        e2e_ok = bool(np.array_equal(hh.array, d_high[:Fe].cpu().numpy()) and np.array_equal(hf.array, flags_host[:Fe]))
+        e2e = {"value": world * Fe * P * 2 / e2e_s / 1e9, "unit": "GB/s", "h2d_bytes_per_step": Fe * P * 2,
+               "d2h_bytes_per_step": Fe * (2 * P + P // 16 + 1), "frames_per_step": Fe, "batch": B,
+               "frames_per_s": world * Fe / e2e_s, "matches_device_path": e2e_ok,
+               "what": "fpv_encode_submit/fpv_wait on pinned host buffers, two slots overlapped (no brotli)"}
 
     clocks = sampler.stop(windows) if rank == 0 else None
 
     # ---- CPU baseline: the reference's own code on this box's host cores (rank 0, N == 1 only) -----
     cpu_baseline = None
-    if rank == 0 and world == 1:
+    if rank == 0 and world == 1 and not args.no_cpu:
         ncpu = os.cpu_count() or 1
         ns = min(F, 4 * ncpu)
         fr = frames[:ns].cpu().numpy()
@@ -360,7 +365,7 @@ def main():
         cpu_baseline = {"value": rate, "unit": "GB/s", "cores": cores, "kind": kind,
                         "sample": f"{ns} frames {W}x{H}, Frame ctor + Frame::Predict, best of {reps} passes"}
 
-    for a in (hin, hh, hl, hp, hf):
+    for a in e2e_bufs:
         a.free()
     if rank == 0:
         uniq, cnt = np.unique(flags_host, return_counts=True)

@@ -2,12 +2,16 @@
 //
 // Citations are file:line into the reference's fusion_power_video.cc.
 //
-// Register packing convention ("lane form"): one 32-bit register carries TWO
-// pixels' byte values in its two 16-bit lanes (pixel 2j in bits 0..15, pixel
-// 2j+1 in bits 16..31), each lane holding a value in [0,255].  sm_100a has
-// native packed-u16 min/max (VIMNMX.U16x2) but only 7-instruction emulations
-// for packed-u8 min/max, and 16-bit lanes let plain 32-bit IADD3 do the
-// byte arithmetic of two pixels without cross-lane carries.
+// Register packing conventions.  One 32-bit register always carries TWO pixels
+// in its two 16-bit lanes (pixel 2j in bits 0..15, pixel 2j+1 in bits 16..31):
+//   "lane form"   each lane holds a byte value in [0,255]           (generic kernels)
+//   "q form"      each lane holds (high << 8) | low, i.e. the left-aligned
+//                 pixel the reference splits into its two planes     (fast kernel)
+//   "S form"      each lane holds (byte << 8) | junk, junk <= 1      (fast kernel)
+// sm_100a has native packed-u16 min/max, also three-input (VIMNMX3.U16x2), but
+// only multi-instruction emulations of packed-u8 arithmetic; 16-bit lanes let
+// plain 32-bit IADD3 do the byte arithmetic of two pixels with the low byte of
+// each lane acting as a guard against cross-lane carries.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -135,6 +139,61 @@ __device__ __forceinline__ uint2 pack8(uint32_t a, uint32_t b, uint32_t c, uint3
   return make_uint2(__byte_perm(a, b, 0x6420), __byte_perm(c, d, 0x6420));
 }
 
+// ---- q form / S form (fast encode kernel) -------------------------------------
+
+constexpr uint32_t kHiBytes = 0xff00ff00u;
+constexpr uint32_t kLoBytes = 0x00ff00ffu;
+
+// Loop-invariant constants of make_q2 for one (mode, shift).
+struct QConst {
+  uint32_t sh_a, sh_b;   // shift amounts
+  uint32_t m_a, m_b;     // masks
+};
+
+__host__ __device__ inline QConst make_qconst(int mode, int s) {
+  QConst c = {0, 0, 0, 0};
+  if (mode == kLE8 || mode == kLEs || mode == kLEbig) {
+    c.sh_a = (uint32_t)s;                                      // q = (x << s) & m_a
+    c.m_a = ((0xffffu << s) & 0xffffu) * 0x00010001u;
+  } else if (mode == kBEs) {
+    c.sh_a = (uint32_t)(s + 8);                                // ((x & m_a) << (s + 8))
+    c.m_a = (0xffu >> s) * 0x00010001u;
+    c.sh_b = (uint32_t)(8 - s);                                // | ((x >> (8 - s)) & m_b)
+    c.m_b = ((((1u << s) - 1u) << 8) | 0xffu) * 0x00010001u;
+  }
+  return c;
+}
+
+// Two raw uint16 pixels as loaded -> q form: per lane (high << 8) | low with
+// exactly the high / low bytes of the six reference expressions (.cc:388-445;
+// table in SURVEY.md 9.1).  For the two no-low modes the low byte is 0.
+template <int MODE>
+__device__ __forceinline__ uint32_t make_q2(uint32_t x, const QConst& c) {
+  if (MODE == kLE0) return x;                                           // high = p >> 8, low = p & 0xff
+  if (MODE == kBE0) return __byte_perm(x, 0u, 0x2301);                  // high = p & 0xff, low = p >> 8
+  if (MODE == kBE8) return x & kHiBytes;                                // high = (p >> 8) & 0xff
+  if (MODE == kBEs)                                                     // high = ((p << s) | (p >> (16 - s))) & 0xff
+    return ((x & c.m_a) << c.sh_a) | ((x >> c.sh_b) & c.m_b);           // low  = (p >> (8 - s)) & 0xff
+  return (x << c.sh_a) & c.m_a;                                         // q = (uint16_t)(p << s), s = 1..16
+}
+
+// Bytes 1 and 3 of a and of b -> 4 consecutive output bytes (S form -> plane).
+__device__ __forceinline__ uint32_t pack_hi(uint32_t a, uint32_t b) { return __byte_perm(a, b, 0x7531); }
+// Bytes 0 and 2 of a and of b.
+__device__ __forceinline__ uint32_t pack_lo(uint32_t a, uint32_t b) { return __byte_perm(a, b, 0x6420); }
+
+// ClampedGradient residual of two pixels in S form:
+//   CG(n, w, nw) = n + w - median(n, w, nw) = min3 + max3 - nw          (.cc:247-252)
+//   residual     = h - CG = h + nw - min3 - max3                        (.cc:570)
+// The +0x0080 per lane keeps the (junk) low bytes in [124, 131] whatever the
+// cross-lane carries are, so bytes 1 and 3 of the result are exact mod 256.
+__device__ __forceinline__ uint32_t cg_residual_s(uint32_t h, uint32_t n, uint32_t w, uint32_t nw) {
+  const uint32_t mn = __vimin3_u16x2(n, w, nw), mx = __vimax3_u16x2(n, w, nw);
+  uint32_t t = h + nw + 0x00800080u;   // one IADD3 ...
+  asm("" : "+r"(t));                   // (keeps the compiler from re-associating into three adds)
+  return t - mn - mx;                  // ... and a second one
+}
+
 // ---- integer entropy heuristic ------------------------------------------------
 
 // Per-frame device-side record shared by every encode kernel.
@@ -146,6 +205,13 @@ struct FrameStat {
   uint32_t assumed;      // flags (bit0 delta, bit1 cg) the last transform pass assumed
   uint32_t final_flags;  // decided FrameFlags byte
   uint32_t done;         // 1 once outputs in memory match final_flags
+  // Fast path: instead of hist_d, the number of delta-decision samples whose
+  // raw high byte has bit k set.  Enough to decide USE_DELTA in all but
+  // near-constant frames (see k_decide), with no shared-memory atomics.
+  uint32_t dbits[8];
+  uint32_t delta_known;  // USE_DELTA decision already taken (redo passes keep it)
+  uint32_t delta_dec;
+  uint32_t pad_[2];
 };
 
 // EstimateEntropy (.cc:235-244) evaluated by one 256-thread block, one bin per

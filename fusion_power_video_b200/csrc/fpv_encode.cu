@@ -48,6 +48,10 @@ __global__ void k_encode_init(FrameStat* stats, uint32_t* lists, uint32_t* count
     st.assumed = guess;
     st.final_flags = 0;
     st.done = 0;
+    st.delta_known = 0;
+    st.delta_dec = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) st.dbits[k] = 0;
     lists[f] = f;
     if (f == 0) {
       counts[0] = n;
@@ -58,6 +62,21 @@ __global__ void k_encode_init(FrameStat* stats, uint32_t* lists, uint32_t* count
   (void)cap;
 }
 
+// split1 with a run-time mode (cold paths only).
+__device__ __forceinline__ uint32_t high1_rt(int mode, uint32_t p, int s) {
+  uint32_t h, l;
+  switch (mode) {
+    case kLE0: split1<kLE0>(p, s, h, l); break;
+    case kLE8: split1<kLE8>(p, s, h, l); break;
+    case kLEs: split1<kLEs>(p, s, h, l); break;
+    case kBE0: split1<kBE0>(p, s, h, l); break;
+    case kBE8: split1<kBE8>(p, s, h, l); break;
+    case kBEs: split1<kBEs>(p, s, h, l); break;
+    default: split1<kLEbig>(p, s, h, l); break;
+  }
+  return h;
+}
+
 // Evaluates the reference's decisions for the frames of list `in`.
 //  phase 0 (fast path): a transform pass just ran with st.assumed.  If the
 //          delta decision differs, redo with the right delta (cg assumption
@@ -65,10 +84,25 @@ __global__ void k_encode_init(FrameStat* stats, uint32_t* lists, uint32_t* count
 //          plane), fix final_flags, redo iff the cg assumption was wrong.
 //  phase 1 (generic): delta decision only  -> st.assumed bit 0.
 //  phase 2 (generic): CG decision only     -> st.final_flags, st.assumed.
+//
+// Delta decision.  countd is {0: N} in the reference (d = a - high_[i] with
+// a == high_[i], .cc:527-529) and EstimateEntropy of it is 0, so
+//     USE_DELTA  <=>  E(counta) > 0  <=>  1024 * S >= N,
+// S = sum_v counta[v] * (floor(log2 N) - floor(log2 counta[v])) (.cc:235-244).
+// At most one bin can reach 2^floor(log2 N) (a zero term); every other
+// non-empty bin adds at least its count.  Hence for ANY split of the byte
+// values into two groups A, B:  S >= min(|A|, |B|).  The fast kernel counts, per
+// frame, the samples with bit k set (k = 0..7), i.e. eight such splits:
+//   * some k with 1024 * min(c_k, N - c_k) >= N   ->  E > 0 is proven;
+//   * every c_k in {0, N}: all samples equal      ->  E == 0 exactly;
+//   * otherwise (a near-constant plane with a few strays) this block builds
+//     the exact 256-bin histogram from the frame's samples.
 __global__ void __launch_bounds__(256)
 k_decide(FrameStat* stats, const uint32_t* in, const uint32_t* in_count, uint32_t* out,
-         uint32_t* out_count, int phase, int has_delta, int has_low) {
+         uint32_t* out_count, int phase, int has_delta, int has_low, const uint16_t* frames,
+         uint64_t P, int mode, int shift) {
   __shared__ uint32_t red[8];
+  __shared__ uint32_t exact[256];
   if (blockIdx.x >= *in_count) return;
   uint32_t f = in[blockIdx.x];
   FrameStat& st = stats[f];
@@ -77,19 +111,43 @@ k_decide(FrameStat* stats, const uint32_t* in, const uint32_t* in_count, uint32_
   uint32_t nolow = has_low ? (st.low_or == 0 ? kFlagNoLow : 0) : kFlagNoLow;
 
   uint32_t dec_delta = assumed & 1u;
-  if (phase == 0 || phase == 1) {
-    // countd is {0: N} in the reference (d = a - high_[i] with a == high_[i],
-    // .cc:527-529), whose EstimateEntropy is 0: USE_DELTA <=> 0 < E(counta).
+  if (phase == 1) {
     uint64_t ea = block_entropy256(st.hist_d[t], red);
     dec_delta = (has_delta && ea > 0) ? 1u : 0u;
-  }
-  if (phase == 1) {
     if (t == 0) st.assumed = dec_delta;
     return;
   }
-  if (phase == 0 && dec_delta != (assumed & 1u)) {
+  if (phase == 0) {
+    if (st.delta_known) {
+      dec_delta = st.delta_dec;
+    } else if (!has_delta) {
+      dec_delta = 0;
+    } else {
+      const uint64_t N = (P + 14) / 15;
+      bool proven = false, constant = true;
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const uint64_t c = st.dbits[k];
+        const uint64_t m = c < N - c ? c : N - c;
+        proven = proven || (1024 * m >= N);
+        constant = constant && (m == 0);
+      }
+      if (proven) dec_delta = 1;
+      else if (constant) dec_delta = 0;
+      else {
+        exact[t] = 0;
+        __syncthreads();
+        const uint16_t* img = frames + (uint64_t)f * P;
+        for (uint64_t i = 15ull * t; i < P; i += 15ull * 256) atomicAdd(&exact[high1_rt(mode, img[i], shift)], 1u);
+        __syncthreads();
+        dec_delta = block_entropy256(exact[t], red) > 0 ? 1u : 0u;
+      }
+    }
     __syncthreads();
-    st.hist_d[t] = 0; st.hist_a[t] = 0; st.hist_b[t] = 0;
+    if (t == 0) { st.delta_known = 1; st.delta_dec = dec_delta; }
+  }
+  if (phase == 0 && dec_delta != (assumed & 1u)) {
+    st.hist_a[t] = 0; st.hist_b[t] = 0;
     if (t == 0) {
       st.assumed = dec_delta | (assumed & 2u);
       out[atomicAdd(out_count, 1u)] = f;
@@ -106,7 +164,7 @@ k_decide(FrameStat* stats, const uint32_t* in, const uint32_t* in_count, uint32_
   }
   __syncthreads();
   if (dec_cg != ((assumed >> 1) & 1u)) {
-    st.hist_d[t] = 0; st.hist_a[t] = 0; st.hist_b[t] = 0;
+    st.hist_a[t] = 0; st.hist_b[t] = 0;
     if (t == 0) {
       st.final_flags = fin;
       st.assumed = fin & 3u;
@@ -333,7 +391,7 @@ bool encode_fast_supported(const Geom& g, const EncodeTuning& t) {
   if (g.W > 32 * 31 * 8) return false;  // at most 31 compute warps + 1 producer
   if (g.W > 4096) return false;
   int stages = t.stages < 2 ? 2 : t.stages;
-  return fast_smem_bytes(g.W, stages) <= (size_t)t.max_smem_optin;
+  return fast_smem_bytes(g.W, stages, t.rows_per_stage == 2 ? 2 : 4) <= (size_t)t.max_smem_optin;
 }
 
 #define FPV_DISPATCH_MODE(mode, CALL)                       \
@@ -347,19 +405,19 @@ bool encode_fast_supported(const Geom& g, const EncodeTuning& t) {
     default:   { constexpr int M = kLEbig; CALL; } break;   \
   }
 
-template <int MODE>
+template <int MODE, bool FULL, int RPS>
 static cudaError_t launch_fast(const FastParams& fp, int grid, int threads, size_t smem,
                                cudaStream_t stream) {
   static bool attr_set[16] = {};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 16 && !attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(k_encode_fast<MODE>,
+    cudaError_t e = cudaFuncSetAttribute(k_encode_fast<MODE, FULL, RPS>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024);
     if (e != cudaSuccess) return e;
     attr_set[dev] = true;
   }
-  k_encode_fast<MODE><<<grid, threads, smem, stream>>>(fp);
+  k_encode_fast<MODE, FULL, RPS><<<grid, threads, smem, stream>>>(fp);
   return cudaGetLastError();
 }
 
@@ -395,20 +453,22 @@ int enqueue_encode(const Geom& g, const EncodeTuning& t, const EncodeScratch& s,
     fp.frames = frames; fp.delta = delta; fp.stats = s.stats;
     fp.high = high; fp.low = low; fp.preview_raw = s.preview_raw;
     fp.W = g.W; fp.H = g.H; fp.P = g.P; fp.PP = g.PP; fp.PW = g.PW; fp.shift = g.shift;
+    const int rps = t.rows_per_stage == 2 ? 2 : 4;
     fp.stages = t.stages < 2 ? 2 : t.stages;
-    fp.stage_bytes = (kRowsPerStage * g.W + kHaloPx) * 2;
+    fp.rows_per_stage = (uint32_t)rps;
+    fp.stage_bytes = ((uint32_t)rps * g.W + kHaloPx) * 2;
     fp.compute_warps = (g.W + kStripPx - 1) / kStripPx;
     // Band height: whole multiples of 4 rows; shrink for small batches so that
     // there are at least ~4 tasks per SM.
     uint32_t band = (uint32_t)t.band_rows;
     band = (band / 4) * 4; if (band < 4) band = 4;
-    if (band > 1024) band = 1024;  // warp-private histogram counters are 16 bit
+    if (band > 1024) band = 1024;  // per-lane delta-decision counters are 16 bit
     while (band > 8 && (uint64_t)n * ((g.H + band - 1) / band) < (uint64_t)t.num_sms * 4) band = ((band / 2) / 4) * 4;
     if (band > g.H) band = g.H;
     fp.band_rows = band;
     fp.bands = (g.H + band - 1) / band;
     const int threads = (int)(fp.compute_warps + 1) * 32;
-    const size_t smem = fast_smem_bytes(g.W, (int)fp.stages);
+    const size_t smem = fast_smem_bytes(g.W, (int)fp.stages, rps);
     int ctas_per_sm = (int)((size_t)(t.max_smem_optin + 1024) / (smem + 1024));
     if (ctas_per_sm < 1) ctas_per_sm = 1;
     int by_threads = 2048 / threads; if (by_threads < 1) by_threads = 1;
@@ -423,13 +483,20 @@ int enqueue_encode(const Geom& g, const EncodeTuning& t, const EncodeScratch& s,
       int gpass = pass == 0 ? grid : (grid < t.num_sms ? grid : t.num_sms);
       cudaError_t e = cudaSuccess;
       if (hook && pass == 0) cudaEventRecord(hook->start, stream);
-      FPV_DISPATCH_MODE(g.mode, (e = launch_fast<M>(fp, gpass, threads, smem, stream)));
+      const bool full = g.W % kStripPx == 0;
+      if (rps == 4) {
+        if (full) { FPV_DISPATCH_MODE(g.mode, (e = launch_fast<M, true, 4>(fp, gpass, threads, smem, stream))); }
+        else { FPV_DISPATCH_MODE(g.mode, (e = launch_fast<M, false, 4>(fp, gpass, threads, smem, stream))); }
+      } else {
+        if (full) { FPV_DISPATCH_MODE(g.mode, (e = launch_fast<M, true, 2>(fp, gpass, threads, smem, stream))); }
+        else { FPV_DISPATCH_MODE(g.mode, (e = launch_fast<M, false, 2>(fp, gpass, threads, smem, stream))); }
+      }
       if (hook && pass == 0) cudaEventRecord(hook->stop, stream);
       launches++;
       if (e != cudaSuccess) { *err = e; return -1; }
       if (pass < 2) {
         k_decide<<<n, 256, 0, stream>>>(s.stats, fp.list, fp.count, s.lists + (size_t)(pass + 1) * s.cap,
-                                        s.counts + pass + 1, 0, has_delta, has_low);
+                                        s.counts + pass + 1, 0, has_delta, has_low, frames, g.P, g.mode, g.shift);
         FPV_CHECK_LAUNCH();
       }
     }
@@ -438,14 +505,14 @@ int enqueue_encode(const Geom& g, const EncodeTuning& t, const EncodeScratch& s,
     dim3 gA((unsigned)((g.P + chunk - 1) / chunk), n);
     FPV_DISPATCH_MODE(g.mode, (k_gen_stats_delta<M><<<gA, 256, 0, stream>>>(frames, s.stats, g.P, g.shift, chunk)));
     FPV_CHECK_LAUNCH();
-    k_decide<<<n, 256, 0, stream>>>(s.stats, s.lists, s.counts, s.lists + s.cap, s.counts + 1, 1, has_delta, has_low);
+    k_decide<<<n, 256, 0, stream>>>(s.stats, s.lists, s.counts, s.lists + s.cap, s.counts + 1, 1, has_delta, has_low, frames, g.P, g.mode, g.shift);
     FPV_CHECK_LAUNCH();
     uint64_t samples = g.P > (uint64_t)g.W + 1 ? (g.P - g.W - 1 + 30) / 31 : 0;
     unsigned gbx = (unsigned)((samples + 255) / 256); if (gbx < 1) gbx = 1; if (gbx > 1024) gbx = 1024;
     dim3 gB(gbx, n);
     FPV_DISPATCH_MODE(g.mode, (k_gen_stats_cg<M><<<gB, 256, 0, stream>>>(frames, delta, s.stats, g.W, g.P, g.shift)));
     FPV_CHECK_LAUNCH();
-    k_decide<<<n, 256, 0, stream>>>(s.stats, s.lists, s.counts, s.lists + s.cap, s.counts + 1, 2, has_delta, has_low);
+    k_decide<<<n, 256, 0, stream>>>(s.stats, s.lists, s.counts, s.lists + s.cap, s.counts + 1, 2, has_delta, has_low, frames, g.P, g.mode, g.shift);
     FPV_CHECK_LAUNCH();
     unsigned gtx = (unsigned)((g.P / 4 + 255) / 256); if (gtx < 1) gtx = 1; if (gtx > 4096) gtx = 4096;
     dim3 gT(gtx, n);
@@ -459,7 +526,9 @@ int enqueue_encode(const Geom& g, const EncodeTuning& t, const EncodeScratch& s,
     FPV_CHECK_LAUNCH();
   }
 
-  unsigned gfx = (unsigned)((g.PP / 4 + 255) / 256); if (gfx < 1) gfx = 1; if (gfx > 64) gfx = 64;
+  // a few fat blocks per frame: block scheduling, not bandwidth, dominates otherwise
+  unsigned gfx = (unsigned)((g.PP / 4 + 255) / 256); if (gfx < 1) gfx = 1;
+  { unsigned cap = n >= 1024 ? 2u : n >= 256 ? 4u : n >= 64 ? 16u : 64u; if (gfx > cap) gfx = cap; }
   dim3 gF(gfx, n);
   k_finalize<<<gF, 256, 0, stream>>>(s.stats, s.preview_raw, preview, flags, s.counts, n, g.PW, g.PP, has_low);
   FPV_CHECK_LAUNCH();

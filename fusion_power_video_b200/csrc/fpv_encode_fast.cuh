@@ -2,30 +2,35 @@
 //
 // One launch = Frame ctor + Frame::Predict (fusion_power_video.cc:370-451,
 // :491-593) for a list of frames under ASSUMED per-frame flags, plus the
-// three decision histograms and the low-byte OR the reference's heuristics
-// need (.cc:447-449, :522-531, :550-562).
+// statistics the reference's two heuristics need (.cc:447-449, :522-531,
+// :550-562).
 //
 // Work decomposition
 //   task   = (frame, band of `band_rows` rows); persistent CTAs take tasks
 //            round-robin.
-//   stage  = up to 4 consecutive rows of the band = ONE contiguous flat range
-//            of the raw frame (and of the delta image), fetched by the producer
-//            warp with cp.async.bulk (TMA, 1-D) into a shared-memory ring and
-//            signalled through an mbarrier.  The range starts 8 pixels early:
-//            with the reference's flat indexing (.cc:556-558) the west
-//            neighbour of column 0 is the last pixel of the previous row, which
-//            is exactly what precedes the row in memory.
+//   stage  = up to 4 (or 2) consecutive rows of the band = ONE contiguous flat range
+//            of the raw frame (and of the delta image), fetched with
+//            cp.async.bulk (TMA, 1-D) into a shared-memory ring and signalled
+//            through an mbarrier.  The range starts 8 pixels early: with the
+//            reference's flat indexing (.cc:556-558) the west neighbour of
+//            column 0 is the last pixel of the previous row, which is exactly
+//            what precedes the row in memory.
 //   strip  = 256 columns of a row, owned by one consumer warp (8 px per lane).
 //            The warp walks down the rows of the band keeping the previous
 //            row's (post-delta) high bytes in registers, so north / north-west
 //            neighbours never touch memory again; a band that does not start at
 //            row 0 is primed by a 1-row halo stage.
+//   service warp = the last warp of the CTA.  Lane 0 is the TMA producer; all 32
+//            lanes then take the delta-decision samples (every 15th pixel of the
+//            flat frame, .cc:526-531) straight out of the landed stage, so the
+//            consumer warps never see them.
 //
-// Per row and lane: 1x LDS.128 raw, 1x LDS.128 delta, 2x LDS.32 for the west
-// pixel, lane-form arithmetic (fpv_common.cuh), 2x STG.64 (+1 STG.16 of
-// preview every 4th row).  Sampling for the histograms is done cooperatively
-// per warp-row out of shared memory into warp-private packed-u16 histograms
-// (no CTA-wide barrier anywhere in the steady state).
+// Arithmetic is done on two pixels per register ("q form" / "S form", see
+// fpv_common.cuh).  Per row and lane: LDS.128 + LDS.32 of raw and of delta,
+// ~70 integer ops, 2x STG.64 (+ 1 STG.16 of preview every 4th row) and two
+// predicated shared atomics for the ClampedGradient decision histograms.
+// The delta decision needs no histogram in the common case: only 8 bit
+// counters per frame (see k_decide).
 #pragma once
 
 #include "fpv_internal.h"
@@ -59,16 +64,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Consumer-side wait: data is normally there already or lands within the
-// hardware suspend window of try_wait.
+// try_wait suspends the thread in hardware until the phase completes or a
+// system time limit passes, so this loop rarely iterates.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
-}
-// Producer-side wait: the producer runs ahead of the consumers by the depth of
-// the ring, so it mostly waits; back off instead of burning issue slots.
-__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) {
-  while (!mbar_try_wait(bar, parity)) __nanosleep(256);
 }
 // 1-D TMA bulk copy global -> shared, completion counted in bytes on `bar`.
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes,
@@ -94,19 +94,11 @@ __device__ __forceinline__ uint32_t lds16(uint32_t a) {
   asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
   return v;
 }
-__device__ __forceinline__ uint32_t lds8(uint32_t a) {
-  uint32_t v;
-  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
-  return v;
-}
 __device__ __forceinline__ void sts32(uint32_t a, uint32_t v) {
   asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
 }
-__device__ __forceinline__ void sts64(uint32_t a, uint2 v) {
-  asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(v.x), "r"(v.y) : "memory");
-}
-__device__ __forceinline__ void red_shared_add(uint32_t a, uint32_t v) {
-  asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+__device__ __forceinline__ void red_shared_inc(uint32_t a) {
+  asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a) : "memory");
 }
 // Streaming stores: outputs are written once and not re-read by this kernel.
 __device__ __forceinline__ void stg64_cs(void* p, uint2 v) {
@@ -114,10 +106,10 @@ __device__ __forceinline__ void stg64_cs(void* p, uint2 v) {
 }
 
 constexpr int kStripPx = 256;       // columns per consumer warp (8 pixels per lane)
-constexpr int kRowsPerStage = 4;    // one preview row group
+constexpr int kMaxRowsPerStage = 4; // rows per stage: 4 (one preview row group) or 2
 constexpr int kHaloPx = 8;          // pixels copied before a stage's first pixel (16 B)
-constexpr int kWarpHistWords = 384; // 3 histograms x 256 bins, two u16 counters per word
-constexpr int kWarpScratchBytes = kWarpHistWords * 4 + 256;  // + residual staging row
+constexpr int kWarpHistWords = 512; // hist_a, hist_b: 256 u32 counters each, warp-private
+constexpr int kWarpScratchBytes = kWarpHistWords * 4;
 
 struct FastParams {
   const uint16_t* frames;
@@ -132,136 +124,156 @@ struct FastParams {
   uint64_t P, PP;
   uint32_t PW;
   int shift;
-  uint32_t band_rows;           // multiple of 4, <= 1024
+  uint32_t band_rows;           // multiple of 4
   uint32_t bands;               // bands per frame
   uint32_t stages;              // ring depth
-  uint32_t stage_bytes;         // bytes of one plane of one stage: (4W + 8) * 2
+  uint32_t rows_per_stage;      // 2 or 4
+  uint32_t stage_bytes;         // bytes of one plane of one stage: (rows_per_stage * W + 8) * 2
   uint32_t compute_warps;       // ceil(W / 256)
 };
 
-// Per-lane running state while walking down a strip.
+// Walks the stage sequence of one CTA: tasks blockIdx.x, +gridDim.x, ...; per
+// task an optional 1-row halo stage (row y0-1) then 4-row stages.  Producer,
+// sampler and consumers each run their own copy and therefore agree on the
+// running stage number.
+struct StageCursor {
+  uint32_t t, f, y0, y1, ys, rps;
+  __device__ __forceinline__ bool load_task(const FastParams& p, uint32_t total) {
+    if (t >= total) return false;
+    f = p.list[t / p.bands];
+    const uint32_t b = t % p.bands;
+    y0 = b * p.band_rows;
+    y1 = min(p.H, y0 + p.band_rows);
+    ys = y0 > 0 ? y0 - 1 : 0;
+    return true;
+  }
+  __device__ __forceinline__ bool halo() const { return ys < y0; }
+  __device__ __forceinline__ uint32_t nrows() const {
+    return ys < y0 ? 1u : min(rps, y1 - ys);
+  }
+  __device__ __forceinline__ bool last_of_task() const { return ys + nrows() >= y1; }
+  __device__ __forceinline__ bool advance(const FastParams& p, uint32_t total) {
+    ys += nrows();
+    if (ys < y1) return true;
+    t += gridDim.x;
+    return load_task(p, total);
+  }
+};
+
+// Position in the shared-memory ring: slot index and the parity of its current use.
+struct RingPos {
+  uint32_t slot = 0, phase = 0;
+  __device__ __forceinline__ void next(uint32_t S) {
+    if (++slot == S) { slot = 0; phase ^= 1u; }
+  }
+};
+
+// Per-lane running state while walking down a strip (all S form).
 struct StripState {
-  uint32_t ph[4];   // previous row, post-delta high bytes, lane form
+  uint32_t ph[4];   // previous row, post-delta high bytes
   uint32_t pw[4];   // previous row shifted one pixel west (= this row's north-west)
-  uint32_t acc0, acc1;  // preview 4x4 box sums (two preview pixels per lane), lane form
-  uint32_t orl;     // OR of split low bytes
+  uint32_t accA, accB;  // preview 4x4 box sums of the RAW high bytes (two preview pixels per lane)
+  uint32_t orl;     // OR of the split pixels (low bytes = OR of low plane)
+  uint32_t kc;      // offset (0..30) from this lane's first pixel to the next CG-decision sample
 };
 
 // One row of one strip.  FIRSTROWS = true compiles the row-0 / row-1 special
-// cases of the first stage of a frame and the halo (not-owned) row; the steady
-// state uses FIRSTROWS = false.
-template <int MODE, bool FIRSTROWS>
+// cases and the halo (not-owned) row; the steady state uses FIRSTROWS = false.
+template <int MODE, bool FIRSTROWS, bool FULL>
 __device__ __forceinline__ void fast_row(
-    StripState& st, const uint32_t raw_a /* shared addr of this lane's 8 px */,
-    const uint32_t del_a, const uint32_t raw_strip_a /* shared addr of the strip's first px */,
-    const uint32_t del_strip_a, const int s, const bool use_delta, const bool use_cg,
-    const bool active, const bool own, const uint32_t y, const bool emit_preview,
-    const uint32_t c0, const int lane, const uint32_t span /* valid px in this strip */,
-    const uint32_t m15 /* flat index of strip start mod 15 */, const uint32_t m31,
+    StripState& st, const uint32_t raw_a /* shared addr of this lane's 8 px */, const uint32_t del_a,
+    const QConst qc, const bool use_delta, const bool use_cg, const bool active, const bool own,
+    const uint32_t y, const bool emit_preview, const uint32_t c0, const uint32_t w31,
     uint8_t* __restrict__ out_high, uint8_t* __restrict__ out_low, uint8_t* __restrict__ out_prev,
-    const uint32_t hist_a, const uint32_t stage_res_a) {
-  uint32_t xh[4], xl[4], h[4], l[4];
-  uint32_t hleft;  // lane form of the two pixels west of this lane's first pixel
+    const uint32_t hist_a) {
+  uint32_t q[4], hs[4], lo[4], w[4];
+  uint32_t hw;  // S form of the two pixels west of this lane's first pixel
   {
-    uint4 x = make_uint4(0, 0, 0, 0);
-    uint32_t xw = 0;
-    if (active) {
-      x = lds128(raw_a);
-      xw = lds32(raw_a - 4);
-    }
-    split2<MODE>(x.x, s, xh[0], xl[0]);
-    split2<MODE>(x.y, s, xh[1], xl[1]);
-    split2<MODE>(x.z, s, xh[2], xl[2]);
-    split2<MODE>(x.w, s, xh[3], xl[3]);
-    uint32_t dummy;
-    split2<MODE>(xw, s, hleft, dummy);
+    // lanes past the end of the row (FULL == false only) read whatever follows
+    // in shared memory; nothing derived from it is ever stored
+    const uint4 x = lds128(raw_a);
+    const uint32_t xw = lds32(raw_a - 4);
+    q[0] = make_q2<MODE>(x.x, qc);
+    q[1] = make_q2<MODE>(x.y, qc);
+    q[2] = make_q2<MODE>(x.z, qc);
+    q[3] = make_q2<MODE>(x.w, qc);
+    hw = make_q2<MODE>(xw, qc) & kHiBytes;
   }
   if (use_delta) {
-    uint4 d = make_uint4(0, 0, 0, 0);
-    uint32_t dw = 0;
-    if (active) {
-      d = lds128(del_a);
-      dw = lds32(del_a - 4);
+    // Bytes wrap independently (.cc:534-537).  High: bits 8-15 / 24-31 of
+    // (q & HI) + 2^16 - (d & HI); bit 16 is junk.  Low: bytes 0 / 2 of
+    // (q | 0x0100 per lane) - (d & LO); the rest is junk the packing drops.
+    const uint4 d = lds128(del_a);
+    const uint32_t dw = lds32(del_a - 4);
+    const uint32_t dd[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      hs[j] = (q[j] & kHiBytes) + 0x00010000u - (dd[j] & kHiBytes);
+      lo[j] = (q[j] | 0x01000100u) - (dd[j] & kLoBytes);
     }
-    uint32_t dh, dl;
-    split2_delta(d.x, dh, dl); h[0] = sub2(xh[0], dh); l[0] = xl[0] + kLaneBias - dl;
-    split2_delta(d.y, dh, dl); h[1] = sub2(xh[1], dh); l[1] = xl[1] + kLaneBias - dl;
-    split2_delta(d.z, dh, dl); h[2] = sub2(xh[2], dh); l[2] = xl[2] + kLaneBias - dl;
-    split2_delta(d.w, dh, dl); h[3] = sub2(xh[3], dh); l[3] = xl[3] + kLaneBias - dl;
-    split2_delta(dw, dh, dl);  hleft = sub2(hleft, dh);
+    hw = hw + 0x00010000u - (dw & kHiBytes);
   } else {
 #pragma unroll
-    for (int j = 0; j < 4; j++) { h[j] = xh[j]; l[j] = xl[j]; }
+    for (int j = 0; j < 4; j++) {
+      hs[j] = q[j] & kHiBytes;
+      lo[j] = q[j];
+    }
   }
-  uint32_t w[4];
-  w[0] = __funnelshift_l(hleft, h[0], 16);
-  w[1] = __funnelshift_l(h[0], h[1], 16);
-  w[2] = __funnelshift_l(h[1], h[2], 16);
-  w[3] = __funnelshift_l(h[2], h[3], 16);
+  w[0] = __funnelshift_l(hw, hs[0], 16);
+  w[1] = __funnelshift_l(hs[0], hs[1], 16);
+  w[2] = __funnelshift_l(hs[1], hs[2], 16);
+  w[3] = __funnelshift_l(hs[2], hs[3], 16);
 
   if (!FIRSTROWS || own) {
     uint32_t res[4];
 #pragma unroll
-    for (int j = 0; j < 4; j++) res[j] = sub2(h[j], cg2(st.ph[j], w[j], st.pw[j]));
+    for (int j = 0; j < 4; j++) res[j] = cg_residual_s(hs[j], st.ph[j], w[j], st.pw[j]);
     if (FIRSTROWS) {
       if (y == 0) {
 #pragma unroll
-        for (int j = 0; j < 4; j++) res[j] = h[j];
+        for (int j = 0; j < 4; j++) res[j] = hs[j];
       } else if (y == 1 && c0 == 0) {
         // flat index W (row 1, column 0) is copied, not predicted (.cc:566, :572)
-        res[0] = (res[0] & 0xffff0000u) | (h[0] & 0x0000ffffu);
+        res[0] = (res[0] & 0xffff0000u) | (hs[0] & 0x0000ffffu);
       }
     }
-    const uint2 res8 = pack8(res[0], res[1], res[2], res[3]);
-    if (active) {
-      stg64_cs(out_high, use_cg ? res8 : pack8(h[0], h[1], h[2], h[3]));
-      if (mode_has_low(MODE)) stg64_cs(out_low, pack8(l[0], l[1], l[2], l[3]));
-      st.orl |= xl[0] | xl[1] | xl[2] | xl[3];
-      st.acc0 += xh[0] + xh[1];
-      st.acc1 += xh[2] + xh[3];
-      sts64(stage_res_a + 8 * lane, res8);
+    const uint2 res8 = make_uint2(pack_hi(res[0], res[1]), pack_hi(res[2], res[3]));
+    const uint2 h8 = make_uint2(pack_hi(hs[0], hs[1]), pack_hi(hs[2], hs[3]));
+    if (FULL || active) {
+      stg64_cs(out_high, use_cg ? res8 : h8);
+      if (mode_has_low(MODE)) stg64_cs(out_low, make_uint2(pack_lo(lo[0], lo[1]), pack_lo(lo[2], lo[3])));
     }
-    // ---- decision histograms, sampled cooperatively per warp-row -------------
-    // delta decision: RAW high byte at flat index % 15 == 0 (.cc:526-531)
-    {
-      const uint32_t pd = (m15 ? 15 - m15 : 0) + 15 * lane;
-      if (pd < span) {
-        uint32_t hv, lv;
-        split1<MODE>(lds16(raw_strip_a + 2 * pd), s, hv, lv);
-        red_shared_add(hist_a + ((hv >> 1) << 2), 1u << ((hv & 1) << 4));
+    st.orl |= (q[0] | q[1]) | (q[2] | q[3]);
+    st.accA = __dp4a(q[0], 0x01000100u, __dp4a(q[1], 0x01000100u, st.accA));
+    st.accB = __dp4a(q[2], 0x01000100u, __dp4a(q[3], 0x01000100u, st.accB));
+    // ---- ClampedGradient decision samples: flat index == W+1 (mod 31), >= W+1,
+    //      a = post-delta high byte, b = a - CG (.cc:554-562).  A lane's 8 pixels
+    //      hold at most one sample; it is picked out of the packed registers.
+    if ((!FIRSTROWS || y >= 1) && st.kc < 8 && (FULL || active)) {
+      const uint32_t a = __byte_perm(h8.x, h8.y, st.kc) & 0xffu;
+      const uint32_t b = __byte_perm(res8.x, res8.y, st.kc) & 0xffu;
+      red_shared_inc(hist_a + 4 * a);
+      red_shared_inc(hist_a + 1024 + 4 * b);
+    }
+    if (emit_preview) {
+      if (FULL || active) {
+        const uint32_t pv = ((st.accA >> 4) & 0xfeu) | (((st.accB >> 4) & 0xfeu) << 8);
+        *reinterpret_cast<uint16_t*>(out_prev) = (uint16_t)pv;
       }
-    }
-    __syncwarp();
-    // CG decision: flat index == W+1 (mod 31), >= W+1, post-delta plane (.cc:554-562)
-    if (!FIRSTROWS || y >= 1) {
-      const uint32_t pc = (m31 ? 31 - m31 : 0) + 31 * lane;
-      if (pc < span) {
-        uint32_t a, lv;
-        split1<MODE>(lds16(raw_strip_a + 2 * pc), s, a, lv);
-        if (use_delta) a = (a - (lds16(del_strip_a + 2 * pc) >> 8)) & 0xffu;
-        const uint32_t b = lds8(stage_res_a + pc);
-        red_shared_add(hist_a + 512 + ((a >> 1) << 2), 1u << ((a & 1) << 4));
-        red_shared_add(hist_a + 1024 + ((b >> 1) << 2), 1u << ((b & 1) << 4));
-      }
-    }
-    __syncwarp();
-    if (emit_preview && active) {
-      const uint32_t s0 = (st.acc0 & 0xffffu) + (st.acc0 >> 16);
-      const uint32_t s1 = (st.acc1 & 0xffffu) + (st.acc1 >> 16);
-      const uint32_t pv = ((s0 >> 4) & 0xfeu) | (((s1 >> 4) & 0xfeu) << 8);
-      *reinterpret_cast<uint16_t*>(out_prev) = (uint16_t)pv;
-      st.acc0 = 0;
-      st.acc1 = 0;
+      st.accA = 0;
+      st.accB = 0;
     }
   }
+  st.kc = min(st.kc - w31, st.kc - w31 + 31u);   // (kc - W) mod 31; one of the two wrapped around
 #pragma unroll
-  for (int j = 0; j < 4; j++) { st.ph[j] = h[j]; st.pw[j] = w[j]; }
+  for (int j = 0; j < 4; j++) { st.ph[j] = hs[j]; st.pw[j] = w[j]; }
 }
 
 // Shared memory: [ring: stages x {raw stage, delta stage}] [per consumer warp:
-// packed histograms + residual staging row] [full barriers] [empty barriers]
-template <int MODE>
-__global__ void __launch_bounds__(544) k_encode_fast(const FastParams p) {
+// hist_a | hist_b] [full barriers] [empty barriers]
+// FULL: xsize is a multiple of 256, every lane of every consumer warp owns pixels.
+template <int MODE, bool FULL, int RPS>
+__global__ void __launch_bounds__(544, 1) k_encode_fast(const FastParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t S = p.stages;
   const uint32_t slot_bytes = 2 * p.stage_bytes;
@@ -273,48 +285,92 @@ __global__ void __launch_bounds__(544) k_encode_fast(const FastParams p) {
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t W = p.W;
+  const QConst qc = make_qconst(MODE, p.shift);
 
   for (uint32_t i = threadIdx.x; i < (uint32_t)NW * kWarpScratchBytes / 4; i += blockDim.x)
     reinterpret_cast<uint32_t*>(scratch)[i] = 0;
   if (threadIdx.x == 0) {
     for (uint32_t i = 0; i < S; i++) {
       mbar_init(full0 + 8 * i, 1);
-      mbar_init(empty0 + 8 * i, NW);
+      mbar_init(empty0 + 8 * i, NW + 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
 
   const uint32_t total_tasks = (*p.count) * p.bands;
-  uint32_t seq = 0;  // running stage number (same sequence in producer and consumers)
+  StageCursor cur;
+  cur.t = blockIdx.x;
+  cur.rps = RPS;
+  bool more = cur.load_task(p, total_tasks);
+  RingPos rp;        // ring position of the stage this warp works on
 
   if (warp == NW) {
-    // ------------------------------ producer ------------------------------------
-    if (lane == 0) {
-      for (uint32_t t = blockIdx.x; t < total_tasks; t += gridDim.x) {
-        const uint32_t f = p.list[t / p.bands], b = t % p.bands;
-        const uint32_t y0 = b * p.band_rows;
-        const uint32_t y1 = min(p.H, y0 + p.band_rows);
-        const bool use_delta = p.delta != nullptr && (p.stats[f].assumed & 1u);
-        const uint16_t* img = p.frames + (uint64_t)f * p.P;
-        // stage list: optional 1-row halo stage (row y0-1), then 4-row stages
-        uint32_t ys = y0 > 0 ? y0 - 1 : 0;
-        while (ys < y1) {
-          const uint32_t nrows = (ys < y0) ? 1 : min((uint32_t)kRowsPerStage, y1 - ys);
-          const uint32_t slot = seq % S, ph = (seq / S) & 1u;
-          mbar_wait_backoff(empty0 + 8 * slot, ph ^ 1u);
-          // contiguous flat range [ys*W - 8, (ys+nrows)*W)
-          const uint64_t px0 = (uint64_t)ys * W;
-          const uint32_t lead = ys > 0 ? kHaloPx : 0;
-          const uint32_t bytes = (nrows * W + lead) * 2;
-          const uint32_t dst = ring0 + slot * slot_bytes + (kHaloPx - lead) * 2;
-          mbar_arrive_expect_tx(full0 + 8 * slot, use_delta ? 2 * bytes : bytes);
-          bulk_g2s(dst, img + px0 - lead, bytes, full0 + 8 * slot);
-          if (use_delta) bulk_g2s(dst + p.stage_bytes, p.delta + px0 - lead, bytes, full0 + 8 * slot);
-          seq++;
-          ys += nrows;
+    // ------------------- service warp: TMA producer + delta-decision sampler -------------------
+    StageCursor ic = cur;  // issue cursor, runs S-1 stages ahead
+    bool imore = more;
+    RingPos ip;
+    auto issue = [&]() {
+      if (lane == 0) {
+        const uint32_t slot = ip.slot;
+        // wait until every reader of the slot's previous stage has released it
+        mbar_wait(empty0 + 8 * slot, ip.phase ^ 1u);
+        const bool use_delta = p.delta != nullptr && (p.stats[ic.f].assumed & 1u);
+        const uint16_t* img = p.frames + (uint64_t)ic.f * p.P;
+        // contiguous flat range [ys*W - 8, (ys+nrows)*W)
+        const uint32_t px0 = ic.ys * W;  // < 2^30 (fpv_create bounds xsize * ysize)
+        const uint32_t lead = ic.ys > 0 ? kHaloPx : 0;
+        const uint32_t bytes = (ic.nrows() * W + lead) * 2;
+        const uint32_t dst = ring0 + slot * slot_bytes + (kHaloPx - lead) * 2;
+        mbar_arrive_expect_tx(full0 + 8 * slot, use_delta ? 2 * bytes : bytes);
+        bulk_g2s(dst, img + px0 - lead, bytes, full0 + 8 * slot);
+        if (use_delta) bulk_g2s(dst + p.stage_bytes, p.delta + px0 - lead, bytes, full0 + 8 * slot);
+      }
+      ip.next(S);
+      imore = ic.advance(p, total_tasks);
+    };
+    for (uint32_t i = 0; i + 1 < S && imore; i++) issue();
+
+    uint32_t acc[4] = {0, 0, 0, 0};  // per-lane counts of set bits {0,2},{1,3},{4,6},{5,7}, two u16 each
+    while (more) {
+      if (imore) issue();
+      const uint32_t slot = rp.slot;
+      mbar_wait(full0 + 8 * slot, rp.phase);
+      if (!cur.halo()) {
+        // samples of this stage: flat index % 15 == 0 (.cc:526-531), RAW high byte
+        const uint32_t base = ring0 + slot * slot_bytes + kHaloPx * 2;
+        const uint32_t npx = cur.nrows() * W;
+        const uint32_t m = (cur.ys * W) % 15u;
+        uint32_t c_lo = 0, c_hi = 0;  // four u8 counters each: bits 0..3, bits 4..7
+        for (uint32_t pos = (m ? 15u - m : 0u) + 15u * (uint32_t)lane; pos < npx; pos += 15u * 32u) {
+          const uint32_t v = make_q2<MODE>(lds16(base + 2 * pos), qc) >> 8;  // lane 1 is zero: v = high byte
+          c_lo += ((v & 15u) * 0x00204081u) & 0x01010101u;
+          c_hi += ((v >> 4) * 0x00204081u) & 0x01010101u;
+        }
+        acc[0] += c_lo & kLoBytes;
+        acc[1] += (c_lo >> 8) & kLoBytes;
+        acc[2] += c_hi & kLoBytes;
+        acc[3] += (c_hi >> 8) & kLoBytes;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty0 + 8 * slot);
+      if (cur.last_of_task()) {
+        uint32_t* gb = p.stats[cur.f].dbits;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const uint32_t s0 = __reduce_add_sync(0xffffffffu, acc[k] & 0xffffu);
+          const uint32_t s1 = __reduce_add_sync(0xffffffffu, acc[k] >> 16);
+          // acc[0]: bits 0,2  acc[1]: bits 1,3  acc[2]: bits 4,6  acc[3]: bits 5,7
+          const int b0 = (k & 1) + 4 * (k >> 1);
+          if (lane == 0) {
+            if (s0) atomicAdd(&gb[b0], s0);
+            if (s1) atomicAdd(&gb[b0 + 2], s1);
+          }
+          acc[k] = 0;
         }
       }
+      more = cur.advance(p, total_tasks);
+      rp.next(S);
     }
     return;
   }
@@ -323,95 +379,91 @@ __global__ void __launch_bounds__(544) k_encode_fast(const FastParams p) {
   const uint32_t sb = (uint32_t)warp * kStripPx;          // first column of this warp's strip
   const uint32_t c0 = sb + (uint32_t)lane * 8;
   const bool active = c0 < W;
-  const uint32_t span = sb < W ? min((uint32_t)kStripPx, W - sb) : 0;
-  const uint32_t w15 = W % 15, w31 = W % 31;
+  const uint32_t w31 = W % 31;
   const uint32_t rowb = W * 2;                            // bytes per row in a stage
-  const int s = p.shift;
-  const uint32_t hist_a = smem_u32(scratch + (size_t)warp * kWarpScratchBytes);
-  const uint32_t res_a = hist_a + kWarpHistWords * 4;
+  uint32_t hist_a = smem_u32(scratch + (size_t)warp * kWarpScratchBytes);
+  asm volatile("" : "+r"(hist_a));  // keep it in a register instead of recomputing it per row
 
-  for (uint32_t t = blockIdx.x; t < total_tasks; t += gridDim.x) {
-    const uint32_t f = p.list[t / p.bands], b = t % p.bands;
-    const uint32_t y0 = b * p.band_rows;
-    const uint32_t y1 = min(p.H, y0 + p.band_rows);
+  while (more) {
+    // ---- start of a task ---------------------------------------------------------
+    const uint32_t f = cur.f;
     const uint32_t assumed = p.stats[f].assumed;
     const bool use_delta = p.delta != nullptr && (assumed & 1u);
     const bool use_cg = (assumed & 2u) != 0;
-
     StripState st;
 #pragma unroll
     for (int j = 0; j < 4; j++) { st.ph[j] = 0; st.pw[j] = 0; }
-    st.acc0 = st.acc1 = st.orl = 0;
-    uint32_t y = y0 > 0 ? y0 - 1 : 0;
-    // residues of the flat index of the STRIP's first pixel in row y
-    const uint64_t i0 = (uint64_t)y * W + sb;
-    uint32_t m15 = (uint32_t)(i0 % 15);
-    uint32_t m31 = (uint32_t)((i0 + 31ull * (W / 31 + 2) - (W + 1)) % 31);
+    st.accA = st.accB = st.orl = 0;
+    uint32_t y = cur.ys;
+    {
+      // offset of the first pixel >= (y, c0) whose flat index is == W+1 (mod 31)
+      const uint64_t i0 = (uint64_t)y * W + c0;
+      const uint32_t r = (uint32_t)((i0 + 31ull * (W / 31 + 2) - (W + 1)) % 31);
+      st.kc = r ? 31 - r : 0;
+    }
     uint8_t* oh = p.high + (uint64_t)f * p.P + (uint64_t)y * W + c0;
     uint8_t* ol = mode_has_low(MODE) ? p.low + (uint64_t)f * p.P + (uint64_t)y * W + c0 : nullptr;
     uint8_t* op = p.preview_raw + (uint64_t)f * p.PP + (uint64_t)(y >> 2) * p.PW + (c0 >> 2);
 
-    while (y < y1) {
-      const uint32_t nrows = (y < y0) ? 1 : min((uint32_t)kRowsPerStage, y1 - y);
-      const uint32_t slot = seq % S, phs = (seq / S) & 1u;
-      mbar_wait(full0 + 8 * slot, phs);
-      const uint32_t raw_strip = ring0 + slot * slot_bytes + kHaloPx * 2 + sb * 2;  // pixel (y, sb)
-      const uint32_t raw_lane = raw_strip + (uint32_t)lane * 16;
+    for (;;) {
+      const uint32_t nrows = cur.nrows();
+      const bool own = !cur.halo();
+      const bool last = cur.last_of_task();
+      const uint32_t slot = rp.slot;
+      mbar_wait(full0 + 8 * slot, rp.phase);
+      const uint32_t raw_lane = ring0 + slot * slot_bytes + kHaloPx * 2 + c0 * 2;  // pixel (y, c0)
 
-      if (y >= 4 && nrows == kRowsPerStage) {
-        // steady state: 4 owned rows, none of them row 0 / row 1
+      if (y >= 4 && nrows == RPS) {
+        // steady state: RPS owned rows, none of them row 0 / row 1; stages start on even rows
+        // (bands on multiples of 4), so a preview row group ends with the last row of a stage
+        const bool group_end = RPS == 4 || (y & 2u);
 #pragma unroll
-        for (int r = 0; r < kRowsPerStage; r++) {
-          fast_row<MODE, false>(st, raw_lane + r * rowb, raw_lane + r * rowb + p.stage_bytes,
-                                raw_strip + r * rowb, raw_strip + r * rowb + p.stage_bytes, s, use_delta,
-                                use_cg, active, true, y + r, r == kRowsPerStage - 1, c0, lane, span, m15,
-                                m31, oh, ol, op, hist_a, res_a);
+        for (int r = 0; r < RPS; r++) {
+          fast_row<MODE, false, FULL>(st, raw_lane + r * rowb, raw_lane + r * rowb + p.stage_bytes, qc, use_delta,
+                                use_cg, active, true, y + r, r == RPS - 1 && group_end, c0, w31, oh, ol, op,
+                                hist_a);
           oh += W;
           if (mode_has_low(MODE)) ol += W;
-          m15 += w15; if (m15 >= 15) m15 -= 15;
-          m31 += w31; if (m31 >= 31) m31 -= 31;
         }
-        op += p.PW;
-        y += kRowsPerStage;
+        if (group_end) op += p.PW;
+        y += RPS;
       } else {
         for (uint32_t r = 0; r < nrows; r++) {
-          fast_row<MODE, true>(st, raw_lane + r * rowb, raw_lane + r * rowb + p.stage_bytes,
-                               raw_strip + r * rowb, raw_strip + r * rowb + p.stage_bytes, s, use_delta,
-                               use_cg, active, y >= y0, y, (y & 3u) == 3u, c0, lane, span, m15, m31, oh, ol,
-                               op, hist_a, res_a);
+          fast_row<MODE, true, FULL>(st, raw_lane + r * rowb, raw_lane + r * rowb + p.stage_bytes, qc, use_delta,
+                               use_cg, active, own, y, (y & 3u) == 3u, c0, w31, oh, ol, op, hist_a);
           oh += W;
           if (mode_has_low(MODE)) ol += W;
           if ((y & 3u) == 3u) op += p.PW;
-          m15 += w15; if (m15 >= 15) m15 -= 15;
-          m31 += w31; if (m31 >= 31) m31 -= 31;
           y++;
         }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(empty0 + 8 * slot);
-      seq++;
+      rp.next(S);
+      more = cur.advance(p, total_tasks);
+      if (last) break;
     }
 
     // ---- end of task: publish low-OR and this warp's histograms -----------------
-    uint32_t orl = st.orl;
-#pragma unroll
-    for (int o = 16; o; o >>= 1) orl |= __shfl_xor_sync(0xffffffffu, orl, o);
-    if (lane == 0 && (orl & kLaneMask)) atomicOr(&p.stats[f].low_or, orl & kLaneMask);
-    uint32_t* gh = p.stats[f].hist_d;  // hist_d, hist_a, hist_b are contiguous: 768 bins
+    if (mode_has_low(MODE)) {
+      // lanes past the end of the row accumulated garbage (see fast_row)
+      const uint32_t orl = __reduce_or_sync(0xffffffffu, (FULL || active) ? (st.orl & kLoBytes) : 0u);
+      if (lane == 0 && orl) atomicOr(&p.stats[f].low_or, orl);
+    }
+    uint32_t* gh = p.stats[f].hist_a;  // hist_a, hist_b are contiguous: 512 bins
     for (uint32_t i = lane; i < kWarpHistWords; i += 32) {
       const uint32_t v = lds32(hist_a + 4 * i);
       if (v) {
         sts32(hist_a + 4 * i, 0);
-        if (v & 0xffffu) atomicAdd(&gh[2 * i], v & 0xffffu);
-        if (v >> 16) atomicAdd(&gh[2 * i + 1], v >> 16);
+        atomicAdd(&gh[i], v);
       }
     }
     __syncwarp();
   }
 }
 
-static inline size_t fast_smem_bytes(uint32_t W, int stages) {
-  const size_t stage_bytes = ((size_t)kRowsPerStage * W + kHaloPx) * 2;
+static inline size_t fast_smem_bytes(uint32_t W, int stages, int rows_per_stage) {
+  const size_t stage_bytes = ((size_t)rows_per_stage * W + kHaloPx) * 2;
   const size_t warps = (W + kStripPx - 1) / kStripPx;
   return (size_t)stages * 2 * stage_bytes + warps * kWarpScratchBytes + 2 * (size_t)stages * 8;
 }

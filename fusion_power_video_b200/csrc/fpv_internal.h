@@ -31,6 +31,7 @@ struct EncodeScratch {
 struct EncodeTuning {
   int num_sms = 148;
   int stages = 3;          // smem ring depth of the fast kernel
+  int rows_per_stage = 4;  // 4 or 2
   int band_rows = 64;      // rows per task (multiple of 4)
   int max_smem_optin = 0;  // bytes
 };
