@@ -301,7 +301,7 @@ def main():
         decode = {"metric": "decode_transform_raw_pixel_throughput", "value": world * F * P * 2 / (dms * 1e-3) / 1e9,
                   "unit": "GB/s", "frames_per_s": world * F / (dms * 1e-3), "ms_per_step": dms, "steps": dsteps,
                   "round_trip_exact": ok,
-                  "roofline": {"bound": "hbm (chain-latency limited, see DESIGN.md)", "kernel": "k_decode_spec",
+                  "roofline": {"bound": "hbm (chain-latency limited, see DESIGN.md)", "kernel": "k_decode_simd",
                                "achieved": dach, "peak": peak, "unit": "GB/s", "frac": dach / peak}}
         del d_out
 

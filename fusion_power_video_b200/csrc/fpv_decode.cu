@@ -20,6 +20,8 @@
 // Rows are staged with cp.async (residual row, low row, delta row) a few rows
 // ahead so that the chain never waits on HBM; the delta add, the high/low
 // recombination and UnextractFrame are fused into the row write-out.
+#include <stdlib.h>
+
 #include "fpv_internal.h"
 
 namespace fpv {
@@ -266,6 +268,246 @@ __global__ void __launch_bounds__(128) k_decode_spec(const DecodeParams p) {
   }
 }
 
+
+// =====================================================================================
+// SIMD row kernel (the default): one warp per frame, 64 segments per row.
+//
+// Lane l owns the 2L contiguous columns [2L*l, 2L*(l+1)) as two half-segments of
+// L = 4*LW pixels.  The two halves are two independent chains run in the two
+// 16-bit lanes of one register ("lane form", values in [0,255]):
+//     x = (c + min3(n, w, nw) + max3(n, w, nw)) & 0x00ff00ff,   c = r + 256 - nw
+// because CG(n, w, nw) = n + w - median = min3 + max3 - nw (.cc:247-252) and the
+// reconstructed byte is r + CG mod 256 (.cc:328-332).  That is two VIMNMX3.U16x2,
+// one IADD3 and one LOP3 per step for TWO pixels, with a dependent depth of 3.
+// The previous row, the current row and the c terms of a lane's 40-odd pixels all
+// stay in registers; shared memory only stages the input rows (cp.async, a few
+// rows ahead).  Segment inputs are speculated and repaired exactly as described
+// at the top of this file: 64 chains start from guessed west values, then rounds
+// of "shuffle the segment ends, re-run until the new values meet the old ones"
+// until no segment's input changes.  Segment 0's input is exact, so by induction
+// over segments the fixed point is the serial result.
+// =====================================================================================
+
+struct SimdParams {
+  const uint8_t* high;
+  const uint8_t* low;      // may be nullptr
+  const uint8_t* flags;
+  const uint16_t* delta;   // image form, may be nullptr
+  uint16_t* out;
+  uint32_t W, H;
+  uint64_t P;
+  int shift, big_endian, unextract;
+  uint32_t n;
+  uint32_t nst;            // staged rows in flight (2..4)
+};
+
+constexpr uint32_t kLaneM = 0x00ff00ffu;
+
+// A16: W % 16 == 0 (16-byte cp.async); otherwise W % 4 == 0 (4-byte cp.async).
+template <int LW, bool A16>
+__global__ void __launch_bounds__(32) k_decode_simd(const SimdParams p) {
+  extern __shared__ __align__(16) uint32_t dsm[];
+  constexpr int L = 4 * LW;
+  constexpr uint32_t RW = 16 * L;            // words per staged byte row (64 L columns)
+  constexpr uint32_t STAGE = 4 * RW;         // residual | low | delta (2 RW)
+  const int lane = threadIdx.x;
+  const uint32_t W = p.W, H = p.H, NST = p.nst;
+  const uint32_t col0 = (uint32_t)lane * 2 * L;
+  const bool v0 = col0 < W, v1 = col0 + L < W;                 // half-segment holds real pixels
+  const uint32_t vmask = (v0 ? 0x0000ffffu : 0u) | (v1 ? 0xffff0000u : 0u);
+  // where the last pixel of a row lives (W % 4 == 0, L % 4 == 0: it ends a 4-step group)
+  const uint32_t last_seg = (W - 1) / L, last_t = (W - 1) % L;
+  const int last_lane = (int)(last_seg >> 1);
+  const bool last_hi = (last_seg & 1u) != 0;
+
+  for (uint32_t f = blockIdx.x; f < p.n; f += gridDim.x) {
+    const uint32_t fl = p.flags[f];
+    const bool use_delta = (fl & kFlagDelta) && p.delta != nullptr;
+    const bool use_cg = (fl & kFlagCG) != 0;
+    const bool has_low = !(fl & kFlagNoLow) && p.low != nullptr;
+    const uint8_t* fh = p.high + (uint64_t)f * p.P;
+    const uint8_t* flow = has_low ? p.low + (uint64_t)f * p.P : nullptr;
+    uint16_t* fout = p.out + (uint64_t)f * p.P;
+
+    auto issue_row = [&](uint32_t y) {
+      if (y < H) {
+        uint32_t* st = dsm + (size_t)(y % NST) * STAGE;
+        uint8_t* rb = reinterpret_cast<uint8_t*>(st);
+        uint8_t* lb = reinterpret_cast<uint8_t*>(st + RW);
+        uint8_t* db = reinterpret_cast<uint8_t*>(st + 2 * RW);
+        const uint8_t* src = fh + (uint64_t)y * W;
+        const uint8_t* dsrc = reinterpret_cast<const uint8_t*>(p.delta + (uint64_t)y * W);
+        if (A16) {
+          for (uint32_t q = lane; q < W / 16; q += 32) cp_async16(rb + 16 * q, src + 16 * q);
+          if (has_low)
+            for (uint32_t q = lane; q < W / 16; q += 32) cp_async16(lb + 16 * q, flow + (uint64_t)y * W + 16 * q);
+          if (use_delta)
+            for (uint32_t q = lane; q < W / 8; q += 32) cp_async16(db + 16 * q, dsrc + 16 * q);
+        } else {
+          for (uint32_t q = lane; q < W / 4; q += 32) cp_async4(rb + 4 * q, src + 4 * q);
+          if (has_low)
+            for (uint32_t q = lane; q < W / 4; q += 32) cp_async4(lb + 4 * q, flow + (uint64_t)y * W + 4 * q);
+          if (use_delta)
+            for (uint32_t q = lane; q < W / 2; q += 32) cp_async4(db + 4 * q, dsrc + 4 * q);
+        }
+      }
+      cp_async_commit();  // one group per row; empty groups keep the count uniform
+    };
+
+    __syncwarp();
+    for (uint32_t y = 0; y + 1 < NST; y++) issue_row(y);
+
+    uint32_t nrow[L], xrow[L], c[L];
+#pragma unroll
+    for (int t = 0; t < L; t++) nrow[t] = 0;
+    uint32_t last_prev = 0, last_prev2 = 0;  // h[y-1][W-1], h[y-2][W-1]
+
+    for (uint32_t y = 0; y < H; y++) {
+      issue_row(y + NST - 1);
+      if (NST == 2) cp_async_wait<1>();
+      else if (NST == 3) cp_async_wait<2>();
+      else cp_async_wait<3>();
+      __syncwarp();
+      const uint32_t* st = dsm + (size_t)(y % NST) * STAGE;
+      const uint32_t* rb = st + (uint32_t)lane * 2 * LW;
+
+      // ---- residual bytes -> lane-form pairs (half 0 in bits 0-15, half 1 in bits 16-31)
+#pragma unroll
+      for (int k = 0; k < LW; k++) {
+        const uint32_t A = rb[k], B = rb[LW + k];
+        const uint32_t Ae = A & kLaneM, Ao = __byte_perm(A, 0u, 0x4341);
+        const uint32_t Be = B & kLaneM, Bo = __byte_perm(B, 0u, 0x4341);
+        xrow[4 * k + 0] = __byte_perm(Ae, Be, 0x5410);
+        xrow[4 * k + 1] = __byte_perm(Ao, Bo, 0x5410);
+        xrow[4 * k + 2] = __byte_perm(Ae, Be, 0x7632);
+        xrow[4 * k + 3] = __byte_perm(Ao, Bo, 0x7632);
+      }
+
+      if (use_cg && y > 0) {
+        // north-west of each half's first pixel: last pixel of the segment to the left, row y-1
+        const uint32_t ln = nrow[L - 1];
+        uint32_t nw_in = __funnelshift_l(__shfl_up_sync(0xffffffffu, ln, 1), ln, 16);
+        if (lane == 0) nw_in = (nw_in & 0xffff0000u) | last_prev2;
+        uint32_t w_in = nw_in;                       // the guess: west == north-west
+        if (lane == 0) w_in = (w_in & 0xffff0000u) | last_prev;   // exact for segment 0
+        // flat index W (row 1, column 0) is not predicted (.cc:327 starts at W+1)
+        const bool copy_first = (y == 1) && (lane == 0);
+        const uint32_t r_first = xrow[0];
+#pragma unroll
+        for (int t = 0; t < L; t++) c[t] = xrow[t] + 0x01000100u - (t == 0 ? nw_in : nrow[t - 1]);
+
+        // round 1: every chain runs its whole segment
+        {
+          uint32_t w = w_in, nw = nw_in;
+#pragma unroll
+          for (int t = 0; t < L; t++) {
+            const uint32_t n = nrow[t];
+            uint32_t x = (c[t] + __vimin3_u16x2(n, w, nw) + __vimax3_u16x2(n, w, nw)) & kLaneM;
+            if (t == 0 && copy_first) x = (x & 0xffff0000u) | (r_first & 0x0000ffffu);
+            xrow[t] = x;
+            w = x;
+            nw = n;
+          }
+        }
+        // repair rounds
+        for (;;) {
+          const uint32_t o = xrow[L - 1];
+          uint32_t w_new = __funnelshift_l(__shfl_up_sync(0xffffffffu, o, 1), o, 16);
+          if (lane == 0) w_new = (w_new & 0xffff0000u) | last_prev;
+          const bool changed = ((w_new ^ w_in) & vmask) != 0;
+          if (!__any_sync(0xffffffffu, changed)) break;
+          w_in = w_new;
+          uint32_t w = w_in, nw = nw_in;
+#pragma unroll
+          for (int k = 0; k < LW; k++) {
+            bool same = true;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+              const int t = 4 * k + j;
+              const uint32_t n = nrow[t];
+              uint32_t x = (c[t] + __vimin3_u16x2(n, w, nw) + __vimax3_u16x2(n, w, nw)) & kLaneM;
+              if (t == 0 && copy_first) x = (x & 0xffff0000u) | (r_first & 0x0000ffffu);
+              if (j == 3) same = ((x ^ xrow[t]) & vmask) == 0;
+              xrow[t] = x;
+              w = x;
+              nw = n;
+            }
+            // every chain met its previous values: the rest of the segment is unchanged
+            if (k + 1 < LW && __all_sync(0xffffffffu, same)) break;
+          }
+        }
+      }
+
+      // ---- the row is final: carry it to the next row ------------------------------
+      {
+        uint32_t v = 0;
+#pragma unroll
+        for (int k = 0; k < LW; k++)
+          if ((uint32_t)(4 * k + 3) == last_t) v = xrow[4 * k + 3];
+        v = last_hi ? (v >> 16) : (v & 0xffffu);
+        last_prev2 = last_prev;
+        last_prev = __shfl_sync(0xffffffffu, v, last_lane);
+      }
+#pragma unroll
+      for (int t = 0; t < L; t++) nrow[t] = xrow[t];
+
+      // ---- write-out: delta add (bytes wrap independently, .cc:337-338),
+      //      recombination, optional UnextractFrame (.cc:850-862) -------------------
+      const uint32_t* lbw = st + RW;
+      const uint2* dbw = reinterpret_cast<const uint2*>(st + 2 * RW);
+      uint16_t* orow = fout + (uint64_t)y * W;
+      const uint32_t um = (0xffffu >> p.shift) * 0x00010001u;
+#pragma unroll
+      for (int k = 0; k < LW; k++) {
+        const uint32_t t01 = __byte_perm(xrow[4 * k + 0], xrow[4 * k + 1], 0x6240);  // a0 a1 b0 b1
+        const uint32_t t23 = __byte_perm(xrow[4 * k + 2], xrow[4 * k + 3], 0x6240);  // a2 a3 b2 b3
+        const uint32_t hw2[2] = {__byte_perm(t01, t23, 0x5410), __byte_perm(t01, t23, 0x7632)};
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          const uint32_t col = col0 + (uint32_t)h * L + 4 * k;
+          if (col < W) {
+            const uint32_t lw = has_low ? lbw[col >> 2] : 0u;
+            uint32_t v01 = __byte_perm(lw, hw2[h], 0x5140);   // (h0<<8|l0) | (h1<<8|l1)<<16
+            uint32_t v23 = __byte_perm(lw, hw2[h], 0x7362);
+            if (use_delta) {
+              const uint2 d = dbw[col >> 2];
+              v01 = __vadd4(v01, d.x);
+              v23 = __vadd4(v23, d.y);
+            }
+            if (p.unextract) {
+              v01 = (v01 >> p.shift) & um;
+              v23 = (v23 >> p.shift) & um;
+              if (p.big_endian) {
+                v01 = __byte_perm(v01, 0u, 0x2301);
+                v23 = __byte_perm(v23, 0u, 0x2301);
+              }
+            }
+            *reinterpret_cast<uint2*>(orow + col) = make_uint2(v01, v23);
+          }
+        }
+      }
+      __syncwarp();  // stage (y % NST) may be overwritten from here on
+    }
+    cp_async_wait<0>();
+    __syncwarp();
+  }
+}
+
+template <int LW>
+static cudaError_t launch_simd(const SimdParams& p, bool a16, int blocks, size_t smem, cudaStream_t stream) {
+  cudaError_t e;
+  if (a16) {
+    e = cudaFuncSetAttribute(k_decode_simd<LW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k_decode_simd<LW, true><<<blocks, 32, smem, stream>>>(p);
+  } else {
+    e = cudaFuncSetAttribute(k_decode_simd<LW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k_decode_simd<LW, false><<<blocks, 32, smem, stream>>>(p);
+  }
+  return cudaGetLastError();
+}
+
 // ---- trivially serial fallback -------------------------------------------------
 // One thread per frame runs .cc:327-332 literally on a scratch copy of the high
 // plane; a second, fully parallel kernel does .cc:335-344 (+ .cc:850-862).
@@ -321,6 +563,38 @@ __global__ void k_planes_add_delta(uint8_t* high, uint8_t* low, const uint8_t* f
 int enqueue_decode(const Geom& g, int num_sms, const uint8_t* high, const uint8_t* low,
                    const uint8_t* flags, const uint16_t* delta, uint32_t n, bool unextract,
                    uint16_t* out, cudaStream_t stream, cudaError_t* err, const TimingHook* hook) {
+  if (g.W % 4 == 0 && g.W <= 64 * 32 && g.W >= 64 && !getenv("FPV_DECODE_SEGMENTED")) {
+    // SIMD row kernel: smallest segment length L = 4 LW with 64 L >= W
+    SimdParams sp;
+    sp.high = high; sp.low = low; sp.flags = flags; sp.delta = delta; sp.out = out;
+    sp.W = g.W; sp.H = g.H; sp.P = g.P; sp.shift = g.shift; sp.big_endian = g.big_endian;
+    sp.unextract = unextract ? 1 : 0; sp.n = n;
+    const int LW = (int)((g.W + 255) / 256);
+    sp.nst = 3;
+    if (const char* v = getenv("FPV_DECODE_STAGES")) { int k = atoi(v); if (k >= 2 && k <= 4) sp.nst = (uint32_t)k; }
+    const size_t smem = (size_t)sp.nst * 4 * 16 * 4 * LW * 4;
+    int per_sm = (int)((size_t)(220 * 1024) / (smem + 1024));
+    if (per_sm > 32) per_sm = 32;
+    if (per_sm < 1) per_sm = 1;
+    int blocks = (int)n;
+    if (blocks > num_sms * per_sm) blocks = num_sms * per_sm;
+    const bool a16 = g.W % 16 == 0;
+    cudaError_t e = cudaSuccess;
+    if (hook) cudaEventRecord(hook->start, stream);
+    switch (LW) {
+      case 1: e = launch_simd<1>(sp, a16, blocks, smem, stream); break;
+      case 2: e = launch_simd<2>(sp, a16, blocks, smem, stream); break;
+      case 3: e = launch_simd<3>(sp, a16, blocks, smem, stream); break;
+      case 4: e = launch_simd<4>(sp, a16, blocks, smem, stream); break;
+      case 5: e = launch_simd<5>(sp, a16, blocks, smem, stream); break;
+      case 6: e = launch_simd<6>(sp, a16, blocks, smem, stream); break;
+      case 7: e = launch_simd<7>(sp, a16, blocks, smem, stream); break;
+      default: e = launch_simd<8>(sp, a16, blocks, smem, stream); break;
+    }
+    if (hook) cudaEventRecord(hook->stop, stream);
+    *err = e;
+    return e == cudaSuccess ? 1 : -1;
+  }
   DecodeParams p;
   p.high = high; p.low = low; p.flags = flags; p.delta = delta; p.out = out;
   p.W = g.W; p.H = g.H; p.P = g.P; p.shift = g.shift; p.big_endian = g.big_endian;
