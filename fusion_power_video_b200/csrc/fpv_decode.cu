@@ -37,6 +37,12 @@ __device__ __forceinline__ void cp_async4(void* dst, const void* src) {
 __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(dst)), "l"(src) : "memory");
 }
+__device__ __forceinline__ void cp_async4_a(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async16_a(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
@@ -303,78 +309,104 @@ struct SimdParams {
 
 constexpr uint32_t kLaneM = 0x00ff00ffu;
 
-// A16: W % 16 == 0 (16-byte cp.async); otherwise W % 4 == 0 (4-byte cp.async).
-template <int LW, bool A16>
+// A16:  W % 16 == 0 (16-byte cp.async); otherwise W % 4 == 0 (4-byte cp.async).
+// FULL: W == 64 L, every half-segment of every lane is complete (no column tests).
+template <int LW, bool A16, bool FULL>
 __global__ void __launch_bounds__(32) k_decode_simd(const SimdParams p) {
   extern __shared__ __align__(16) uint32_t dsm[];
   constexpr int L = 4 * LW;
   constexpr uint32_t RW = 16 * L;            // words per staged byte row (64 L columns)
   constexpr uint32_t STAGE = 4 * RW;         // residual | low | delta (2 RW)
+  constexpr int CB = A16 ? 16 : 4;           // cp.async chunk bytes
+  constexpr int NJ = (64 * L / CB + 31) / 32;   // chunks per lane per byte row (upper bound)
   const int lane = threadIdx.x;
   const uint32_t W = p.W, H = p.H, NST = p.nst;
   const uint32_t col0 = (uint32_t)lane * 2 * L;
-  const bool v0 = col0 < W, v1 = col0 + L < W;                 // half-segment holds real pixels
+  const bool v0 = FULL || col0 < W, v1 = FULL || col0 + L < W;   // half-segment holds real pixels
   const uint32_t vmask = (v0 ? 0x0000ffffu : 0u) | (v1 ? 0xffff0000u : 0u);
   // where the last pixel of a row lives (W % 4 == 0, L % 4 == 0: it ends a 4-step group)
-  const uint32_t last_seg = (W - 1) / L, last_t = (W - 1) % L;
+  const uint32_t last_seg = FULL ? 63u : (W - 1) / L, last_t = FULL ? (uint32_t)(L - 1) : (W - 1) % L;
   const int last_lane = (int)(last_seg >> 1);
   const bool last_hi = (last_seg & 1u) != 0;
+  const bool do_shift = p.unextract && p.shift != 0, do_swap = p.unextract && p.big_endian;
+  const uint32_t ush = (uint32_t)p.shift, um = (0xffffu >> p.shift) * 0x00010001u;
+  // cp.async chunk validity of this lane: bit j <=> chunk (lane + 32 j) lies inside the row
+  uint32_t cmask1 = 0, cmask2 = 0;   // byte rows (W bytes) / delta rows (2 W bytes)
+#pragma unroll
+  for (int j = 0; j < 2 * NJ; j++) {
+    if (j < NJ && (uint32_t)(lane + 32 * j) * CB < W) cmask1 |= 1u << j;
+    if ((uint32_t)(lane + 32 * j) * CB < 2 * W) cmask2 |= 1u << j;
+  }
+  const uint32_t dsm_a = smem_addr(dsm) + (uint32_t)lane * CB;
 
   for (uint32_t f = blockIdx.x; f < p.n; f += gridDim.x) {
     const uint32_t fl = p.flags[f];
     const bool use_delta = (fl & kFlagDelta) && p.delta != nullptr;
     const bool use_cg = (fl & kFlagCG) != 0;
     const bool has_low = !(fl & kFlagNoLow) && p.low != nullptr;
-    const uint8_t* fh = p.high + (uint64_t)f * p.P;
-    const uint8_t* flow = has_low ? p.low + (uint64_t)f * p.P : nullptr;
-    uint16_t* fout = p.out + (uint64_t)f * p.P;
+    // running source pointers of the next row to stage (this lane's first chunk)
+    const uint8_t* src_r = p.high + (uint64_t)f * p.P + (uint32_t)lane * CB;
+    const uint8_t* src_l = has_low ? p.low + (uint64_t)f * p.P + (uint32_t)lane * CB : nullptr;
+    const uint8_t* src_d = reinterpret_cast<const uint8_t*>(p.delta) + (uint32_t)lane * CB;
+    uint16_t* orow = p.out + (uint64_t)f * p.P + col0;
+    uint32_t issue_y = 0, issue_slot = 0;
 
-    auto issue_row = [&](uint32_t y) {
-      if (y < H) {
-        uint32_t* st = dsm + (size_t)(y % NST) * STAGE;
-        uint8_t* rb = reinterpret_cast<uint8_t*>(st);
-        uint8_t* lb = reinterpret_cast<uint8_t*>(st + RW);
-        uint8_t* db = reinterpret_cast<uint8_t*>(st + 2 * RW);
-        const uint8_t* src = fh + (uint64_t)y * W;
-        const uint8_t* dsrc = reinterpret_cast<const uint8_t*>(p.delta + (uint64_t)y * W);
-        if (A16) {
-          for (uint32_t q = lane; q < W / 16; q += 32) cp_async16(rb + 16 * q, src + 16 * q);
-          if (has_low)
-            for (uint32_t q = lane; q < W / 16; q += 32) cp_async16(lb + 16 * q, flow + (uint64_t)y * W + 16 * q);
-          if (use_delta)
-            for (uint32_t q = lane; q < W / 8; q += 32) cp_async16(db + 16 * q, dsrc + 16 * q);
-        } else {
-          for (uint32_t q = lane; q < W / 4; q += 32) cp_async4(rb + 4 * q, src + 4 * q);
-          if (has_low)
-            for (uint32_t q = lane; q < W / 4; q += 32) cp_async4(lb + 4 * q, flow + (uint64_t)y * W + 4 * q);
-          if (use_delta)
-            for (uint32_t q = lane; q < W / 2; q += 32) cp_async4(db + 4 * q, dsrc + 4 * q);
+    auto issue_row = [&]() {
+      if (issue_y < H) {
+        const uint32_t st = dsm_a + issue_slot * (STAGE * 4);
+#pragma unroll
+        for (int j = 0; j < NJ; j++)
+          if (cmask1 & (1u << j)) {
+            if (A16) cp_async16_a(st + 32 * CB * j, src_r + 32 * CB * j);
+            else cp_async4_a(st + 32 * CB * j, src_r + 32 * CB * j);
+          }
+        if (has_low) {
+#pragma unroll
+          for (int j = 0; j < NJ; j++)
+            if (cmask1 & (1u << j)) {
+              if (A16) cp_async16_a(st + RW * 4 + 32 * CB * j, src_l + 32 * CB * j);
+              else cp_async4_a(st + RW * 4 + 32 * CB * j, src_l + 32 * CB * j);
+            }
+          src_l += W;
         }
+        if (use_delta) {
+#pragma unroll
+          for (int j = 0; j < 2 * NJ; j++)
+            if (cmask2 & (1u << j)) {
+              if (A16) cp_async16_a(st + 2 * RW * 4 + 32 * CB * j, src_d + 32 * CB * j);
+              else cp_async4_a(st + 2 * RW * 4 + 32 * CB * j, src_d + 32 * CB * j);
+            }
+          src_d += 2 * W;
+        }
+        src_r += W;
       }
       cp_async_commit();  // one group per row; empty groups keep the count uniform
+      issue_y++;
+      if (++issue_slot == NST) issue_slot = 0;
     };
 
     __syncwarp();
-    for (uint32_t y = 0; y + 1 < NST; y++) issue_row(y);
+    for (uint32_t y = 0; y + 1 < NST; y++) issue_row();
 
     uint32_t nrow[L], xrow[L], c[L];
 #pragma unroll
     for (int t = 0; t < L; t++) nrow[t] = 0;
     uint32_t last_prev = 0, last_prev2 = 0;  // h[y-1][W-1], h[y-2][W-1]
+    uint32_t slot = 0;
 
     for (uint32_t y = 0; y < H; y++) {
-      issue_row(y + NST - 1);
+      issue_row();
       if (NST == 2) cp_async_wait<1>();
       else if (NST == 3) cp_async_wait<2>();
       else cp_async_wait<3>();
       __syncwarp();
-      const uint32_t* st = dsm + (size_t)(y % NST) * STAGE;
-      const uint32_t* rb = st + (uint32_t)lane * 2 * LW;
+      const uint32_t* st = dsm + (size_t)slot * STAGE + (uint32_t)lane * 2 * LW;   // this lane's chunk
+      if (++slot == NST) slot = 0;
 
       // ---- residual bytes -> lane-form pairs (half 0 in bits 0-15, half 1 in bits 16-31)
 #pragma unroll
       for (int k = 0; k < LW; k++) {
-        const uint32_t A = rb[k], B = rb[LW + k];
+        const uint32_t A = st[k], B = st[LW + k];
         const uint32_t Ae = A & kLaneM, Ao = __byte_perm(A, 0u, 0x4341);
         const uint32_t Be = B & kLaneM, Bo = __byte_perm(B, 0u, 0x4341);
         xrow[4 * k + 0] = __byte_perm(Ae, Be, 0x5410);
@@ -440,10 +472,12 @@ __global__ void __launch_bounds__(32) k_decode_simd(const SimdParams p) {
 
       // ---- the row is final: carry it to the next row ------------------------------
       {
-        uint32_t v = 0;
+        uint32_t v = xrow[L - 1];
+        if (!FULL) {
 #pragma unroll
-        for (int k = 0; k < LW; k++)
-          if ((uint32_t)(4 * k + 3) == last_t) v = xrow[4 * k + 3];
+          for (int k = 0; k < LW; k++)
+            if ((uint32_t)(4 * k + 3) == last_t) v = xrow[4 * k + 3];
+        }
         v = last_hi ? (v >> 16) : (v & 0xffffu);
         last_prev2 = last_prev;
         last_prev = __shfl_sync(0xffffffffu, v, last_lane);
@@ -453,10 +487,8 @@ __global__ void __launch_bounds__(32) k_decode_simd(const SimdParams p) {
 
       // ---- write-out: delta add (bytes wrap independently, .cc:337-338),
       //      recombination, optional UnextractFrame (.cc:850-862) -------------------
-      const uint32_t* lbw = st + RW;
-      const uint2* dbw = reinterpret_cast<const uint2*>(st + 2 * RW);
-      uint16_t* orow = fout + (uint64_t)y * W;
-      const uint32_t um = (0xffffu >> p.shift) * 0x00010001u;
+      const uint32_t* lbw = st + RW;                                        // this lane's low bytes
+      const uint2* dbw = reinterpret_cast<const uint2*>(st + 2 * RW + (uint32_t)lane * 2 * LW);  // delta: 2x the offset
 #pragma unroll
       for (int k = 0; k < LW; k++) {
         const uint32_t t01 = __byte_perm(xrow[4 * k + 0], xrow[4 * k + 1], 0x6240);  // a0 a1 b0 b1
@@ -464,29 +496,29 @@ __global__ void __launch_bounds__(32) k_decode_simd(const SimdParams p) {
         const uint32_t hw2[2] = {__byte_perm(t01, t23, 0x5410), __byte_perm(t01, t23, 0x7632)};
 #pragma unroll
         for (int h = 0; h < 2; h++) {
-          const uint32_t col = col0 + (uint32_t)h * L + 4 * k;
-          if (col < W) {
-            const uint32_t lw = has_low ? lbw[col >> 2] : 0u;
+          if (FULL || col0 + (uint32_t)(h * L + 4 * k) < W) {
+            const uint32_t lw = has_low ? lbw[h * LW + k] : 0u;
             uint32_t v01 = __byte_perm(lw, hw2[h], 0x5140);   // (h0<<8|l0) | (h1<<8|l1)<<16
             uint32_t v23 = __byte_perm(lw, hw2[h], 0x7362);
             if (use_delta) {
-              const uint2 d = dbw[col >> 2];
+              const uint2 d = dbw[h * LW + k];
               v01 = __vadd4(v01, d.x);
               v23 = __vadd4(v23, d.y);
             }
-            if (p.unextract) {
-              v01 = (v01 >> p.shift) & um;
-              v23 = (v23 >> p.shift) & um;
-              if (p.big_endian) {
-                v01 = __byte_perm(v01, 0u, 0x2301);
-                v23 = __byte_perm(v23, 0u, 0x2301);
-              }
+            if (do_shift) {
+              v01 = (v01 >> ush) & um;
+              v23 = (v23 >> ush) & um;
             }
-            *reinterpret_cast<uint2*>(orow + col) = make_uint2(v01, v23);
+            if (do_swap) {
+              v01 = __byte_perm(v01, 0u, 0x2301);
+              v23 = __byte_perm(v23, 0u, 0x2301);
+            }
+            *reinterpret_cast<uint2*>(orow + h * L + 4 * k) = make_uint2(v01, v23);
           }
         }
       }
-      __syncwarp();  // stage (y % NST) may be overwritten from here on
+      orow += W;
+      __syncwarp();  // the consumed stage may be overwritten from here on
     }
     cp_async_wait<0>();
     __syncwarp();
@@ -494,18 +526,19 @@ __global__ void __launch_bounds__(32) k_decode_simd(const SimdParams p) {
 }
 
 template <int LW>
-static cudaError_t launch_simd(const SimdParams& p, bool a16, int blocks, size_t smem, cudaStream_t stream) {
-  cudaError_t e;
-  if (a16) {
-    e = cudaFuncSetAttribute(k_decode_simd<LW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    k_decode_simd<LW, true><<<blocks, 32, smem, stream>>>(p);
-  } else {
-    e = cudaFuncSetAttribute(k_decode_simd<LW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    k_decode_simd<LW, false><<<blocks, 32, smem, stream>>>(p);
-  }
-  return cudaGetLastError();
+static cudaError_t launch_simd(const SimdParams& p, bool a16, bool full, int blocks, size_t smem,
+                               cudaStream_t stream) {
+  cudaError_t e = cudaSuccess;
+#define FPV_LAUNCH_SIMD(A, F)                                                                                \
+  do {                                                                                                       \
+    e = cudaFuncSetAttribute(k_decode_simd<LW, A, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    if (e == cudaSuccess) k_decode_simd<LW, A, F><<<blocks, 32, smem, stream>>>(p);                          \
+  } while (0)
+  if (a16 && full) FPV_LAUNCH_SIMD(true, true);
+  else if (a16) FPV_LAUNCH_SIMD(true, false);
+  else FPV_LAUNCH_SIMD(false, false);
+#undef FPV_LAUNCH_SIMD
+  return e == cudaSuccess ? cudaGetLastError() : e;
 }
 
 // ---- trivially serial fallback -------------------------------------------------
@@ -579,17 +612,18 @@ int enqueue_decode(const Geom& g, int num_sms, const uint8_t* high, const uint8_
     int blocks = (int)n;
     if (blocks > num_sms * per_sm) blocks = num_sms * per_sm;
     const bool a16 = g.W % 16 == 0;
+    const bool full = g.W == 256u * (uint32_t)LW;
     cudaError_t e = cudaSuccess;
     if (hook) cudaEventRecord(hook->start, stream);
     switch (LW) {
-      case 1: e = launch_simd<1>(sp, a16, blocks, smem, stream); break;
-      case 2: e = launch_simd<2>(sp, a16, blocks, smem, stream); break;
-      case 3: e = launch_simd<3>(sp, a16, blocks, smem, stream); break;
-      case 4: e = launch_simd<4>(sp, a16, blocks, smem, stream); break;
-      case 5: e = launch_simd<5>(sp, a16, blocks, smem, stream); break;
-      case 6: e = launch_simd<6>(sp, a16, blocks, smem, stream); break;
-      case 7: e = launch_simd<7>(sp, a16, blocks, smem, stream); break;
-      default: e = launch_simd<8>(sp, a16, blocks, smem, stream); break;
+      case 1: e = launch_simd<1>(sp, a16, full, blocks, smem, stream); break;
+      case 2: e = launch_simd<2>(sp, a16, full, blocks, smem, stream); break;
+      case 3: e = launch_simd<3>(sp, a16, full, blocks, smem, stream); break;
+      case 4: e = launch_simd<4>(sp, a16, full, blocks, smem, stream); break;
+      case 5: e = launch_simd<5>(sp, a16, full, blocks, smem, stream); break;
+      case 6: e = launch_simd<6>(sp, a16, full, blocks, smem, stream); break;
+      case 7: e = launch_simd<7>(sp, a16, full, blocks, smem, stream); break;
+      default: e = launch_simd<8>(sp, a16, full, blocks, smem, stream); break;
     }
     if (hook) cudaEventRecord(hook->stop, stream);
     *err = e;
