@@ -1,0 +1,135 @@
+// capi.cc -- plain-C entry points over the fpvc:: classes, for language
+// bindings (tests/ and bench.py reach the host layer through these).
+#include <string.h>
+
+#include <chrono>
+#include <vector>
+
+#include "fusion_power_video.h"
+
+namespace {
+
+void Append(const uint8_t* data, size_t size, void* payload) {
+  auto* v = static_cast<std::vector<uint8_t>*>(payload);
+  v->insert(v->end(), data, data + size);
+}
+
+double Now() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* fpvh_last_error(void) { return fpvc::LastError().c_str(); }
+
+// Encodes `nframes` frames with fpvc::Encoder.  Returns the stream size (also
+// when it exceeds `cap`, in which case nothing is copied), 0 on failure.
+size_t fpvh_encode_stream(size_t xsize, size_t ysize, int shift, int big_endian, size_t threads, uint32_t batch,
+                          int device, const uint16_t* delta, const uint16_t* frames, size_t nframes, uint8_t* out,
+                          size_t cap) {
+  std::vector<uint8_t> stream;
+  fpvc::GpuOptions opt;
+  opt.device = device;
+  if (batch) opt.batch = batch;
+  {
+    fpvc::Encoder enc(threads, shift, big_endian != 0, opt);
+    enc.Init(delta, xsize, ysize, Append, &stream);
+    if (!enc.ok()) return 0;
+    for (size_t i = 0; i < nframes; i++) enc.CompressFrame(frames + i * xsize * ysize, Append, &stream);
+    enc.Finish(Append, &stream);
+    if (!enc.ok()) return 0;
+  }
+  if (out && stream.size() <= cap) memcpy(out, stream.data(), stream.size());
+  return stream.size();
+}
+
+// Same work, timed like the reference's benchmark (benchmark.cc:153-180: from
+// before Encoder construction to after Finish); compressed bytes are counted,
+// not kept.  Returns seconds, < 0 on failure.
+double fpvh_time_encode(size_t xsize, size_t ysize, int shift, int big_endian, size_t threads, uint32_t batch,
+                        int device, const uint16_t* delta, const uint16_t* frames, size_t nframes,
+                        size_t* stream_size) {
+  size_t total = 0;
+  auto count = [](const uint8_t*, size_t size, void* payload) { *static_cast<size_t*>(payload) += size; };
+  fpvc::GpuOptions opt;
+  opt.device = device;
+  if (batch) opt.batch = batch;
+  const double t0 = Now();
+  {
+    fpvc::Encoder enc(threads, shift, big_endian != 0, opt);
+    enc.Init(delta, xsize, ysize, count, &total);
+    if (!enc.ok()) return -1.0;
+    for (size_t i = 0; i < nframes; i++) enc.CompressFrame(frames + i * xsize * ysize, count, &total);
+    enc.Finish(count, &total);
+    if (!enc.ok()) return -1.0;
+  }
+  const double t1 = Now();
+  if (stream_size) *stream_size = total;
+  return t1 - t0;
+}
+
+// Decodes a stream with fpvc::StreamingDecoder fed in `block`-byte pieces
+// (0 = all at once).  raw_shift < 0: frames are 16-bit images; otherwise raw
+// file bytes (UnextractFrame on the GPU) with that shift / endianness.
+// Returns the number of frames, -1 on a decoder failure.
+long fpvh_decode_stream(const uint8_t* bytes, size_t size, size_t block, uint32_t batch, int device, int raw_shift,
+                        int big_endian, uint16_t* frames, size_t max_frames, size_t* xsize_out, size_t* ysize_out,
+                        double* seconds) {
+  struct State {
+    uint16_t* frames;
+    size_t max_frames, count = 0, W = 0, H = 0;
+    bool failed = false;
+  } st;
+  st.frames = frames;
+  st.max_frames = max_frames;
+  fpvc::GpuOptions opt;
+  opt.device = device;
+  if (batch) opt.batch = batch;
+  const double t0 = Now();
+  {
+    fpvc::StreamingDecoder dec(opt);
+    if (raw_shift >= 0) dec.SetRawOutput(raw_shift, big_endian != 0);
+    if (block == 0) block = size ? size : 1;
+    for (size_t pos = 0; pos < size && !st.failed; pos += block) {
+      const size_t n = pos + block > size ? size - pos : block;
+      dec.Decode(bytes + pos, n,
+                 [&st](bool ok, uint16_t* frame, size_t xs, size_t ys, void*) {
+                   if (!ok) { st.failed = true; return; }
+                   st.W = xs;
+                   st.H = ys;
+                   if (st.frames && st.count < st.max_frames) memcpy(st.frames + st.count * xs * ys, frame, xs * ys * 2);
+                   st.count++;
+                 },
+                 nullptr);
+    }
+  }
+  if (seconds) *seconds = Now() - t0;
+  if (xsize_out) *xsize_out = st.W;
+  if (ysize_out) *ysize_out = st.H;
+  return st.failed ? -1 : (long)st.count;
+}
+
+// RandomAccessDecoder: `count` frames from `first` (frames may be NULL) and the
+// preview of frame `first` (preview may be NULL).  Returns 1 on success.
+int fpvh_random_access(const uint8_t* bytes, size_t size, uint32_t batch, int device, size_t first, size_t count,
+                       uint16_t* frames, uint8_t* preview, size_t* numframes, size_t* xsize_out, size_t* ysize_out) {
+  fpvc::GpuOptions opt;
+  opt.device = device;
+  if (batch) opt.batch = batch;
+  fpvc::RandomAccessDecoder dec(opt);
+  if (!dec.Init(bytes, size)) return 0;
+  if (numframes) *numframes = dec.numframes();
+  if (xsize_out) *xsize_out = dec.xsize();
+  if (ysize_out) *ysize_out = dec.ysize();
+  if (frames && count && !dec.DecodeFrames(first, count, frames)) return 0;
+  if (preview && !dec.DecodePreview(first, preview)) return 0;
+  return 1;
+}
+
+void fpvh_unextract(const uint16_t* img, size_t xsize, size_t ysize, int shift, int big_endian, uint8_t* out) {
+  fpvc::UnextractFrame(img, xsize, ysize, shift, big_endian != 0, out);
+}
+
+}  // extern "C"

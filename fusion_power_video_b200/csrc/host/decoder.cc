@@ -1,0 +1,300 @@
+// decoder.cc -- fpvc::StreamingDecoder and fpvc::RandomAccessDecoder on the GPU
+// inverse transform.
+//
+// Both follow the reference's parsing and error behaviour
+// (fusion_power_video.cc:866-956 and :961-1070) but split DecompressImage
+// (.cc:296-347) in two: the brotli streams of all frames that are available are
+// decoded on host threads straight into pinned plane buffers, then ONE
+// fpv_decode call runs .cc:326-344 for the whole batch on the GPU.
+#include <string.h>
+
+#include <algorithm>
+#include <thread>
+
+#include "fusion_power_video.h"
+#include "host_internal.h"
+
+namespace fpvc {
+
+using namespace internal;
+
+namespace {
+
+// Everything a decoder needs on the GPU side for one geometry.
+struct GpuDecoder {
+  fpv_ctx* ctx = nullptr;
+  size_t W = 0, H = 0, P = 0;
+  uint32_t B = 1;
+  Pinned high, low, flags, out;
+  std::unique_ptr<Pool> pool;
+
+  ~GpuDecoder() {
+    if (ctx) fpv_destroy(ctx);
+  }
+
+  bool open(const GpuOptions& opt, size_t xsize, size_t ysize, int shift, bool big_endian, uint32_t batch) {
+    W = xsize;
+    H = ysize;
+    P = xsize * ysize;
+    B = batch ? batch : 1;
+    if (fpv_create(&ctx, opt.device, (uint32_t)xsize, (uint32_t)ysize, shift, big_endian ? 1 : 0, B) != FPV_OK)
+      return FPV_FAIL(std::string("fpv_create: ") + fpv_last_error(nullptr));
+    if (!high.alloc((size_t)B * P) || !low.alloc((size_t)B * P) || !flags.alloc(B) || !out.alloc((size_t)B * P * 2))
+      return FPV_FAIL("pinned allocation failed");
+    size_t t = std::thread::hardware_concurrency();
+    t = std::min<size_t>(t ? t : 1, 32);
+    if (B > 1 && t > 1) pool.reset(new Pool(std::min<size_t>(t, B)));
+    return true;
+  }
+
+  // cores[i] / sizes[i]: the core chunk of frame i.  Decodes n <= B frames into
+  // `out` (uint16 images, or raw file bytes with FPV_DEC_UNEXTRACT).  Returns the
+  // number of leading frames that decoded correctly (n on success).
+  size_t decode(const uint8_t* const* cores, const size_t* sizes, size_t n, uint32_t options, bool allow_delta) {
+    std::vector<char> good(n, 0);
+    ParallelFor(pool.get(), n, [&](size_t i) {
+      uint8_t f = 0;
+      bool ok = ParseCore(cores[i], sizes[i], P, &f, high.as<uint8_t>() + i * P, low.as<uint8_t>() + i * P);
+      if (ok && (f & FPV_FLAG_USE_DELTA) && !allow_delta) ok = FPV_FAIL("delta frame not given");
+      flags.as<uint8_t>()[i] = f;
+      good[i] = ok ? 1 : 0;
+    });
+    size_t k = 0;
+    while (k < n && good[k]) k++;
+    if (k == 0) return 0;
+    if (fpv_decode(ctx, high.as<uint8_t>(), low.as<uint8_t>(), flags.as<uint8_t>(), (uint32_t)k, options,
+                   out.as<uint8_t>()) != FPV_OK) {
+      FPV_FAIL(std::string("fpv_decode: ") + fpv_last_error(ctx));
+      return 0;
+    }
+    return k;
+  }
+};
+
+bool CheckDims(size_t xsize, size_t ysize) {
+  if (xsize == 0 || ysize == 0) return FPV_FAIL("invalid image dimensions");
+  if (xsize > 65536 || ysize > 65536 || xsize * ysize > kMaxPixels) return FPV_FAIL("image too large");
+  return true;
+}
+
+}  // namespace
+
+// =====================================================================================
+// StreamingDecoder
+// =====================================================================================
+
+struct StreamingDecoder::Impl {
+  GpuOptions opt;
+  GpuDecoder gpu;
+  std::vector<uint8_t> buffer;
+  bool have_delta = false;
+  bool raw_output = false;
+  int shift = 0;
+  bool big_endian = false;
+  size_t id = 0;
+};
+
+StreamingDecoder::StreamingDecoder() : StreamingDecoder(GpuOptions()) {}
+StreamingDecoder::StreamingDecoder(const GpuOptions& options) : impl_(new Impl) { impl_->opt = options; }
+StreamingDecoder::~StreamingDecoder() = default;
+
+void StreamingDecoder::SetRawOutput(int shift, bool big_endian) {
+  impl_->raw_output = true;
+  impl_->shift = shift;
+  impl_->big_endian = big_endian;
+}
+
+void StreamingDecoder::Decode(
+    const uint8_t* bytes, size_t size,
+    std::function<void(bool ok, uint16_t* frame, size_t xsize, size_t ysize, void* payload)> callback,
+    void* payload) {
+  Impl& s = *impl_;
+  // As the reference: only copy when bytes from an earlier call are pending.
+  if (!s.buffer.empty()) s.buffer.insert(s.buffer.end(), bytes, bytes + size);
+  const uint8_t* in = s.buffer.empty() ? bytes : s.buffer.data();
+  const size_t insize = s.buffer.empty() ? size : s.buffer.size();
+  auto fail = [&](const char* what) { callback(FPV_FAIL(what), nullptr, 0, 0, payload); };
+
+  size_t pos = 0;
+  if (!s.have_delta && insize > 13) {
+    const size_t xsize = LoadU32(in), ysize = LoadU32(in + 4);
+    if (!CheckDims(xsize, ysize)) return fail("invalid stream header");
+    const size_t chunk = LoadU32(in + 8);
+    if (chunk < 5) return fail("too small for delta frame");
+    if (in[12] != kChunkDelta) return fail("not a delta frame");
+    if (8 + chunk <= insize) {
+      if (!s.gpu.ctx && !s.gpu.open(s.opt, xsize, ysize, s.shift, s.big_endian, s.opt.batch))
+        return fail("no GPU decoder");
+      const uint8_t* core = in + 13;
+      const size_t core_size = chunk - 5;
+      if (s.gpu.decode(&core, &core_size, 1, FPV_DEC_DEFAULT, false) != 1)
+        return fail("decompressing delta frame failed");
+      if (fpv_set_delta_image(s.gpu.ctx, s.gpu.out.as<uint16_t>()) != FPV_OK) return fail("fpv_set_delta_image");
+      s.have_delta = true;
+      pos = 8 + chunk;
+    }
+  }
+
+  const uint32_t options = s.raw_output ? FPV_DEC_UNEXTRACT : FPV_DEC_DEFAULT;
+  std::vector<const uint8_t*> cores;
+  std::vector<size_t> sizes;
+  bool stream_bad = false;
+  const char* bad_what = nullptr;
+  while (s.have_delta && !stream_bad) {
+    // gather the frames that are complete in the buffer, up to one GPU batch
+    cores.clear();
+    sizes.clear();
+    size_t scan = pos;
+    while (cores.size() < s.gpu.B) {
+      if (scan + 9 > insize) break;
+      const size_t frame_size = LoadU32(in + scan);
+      const uint8_t flag = in[scan + 4];
+      if (flag == kChunkIndex) break;  // frame index: end of frames
+      if (flag != kChunkFrame) { stream_bad = true; bad_what = "not a standard frame"; break; }
+      if (scan + frame_size > insize) break;
+      const size_t preview_size = LoadU32(in + scan + 5);
+      if (preview_size > frame_size || frame_size < preview_size + 9) {
+        stream_bad = true;
+        bad_what = "preview size too large";
+        break;
+      }
+      cores.push_back(in + scan + 9 + preview_size);
+      sizes.push_back(frame_size - preview_size - 9);
+      scan += frame_size;
+    }
+    if (cores.empty()) break;
+    const size_t good = s.gpu.decode(cores.data(), sizes.data(), cores.size(), options, true);
+    for (size_t i = 0; i < good; i++) {
+      callback(true, s.gpu.out.as<uint16_t>() + i * s.gpu.P, s.gpu.W, s.gpu.H, payload);
+      s.id++;
+    }
+    if (good != cores.size()) return fail("decompressing frame failed");
+    pos = scan;
+  }
+  if (stream_bad) return fail(bad_what);
+
+  // keep what was not consumed
+  if (s.buffer.empty()) {
+    if (pos < size) s.buffer.assign(bytes + pos, bytes + size);
+  } else if (pos > 0) {
+    s.buffer.erase(s.buffer.begin(), s.buffer.begin() + (ptrdiff_t)pos);
+  }
+}
+
+// =====================================================================================
+// RandomAccessDecoder
+// =====================================================================================
+
+struct RandomAccessDecoder::Impl {
+  GpuOptions opt;
+  mutable std::mutex m;             // DecodeFrame / DecodePreview are const but share GPU staging
+  mutable GpuDecoder gpu, preview_gpu;
+  size_t xsize = 0, ysize = 0;
+  std::vector<uint64_t> offsets;
+  const uint8_t* data = nullptr;
+  size_t size = 0;
+
+  // Validates the frame chunk at `index`; returns its start and sizes.
+  bool locate(size_t index, const uint8_t** chunk, size_t* frame_size, size_t* preview_size) const {
+    if (index >= offsets.size()) return FPV_FAIL("invalid frame index");
+    const uint64_t off = offsets[index];
+    if (off > size || size - off < 9) return FPV_FAIL("out of bounds");
+    const uint8_t* p = data + off;
+    *frame_size = LoadU32(p);
+    if (*frame_size < 9) return FPV_FAIL("frame too small");
+    if (size - off < *frame_size) return FPV_FAIL("out of bounds");
+    if (p[4] != kChunkFrame) return FPV_FAIL("not a standard frame");
+    *preview_size = LoadU32(p + 5);
+    if (*preview_size > *frame_size - 9) return FPV_FAIL("preview too large");
+    *chunk = p;
+    return true;
+  }
+};
+
+RandomAccessDecoder::RandomAccessDecoder() : RandomAccessDecoder(GpuOptions()) {}
+RandomAccessDecoder::RandomAccessDecoder(const GpuOptions& options) : impl_(new Impl) { impl_->opt = options; }
+RandomAccessDecoder::~RandomAccessDecoder() = default;
+
+size_t RandomAccessDecoder::xsize() const { return impl_->xsize; }
+size_t RandomAccessDecoder::ysize() const { return impl_->ysize; }
+size_t RandomAccessDecoder::numframes() const { return impl_->offsets.size(); }
+
+bool RandomAccessDecoder::Init(const uint8_t* data, size_t size) {
+  Impl& s = *impl_;
+  if (size < 12) return FPV_FAIL("data too small to contain header");
+  s.data = data;
+  s.size = size;
+  s.xsize = LoadU32(data);
+  s.ysize = LoadU32(data + 4);
+  if (!CheckDims(s.xsize, s.ysize)) return false;
+
+  const size_t chunk = LoadU32(data + 8);
+  if (chunk > size - 8) return FPV_FAIL("out of bounds");
+  if (chunk < 5) return FPV_FAIL("delta frame too small");
+  if (data[12] != kChunkDelta) return FPV_FAIL("must begin with delta frame");
+  if (!s.gpu.ctx && !s.gpu.open(s.opt, s.xsize, s.ysize, 0, false, s.opt.batch)) return false;
+  const uint8_t* core = data + 13;
+  const size_t core_size = chunk - 5;
+  if (s.gpu.decode(&core, &core_size, 1, FPV_DEC_DEFAULT, false) != 1) return FPV_FAIL("failed to decode delta frame");
+  if (fpv_set_delta_image(s.gpu.ctx, s.gpu.out.as<uint16_t>()) != FPV_OK) return FPV_FAIL("fpv_set_delta_image");
+
+  // frame index at the end of the file
+  if (size < 8 + chunk + 13) return FPV_FAIL("footer missing");
+  const uint64_t n = LoadU64(data + size - 8);
+  if (n > size / 16) return FPV_FAIL("too many frames");
+  const size_t footer = 5 + 8 * (size_t)n + 8;
+  if (footer > size) return FPV_FAIL("footer too large");
+  const uint8_t* f = data + size - footer;
+  if (LoadU32(f) != footer) return FPV_FAIL("footer size mismatch");
+  if (f[4] != kChunkIndex) return FPV_FAIL("must end with frame index");
+  s.offsets.resize((size_t)n);
+  for (size_t i = 0; i < (size_t)n; i++) s.offsets[i] = LoadU64(f + 5 + 8 * i);
+  return true;
+}
+
+bool RandomAccessDecoder::DecodeFrame(size_t index, uint16_t* frame) const { return DecodeFrames(index, 1, frame); }
+
+bool RandomAccessDecoder::DecodeFrames(size_t first, size_t count, uint16_t* frames) const {
+  Impl& s = *impl_;
+  std::lock_guard<std::mutex> l(s.m);
+  if (!s.gpu.ctx) return FPV_FAIL("decoder not initialised");
+  std::vector<const uint8_t*> cores;
+  std::vector<size_t> sizes;
+  for (size_t done = 0; done < count;) {
+    const size_t n = std::min<size_t>(s.gpu.B, count - done);
+    cores.clear();
+    sizes.clear();
+    for (size_t i = 0; i < n; i++) {
+      const uint8_t* chunk;
+      size_t frame_size, preview_size;
+      if (!s.locate(first + done + i, &chunk, &frame_size, &preview_size)) return false;
+      cores.push_back(chunk + 9 + preview_size);
+      sizes.push_back(frame_size - preview_size - 9);
+    }
+    if (s.gpu.decode(cores.data(), sizes.data(), n, FPV_DEC_DEFAULT, true) != n) return false;
+    memcpy(frames + done * s.gpu.P, s.gpu.out.as<uint16_t>(), n * s.gpu.P * 2);
+    done += n;
+  }
+  return true;
+}
+
+bool RandomAccessDecoder::DecodePreview(size_t index, uint8_t* preview) const {
+  Impl& s = *impl_;
+  std::lock_guard<std::mutex> l(s.m);
+  const uint8_t* chunk;
+  size_t frame_size, preview_size;
+  if (!s.locate(index, &chunk, &frame_size, &preview_size)) return false;
+  const size_t pw = s.xsize / 4, ph = s.ysize / 4;
+  if (pw == 0 || ph == 0) return FPV_FAIL("invalid image dimensions");
+  if (!s.preview_gpu.ctx && !s.preview_gpu.open(s.opt, pw, ph, 0, false, 1)) return false;
+  // The preview chunk is a core chunk of a (xsize/4) x (ysize/4) image whose
+  // flags never carry USE_DELTA (reference .cc:842, :1061-1064).
+  const uint8_t* core = chunk + 9;
+  if (s.preview_gpu.decode(&core, &preview_size, 1, FPV_DEC_DEFAULT, false) != 1)
+    return FPV_FAIL("failed to decompress preview");
+  const uint16_t* img = s.preview_gpu.out.as<uint16_t>();
+  for (size_t i = 0; i < pw * ph; i++) preview[i] = (uint8_t)(img[i] >> 8);
+  return true;
+}
+
+}  // namespace fpvc

@@ -1,0 +1,351 @@
+// encoder.cc -- fpvc::Encoder on the GPU transform.
+//
+// Replaces the reference's worker loop (fusion_power_video.cc:1128-1230): where
+// the reference runs Frame ctor + Predict + brotli per frame on a pool thread,
+// this encoder
+//   1. copies each submitted frame into a pinned batch buffer (CompressFrame),
+//   2. hands full batches -- or whatever is there when the GPU is idle -- to one
+//      GPU thread, which keeps two fpv_encode_submit slots in flight (H2D of
+//      batch k+1 overlaps kernels / D2H of batch k),
+//   3. fans the landed planes out to the brotli workers, one frame per task,
+//   4. emits finished frames in submission order under one mutex, recording the
+//      frame offsets for the footer exactly as FinishTask does (.cc:1179-1183).
+#include <string.h>
+
+#include <atomic>
+#include <iostream>
+#include <map>
+
+#include "fusion_power_video.h"
+#include "host_internal.h"
+
+namespace fpvc {
+
+using namespace internal;
+
+namespace {
+constexpr int kNumBatches = 4;  // one filling, up to two on the GPU, one in brotli
+}
+
+struct Encoder::Impl {
+  size_t threads = 0;
+  int shift = 0;
+  bool big_endian = false;
+  GpuOptions opt;
+
+  fpv_ctx* ctx = nullptr;
+  bool ok = false;
+  size_t W = 0, H = 0, P = 0, PP = 0;
+  bool has_low = true;
+  uint32_t B = 1;
+
+  struct Batch {
+    Pinned frames, high, low, preview, flags;
+    uint32_t n = 0;
+    uint64_t first_id = 0;
+    std::vector<Callback> callbacks;
+    std::vector<void*> payloads;
+    std::atomic<uint32_t> pending{0};
+    uint32_t slot = 0;
+  };
+  Batch batches[kNumBatches];
+
+  std::mutex m;                       // batch lists, ids, stop flag
+  std::condition_variable cv_free, cv_ready, cv_drained;
+  std::deque<Batch*> free_, ready_;
+  Batch* filling = nullptr;
+  size_t gpu_busy = 0;                // batches handed to the GPU thread, not yet landed
+  bool stop = false;
+  uint64_t next_id = 0;
+  std::thread gpu_thread;
+  std::unique_ptr<Pool> pool;
+
+  std::mutex out_m;                   // ordered emission
+  struct Done {
+    std::vector<uint8_t> bytes;
+    Callback callback;
+    void* payload;
+  };
+  std::map<uint64_t, Done> done;
+  uint64_t next_emit = 0;
+  std::vector<uint64_t> offsets;
+  uint64_t bytes_written = 0;
+  bool finished = false;
+
+  ~Impl() {
+    shutdown();
+    if (ctx) fpv_destroy(ctx);
+  }
+
+  void shutdown() {
+    if (gpu_thread.joinable()) {
+      {
+        std::lock_guard<std::mutex> l(m);
+        stop = true;
+      }
+      cv_ready.notify_all();
+      gpu_thread.join();
+    }
+    pool.reset();  // joins the brotli workers after their queue has drained
+  }
+
+  bool fail(const std::string& what) {
+    ok = false;
+    return FPV_FAIL(what + (ctx ? std::string(": ") + fpv_last_error(ctx) : std::string()));
+  }
+
+  // frame -> chunk bytes (frame := total | 0 | 1+|bp| | pflags | bp | core)
+  void build_chunk(uint8_t flags, const uint8_t* high, const uint8_t* low, const uint8_t* preview,
+                   std::vector<uint8_t>* scratch, std::vector<uint8_t>* out) {
+    out->clear();
+    out->reserve(P / 2 + 64);
+    out->resize(10);
+    BrotliPlane(preview, PP, scratch, out);
+    const size_t bp = out->size() - 10;
+    AppendCore(flags, high, low, P, scratch, out);
+    uint8_t* p = out->data();
+    StoreU32((uint32_t)out->size(), p);
+    p[4] = kChunkFrame;
+    StoreU32((uint32_t)(bp + 1), p + 5);
+    p[9] = (uint8_t)((flags & FPV_FLAG_USE_CG) | FPV_FLAG_NO_LOW_BYTES);
+  }
+
+  // Called by whoever finished frame `id`; emits every frame that is now in order.
+  void deliver(uint64_t id, Done&& d) {
+    std::lock_guard<std::mutex> l(out_m);
+    done.emplace(id, std::move(d));
+    for (auto it = done.find(next_emit); it != done.end(); it = done.find(next_emit)) {
+      offsets.push_back(bytes_written);
+      bytes_written += it->second.bytes.size();
+      it->second.callback(it->second.bytes.data(), it->second.bytes.size(), it->second.payload);
+      done.erase(it);
+      next_emit++;
+    }
+  }
+
+  void recycle(Batch* b) {
+    {
+      std::lock_guard<std::mutex> l(m);
+      b->n = 0;
+      b->callbacks.clear();
+      b->payloads.clear();
+      free_.push_back(b);
+    }
+    cv_free.notify_all();
+    cv_drained.notify_all();
+  }
+
+  void compress_batch(Batch* b) {
+    b->pending.store(b->n);
+    for (uint32_t i = 0; i < b->n; i++) {
+      pool->run([this, b, i] {
+        thread_local std::vector<uint8_t> scratch;
+        Done d;
+        d.callback = b->callbacks[i];
+        d.payload = b->payloads[i];
+        build_chunk(b->flags.as<uint8_t>()[i], b->high.as<uint8_t>() + (size_t)i * P,
+                    has_low ? b->low.as<uint8_t>() + (size_t)i * P : nullptr,
+                    b->preview.as<uint8_t>() + (size_t)i * PP, &scratch, &d.bytes);
+        deliver(b->first_id + i, std::move(d));
+        if (b->pending.fetch_sub(1) == 1) recycle(b);
+      });
+    }
+  }
+
+  void gpu_loop() {
+    std::deque<Batch*> inflight;
+    uint32_t next_slot = 0;
+    auto land = [&] {
+      Batch* b = inflight.front();
+      inflight.pop_front();
+      if (fpv_wait(ctx, b->slot) != FPV_OK) fail("fpv_wait");
+      {
+        std::lock_guard<std::mutex> l(m);
+        gpu_busy--;
+      }
+      compress_batch(b);
+    };
+    for (;;) {
+      Batch* b = nullptr;
+      {
+        std::unique_lock<std::mutex> l(m);
+        if (inflight.empty()) cv_ready.wait(l, [&] { return stop || !ready_.empty(); });
+        if (!ready_.empty()) {
+          b = ready_.front();
+          ready_.pop_front();
+        } else if (inflight.empty()) {
+          return;  // stop requested and nothing left
+        }
+      }
+      if (b) {
+        if (inflight.size() == 2) land();  // its slot is about to be reused
+        b->slot = next_slot;
+        next_slot ^= 1u;
+        int rc = fpv_encode_submit(ctx, b->slot, b->frames.as<uint16_t>(), b->n, FPV_ENC_DEFAULT,
+                                   b->flags.as<uint8_t>(), b->high.as<uint8_t>(),
+                                   has_low ? b->low.as<uint8_t>() : nullptr, b->preview.as<uint8_t>());
+        if (rc != FPV_OK) fail("fpv_encode_submit");
+        inflight.push_back(b);
+      } else {
+        land();  // nothing new to submit: collect the oldest batch
+      }
+    }
+  }
+};
+
+Encoder::Encoder(size_t num_threads, int shift_to_left_align, bool big_endian)
+    : Encoder(num_threads, shift_to_left_align, big_endian, GpuOptions()) {}
+
+Encoder::Encoder(size_t num_threads, int shift_to_left_align, bool big_endian, const GpuOptions& options)
+    : impl_(new Impl) {
+  impl_->threads = num_threads;
+  impl_->shift = shift_to_left_align;
+  impl_->big_endian = big_endian;
+  impl_->opt = options;
+}
+
+Encoder::~Encoder() = default;
+
+bool Encoder::ok() const { return impl_->ok; }
+
+size_t Encoder::MaxQueued() const {
+  const size_t t = impl_->threads;
+  return t == 0 ? 1 : t + (t + 1) / 2;
+}
+
+void Encoder::Init(const uint16_t* delta_frame, size_t xsize, size_t ysize, Callback callback, void* payload) {
+  Impl& s = *impl_;
+  s.W = xsize;
+  s.H = ysize;
+  s.P = xsize * ysize;
+  s.PP = (xsize / 4) * (ysize / 4);
+  s.has_low = s.shift != 8;
+  s.B = s.threads == 0 ? 1 : (s.opt.batch ? s.opt.batch : 1);
+  if (fpv_create(&s.ctx, s.opt.device, (uint32_t)xsize, (uint32_t)ysize, s.shift, s.big_endian ? 1 : 0, s.B) !=
+      FPV_OK) {
+    FPV_FAIL(std::string("fpv_create: ") + fpv_last_error(nullptr));
+    return;
+  }
+  s.ok = true;
+  const int nb = s.threads == 0 ? 1 : kNumBatches;
+  for (int i = 0; i < nb; i++) {
+    Impl::Batch& b = s.batches[i];
+    if (!b.frames.alloc((size_t)s.B * s.P * 2) || !b.high.alloc((size_t)s.B * s.P) ||
+        !b.low.alloc((size_t)s.B * s.P) || !b.preview.alloc((size_t)s.B * (s.PP ? s.PP : 1)) ||
+        !b.flags.alloc(s.B)) {
+      s.fail("pinned allocation");
+      return;
+    }
+    s.free_.push_back(&b);
+  }
+  if (fpv_set_delta_raw(s.ctx, delta_frame) != FPV_OK) {
+    s.fail("fpv_set_delta_raw");
+    return;
+  }
+  // Header: the delta frame itself, predicted without a delta frame
+  // (Frame df = delta_frame_; df.Compress(), reference .cc:1099-1101).
+  Impl::Batch& b = s.batches[0];
+  memcpy(b.frames.as<uint16_t>(), delta_frame, s.P * 2);
+  if (fpv_encode(s.ctx, b.frames.as<uint16_t>(), 1, FPV_ENC_NO_DELTA, b.flags.as<uint8_t>(), b.high.as<uint8_t>(),
+                 s.has_low ? b.low.as<uint8_t>() : nullptr, b.preview.as<uint8_t>()) != FPV_OK) {
+    s.fail("fpv_encode (delta frame)");
+    return;
+  }
+  std::vector<uint8_t> header, scratch;
+  AppendU32((uint32_t)xsize, &header);
+  AppendU32((uint32_t)ysize, &header);
+  AppendU32(0, &header);
+  header.push_back(kChunkDelta);
+  AppendCore(b.flags.as<uint8_t>()[0], b.high.as<uint8_t>(), s.has_low ? b.low.as<uint8_t>() : nullptr, s.P,
+             &scratch, &header);
+  StoreU32((uint32_t)(header.size() - 8), header.data() + 8);
+  s.bytes_written = header.size();
+  if (s.threads > 0) {
+    s.pool.reset(new Pool(s.threads));
+    s.gpu_thread = std::thread([&s] { s.gpu_loop(); });
+  }
+  callback(header.data(), header.size(), payload);
+}
+
+void Encoder::CompressFrame(const uint16_t* img, Callback callback, void* payload) {
+  Impl& s = *impl_;
+  if (!s.ok) return;
+  if (s.threads == 0) {
+    // synchronous: transform, brotli and the callback all happen here
+    Impl::Batch& b = s.batches[0];
+    memcpy(b.frames.as<uint16_t>(), img, s.P * 2);
+    if (fpv_encode(s.ctx, b.frames.as<uint16_t>(), 1, FPV_ENC_DEFAULT, b.flags.as<uint8_t>(),
+                   b.high.as<uint8_t>(), s.has_low ? b.low.as<uint8_t>() : nullptr,
+                   b.preview.as<uint8_t>()) != FPV_OK) {
+      s.fail("fpv_encode");
+      return;
+    }
+    static thread_local std::vector<uint8_t> scratch;
+    Impl::Done d;
+    d.callback = callback;
+    d.payload = payload;
+    s.build_chunk(b.flags.as<uint8_t>()[0], b.high.as<uint8_t>(), s.has_low ? b.low.as<uint8_t>() : nullptr,
+                  b.preview.as<uint8_t>(), &scratch, &d.bytes);
+    s.deliver(s.next_id++, std::move(d));
+    return;
+  }
+  Impl::Batch* b;
+  {
+    std::unique_lock<std::mutex> l(s.m);
+    if (!s.filling) {
+      s.cv_free.wait(l, [&] { return !s.free_.empty(); });
+      s.filling = s.free_.front();
+      s.free_.pop_front();
+      s.filling->first_id = s.next_id;
+    }
+    b = s.filling;
+    s.next_id++;
+  }
+  // only this (the submitting) thread touches a filling batch
+  memcpy(b->frames.as<uint16_t>() + (size_t)b->n * s.P, img, s.P * 2);
+  b->callbacks.push_back(callback);
+  b->payloads.push_back(payload);
+  b->n++;
+  bool hand_over = b->n == s.B;
+  {
+    std::lock_guard<std::mutex> l(s.m);
+    if (!hand_over && s.gpu_busy == 0 && s.ready_.empty()) hand_over = true;  // idle pipeline: go now
+    if (hand_over) {
+      s.ready_.push_back(b);
+      s.gpu_busy++;
+      s.filling = nullptr;
+    }
+  }
+  if (hand_over) s.cv_ready.notify_all();
+}
+
+void Encoder::Finish(Callback callback, void* payload) {
+  Impl& s = *impl_;
+  if (s.finished) return;
+  s.finished = true;
+  if (s.ok && s.threads > 0) {
+    {
+      std::unique_lock<std::mutex> l(s.m);
+      if (s.filling && s.filling->n > 0) {
+        s.ready_.push_back(s.filling);
+        s.gpu_busy++;
+        s.filling = nullptr;
+      }
+    }
+    s.cv_ready.notify_all();
+    {
+      // every batch back on the free list <=> every frame emitted
+      std::unique_lock<std::mutex> l(s.m);
+      s.cv_drained.wait(l, [&] { return s.free_.size() + (s.filling ? 1 : 0) == (size_t)kNumBatches; });
+    }
+    s.shutdown();
+  }
+  std::vector<uint8_t> footer(5 + 8 * s.offsets.size() + 8);
+  StoreU32((uint32_t)footer.size(), footer.data());
+  footer[4] = kChunkIndex;
+  for (size_t i = 0; i < s.offsets.size(); i++) StoreU64(s.offsets[i], footer.data() + 5 + 8 * i);
+  StoreU64(s.offsets.size(), footer.data() + 5 + 8 * s.offsets.size());
+  callback(footer.data(), footer.size(), payload);
+}
+
+}  // namespace fpvc

@@ -1,0 +1,169 @@
+// host_common.cc -- error reporting, brotli glue, worker pool, UnextractFrame.
+#include <brotli/decode.h>
+#include <brotli/encode.h>
+#include <string.h>
+
+#include <iostream>
+
+#include "fusion_power_video.h"
+#include "host_internal.h"
+
+namespace fpvc {
+
+namespace {
+thread_local std::string g_last_error;
+}
+
+const std::string& LastError() { return g_last_error; }
+
+namespace internal {
+
+bool Fail(const char* file, int line, const std::string& message) {
+  g_last_error = message;
+  std::cerr << "failure at: " << file << ":" << line;
+  if (!message.empty()) std::cerr << ": " << message;
+  std::cerr << std::endl;
+  return false;
+}
+
+bool BrotliPlane(const uint8_t* plane, size_t size, std::vector<uint8_t>* scratch, std::vector<uint8_t>* out) {
+  // BrotliEncoderMaxCompressedSize is what the reference sizes its buffer with
+  // (.cc:355-357); with it the one-shot call cannot fail for lack of room.
+  size_t cap = BrotliEncoderMaxCompressedSize(size);
+  if (cap == 0) cap = size + 1024;
+  if (scratch->size() < cap) scratch->resize(cap);
+  size_t n = cap;
+  if (!BrotliEncoderCompress(1, BROTLI_DEFAULT_WINDOW, BROTLI_DEFAULT_MODE, size, plane, &n, scratch->data()))
+    return FPV_FAIL("brotli compression failed");
+  out->insert(out->end(), scratch->data(), scratch->data() + n);
+  return true;
+}
+
+bool BrotliUnplane(const uint8_t* in, size_t size, size_t* pos, uint8_t* out, size_t expect) {
+  if (*pos > size) return FPV_FAIL("out of bounds");
+  BrotliDecoderState* st = BrotliDecoderCreateInstance(nullptr, nullptr, nullptr);
+  if (!st) return FPV_FAIL("couldn't init brotli decoder");
+  size_t avail_in = size - *pos;
+  const uint8_t* next_in = in + *pos;
+  size_t avail_out = expect;
+  uint8_t* next_out = out;
+  uint8_t spill[256];
+  bool overflow = false;
+  BrotliDecoderResult r;
+  for (;;) {
+    r = BrotliDecoderDecompressStream(st, &avail_in, &next_in, &avail_out, &next_out, nullptr);
+    if (r != BROTLI_DECODER_RESULT_NEEDS_MORE_OUTPUT) break;
+    // more data than the plane holds: keep consuming to find the stream end, then report the mismatch
+    overflow = true;
+    avail_out = sizeof spill;
+    next_out = spill;
+  }
+  BrotliDecoderDestroyInstance(st);
+  *pos = size - avail_in;
+  if (r != BROTLI_DECODER_RESULT_SUCCESS) return FPV_FAIL("brotli decompression failed");
+  if (overflow || avail_out != 0) return FPV_FAIL("wrong decompressed plane size");
+  return true;
+}
+
+void AppendCore(uint8_t flags, const uint8_t* high, const uint8_t* low, size_t plane_bytes,
+                std::vector<uint8_t>* scratch, std::vector<uint8_t>* out) {
+  out->push_back(flags);
+  if (!(flags & FPV_FLAG_NO_LOW_BYTES)) BrotliPlane(low, plane_bytes, scratch, out);
+  BrotliPlane(high, plane_bytes, scratch, out);
+}
+
+bool ParseCore(const uint8_t* in, size_t size, size_t plane_bytes, uint8_t* flags, uint8_t* high, uint8_t* low) {
+  if (size == 0) return FPV_FAIL("out of bounds");
+  size_t pos = 0;
+  *flags = in[pos++];
+  if (*flags & FPV_FLAG_NO_LOW_BYTES) {
+    if (low) memset(low, 0, plane_bytes);
+  } else {
+    if (!low) return FPV_FAIL("low plane buffer missing");
+    if (!BrotliUnplane(in, size, &pos, low, plane_bytes)) return false;
+  }
+  return BrotliUnplane(in, size, &pos, high, plane_bytes);
+}
+
+// ---- Pool ----------------------------------------------------------------------------
+Pool::Pool(size_t threads) {
+  for (size_t i = 0; i < threads; i++) threads_.emplace_back([this] { loop(); });
+}
+
+Pool::~Pool() {
+  {
+    std::lock_guard<std::mutex> l(m_);
+    stop_ = true;
+  }
+  cv_work_.notify_all();
+  for (auto& t : threads_) t.join();
+}
+
+void Pool::run(std::function<void()> task) {
+  if (threads_.empty()) {
+    task();
+    return;
+  }
+  {
+    std::lock_guard<std::mutex> l(m_);
+    q_.push_back(std::move(task));
+  }
+  cv_work_.notify_one();
+}
+
+void Pool::wait_idle() {
+  std::unique_lock<std::mutex> l(m_);
+  cv_idle_.wait(l, [this] { return q_.empty() && busy_ == 0; });
+}
+
+void Pool::loop() {
+  for (;;) {
+    std::function<void()> task;
+    {
+      std::unique_lock<std::mutex> l(m_);
+      cv_work_.wait(l, [this] { return stop_ || !q_.empty(); });
+      if (q_.empty()) return;  // stop_ and drained
+      task = std::move(q_.front());
+      q_.pop_front();
+      busy_++;
+    }
+    task();
+    {
+      std::lock_guard<std::mutex> l(m_);
+      busy_--;
+      if (q_.empty() && busy_ == 0) cv_idle_.notify_all();
+    }
+  }
+}
+
+void ParallelFor(Pool* pool, size_t n, const std::function<void(size_t)>& body) {
+  if (!pool || pool->size() == 0 || n <= 1) {
+    for (size_t i = 0; i < n; i++) body(i);
+    return;
+  }
+  std::mutex m;
+  std::condition_variable cv;
+  size_t left = n;
+  for (size_t i = 0; i < n; i++)
+    pool->run([&, i] {
+      body(i);
+      std::lock_guard<std::mutex> l(m);
+      if (--left == 0) cv.notify_all();
+    });
+  std::unique_lock<std::mutex> l(m);
+  cv.wait(l, [&] { return left == 0; });
+}
+
+}  // namespace internal
+
+void UnextractFrame(const uint16_t* img, size_t xsize, size_t ysize, int shift, bool big_endian, uint8_t* out) {
+  const size_t n = xsize * ysize;
+  const int lo = big_endian ? 1 : 0, hi = big_endian ? 0 : 1;
+  for (size_t i = 0; i < n; i++) {
+    const uint16_t v = (uint16_t)(img[i] >> shift);
+    out[2 * i + lo] = (uint8_t)(v & 0xff);
+    out[2 * i + hi] = (uint8_t)(v >> 8);
+  }
+}
+
+}  // namespace fpvc

@@ -1,0 +1,126 @@
+"""ctypes binding of the host layer's C entry points (csrc/host/capi.cc):
+the fpvc::Encoder / StreamingDecoder / RandomAccessDecoder classes of
+``lib/libfusion_power_video_b200.so`` driven end to end (GPU transform + host
+brotli + stream framing).  No compute happens in Python."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "lib", "libfusion_power_video_b200.so")
+_lib = None
+
+
+def lib_path() -> str:
+    return _LIB_PATH
+
+
+def lib() -> C.CDLL:
+    """Loads the host library (which links libfpv_b200.so).  Raises if missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise ImportError(f"{_LIB_PATH} not found: run `make -C fusion_power_video_b200/csrc all`")
+    from . import binding
+
+    binding.lib()  # the C ABI first, so the dependency resolves from lib/
+    L = C.CDLL(_LIB_PATH)
+    vp, sz, i32, u32 = C.c_void_p, C.c_size_t, C.c_int, C.c_uint32
+    L.fpvh_last_error.restype = C.c_char_p
+    L.fpvh_encode_stream.argtypes = [sz, sz, i32, i32, sz, u32, i32, vp, vp, sz, vp, sz]
+    L.fpvh_encode_stream.restype = sz
+    L.fpvh_time_encode.argtypes = [sz, sz, i32, i32, sz, u32, i32, vp, vp, sz, C.POINTER(sz)]
+    L.fpvh_time_encode.restype = C.c_double
+    L.fpvh_decode_stream.argtypes = [vp, sz, sz, u32, i32, i32, i32, vp, sz, C.POINTER(sz), C.POINTER(sz),
+                                     C.POINTER(C.c_double)]
+    L.fpvh_decode_stream.restype = C.c_long
+    L.fpvh_random_access.argtypes = [vp, sz, u32, i32, sz, sz, vp, vp, C.POINTER(sz), C.POINTER(sz), C.POINTER(sz)]
+    L.fpvh_random_access.restype = i32
+    L.fpvh_unextract.argtypes = [vp, sz, sz, i32, i32, vp]
+    L.fpvh_unextract.restype = None
+    _lib = L
+    return L
+
+
+class HostError(RuntimeError):
+    pass
+
+
+def _p(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+def last_error() -> str:
+    return lib().fpvh_last_error().decode()
+
+
+def encode_stream(frames, xsize, ysize, shift=0, big_endian=False, threads=4, batch=32, delta=None, device=0):
+    """frames: uint16 [n, ysize*xsize]; delta defaults to frames[0].  Returns the stream as bytes."""
+    L = lib()
+    frames = np.ascontiguousarray(frames, dtype=np.uint16).reshape(-1, xsize * ysize)
+    delta = frames[0] if delta is None else np.ascontiguousarray(delta, dtype=np.uint16).reshape(-1)
+    n = frames.shape[0]
+    cap = 64 + (n + 1) * (xsize * ysize * 5 // 2 + 4096)
+    out = np.empty(cap, np.uint8)
+    size = L.fpvh_encode_stream(xsize, ysize, shift, int(big_endian), threads, batch, device, _p(delta), _p(frames), n,
+                                _p(out), cap)
+    if size == 0:
+        raise HostError(f"encode failed: {last_error()}")
+    if size > cap:
+        raise HostError("stream larger than the output buffer")
+    return out[:size].tobytes()
+
+
+def time_encode(frames, xsize, ysize, shift=0, big_endian=False, threads=4, batch=32, delta=None, device=0):
+    """(seconds, stream bytes) of Encoder Init + CompressFrame x n + Finish (benchmark.cc's timing window)."""
+    L = lib()
+    frames = np.ascontiguousarray(frames, dtype=np.uint16).reshape(-1, xsize * ysize)
+    delta = frames[0] if delta is None else np.ascontiguousarray(delta, dtype=np.uint16).reshape(-1)
+    size = C.c_size_t(0)
+    t = L.fpvh_time_encode(xsize, ysize, shift, int(big_endian), threads, batch, device, _p(delta), _p(frames),
+                           frames.shape[0], C.byref(size))
+    if t < 0:
+        raise HostError(f"encode failed: {last_error()}")
+    return t, size.value
+
+
+def decode_stream(stream, max_frames, xsize, ysize, block=0, batch=32, raw_shift=-1, big_endian=False, device=0,
+                  return_time=False):
+    """Decodes with StreamingDecoder in `block`-byte pieces.  Returns uint16 [n, ysize*xsize] (images, or the raw
+    file words when raw_shift >= 0)."""
+    L = lib()
+    buf = np.frombuffer(stream, np.uint8)
+    out = np.zeros((max_frames, xsize * ysize), np.uint16)
+    W, H, sec = C.c_size_t(0), C.c_size_t(0), C.c_double(0)
+    n = L.fpvh_decode_stream(_p(buf), buf.size, block, batch, device, raw_shift, int(big_endian), _p(out), max_frames,
+                             C.byref(W), C.byref(H), C.byref(sec))
+    if n < 0:
+        raise HostError(f"decode failed: {last_error()}")
+    if n and (W.value, H.value) != (xsize, ysize):
+        raise HostError(f"stream is {W.value}x{H.value}, expected {xsize}x{ysize}")
+    return (out[:n], sec.value) if return_time else out[:n]
+
+
+def random_access(stream, first, count, xsize, ysize, batch=32, device=0, want_preview=True):
+    """(numframes, frames uint16 [count, P], preview uint8 [(ysize//4)*(xsize//4)] of frame `first`)."""
+    L = lib()
+    buf = np.frombuffer(stream, np.uint8)
+    frames = np.zeros((count, xsize * ysize), np.uint16)
+    preview = np.zeros((ysize // 4) * (xsize // 4), np.uint8) if want_preview else None
+    nf, W, H = C.c_size_t(0), C.c_size_t(0), C.c_size_t(0)
+    ok = L.fpvh_random_access(_p(buf), buf.size, batch, device, first, count, _p(frames), _p(preview), C.byref(nf),
+                              C.byref(W), C.byref(H))
+    if not ok:
+        raise HostError(f"random access decode failed: {last_error()}")
+    return nf.value, frames, preview
+
+
+def unextract(img, xsize, ysize, shift, big_endian):
+    img = np.ascontiguousarray(img, dtype=np.uint16).reshape(-1)
+    out = np.empty(xsize * ysize * 2, np.uint8)
+    lib().fpvh_unextract(_p(img), xsize, ysize, shift, int(big_endian), _p(out))
+    return out

@@ -60,3 +60,27 @@ def test_product_does_not_reference_oracle():
                 if re.search(r"fpv_oracle|libfpv_ref|oracle_binding|fpvo_|/oracle/", t):
                     bad.append(os.path.join(d, f))
     assert not bad, bad
+
+
+def test_host_library_loads_and_fails_loudly_without_device():
+    """libfusion_power_video_b200.so (fpvc:: classes + fpvh_* C entry points) loads on a CPU-only box;
+    without a CUDA device encoding must fail with a message, not fall back to a CPU path."""
+    import numpy as np
+
+    from fusion_power_video_b200 import host
+
+    L = host.lib()
+    for n in ("fpvh_encode_stream", "fpvh_time_encode", "fpvh_decode_stream", "fpvh_random_access", "fpvh_unextract",
+              "fpvh_last_error"):
+        assert hasattr(L, n), n
+    img = (np.arange(64 * 32, dtype=np.uint32) * 37 % 65536).astype(np.uint16)
+    out = host.unextract(img, 64, 32, 4, True)
+    assert out[0] == ((int(img[0]) >> 4) >> 8) and out[1] == ((int(img[0]) >> 4) & 0xff)
+    if fpv.device_count() > 0:
+        return
+    try:
+        host.encode_stream(img.reshape(1, -1), 64, 32, threads=0)
+    except host.HostError as e:
+        assert "fpv_create" in str(e) or "CUDA" in str(e)
+    else:
+        raise AssertionError("encode_stream succeeded without a CUDA device")
