@@ -30,6 +30,7 @@ std::string g_create_error = "no error";
 
 struct Slot {
   cudaStream_t stream = nullptr;
+  cudaEvent_t done = nullptr;    // blocking-sync event: fpv_wait sleeps instead of spinning on a host core
   uint16_t* d_frames = nullptr;  // raw frames in / decoded images out
   uint8_t* d_high = nullptr;
   uint8_t* d_low = nullptr;
@@ -112,6 +113,7 @@ int ensure_slot(fpv_ctx* c, int idx) {
   if (s.allocated) return FPV_OK;
   size_t B = c->max_batch, P = c->g.P, PP = c->g.PP ? c->g.PP : 1;
   FPV_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+  FPV_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventBlockingSync | cudaEventDisableTiming));
   FPV_CUDA(cudaMalloc(&s.d_frames, B * P * 2));
   FPV_CUDA(cudaMalloc(&s.d_high, B * P));
   FPV_CUDA(cudaMalloc(&s.d_low, B * P));
@@ -260,6 +262,7 @@ void fpv_destroy(fpv_ctx* c) {
     if (s.d_low) cudaFree(s.d_low);
     if (s.d_preview) cudaFree(s.d_preview);
     if (s.d_flags) cudaFree(s.d_flags);
+    if (s.done) cudaEventDestroy(s.done);
     if (s.stream) cudaStreamDestroy(s.stream);
   }
   for (auto& h : c->timing) {
@@ -421,6 +424,7 @@ int fpv_encode_submit(fpv_ctx* c, uint32_t slot, const uint16_t* frames_host, ui
     FPV_CUDA(cudaMemcpyAsync(low_host, s.d_low, (size_t)n * P, cudaMemcpyDeviceToHost, s.stream));
   FPV_CUDA(cudaMemcpyAsync(preview_host, s.d_preview, (size_t)n * PP, cudaMemcpyDeviceToHost, s.stream));
   FPV_CUDA(cudaMemcpyAsync(flags_host, s.d_flags, (size_t)n, cudaMemcpyDeviceToHost, s.stream));
+  FPV_CUDA(cudaEventRecord(s.done, s.stream));
   return FPV_OK;
 }
 
@@ -429,7 +433,8 @@ int fpv_wait(fpv_ctx* c, uint32_t slot) {
   if (slot >= kNumSlots) return fail(c, FPV_ERR_INVALID_ARG, "slot out of range");
   if (!c->slots[slot].allocated) return FPV_OK;
   FPV_CUDA(cudaSetDevice(c->device));
-  FPV_CUDA(cudaStreamSynchronize(c->slots[slot].stream));
+  FPV_CUDA(cudaEventSynchronize(c->slots[slot].done));   // everything submitted on the slot so far
+  FPV_CUDA(cudaStreamSynchronize(c->slots[slot].stream)); // (returns at once; surfaces stream errors)
   return FPV_OK;
 }
 
@@ -493,6 +498,7 @@ int fpv_decode_submit(fpv_ctx* c, uint32_t slot, const uint8_t* high_host, const
                           s.stream, true);
   if (rc != FPV_OK) return rc;
   FPV_CUDA(cudaMemcpyAsync(out_host, s.d_frames, (size_t)n * P * 2, cudaMemcpyDeviceToHost, s.stream));
+  FPV_CUDA(cudaEventRecord(s.done, s.stream));
   return FPV_OK;
 }
 

@@ -7,11 +7,13 @@
 //   2. hands full batches -- or whatever is there when the GPU is idle -- to one
 //      GPU thread, which keeps two fpv_encode_submit slots in flight (H2D of
 //      batch k+1 overlaps kernels / D2H of batch k),
-//   3. fans the landed planes out to the brotli workers, one frame per task,
+//   3. fans the landed planes out to the brotli workers, two tasks per frame
+//      (low plane; preview + high plane), the second to finish assembles the chunk,
 //   4. emits finished frames in submission order under one mutex, recording the
 //      frame offsets for the footer exactly as FinishTask does (.cc:1179-1183).
 #include <string.h>
 
+#include <algorithm>
 #include <atomic>
 #include <iostream>
 #include <map>
@@ -24,7 +26,7 @@ namespace fpvc {
 using namespace internal;
 
 namespace {
-constexpr int kNumBatches = 4;  // one filling, up to two on the GPU, one in brotli
+constexpr int kMaxBatches = 16;
 }
 
 struct Encoder::Impl {
@@ -39,16 +41,25 @@ struct Encoder::Impl {
   bool has_low = true;
   uint32_t B = 1;
 
+  // Compressed pieces of one frame, filled by its two brotli tasks.
+  struct Pieces {
+    std::vector<uint8_t> low, preview_high;   // brotli(low) ; brotli(preview) ++ brotli(high)
+    size_t preview_bytes = 0;
+    std::atomic<int> parts{0};
+  };
   struct Batch {
     Pinned frames, high, low, preview, flags;
+    bool allocated = false;
     uint32_t n = 0;
     uint64_t first_id = 0;
     std::vector<Callback> callbacks;
     std::vector<void*> payloads;
+    std::vector<Pieces> pieces;
     std::atomic<uint32_t> pending{0};
     uint32_t slot = 0;
   };
-  Batch batches[kNumBatches];
+  Batch batches[kMaxBatches];
+  int num_batches = 1;   // one filling, up to two on the GPU, the rest feeding brotli
 
   std::mutex m;                       // batch lists, ids, stop flag
   std::condition_variable cv_free, cv_ready, cv_drained;
@@ -110,6 +121,16 @@ struct Encoder::Impl {
     p[9] = (uint8_t)((flags & FPV_FLAG_USE_CG) | FPV_FLAG_NO_LOW_BYTES);
   }
 
+  bool alloc_batch(Batch* b) {
+    if (b->allocated) return true;
+    if (!b->frames.alloc((size_t)B * P * 2) || !b->high.alloc((size_t)B * P) || !b->low.alloc((size_t)B * P) ||
+        !b->preview.alloc((size_t)B * (PP ? PP : 1)) || !b->flags.alloc(B))
+      return fail("pinned allocation");
+    b->pieces = std::vector<Pieces>(B);
+    b->allocated = true;
+    return true;
+  }
+
   // Called by whoever finished frame `id`; emits every frame that is now in order.
   void deliver(uint64_t id, Done&& d) {
     std::lock_guard<std::mutex> l(out_m);
@@ -135,19 +156,50 @@ struct Encoder::Impl {
     cv_drained.notify_all();
   }
 
+  // The second of a frame's two brotli tasks to finish builds the chunk
+  // (frame := total | 0 | 1+|bp| | pflags | bp | flags | low? | high) and hands it on.
+  void part_done(Batch* b, uint32_t i) {
+    Pieces& pc = b->pieces[i];
+    if (pc.parts.fetch_add(1) == 0) return;
+    const uint8_t flags = b->flags.as<uint8_t>()[i];
+    Done d;
+    d.callback = b->callbacks[i];
+    d.payload = b->payloads[i];
+    d.bytes.resize(10);
+    d.bytes.reserve(11 + pc.preview_high.size() + pc.low.size());
+    d.bytes.insert(d.bytes.end(), pc.preview_high.begin(), pc.preview_high.begin() + (ptrdiff_t)pc.preview_bytes);
+    d.bytes.push_back(flags);
+    d.bytes.insert(d.bytes.end(), pc.low.begin(), pc.low.end());
+    d.bytes.insert(d.bytes.end(), pc.preview_high.begin() + (ptrdiff_t)pc.preview_bytes, pc.preview_high.end());
+    uint8_t* p = d.bytes.data();
+    StoreU32((uint32_t)d.bytes.size(), p);
+    p[4] = kChunkFrame;
+    StoreU32((uint32_t)(pc.preview_bytes + 1), p + 5);
+    p[9] = (uint8_t)((flags & FPV_FLAG_USE_CG) | FPV_FLAG_NO_LOW_BYTES);
+    deliver(b->first_id + i, std::move(d));
+    if (b->pending.fetch_sub(1) == 1) recycle(b);
+  }
+
   void compress_batch(Batch* b) {
     b->pending.store(b->n);
     for (uint32_t i = 0; i < b->n; i++) {
-      pool->run([this, b, i] {
+      Pieces& pc = b->pieces[i];
+      pc.parts.store(0);
+      pc.low.clear();
+      pc.preview_high.clear();
+      // the low plane carries most of the entropy and takes longest: queue it first
+      pool->run([this, b, i, &pc] {
         thread_local std::vector<uint8_t> scratch;
-        Done d;
-        d.callback = b->callbacks[i];
-        d.payload = b->payloads[i];
-        build_chunk(b->flags.as<uint8_t>()[i], b->high.as<uint8_t>() + (size_t)i * P,
-                    has_low ? b->low.as<uint8_t>() + (size_t)i * P : nullptr,
-                    b->preview.as<uint8_t>() + (size_t)i * PP, &scratch, &d.bytes);
-        deliver(b->first_id + i, std::move(d));
-        if (b->pending.fetch_sub(1) == 1) recycle(b);
+        if (!(b->flags.as<uint8_t>()[i] & FPV_FLAG_NO_LOW_BYTES))
+          BrotliPlane(b->low.as<uint8_t>() + (size_t)i * P, P, &scratch, &pc.low);
+        part_done(b, i);
+      });
+      pool->run([this, b, i, &pc] {
+        thread_local std::vector<uint8_t> scratch;
+        BrotliPlane(b->preview.as<uint8_t>() + (size_t)i * PP, PP, &scratch, &pc.preview_high);
+        pc.preview_bytes = pc.preview_high.size();
+        BrotliPlane(b->high.as<uint8_t>() + (size_t)i * P, P, &scratch, &pc.preview_high);
+        part_done(b, i);
       });
     }
   }
@@ -227,17 +279,12 @@ void Encoder::Init(const uint16_t* delta_frame, size_t xsize, size_t ysize, Call
     return;
   }
   s.ok = true;
-  const int nb = s.threads == 0 ? 1 : kNumBatches;
-  for (int i = 0; i < nb; i++) {
-    Impl::Batch& b = s.batches[i];
-    if (!b.frames.alloc((size_t)s.B * s.P * 2) || !b.high.alloc((size_t)s.B * s.P) ||
-        !b.low.alloc((size_t)s.B * s.P) || !b.preview.alloc((size_t)s.B * (s.PP ? s.PP : 1)) ||
-        !b.flags.alloc(s.B)) {
-      s.fail("pinned allocation");
-      return;
-    }
-    s.free_.push_back(&b);
-  }
+  // enough batches that the brotli workers always have about two frames each queued
+  // behind the (up to) three batches that are filling / on the GPU; pinned memory is
+  // only allocated when a batch is first used
+  s.num_batches = s.threads == 0 ? 1 : (int)std::min<size_t>(kMaxBatches, 3 + (2 * s.threads + s.B - 1) / s.B);
+  for (int i = 0; i < s.num_batches; i++) s.free_.push_back(&s.batches[i]);
+  if (!s.alloc_batch(&s.batches[0])) return;
   if (fpv_set_delta_raw(s.ctx, delta_frame) != FPV_OK) {
     s.fail("fpv_set_delta_raw");
     return;
@@ -301,6 +348,7 @@ void Encoder::CompressFrame(const uint16_t* img, Callback callback, void* payloa
     b = s.filling;
     s.next_id++;
   }
+  if (!b->allocated && !s.alloc_batch(b)) return;
   // only this (the submitting) thread touches a filling batch
   memcpy(b->frames.as<uint16_t>() + (size_t)b->n * s.P, img, s.P * 2);
   b->callbacks.push_back(callback);
@@ -336,7 +384,7 @@ void Encoder::Finish(Callback callback, void* payload) {
     {
       // every batch back on the free list <=> every frame emitted
       std::unique_lock<std::mutex> l(s.m);
-      s.cv_drained.wait(l, [&] { return s.free_.size() + (s.filling ? 1 : 0) == (size_t)kNumBatches; });
+      s.cv_drained.wait(l, [&] { return s.free_.size() + (s.filling ? 1 : 0) == (size_t)s.num_batches; });
     }
     s.shutdown();
   }

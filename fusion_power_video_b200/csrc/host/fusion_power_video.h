@@ -51,7 +51,7 @@ const std::string& LastError();
 // submission (the encoder submits earlier when its pipeline is idle).
 struct GpuOptions {
   int device = 0;
-  uint32_t batch = 32;
+  uint32_t batch = 8;
 };
 
 class StreamingDecoder {

@@ -2,8 +2,12 @@
 #include <brotli/decode.h>
 #include <brotli/encode.h>
 #include <string.h>
+#include <sys/resource.h>
+#include <sys/syscall.h>
+#include <unistd.h>
 
 #include <iostream>
+#include <map>
 
 #include "fusion_power_video.h"
 #include "host_internal.h"
@@ -85,6 +89,43 @@ bool ParseCore(const uint8_t* in, size_t size, size_t plane_bytes, uint8_t* flag
   return BrotliUnplane(in, size, &pos, high, plane_bytes);
 }
 
+// ---- pinned block cache -------------------------------------------------------------------
+namespace {
+std::mutex g_pin_m;
+std::multimap<size_t, void*> g_pin_cache;
+size_t g_pin_cached_bytes = 0;
+constexpr size_t kPinCacheLimit = (size_t)1 << 30;
+}  // namespace
+
+void* PinnedAcquire(size_t bytes) {
+  if (bytes == 0) bytes = 1;
+  {
+    std::lock_guard<std::mutex> l(g_pin_m);
+    auto it = g_pin_cache.find(bytes);
+    if (it != g_pin_cache.end()) {
+      void* p = it->second;
+      g_pin_cache.erase(it);
+      g_pin_cached_bytes -= bytes;
+      return p;
+    }
+  }
+  return fpv_host_alloc(bytes);
+}
+
+void PinnedRelease(void* p, size_t bytes) {
+  if (!p) return;
+  if (bytes == 0) bytes = 1;
+  {
+    std::lock_guard<std::mutex> l(g_pin_m);
+    if (g_pin_cached_bytes + bytes <= kPinCacheLimit) {
+      g_pin_cache.emplace(bytes, p);
+      g_pin_cached_bytes += bytes;
+      return;
+    }
+  }
+  fpv_host_free(p);
+}
+
 // ---- Pool ----------------------------------------------------------------------------
 Pool::Pool(size_t threads) {
   for (size_t i = 0; i < threads; i++) threads_.emplace_back([this] { loop(); });
@@ -117,6 +158,10 @@ void Pool::wait_idle() {
 }
 
 void Pool::loop() {
+  // The workers only run brotli.  The threads that feed them (the caller copying
+  // frames into pinned memory, the GPU thread) need a core the moment they become
+  // runnable or the whole pipeline starves, so the workers step back a little.
+  setpriority(PRIO_PROCESS, (id_t)syscall(SYS_gettid), 5);
   for (;;) {
     std::function<void()> task;
     {

@@ -68,6 +68,11 @@ void AppendCore(uint8_t flags, const uint8_t* high, const uint8_t* low, size_t p
 bool ParseCore(const uint8_t* in, size_t size, size_t plane_bytes, uint8_t* flags, uint8_t* high, uint8_t* low);
 
 // ---- pinned memory -----------------------------------------------------------------
+// Page-locking memory costs on the order of a millisecond per few MB, so freed
+// blocks go to a small process-wide cache and are handed out again by size.
+void* PinnedAcquire(size_t bytes);
+void PinnedRelease(void* p, size_t bytes);
+
 class Pinned {
  public:
   Pinned() = default;
@@ -76,12 +81,12 @@ class Pinned {
   Pinned& operator=(const Pinned&) = delete;
   bool alloc(size_t bytes) {
     reset();
-    p_ = fpv_host_alloc(bytes);
+    p_ = PinnedAcquire(bytes);
     n_ = p_ ? bytes : 0;
     return p_ != nullptr;
   }
   void reset() {
-    if (p_) fpv_host_free(p_);
+    if (p_) PinnedRelease(p_, n_);
     p_ = nullptr;
     n_ = 0;
   }

@@ -58,7 +58,7 @@ def last_error() -> str:
     return lib().fpvh_last_error().decode()
 
 
-def encode_stream(frames, xsize, ysize, shift=0, big_endian=False, threads=4, batch=32, delta=None, device=0):
+def encode_stream(frames, xsize, ysize, shift=0, big_endian=False, threads=4, batch=8, delta=None, device=0):
     """frames: uint16 [n, ysize*xsize]; delta defaults to frames[0].  Returns the stream as bytes."""
     L = lib()
     frames = np.ascontiguousarray(frames, dtype=np.uint16).reshape(-1, xsize * ysize)
@@ -75,7 +75,7 @@ def encode_stream(frames, xsize, ysize, shift=0, big_endian=False, threads=4, ba
     return out[:size].tobytes()
 
 
-def time_encode(frames, xsize, ysize, shift=0, big_endian=False, threads=4, batch=32, delta=None, device=0):
+def time_encode(frames, xsize, ysize, shift=0, big_endian=False, threads=4, batch=8, delta=None, device=0):
     """(seconds, stream bytes) of Encoder Init + CompressFrame x n + Finish (benchmark.cc's timing window)."""
     L = lib()
     frames = np.ascontiguousarray(frames, dtype=np.uint16).reshape(-1, xsize * ysize)
