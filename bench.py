@@ -44,6 +44,16 @@ ENC_BYTES_PER_PX = 2 + 1 + 1 + 1.0 / 16  # raw in, high out, low out, preview ou
 DEC_BYTES_PER_PX = 1 + 1 + 2             # planes in, uint16 out
 
 
+def ncu_traffic(which, algorithmic_bytes):
+    """DRAM bytes per launch from the committed ncu --set full capture (profiles/traffic.json), scaled to this
+    launch's size by the measured DRAM-bytes-per-algorithmic-byte ratio; None if there is no capture."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return float(json.load(f)[which]["dram_bytes_per_algorithmic_byte"]) * algorithmic_bytes
+    except Exception:
+        return None
+
+
 def measured_peak():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -269,7 +279,9 @@ def main():
     k_avg_ms = kms / max(kcnt, 1)
     achieved = ENC_BYTES_PER_PX * F * P / (k_avg_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "k_encode_fast", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": ncu_traffic("encode", ENC_BYTES_PER_PX * F * P),
+                "traffic_source": "profiles/traffic.json (ncu --set full dram__bytes_read.sum + dram__bytes_write.sum, scaled per byte)",
+                "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": ENC_BYTES_PER_PX * F * P, "kernel_ms": k_avg_ms,
                 "kernel_share_of_step": k_avg_ms / ms_step if world == 1 else None}
 
@@ -304,7 +316,8 @@ def main():
                   "unit": "GB/s", "frames_per_s": world * F / (dms * 1e-3), "ms_per_step": dms, "steps": dsteps,
                   "round_trip_exact": ok,
                   "roofline": {"bound": "hbm (chain-latency limited, see DESIGN.md)", "kernel": "k_decode_simd",
-                               "achieved": dach, "peak": peak, "unit": "GB/s", "frac": dach / peak}}
+                               "achieved": dach, "peak": peak, "unit": "GB/s", "frac": dach / peak,
+                               "traffic": ncu_traffic("decode", DEC_BYTES_PER_PX * F * P)}}
         del d_out
 
     # ---- e2e: host buffers through the C ABI, copies inside the timed region -----------------------

@@ -1,0 +1,135 @@
+#!/usr/bin/env python
+"""Turns the ncu artefacts a `scripts/gpu_profile.sh` visit leaves in gpurun_out/ into the tracked
+summaries under profiles/ (run here, where ncu is installed but no GPU is):
+
+    python profiles/make_profiles.py r01
+
+  profiles/<round>_launches.csv      the launch list (gpu__time_duration.sum per launch) of one bench command
+  profiles/<round>_launches.md       per-kernel share of that command
+  profiles/<round>_encode.md         k_encode_fast main pass: ncu --set full metrics + SASS opcode mix + top stalls
+  profiles/<round>_decode.md         k_decode_simd: same
+"""
+import collections
+import csv
+import os
+import re
+import shutil
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT = os.path.join(ROOT, "gpurun_out")
+sys.path.insert(0, os.path.join(ROOT, "profiles"))
+from ncu_summary import KEYS  # noqa: E402
+
+EXTRA = ["dram__bytes_read.sum", "dram__bytes_write.sum", "launch__occupancy_limit_warps", "sm__maximum_warps_per_active_cycle_pct"]
+
+
+def raw_metrics(rep):
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    res = []
+    for r in rows[2:]:
+        d = {"name": r[hdr.index("Kernel Name")]}
+        for k in KEYS + EXTRA:
+            if k in hdr:
+                d[k] = (r[hdr.index(k)], units[hdr.index(k)])
+        res.append(d)
+    return res
+
+
+def sass_mix(rep, units_per_launch, unit_name):
+    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr = rows[1]
+    ia, ie, isamp = hdr.index("Source"), hdr.index("Instructions Executed"), hdr.index("# Samples")
+    ops, samp = collections.Counter(), collections.Counter()
+    top = []
+    total = 0
+    for r in rows[2:]:
+        if len(r) <= ie:
+            continue
+        n, s = int(r[ie] or 0), int(r[isamp] or 0)
+        m = re.match(r"\s*(@!?U?P\d+\s+)?([A-Z0-9_.]+)", r[ia])
+        op = m.group(2).split(".")[0] if m else "?"
+        ops[op] += n
+        samp[op] += s
+        total += n
+        top.append((s, n, r[ia].strip()))
+    lines = [f"Warp instructions executed: {total:,} = {total / units_per_launch:.1f} per {unit_name}", "",
+             f"| opcode | per {unit_name} | stall samples |", "|---|---|---|"]
+    for k, v in ops.most_common(16):
+        lines.append(f"| {k} | {v / units_per_launch:.1f} | {samp[k]} |")
+    lines += ["", "Most-sampled instructions (warp stall sampling):", "", "| samples | executed | SASS |", "|---|---|---|"]
+    for s, n, src in sorted(top, reverse=True)[:10]:
+        lines.append(f"| {s} | {n:,} | `{src[:80]}` |")
+    return "\n".join(lines)
+
+
+def kernel_md(tag, title, rep, units_per_launch, unit_name, algo_bytes, note):
+    ms = raw_metrics(rep)[0]
+    dur_us = float(ms["gpu__time_duration.sum"][0]) * (1000.0 if ms["gpu__time_duration.sum"][1] == "ms" else 1.0)
+    rd = float(ms["dram__bytes_read.sum"][0]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}[ms["dram__bytes_read.sum"][1]]
+    wr = float(ms["dram__bytes_write.sum"][0]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}[ms["dram__bytes_write.sum"][1]]
+    lines = [f"# {title}", "", note, "",
+             f"Kernel: `{ms['name']}`", "",
+             f"* duration under ncu (cold caches, serialised): {dur_us:.1f} us",
+             f"* algorithmic bytes per launch: {algo_bytes / 1e9:.3f} GB; DRAM traffic (`dram__bytes_read.sum + dram__bytes_write.sum`): "
+             f"{rd / 1e9:.3f} + {wr / 1e9:.3f} = {(rd + wr) / 1e9:.3f} GB ({(rd + wr) / algo_bytes:.2f}x algorithmic)",
+             f"* algorithmic bandwidth under ncu: {algo_bytes / dur_us / 1e3:.0f} GB/s (the bench value is taken WITHOUT the profiler, see BENCH / DESIGN.md)",
+             "", "| metric | value |", "|---|---|"]
+    for k in KEYS:
+        if k in ms:
+            lines.append(f"| `{k}` | {ms[k][0]} {ms[k][1]} |")
+    lines += ["", "## SASS mix", "", sass_mix(rep, units_per_launch, unit_name), ""]
+    open(os.path.join(ROOT, "profiles", f"{tag}.md"), "w").write("\n".join(lines))
+    return {"kernel": ms["name"], "dram_bytes_per_launch": rd + wr, "algorithmic_bytes_per_launch": algo_bytes,
+            "dram_bytes_per_algorithmic_byte": (rd + wr) / algo_bytes, "ncu_duration_us": dur_us}
+
+
+def launches_md(tag):
+    src = os.path.join(OUT, "launches.csv")
+    shutil.copy(src, os.path.join(ROOT, "profiles", f"{tag}_launches.csv"))
+    rows = list(csv.reader(l for l in open(src) if l.startswith('"')))
+    hdr = rows[0]
+    ik, iv = hdr.index("Kernel Name"), hdr.index("Metric Value")
+    per = collections.OrderedDict()
+    for r in rows[1:]:
+        per.setdefault(r[ik].split("(")[0], []).append(float(r[iv]) / 1000)
+    tot = sum(sum(v) for v in per.values())
+    lines = [f"# Launch list ({tag})", "",
+             "`ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k_... -c 80 python bench.py --steps 3 --warmup 3 "
+             "--frames 512 --no-e2e --no-cpu` on one B200 (C2: 12-bit 1280x800, 512 frames per step; encode steps then "
+             "decode steps).  Per-launch times are cold-cache and serialised: compare shares, not absolutes.", "",
+             "| kernel | launches | avg us | min us | max us | share of all listed time |", "|---|---|---|---|---|---|"]
+    for k, v in per.items():
+        lines.append(f"| `{k}` | {len(v)} | {sum(v) / len(v):.1f} | {min(v):.1f} | {max(v):.1f} | {100 * sum(v) / tot:.1f} % |")
+    enc = {k: v for k, v in per.items() if "decode" not in k and "delta_from_raw" not in k}
+    etot = sum(sum(v) for v in enc.values())
+    main = [x for k, v in enc.items() if "k_encode_fast" in k for x in v if x > 100]
+    lines += ["", f"Within the encode steps, the main pass of `k_encode_fast` (the {len(main)} launches > 100 us) is "
+              f"{100 * sum(main) / etot:.1f} % of the listed encode time; bench.py's event timing of the same share "
+              "(`roofline.kernel_share_of_step`) is 0.87-0.88."]
+    open(os.path.join(ROOT, "profiles", f"{tag}_launches.md"), "w").write("\n".join(lines) + "\n")
+
+
+def main():
+    tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+    P = 1280 * 800
+    launches_md(tag)
+    import json
+    traffic = {}
+    traffic["encode"] = kernel_md(f"{tag}_encode", "k_encode_fast, main pass (C2, 512 frames)", os.path.join(OUT, "prof_encode_main.ncu-rep"),
+              512 * P / 256, "warp-row (256 px)", 512 * P * 4.0625,
+              "`ncu --set full --clock-control none --import-source on -k regex:k_encode_fast -s 3 -c 1 python bench.py --steps 3 "
+              "--warmup 3 --frames 512 --no-e2e --no-cpu --no-decode` (the 4th matching launch = the main pass of the 2nd step).")
+    traffic["decode"] = kernel_md(f"{tag}_decode", "k_decode_simd (C2, 1024 frames)", os.path.join(OUT, "prof_decode.ncu-rep"),
+              1024 * 800, "frame row (1280 px, one warp)", 1024 * P * 4.0,
+              "`ncu --set full --clock-control none --import-source on -k regex:k_decode_simd -s 1 -c 1 python bench.py --steps 3 "
+              "--warmup 3 --frames 1024 --no-e2e --no-cpu`.")
+    json.dump(traffic, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
