@@ -48,6 +48,7 @@ struct fpv_ctx {
   uint32_t max_batch = 0;
   bool encode_ok = false;        // W % 4 == 0 && H % 4 == 0
   uint16_t* d_delta = nullptr;   // image form, P pixels
+  uint32_t* d_delta_dup = nullptr;  // (d | d << 16) per pixel, for the pair decode kernel
   bool has_delta = false;
   EncodeScratch scratch[kNumSlots + 1];
   Slot slots[kNumSlots];
@@ -157,8 +158,8 @@ int decode_device_impl(fpv_ctx* c, const uint8_t* high, const uint8_t* low, cons
   const bool unextract = (options & FPV_DEC_UNEXTRACT) != 0;
   int l = -1;
   if (!getenv("FPV_DECODE_SERIAL"))
-    l = enqueue_decode(c->g, c->tune.num_sms, high, low, flags, delta, n, unextract, out, stream, &e,
-                       next_hook(c));
+    l = enqueue_decode(c->g, c->tune.num_sms, high, low, flags, delta, c->d_delta_dup, n, unextract, out,
+                       stream, &e, next_hook(c));
   if (l < 0) {
     // rows too wide for the shared-memory row pipeline (or forced): serial chain
     uint8_t* scratch = const_cast<uint8_t*>(high);
@@ -236,6 +237,7 @@ int fpv_create(fpv_ctx** out, int device, uint32_t xsize, uint32_t ysize, int sh
   if (c->tune.band_rows < 4) c->tune.band_rows = 4;
   c->force_generic = getenv("FPV_FORCE_GENERIC") != nullptr;
   cudaError_t e2 = cudaMalloc(&c->d_delta, c->g.P * 2);
+  if (e2 == cudaSuccess) e2 = cudaMalloc(&c->d_delta_dup, c->g.P * 4);
   if (e2 == cudaSuccess) e2 = cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking);
   if (e2 != cudaSuccess) {
     int rc = cuda_fail(nullptr, e2, "fpv_create allocation");
@@ -271,6 +273,7 @@ void fpv_destroy(fpv_ctx* c) {
   }
   if (c->d_serial_scratch) cudaFree(c->d_serial_scratch);
   if (c->d_delta) cudaFree(c->d_delta);
+  if (c->d_delta_dup) cudaFree(c->d_delta_dup);
   if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
   delete c;
 }
@@ -321,6 +324,15 @@ void fpv_host_free(void* p) {
 
 // ---- delta frame ------------------------------------------------------------
 
+// Every way of setting the delta image also refreshes its duplicated form.
+static int refresh_delta_dup(fpv_ctx* c, cudaStream_t stream) {
+  cudaError_t e = cudaSuccess;
+  int l = enqueue_delta_dup(c->g, c->d_delta, c->d_delta_dup, stream, &e);
+  if (l < 0) return cuda_fail(c, e, "delta duplication kernel launch");
+  c->launches += (uint64_t)l;
+  return FPV_OK;
+}
+
 int fpv_set_delta_raw_device(fpv_ctx* c, const void* raw_dev, void* stream) {
   if (!c) return FPV_ERR_INVALID_ARG;
   FPV_CUDA(cudaSetDevice(c->device));
@@ -330,6 +342,8 @@ int fpv_set_delta_raw_device(fpv_ctx* c, const void* raw_dev, void* stream) {
                                  static_cast<cudaStream_t>(stream), &e);
   if (l < 0) return cuda_fail(c, e, "delta split kernel launch");
   c->launches += (uint64_t)l;
+  int rc = refresh_delta_dup(c, static_cast<cudaStream_t>(stream));
+  if (rc != FPV_OK) return rc;
   c->has_delta = true;
   return FPV_OK;
 }
@@ -356,6 +370,8 @@ int fpv_set_delta_image_device(fpv_ctx* c, const void* image_dev, void* stream) 
   if (!image_dev) { c->has_delta = false; return FPV_OK; }
   FPV_CUDA(cudaMemcpyAsync(c->d_delta, image_dev, c->g.P * 2, cudaMemcpyDeviceToDevice,
                            static_cast<cudaStream_t>(stream)));
+  int rc = refresh_delta_dup(c, static_cast<cudaStream_t>(stream));
+  if (rc != FPV_OK) return rc;
   c->has_delta = true;
   return FPV_OK;
 }
@@ -365,6 +381,9 @@ int fpv_set_delta_image(fpv_ctx* c, const uint16_t* image_host) {
   FPV_CUDA(cudaSetDevice(c->device));
   if (!image_host) { c->has_delta = false; return FPV_OK; }
   FPV_CUDA(cudaMemcpy(c->d_delta, image_host, c->g.P * 2, cudaMemcpyHostToDevice));
+  int rc = refresh_delta_dup(c, nullptr);
+  if (rc != FPV_OK) return rc;
+  FPV_CUDA(cudaStreamSynchronize(nullptr));
   c->has_delta = true;
   return FPV_OK;
 }
@@ -377,6 +396,8 @@ int fpv_copy_delta_peer(fpv_ctx* dst, const fpv_ctx* src) {
   FPV_CUDA(cudaSetDevice(dst->device));
   FPV_CUDA(cudaMemcpyPeerAsync(dst->d_delta, dst->device, src->d_delta, src->device, dst->g.P * 2,
                                dst->aux_stream));
+  int rc = refresh_delta_dup(dst, dst->aux_stream);
+  if (rc != FPV_OK) return rc;
   FPV_CUDA(cudaStreamSynchronize(dst->aux_stream));
   dst->has_delta = true;
   return FPV_OK;

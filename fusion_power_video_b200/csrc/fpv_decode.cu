@@ -21,8 +21,10 @@
 // ahead so that the chain never waits on HBM; the delta add, the high/low
 // recombination and UnextractFrame are fused into the row write-out.
 #include <stdlib.h>
+#include <string.h>
 
 #include "fpv_internal.h"
+#include "fpv_decode_pair.cuh"
 
 namespace fpv {
 
@@ -591,12 +593,72 @@ __global__ void k_planes_add_delta(uint8_t* high, uint8_t* low, const uint8_t* f
   }
 }
 
+// delta image -> (d | d << 16) per pixel: the form k_decode_pair adds to the same
+// column of two frames at once.
+__global__ void k_delta_dup(const uint16_t* delta, uint32_t* ddup, uint64_t P) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t d = delta[i];
+    ddup[i] = d | (d << 16);
+  }
+}
+
 }  // namespace
 
+int enqueue_delta_dup(const Geom& g, const uint16_t* delta_image, uint32_t* ddup, cudaStream_t stream,
+                      cudaError_t* err) {
+  unsigned gx = (unsigned)((g.P + 255) / 256);
+  if (gx > 1184) gx = 1184;
+  k_delta_dup<<<gx, 256, 0, stream>>>(delta_image, ddup, g.P);
+  *err = cudaGetLastError();
+  return *err == cudaSuccess ? 1 : -1;
+}
+
+// Which decode kernel handles a geometry; FPV_DECODE_KERNEL=pair|simd|spec forces one
+// (tests run every kernel on every case it supports).
+enum DecodeKernel { kDecPair, kDecSimd, kDecSpec };
+
+static DecodeKernel pick_decode_kernel(const Geom& g, const uint16_t* delta, const uint32_t* ddup) {
+  const bool pair_ok = g.W % 16 == 0 && g.W >= 64 && g.W <= 1280 && (delta == nullptr || ddup != nullptr);
+  const bool simd_ok = g.W % 4 == 0 && g.W <= 64 * 32 && g.W >= 64;
+  if (const char* v = getenv("FPV_DECODE_KERNEL")) {
+    if (!strcmp(v, "pair") && pair_ok) return kDecPair;
+    if (!strcmp(v, "simd") && simd_ok) return kDecSimd;
+    if (!strcmp(v, "spec")) return kDecSpec;
+  }
+  if (getenv("FPV_DECODE_SEGMENTED")) return kDecSpec;
+  if (pair_ok) return kDecPair;
+  if (simd_ok) return kDecSimd;
+  return kDecSpec;
+}
+
 int enqueue_decode(const Geom& g, int num_sms, const uint8_t* high, const uint8_t* low,
-                   const uint8_t* flags, const uint16_t* delta, uint32_t n, bool unextract,
-                   uint16_t* out, cudaStream_t stream, cudaError_t* err, const TimingHook* hook) {
-  if (g.W % 4 == 0 && g.W <= 64 * 32 && g.W >= 64 && !getenv("FPV_DECODE_SEGMENTED")) {
+                   const uint8_t* flags, const uint16_t* delta, const uint32_t* ddup, uint32_t n,
+                   bool unextract, uint16_t* out, cudaStream_t stream, cudaError_t* err,
+                   const TimingHook* hook) {
+  const DecodeKernel which = pick_decode_kernel(g, delta, ddup);
+  if (which == kDecPair) {
+    PairParams pp;
+    pp.high = high; pp.low = low; pp.flags = flags; pp.ddup = delta ? ddup : nullptr; pp.out = out;
+    pp.W = g.W; pp.H = g.H; pp.P = g.P; pp.shift = g.shift; pp.big_endian = g.big_endian;
+    pp.unextract = unextract ? 1 : 0; pp.n = n;
+    const int LW2 = (int)((g.W + 255) / 256);
+    const bool full = g.W == 256u * (uint32_t)LW2;
+    const int blocks = (int)((n + 1) / 2);
+    cudaError_t e = cudaSuccess;
+    if (hook) cudaEventRecord(hook->start, stream);
+    switch (LW2) {
+      case 1: e = launch_pair<1>(pp, full, blocks, stream); break;
+      case 2: e = launch_pair<2>(pp, full, blocks, stream); break;
+      case 3: e = launch_pair<3>(pp, full, blocks, stream); break;
+      case 4: e = launch_pair<4>(pp, full, blocks, stream); break;
+      default: e = launch_pair<5>(pp, full, blocks, stream); break;
+    }
+    if (hook) cudaEventRecord(hook->stop, stream);
+    *err = e;
+    return e == cudaSuccess ? 1 : -1;
+  }
+  if (which == kDecSimd) {
     // SIMD row kernel: smallest segment length L = 4 LW with 64 L >= W
     SimdParams sp;
     sp.high = high; sp.low = low; sp.flags = flags; sp.delta = delta; sp.out = out;

@@ -1,0 +1,416 @@
+// fpv_decode_pair.cuh -- the warp-specialised decode kernel (k_decode_pair).
+//
+// Same job as the rest of fpv_decode.cu: the post-brotli part of DecompressImage
+// (fusion_power_video.cc:326-344) fused with UnextractFrame (.cc:850-862).
+//
+// The inverse ClampedGradient (.cc:327-332) is a serial chain in flat pixel
+// order, so rows of a frame are processed strictly one after the other and the
+// only freedom is (a) frames are independent, (b) a row can be cut into
+// segments whose incoming west value is speculated and repaired (see the top of
+// fpv_decode.cu).  Measured on plasma-like frames a wrong incoming value heals
+// with a probability of only ~0.23 per pixel, so short segments pay a full
+// second pass; this kernel therefore uses
+//
+//   * ONE CTA PER PAIR OF FRAMES, three warps:
+//       warp 0      the chain warp.  Lane l owns the segment of L = 8*LW2 columns
+//                   [l*L, (l+1)*L) of BOTH frames: frame A in the low 16-bit lane
+//                   of a register, frame B in the high one ("pair form", byte
+//                   values in [0,255]).  One step for both frames is
+//                       x = (c + min3(n,w,nw) + max3(n,w,nw)) & 0x00ff00ff
+//                   with c = r + 256 - nw, because CG = n + w - median(n,w,nw)
+//                   = min3 + max3 - nw (.cc:247-252): 2 VIMNMX3.U16x2 + IADD3 +
+//                   LOP3.  32 segments per frame (instead of 64) are long enough
+//                   for a cheap look-ahead: pass 0 runs only the last K0 pixels
+//                   of every segment from a guess and hands the result to the
+//                   right neighbour as its incoming west value (right in ~99 %
+//                   of the segments), pass 1 runs every segment in full, and a
+//                   repair loop re-runs segments whose input turned out wrong
+//                   until nothing changes.  Lane 0's input is exact (last pixel
+//                   of the previous row: flat indexing, .cc:327-332), so by
+//                   induction over lanes the fixed point is the serial result.
+//       warps 1, 2  the IO warps.  They turn the residual bytes of row y+1 into
+//                   pair form for the chain warp, and turn the finished row y-1
+//                   into output pixels: delta add with independent byte wrap
+//                   (.cc:337-338), high/low recombination, UnextractFrame shift
+//                   and byte swap -- all on two pixels per register, the delta
+//                   image coming in a pre-duplicated form (d | d << 16) so that
+//                   one word serves the same column of both frames.
+//   * TMA both ways: rows are fetched with 1-D cp.async.bulk into 3-deep rings
+//     signalled by mbarriers (one elected thread issues), finished rows leave
+//     through a shared-memory row buffer and cp.async.bulk stores, so global
+//     traffic is fully coalesced and costs no LSU instructions.
+//   * one CTA barrier per row couples the two roles; pre/post buffers are
+//     double-buffered so the chain warp never waits for the IO warps' work of
+//     the same row.
+//
+// Algorithmic traffic 4 B/px (1 + 1 in, 2 out); the duplicated delta (4 B per
+// column for two frames) is L2-resident.
+#pragma once
+
+#include "fpv_internal.h"
+#include "fpv_ptx.cuh"
+
+namespace fpv {
+
+struct PairParams {
+  const uint8_t* high;
+  const uint8_t* low;      // may be nullptr
+  const uint8_t* flags;
+  const uint32_t* ddup;    // delta image, (d | d << 16) per pixel; may be nullptr
+  uint16_t* out;
+  uint32_t W, H;
+  uint64_t P;
+  int shift, big_endian, unextract;
+  uint32_t n;
+};
+
+constexpr int kPairThreads = 96;
+constexpr int kPairRing = 3;
+
+// Shared-memory plan (RB = 32 * L bytes = one padded byte row):
+//   R1   ring x { residual A | residual B }                      2 RB each
+//   R2   ring x { low A | low B | duplicated delta (4 B/col) }   6 RB each
+//   PRE  2 x pair-form residual row  (L words per chain lane)    4 RB each
+//   POST 2 x pair-form finished row                              4 RB each
+//   OUT  { output row A | output row B }  (uint16 pixels)        4 RB
+//   6 mbarriers
+static inline size_t pair_smem_bytes(int LW2) {
+  const size_t RB = 32 * 8 * (size_t)LW2;
+  return RB * (kPairRing * 2 + kPairRing * 6 + 8 + 8 + 4) + 2 * kPairRing * 8;
+}
+
+// (a & m) | (b & ~m) in one LOP3.
+__device__ __forceinline__ uint32_t bitselect(uint32_t a, uint32_t b, uint32_t m) {
+  uint32_t r;
+  asm("lop3.b32 %0, %1, %2, %3, 0xE4;" : "=r"(r) : "r"(a), "r"(b), "r"(m));
+  return r;
+}
+
+// One row of the chain warp: residual row (pair form, in PRE) -> finished row in x[] and in POST.
+// n[] is the finished previous row; the caller alternates two register arrays between rows so
+// that nothing is copied.
+template <int LW2, bool FULL>
+__device__ __forceinline__ void pair_chain_row(const uint32_t (&n)[8 * LW2], uint32_t (&x)[8 * LW2], const uint32_t y,
+                                               const uint32_t pre, const uint32_t post, const uint32_t cgmask,
+                                               const uint32_t vmask, const int lane, const uint32_t last_lane,
+                                               const uint32_t last_t, uint32_t& last_prev, uint32_t& last_prev2) {
+  constexpr int L = 8 * LW2;
+  constexpr int K0 = (L >= 24) ? 16 : L / 2;      // look-ahead pixels of pass 0
+  // word quad k of this lane sits at slot k*32 + lane (first half) / k*32 + (lane ^ 4) (second half)
+  const uint32_t a_lo = (uint32_t)lane * 16, a_hi = (uint32_t)(lane ^ 4) * 16;
+#pragma unroll
+  for (int k = 0; k < 2 * LW2; k++) {
+    const uint4 v = lds128(pre + k * 512 + (k < LW2 ? a_lo : a_hi));
+    x[4 * k + 0] = v.x; x[4 * k + 1] = v.y; x[4 * k + 2] = v.z; x[4 * k + 3] = v.w;
+  }
+  if (cgmask != 0 && y > 0) {
+    uint32_t c[L];
+    uint32_t nw_in = __shfl_up_sync(0xffffffffu, n[L - 1], 1);
+    if (lane == 0) nw_in = last_prev2;
+    // flat index W (row 1, column 0) is not predicted (.cc:327 starts at W+1)
+    const bool copy_first = (y == 1) && (lane == 0);
+    const uint32_t r_first = x[0];
+#pragma unroll
+    for (int t = 0; t < L; t++) c[t] = x[t] + kLaneBias - (t == 0 ? nw_in : n[t - 1]);
+
+    // pass 0: estimate this segment's last pixel from a guess K0 pixels back
+    uint32_t w_in;
+    {
+      uint32_t nw = n[L - K0 - 1], w = nw;          // the guess: west == north-west
+#pragma unroll
+      for (int t = L - K0; t < L; t++) {
+        const uint32_t nn = n[t];
+        w = (c[t] + __vimin3_u16x2(nn, w, nw) + __vimax3_u16x2(nn, w, nw)) & kLaneMask;
+        nw = nn;
+      }
+      w_in = __shfl_up_sync(0xffffffffu, w, 1);
+      if (lane == 0) w_in = last_prev;              // exact for segment 0
+    }
+    // pass 1: every segment in full
+    {
+      uint32_t w = w_in, nw = nw_in;
+#pragma unroll
+      for (int t = 0; t < L; t++) {
+        const uint32_t nn = n[t];
+        uint32_t v = (c[t] + __vimin3_u16x2(nn, w, nw) + __vimax3_u16x2(nn, w, nw)) & kLaneMask;
+        if (t == 0 && copy_first) v = r_first;
+        x[t] = v;
+        w = v;
+        nw = nn;
+      }
+    }
+    // repair: re-run segments whose incoming value was wrong until nothing changes
+    for (;;) {
+      uint32_t w_new = __shfl_up_sync(0xffffffffu, x[L - 1], 1);
+      if (lane == 0) w_new = last_prev;
+      const bool changed = ((w_new ^ w_in) & vmask) != 0;
+      if (!__any_sync(0xffffffffu, changed)) break;
+      w_in = w_new;
+      uint32_t w = w_in, nw = nw_in;
+#pragma unroll
+      for (int k = 0; k < 2 * LW2; k++) {
+        bool same = true;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const int t = 4 * k + j;
+          const uint32_t nn = n[t];
+          uint32_t v = (c[t] + __vimin3_u16x2(nn, w, nw) + __vimax3_u16x2(nn, w, nw)) & kLaneMask;
+          if (t == 0 && copy_first) v = r_first;
+          if (j == 3) same = ((v ^ x[t]) & vmask) == 0;
+          x[t] = v;
+          w = v;
+          nw = nn;
+        }
+        // every chain met its previous values: the rest of the segment is unchanged
+        if (k + 1 < 2 * LW2 && __all_sync(0xffffffffu, same)) break;
+      }
+    }
+    if (cgmask != 0xffffffffu) {
+      // one of the two frames is not ClampedGradient-predicted: its row is the residual row
+#pragma unroll
+      for (int k = 0; k < 2 * LW2; k++) {
+        const uint4 v = lds128(pre + k * 512 + (k < LW2 ? a_lo : a_hi));
+        x[4 * k + 0] = (x[4 * k + 0] & cgmask) | (v.x & ~cgmask);
+        x[4 * k + 1] = (x[4 * k + 1] & cgmask) | (v.y & ~cgmask);
+        x[4 * k + 2] = (x[4 * k + 2] & cgmask) | (v.z & ~cgmask);
+        x[4 * k + 3] = (x[4 * k + 3] & cgmask) | (v.w & ~cgmask);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 2 * LW2; k++)
+    sts128(post + k * 512 + (k < LW2 ? a_lo : a_hi), x[4 * k + 0], x[4 * k + 1], x[4 * k + 2], x[4 * k + 3]);
+  {
+    uint32_t v = x[L - 1];
+    if (!FULL) {
+#pragma unroll
+      for (int k = 0; k < 2 * LW2; k++)
+        if ((uint32_t)(4 * k + 3) == last_t) v = x[4 * k + 3];   // W % 4 == 0: the row ends a quad
+    }
+    last_prev2 = last_prev;
+    last_prev = __shfl_sync(0xffffffffu, v, (int)last_lane);
+  }
+  named_bar_sync(0, kPairThreads);
+}
+
+// LW2:   words (4 px) per IO thread and frame row; the chain lane's segment is L = 8 LW2 px.
+// FULL:  W == 32 L (every lane owns a complete segment).
+// SHIFT: UnextractFrame with a non-zero shift is fused into the write-out.
+template <int LW2, bool FULL, bool SHIFT>
+__global__ void __launch_bounds__(kPairThreads, 4) k_decode_pair(const PairParams p) {
+  extern __shared__ __align__(128) uint8_t psm[];
+  constexpr int L = 8 * LW2;
+  constexpr uint32_t RB = 32 * L;
+  constexpr uint32_t kR1 = 0, kR1Slot = 2 * RB;
+  constexpr uint32_t kR2 = kR1 + kPairRing * kR1Slot, kR2Slot = 6 * RB;
+  constexpr uint32_t kPre = kR2 + kPairRing * kR2Slot, kBuf = 4 * RB;
+  constexpr uint32_t kPost = kPre + 2 * kBuf;
+  constexpr uint32_t kOut = kPost + 2 * kBuf;
+  constexpr uint32_t kBars = kOut + 4 * RB;
+  const uint32_t sm0 = smem_u32(psm);
+  const uint32_t full1 = sm0 + kBars, full2 = full1 + 8 * kPairRing;
+  const uint32_t W = p.W, H = p.H;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  const uint32_t fA = 2 * blockIdx.x;
+  const uint32_t fB = fA + 1 < p.n ? fA + 1 : fA;   // odd tail: the pair is (A, A), B is not stored
+  const uint32_t flA = p.flags[fA], flB = p.flags[fB];
+  const bool lowA = !(flA & kFlagNoLow) && p.low != nullptr, lowB = !(flB & kFlagNoLow) && p.low != nullptr;
+  const bool delA = (flA & kFlagDelta) && p.ddup != nullptr, delB = (flB & kFlagDelta) && p.ddup != nullptr;
+  const uint32_t cgmask = ((flA & kFlagCG) ? 0x0000ffffu : 0u) | ((flB & kFlagCG) ? 0xffff0000u : 0u);
+
+  if (threadIdx.x == 32) {
+    for (int i = 0; i < 2 * kPairRing; i++) mbar_init(full1 + 8 * i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (lowA != lowB) {
+    // only one frame of the pair has a low plane: the other one's ring rows are never written
+    // by TMA and must read as zero
+    for (uint32_t i = threadIdx.x; i < kPairRing * RB / 4; i += kPairThreads) {
+      const uint32_t s = i / (RB / 4), o = i % (RB / 4);
+      sts32(sm0 + kR2 + s * kR2Slot + (lowA ? RB : 0u) + 4 * o, 0u);
+    }
+  }
+  __syncthreads();
+
+  if (warp == 0) {
+    // =============================== chain warp ===================================
+    const uint32_t col0 = (uint32_t)lane * L;
+    const bool lane_valid = FULL || col0 < W;
+    const uint32_t vmask = lane_valid ? cgmask : 0u;
+    const uint32_t last_lane = FULL ? 31u : (W - 1) / L, last_t = FULL ? (uint32_t)(L - 1) : (W - 1) % L;
+    uint32_t ra[L], rb[L];                    // finished rows, alternating roles
+#pragma unroll
+    for (int t = 0; t < L; t++) rb[t] = 0;
+    uint32_t last_prev = 0, last_prev2 = 0;   // h[y-1][W-1], h[y-2][W-1] of both frames
+
+    named_bar_sync(0, kPairThreads);          // row 0 is in PRE[0] (the IO warps' prologue)
+    for (uint32_t y = 0; y < H; y += 2) {
+      pair_chain_row<LW2, FULL>(rb, ra, y, sm0 + kPre, sm0 + kPost, cgmask, vmask, lane, last_lane, last_t,
+                                last_prev, last_prev2);
+      if (y + 1 < H)
+        pair_chain_row<LW2, FULL>(ra, rb, y + 1, sm0 + kPre + kBuf, sm0 + kPost + kBuf, cgmask, vmask, lane,
+                                  last_lane, last_t, last_prev, last_prev2);
+    }
+    return;
+  }
+
+  // ================================= IO warps =====================================
+  const uint32_t i = threadIdx.x - 32;              // 0..63: columns [4 LW2 i, 4 LW2 (i+1))
+  const bool elected = i == 0;
+  const uint32_t wo = i * LW2;                      // first word (4 px) of this thread in a byte row
+  const uint32_t slot0 = ((i & 1u) * LW2 * 32 + ((i & 1u) ? ((i >> 1) ^ 4u) : (i >> 1))) * 16;
+  const bool do_swap = p.unextract && p.big_endian;
+  const uint32_t shmul = 1u << ((32 - p.shift) & 31), um = (0xffffu >> (p.shift & 31)) * 0x00010001u;
+  // output words: two consecutive pixels of one frame out of two pair-form registers; the
+  // UnextractFrame byte swap (.cc:857-860) is folded into the selector
+  const uint32_t selA = do_swap ? 0x4501u : 0x5410u, selB = do_swap ? 0x6723u : 0x7632u;
+  const bool any_low = lowA || lowB;
+  const uint32_t dmask = (delA ? 0x0000ffffu : 0u) | (delB ? 0xffff0000u : 0u);
+  const uint32_t mh = kHiBytes & dmask, ml = kLoBytes & dmask;
+  const uint32_t r2_bytes = (lowA ? W : 0u) + (lowB ? W : 0u) + (dmask ? 4 * W : 0u);
+
+  // ---- TMA issue state (elected thread): running source pointers and ring slots ------------
+  const uint8_t* s1A = p.high + (uint64_t)fA * p.P;   // next residual row to fetch
+  const uint8_t* s1B = p.high + (uint64_t)fB * p.P;
+  const uint8_t* s2A = lowA ? p.low + (uint64_t)fA * p.P : nullptr;
+  const uint8_t* s2B = lowB ? p.low + (uint64_t)fB * p.P : nullptr;
+  const uint32_t* s2D = p.ddup;
+  uint32_t i1_row = 0, i1_slot = 0, i2_row = 0, i2_slot = 0;
+  auto issue_r1 = [&]() {     // residual rows of both frames
+    if (i1_row < H) {
+      const uint32_t dst = sm0 + kR1 + i1_slot * kR1Slot, bar = full1 + 8 * i1_slot;
+      mbar_arrive_expect_tx(bar, 2 * W);
+      bulk_g2s(dst, s1A, W, bar);
+      bulk_g2s(dst + RB, s1B, W, bar);
+      s1A += W; s1B += W;
+    }
+    i1_row++;
+    if (++i1_slot == kPairRing) i1_slot = 0;
+  };
+  auto issue_r2 = [&]() {     // low rows and the duplicated delta row
+    if (i2_row < H && r2_bytes) {
+      const uint32_t dst = sm0 + kR2 + i2_slot * kR2Slot, bar = full2 + 8 * i2_slot;
+      mbar_arrive_expect_tx(bar, r2_bytes);
+      if (lowA) { bulk_g2s(dst, s2A, W, bar); s2A += W; }
+      if (lowB) { bulk_g2s(dst + RB, s2B, W, bar); s2B += W; }
+      if (dmask) { bulk_g2s(dst + 2 * RB, s2D, 4 * W, bar); s2D += W; }
+    }
+    i2_row++;
+    if (++i2_slot == kPairRing) i2_slot = 0;
+  };
+
+  // ---- consumer state: ring slot and mbarrier parity of the next row of each kind ------------
+  uint32_t c1_slot = 0, c1_par = 0, c2_slot = 0, c2_par = 0;
+  uint16_t* oA = p.out + (uint64_t)fA * p.P;        // next output row (elected thread)
+  uint16_t* oB = p.out + (uint64_t)fB * p.P;
+
+  // residual bytes of the next row -> pair form for the chain warp, into PRE[buf]
+  auto pre_row = [&](uint32_t buf) {
+    mbar_wait(full1 + 8 * c1_slot, c1_par);
+    const uint32_t ra = sm0 + kR1 + c1_slot * kR1Slot + wo * 4, dst = sm0 + kPre + buf * kBuf + slot0;
+    if (++c1_slot == kPairRing) { c1_slot = 0; c1_par ^= 1u; }
+    uint32_t A[LW2], B[LW2];
+#pragma unroll
+    for (int kk = 0; kk < LW2; kk++) { A[kk] = lds32(ra + 4 * kk); B[kk] = lds32(ra + RB + 4 * kk); }
+#pragma unroll
+    for (int kk = 0; kk < LW2; kk++) {
+      const uint32_t t = B[kk] << 16, u = B[kk] >> 16;
+      sts128(dst + kk * 512, __byte_perm(A[kk], t, 0x4640), __byte_perm(A[kk], t, 0x4741),
+             __byte_perm(A[kk], u, 0x6462), __byte_perm(A[kk], u, 0x6563));
+    }
+  };
+  // finished row in POST[buf] -> output pixels (.cc:335-344 and .cc:850-862), then one bulk store per frame
+  auto post_row = [&](uint32_t buf) {
+    if (r2_bytes) mbar_wait(full2 + 8 * c2_slot, c2_par);
+    const uint32_t src = sm0 + kPost + buf * kBuf + slot0;
+    const uint32_t la = sm0 + kR2 + c2_slot * kR2Slot + wo * 4, da = la + 2 * RB + wo * 12;
+    if (++c2_slot == kPairRing) { c2_slot = 0; c2_par ^= 1u; }
+    const uint32_t oa = sm0 + kOut + wo * 8;
+    uint4 X[LW2], D[LW2];
+    uint32_t A[LW2], B[LW2];
+#pragma unroll
+    for (int kk = 0; kk < LW2; kk++) X[kk] = lds128(src + kk * 512);
+    if (any_low) {
+#pragma unroll
+      for (int kk = 0; kk < LW2; kk++) { A[kk] = lds32(la + 4 * kk); B[kk] = lds32(la + RB + 4 * kk); }
+    }
+    if (dmask) {
+#pragma unroll
+      for (int kk = 0; kk < LW2; kk++) D[kk] = lds128(da + kk * 16);
+    } else {
+#pragma unroll
+      for (int kk = 0; kk < LW2; kk++) D[kk] = make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int kk = 0; kk < LW2; kk++) {
+      uint32_t Z[4] = {0, 0, 0, 0};
+      if (any_low) {
+        const uint32_t t = B[kk] << 16, u = B[kk] >> 16;
+        Z[0] = __byte_perm(A[kk], t, 0x4640); Z[1] = __byte_perm(A[kk], t, 0x4741);
+        Z[2] = __byte_perm(A[kk], u, 0x6462); Z[3] = __byte_perm(A[kk], u, 0x6563);
+      }
+      const uint32_t Xs[4] = {X[kk].x, X[kk].y, X[kk].z, X[kk].w}, Ds[4] = {D[kk].x, D[kk].y, D[kk].z, D[kk].w};
+      uint32_t V[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        // per 16-bit lane: ((x + dh) & 0xff) << 8 | ((l + dl) & 0xff).  The delta's high and low
+        // bytes are added separately so that a carry out of one byte only ever lands in a bit the
+        // final select drops (.cc:337-338: the bytes wrap independently); mh / ml also switch the
+        // delta off for a frame of the pair that does not use it.
+        const uint32_t hi = Xs[j] * 256u + (Ds[j] & mh), lo = Z[j] + (Ds[j] & ml);
+        V[j] = bitselect(hi, lo, kHiBytes);
+        if (SHIFT) V[j] = __umulhi(V[j], shmul) & um;     // per lane: (pixel >> shift), .cc:855
+      }
+      sts64(oa + kk * 8, __byte_perm(V[0], V[1], selA), __byte_perm(V[2], V[3], selA));            // frame A: px 0 1 | 2 3
+      sts64(oa + 2 * RB + kk * 8, __byte_perm(V[0], V[1], selB), __byte_perm(V[2], V[3], selB));   // frame B
+    }
+    fence_proxy_async();
+    named_bar_sync(1, 64);
+    if (elected) {
+      bulk_s2g(oA, sm0 + kOut, 2 * W);
+      if (fB != fA) bulk_s2g(oB, sm0 + kOut + 2 * RB, 2 * W);
+      bulk_commit();
+      oA += W; oB += W;
+    }
+  };
+
+  if (elected) {
+    issue_r1(); issue_r1(); issue_r1();
+    issue_r2();
+  }
+  pre_row(0);
+  named_bar_sync(0, kPairThreads);
+  for (uint32_t y = 0; y < H; y++) {
+    if (elected) {
+      issue_r1();        // row y + 3 into slot y % 3: its row y was consumed in iteration y - 1
+      issue_r2();        // row y + 1 into slot (y + 1) % 3: its row y - 2 was consumed in iteration y - 1
+    }
+    if (y >= 1) post_row((y - 1) & 1u);
+    if (y + 1 < H) pre_row((y + 1) & 1u);
+    if (elected) bulk_wait_read0();   // the output row buffer may be rewritten after the barrier
+    named_bar_sync(0, kPairThreads);
+  }
+  post_row((H - 1) & 1u);
+  if (elected) bulk_wait0();
+}
+
+template <int LW2>
+static cudaError_t launch_pair(const PairParams& p, bool full, int blocks, cudaStream_t stream) {
+  const size_t smem = pair_smem_bytes(LW2);
+  const bool shift = p.unextract && p.shift != 0;
+  cudaError_t e = cudaSuccess;
+#define FPV_LAUNCH_PAIR(F, S)                                                                                     \
+  do {                                                                                                            \
+    e = cudaFuncSetAttribute(k_decode_pair<LW2, F, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
+    if (e == cudaSuccess) k_decode_pair<LW2, F, S><<<blocks, kPairThreads, smem, stream>>>(p);                    \
+  } while (0)
+  if (full && shift) FPV_LAUNCH_PAIR(true, true);
+  else if (full) FPV_LAUNCH_PAIR(true, false);
+  else if (shift) FPV_LAUNCH_PAIR(false, true);
+  else FPV_LAUNCH_PAIR(false, false);
+#undef FPV_LAUNCH_PAIR
+  return e == cudaSuccess ? cudaGetLastError() : e;
+}
+
+}  // namespace fpv

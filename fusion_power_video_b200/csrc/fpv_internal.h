@@ -61,10 +61,16 @@ int enqueue_delta_from_raw(const Geom& g, const uint16_t* raw, uint16_t* delta_i
 
 // Inverse transform for n frames (any n).  out: uint16[n][P] images, or raw
 // file bytes when `unextract`.
+// `ddup` is the delta image in duplicated form ((d | d << 16) per pixel, see
+// enqueue_delta_dup); without it the pair kernel is not used for delta streams.
 int enqueue_decode(const Geom& g, int num_sms, const uint8_t* high, const uint8_t* low,
-                   const uint8_t* flags, const uint16_t* delta, uint32_t n, bool unextract,
-                   uint16_t* out, cudaStream_t stream, cudaError_t* err,
+                   const uint8_t* flags, const uint16_t* delta, const uint32_t* ddup, uint32_t n,
+                   bool unextract, uint16_t* out, cudaStream_t stream, cudaError_t* err,
                    const TimingHook* hook = nullptr);
+
+// delta image -> uint32[P] duplicated form for the pair decode kernel.
+int enqueue_delta_dup(const Geom& g, const uint16_t* delta_image, uint32_t* ddup, cudaStream_t stream,
+                      cudaError_t* err);
 
 // Serial fallback (one thread per frame runs the chain literally); used for
 // rows too wide for the shared-memory row pipeline and as a cross-check.

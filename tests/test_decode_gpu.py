@@ -64,10 +64,13 @@ def test_arbitrary_geometry_random_planes(oracle, W, H):
             assert np.array_equal(raw[i].view(np.uint8), oracle.unextract(exp, 3, 0))
 
 
+@pytest.mark.parametrize("kernel", ["default", "simd"])
 @pytest.mark.parametrize("kind", ["random", "smooth", "sparse", "sawtooth"])
 @pytest.mark.parametrize("W,H", [(1280, 40), (1024, 64), (2048, 16), (4096, 8)])
-def test_speculation_adversarial(oracle, W, H, kind):
+def test_speculation_adversarial(oracle, W, H, kind, kernel, monkeypatch):
     """Residual planes chosen to make the incoming-west guess wrong as often as possible."""
+    if kernel != "default":
+        monkeypatch.setenv("FPV_DECODE_KERNEL", kernel)
     rng = np.random.default_rng(7)
     n = 3
     if kind == "random":
@@ -86,6 +89,48 @@ def test_speculation_adversarial(oracle, W, H, kind):
         for i in range(n):
             exp = oracle.inverse(high[i], None, None, W, H, 6)
             assert np.array_equal(img[i], exp), f"frame {i}: first diff at {np.flatnonzero(img[i] != exp)[:8]}"
+
+
+PAIR_GEOMS = [(64, 5), (80, 7), (128, 3), (256, 9), (320, 6), (512, 4), (768, 5), (1024, 6), (1040, 3),
+              (1280, 1), (1280, 2), (1280, 9)]
+
+
+@pytest.mark.parametrize("kernel", ["pair", "simd", "spec"])
+@pytest.mark.parametrize("W,H", PAIR_GEOMS)
+def test_every_kernel_mixed_flags(oracle, W, H, kernel, monkeypatch):
+    """All three row kernels on the same planes; neighbouring frames differ in every flag, so the
+    pair kernel sees frame pairs that mix delta / ClampedGradient / low-plane use, and an odd tail."""
+    monkeypatch.setenv("FPV_DECODE_KERNEL", kernel)
+    rng = np.random.default_rng(W * 31 + H)
+    flags = np.array([3, 1, 2, 0, 7, 3, 5, 2, 6, 4, 3], np.uint8)
+    n = len(flags)
+    high = rng.integers(0, 256, (n, W * H), dtype=np.uint8)
+    img = synth.plasma_frames(n, W, H, bits=16, seed=W + H).reshape(n, -1)
+    for i in range(0, n, 3):  # realistic residuals (long healing distances) next to white noise
+        high[i] = oracle.cg_forward((img[i] >> 8).astype(np.uint8), W)
+    low = rng.integers(0, 256, (n, W * H), dtype=np.uint8)
+    delta = rng.integers(0, 65536, W * H, dtype=np.uint16)
+    delta[: W * H // 2] |= 0x80FF  # carries out of both bytes of the delta add
+    for shift, be in ((4, 0), (0, 1)):
+        with fpv.Context(W, H, shift, be, max_batch=16) as ctx:
+            ctx.set_delta_image(delta)
+            out = ctx.decode(high, low, flags)
+            raw = ctx.decode(high, low, flags, fpv.DEC_UNEXTRACT)
+            for i in range(n):
+                exp = oracle.inverse(high[i], None if flags[i] & 4 else low[i], delta, W, H, int(flags[i]))
+                assert np.array_equal(out[i], exp), f"frame {i} flags {flags[i]}: first diff at {np.flatnonzero(out[i] != exp)[:8]}"
+                assert np.array_equal(raw[i].view(np.uint8), oracle.unextract(exp, shift, be)), f"unextract, frame {i}"
+
+
+def test_pair_kernel_without_delta_and_low(oracle, monkeypatch):
+    monkeypatch.setenv("FPV_DECODE_KERNEL", "pair")
+    W, H, n = 1280, 24, 5
+    img = synth.plasma_frames(n, W, H, bits=8, seed=77).reshape(n, -1)
+    high = np.stack([oracle.cg_forward(f.astype(np.uint8), W) for f in img])
+    flags = np.full(n, 2 | 4, np.uint8)
+    with fpv.Context(W, H, 8, 0, max_batch=8) as ctx:
+        out = ctx.decode(high, None, flags, fpv.DEC_UNEXTRACT)
+        assert np.array_equal(out.reshape(n, -1), img)
 
 
 def test_big_endian_unextract(oracle):
