@@ -47,6 +47,9 @@
 // column for two frames) is L2-resident.
 #pragma once
 
+#include <stdio.h>
+#include <stdlib.h>
+
 #include "fpv_internal.h"
 #include "fpv_ptx.cuh"
 
@@ -64,6 +67,9 @@ struct PairParams {
   uint32_t n;
 };
 
+#ifndef FPV_PAIR_K0
+#define FPV_PAIR_K0 24
+#endif
 constexpr int kPairThreads = 96;
 constexpr int kPairRing = 3;
 
@@ -89,13 +95,13 @@ __device__ __forceinline__ uint32_t bitselect(uint32_t a, uint32_t b, uint32_t m
 // One row of the chain warp: residual row (pair form, in PRE) -> finished row in x[] and in POST.
 // n[] is the finished previous row; the caller alternates two register arrays between rows so
 // that nothing is copied.
-template <int LW2, bool FULL>
+template <int LW2, bool FULL, int K0T, int G>
 __device__ __forceinline__ void pair_chain_row(const uint32_t (&n)[8 * LW2], uint32_t (&x)[8 * LW2], const uint32_t y,
                                                const uint32_t pre, const uint32_t post, const uint32_t cgmask,
                                                const uint32_t vmask, const int lane, const uint32_t last_lane,
                                                const uint32_t last_t, uint32_t& last_prev, uint32_t& last_prev2) {
   constexpr int L = 8 * LW2;
-  constexpr int K0 = (L >= 24) ? 16 : L / 2;      // look-ahead pixels of pass 0
+  constexpr int K0 = K0T < L ? K0T : L / 2;   // look-ahead pixels of pass 0
   // word quad k of this lane sits at slot k*32 + lane (first half) / k*32 + (lane ^ 4) (second half)
   const uint32_t a_lo = (uint32_t)lane * 16, a_hi = (uint32_t)(lane ^ 4) * 16;
 #pragma unroll
@@ -148,21 +154,21 @@ __device__ __forceinline__ void pair_chain_row(const uint32_t (&n)[8 * LW2], uin
       w_in = w_new;
       uint32_t w = w_in, nw = nw_in;
 #pragma unroll
-      for (int k = 0; k < 2 * LW2; k++) {
+      for (int k = 0; k < L / G; k++) {
         bool same = true;
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const int t = 4 * k + j;
+        for (int j = 0; j < G; j++) {
+          const int t = G * k + j;
           const uint32_t nn = n[t];
           uint32_t v = (c[t] + __vimin3_u16x2(nn, w, nw) + __vimax3_u16x2(nn, w, nw)) & kLaneMask;
           if (t == 0 && copy_first) v = r_first;
-          if (j == 3) same = ((v ^ x[t]) & vmask) == 0;
+          if (j == G - 1) same = ((v ^ x[t]) & vmask) == 0;
           x[t] = v;
           w = v;
           nw = nn;
         }
         // every chain met its previous values: the rest of the segment is unchanged
-        if (k + 1 < 2 * LW2 && __all_sync(0xffffffffu, same)) break;
+        if (k + 1 < L / G && __all_sync(0xffffffffu, same)) break;
       }
     }
     if (cgmask != 0xffffffffu) {
@@ -196,7 +202,7 @@ __device__ __forceinline__ void pair_chain_row(const uint32_t (&n)[8 * LW2], uin
 // LW2:   words (4 px) per IO thread and frame row; the chain lane's segment is L = 8 LW2 px.
 // FULL:  W == 32 L (every lane owns a complete segment).
 // SHIFT: UnextractFrame with a non-zero shift is fused into the write-out.
-template <int LW2, bool FULL, bool SHIFT>
+template <int LW2, bool FULL, bool SHIFT, int K0T = FPV_PAIR_K0, int G = 4>
 __global__ void __launch_bounds__(kPairThreads, 4) k_decode_pair(const PairParams p) {
   extern __shared__ __align__(128) uint8_t psm[];
   constexpr int L = 8 * LW2;
@@ -246,10 +252,10 @@ __global__ void __launch_bounds__(kPairThreads, 4) k_decode_pair(const PairParam
 
     named_bar_sync(0, kPairThreads);          // row 0 is in PRE[0] (the IO warps' prologue)
     for (uint32_t y = 0; y < H; y += 2) {
-      pair_chain_row<LW2, FULL>(rb, ra, y, sm0 + kPre, sm0 + kPost, cgmask, vmask, lane, last_lane, last_t,
+      pair_chain_row<LW2, FULL, K0T, G>(rb, ra, y, sm0 + kPre, sm0 + kPost, cgmask, vmask, lane, last_lane, last_t,
                                 last_prev, last_prev2);
       if (y + 1 < H)
-        pair_chain_row<LW2, FULL>(ra, rb, y + 1, sm0 + kPre + kBuf, sm0 + kPost + kBuf, cgmask, vmask, lane,
+        pair_chain_row<LW2, FULL, K0T, G>(ra, rb, y + 1, sm0 + kPre + kBuf, sm0 + kPost + kBuf, cgmask, vmask, lane,
                                   last_lane, last_t, last_prev, last_prev2);
     }
     return;
@@ -270,39 +276,41 @@ __global__ void __launch_bounds__(kPairThreads, 4) k_decode_pair(const PairParam
   const uint32_t mh = kHiBytes & dmask, ml = kLoBytes & dmask;
   const uint32_t r2_bytes = (lowA ? W : 0u) + (lowB ? W : 0u) + (dmask ? 4 * W : 0u);
 
-  // ---- TMA issue state (elected thread): running source pointers and ring slots ------------
+  // ---- TMA issue state.  Every IO thread keeps it (it is warp-uniform, which lets the compiler
+  //      hold it in uniform registers); only the elected thread executes the copy instructions.
   const uint8_t* s1A = p.high + (uint64_t)fA * p.P;   // next residual row to fetch
   const uint8_t* s1B = p.high + (uint64_t)fB * p.P;
-  const uint8_t* s2A = lowA ? p.low + (uint64_t)fA * p.P : nullptr;
-  const uint8_t* s2B = lowB ? p.low + (uint64_t)fB * p.P : nullptr;
+  const uint8_t* s2A = p.low + (uint64_t)fA * p.P;    // next low row (dereferenced only if lowA / lowB)
+  const uint8_t* s2B = p.low + (uint64_t)fB * p.P;
   const uint32_t* s2D = p.ddup;
   uint32_t i1_row = 0, i1_slot = 0, i2_row = 0, i2_slot = 0;
   auto issue_r1 = [&]() {     // residual rows of both frames
-    if (i1_row < H) {
+    if (i1_row < H && elected) {
       const uint32_t dst = sm0 + kR1 + i1_slot * kR1Slot, bar = full1 + 8 * i1_slot;
       mbar_arrive_expect_tx(bar, 2 * W);
       bulk_g2s(dst, s1A, W, bar);
       bulk_g2s(dst + RB, s1B, W, bar);
-      s1A += W; s1B += W;
     }
+    s1A += W; s1B += W;
     i1_row++;
     if (++i1_slot == kPairRing) i1_slot = 0;
   };
   auto issue_r2 = [&]() {     // low rows and the duplicated delta row
-    if (i2_row < H && r2_bytes) {
+    if (i2_row < H && r2_bytes && elected) {
       const uint32_t dst = sm0 + kR2 + i2_slot * kR2Slot, bar = full2 + 8 * i2_slot;
       mbar_arrive_expect_tx(bar, r2_bytes);
-      if (lowA) { bulk_g2s(dst, s2A, W, bar); s2A += W; }
-      if (lowB) { bulk_g2s(dst + RB, s2B, W, bar); s2B += W; }
-      if (dmask) { bulk_g2s(dst + 2 * RB, s2D, 4 * W, bar); s2D += W; }
+      if (lowA) bulk_g2s(dst, s2A, W, bar);
+      if (lowB) bulk_g2s(dst + RB, s2B, W, bar);
+      if (dmask) bulk_g2s(dst + 2 * RB, s2D, 4 * W, bar);
     }
+    s2A += W; s2B += W; s2D += W;
     i2_row++;
     if (++i2_slot == kPairRing) i2_slot = 0;
   };
 
   // ---- consumer state: ring slot and mbarrier parity of the next row of each kind ------------
   uint32_t c1_slot = 0, c1_par = 0, c2_slot = 0, c2_par = 0;
-  uint16_t* oA = p.out + (uint64_t)fA * p.P;        // next output row (elected thread)
+  uint16_t* oA = p.out + (uint64_t)fA * p.P;        // next output row
   uint16_t* oB = p.out + (uint64_t)fB * p.P;
 
   // residual bytes of the next row -> pair form for the chain warp, into PRE[buf]
@@ -371,21 +379,17 @@ __global__ void __launch_bounds__(kPairThreads, 4) k_decode_pair(const PairParam
       bulk_s2g(oA, sm0 + kOut, 2 * W);
       if (fB != fA) bulk_s2g(oB, sm0 + kOut + 2 * RB, 2 * W);
       bulk_commit();
-      oA += W; oB += W;
     }
+    oA += W; oB += W;
   };
 
-  if (elected) {
-    issue_r1(); issue_r1(); issue_r1();
-    issue_r2();
-  }
+  issue_r1(); issue_r1(); issue_r1();
+  issue_r2();
   pre_row(0);
   named_bar_sync(0, kPairThreads);
   for (uint32_t y = 0; y < H; y++) {
-    if (elected) {
-      issue_r1();        // row y + 3 into slot y % 3: its row y was consumed in iteration y - 1
-      issue_r2();        // row y + 1 into slot (y + 1) % 3: its row y - 2 was consumed in iteration y - 1
-    }
+    issue_r1();          // row y + 3 into slot y % 3: its row y was consumed in iteration y - 1
+    issue_r2();          // row y + 1 into slot (y + 1) % 3: its row y - 2 was consumed in iteration y - 1
     if (y >= 1) post_row((y - 1) & 1u);
     if (y + 1 < H) pre_row((y + 1) & 1u);
     if (elected) bulk_wait_read0();   // the output row buffer may be rewritten after the barrier
@@ -405,7 +409,25 @@ static cudaError_t launch_pair(const PairParams& p, bool full, int blocks, cudaS
     e = cudaFuncSetAttribute(k_decode_pair<LW2, F, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
     if (e == cudaSuccess) k_decode_pair<LW2, F, S><<<blocks, kPairThreads, smem, stream>>>(p);                    \
   } while (0)
-  if (full && shift) FPV_LAUNCH_PAIR(true, true);
+  if (LW2 == 5 && full && shift && getenv("FPV_PAIR_TUNE")) {
+    // tuning builds only: "K0,G"
+    int k0 = 16, g = 4;
+    sscanf(getenv("FPV_PAIR_TUNE"), "%d,%d", &k0, &g);
+#define FPV_LAUNCH_TUNE(K, GG)                                                                                        \
+  do {                                                                                                                \
+    e = cudaFuncSetAttribute(k_decode_pair<5, true, true, K, GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    if (e == cudaSuccess) k_decode_pair<5, true, true, K, GG><<<blocks, kPairThreads, smem, stream>>>(p);             \
+  } while (0)
+    if (k0 == 8 && g == 4) FPV_LAUNCH_TUNE(8, 4);
+    else if (k0 == 8 && g == 8) FPV_LAUNCH_TUNE(8, 8);
+    else if (k0 == 16 && g == 4) FPV_LAUNCH_TUNE(16, 4);
+    else if (k0 == 16 && g == 8) FPV_LAUNCH_TUNE(16, 8);
+    else if (k0 == 24 && g == 8) FPV_LAUNCH_TUNE(24, 8);
+    else if (k0 == 12 && g == 4) FPV_LAUNCH_TUNE(12, 4);
+    else if (k0 == 20 && g == 4) FPV_LAUNCH_TUNE(20, 4);
+    else FPV_LAUNCH_TUNE(24, 4);
+#undef FPV_LAUNCH_TUNE
+  } else if (full && shift) FPV_LAUNCH_PAIR(true, true);
   else if (full) FPV_LAUNCH_PAIR(true, false);
   else if (shift) FPV_LAUNCH_PAIR(false, true);
   else FPV_LAUNCH_PAIR(false, false);
