@@ -47,9 +47,6 @@
 // column for two frames) is L2-resident.
 #pragma once
 
-#include <stdio.h>
-#include <stdlib.h>
-
 #include "fpv_internal.h"
 #include "fpv_ptx.cuh"
 
@@ -68,7 +65,7 @@ struct PairParams {
 };
 
 #ifndef FPV_PAIR_K0
-#define FPV_PAIR_K0 24
+#define FPV_PAIR_K0 16
 #endif
 constexpr int kPairThreads = 96;
 constexpr int kPairRing = 3;
@@ -202,7 +199,7 @@ __device__ __forceinline__ void pair_chain_row(const uint32_t (&n)[8 * LW2], uin
 // LW2:   words (4 px) per IO thread and frame row; the chain lane's segment is L = 8 LW2 px.
 // FULL:  W == 32 L (every lane owns a complete segment).
 // SHIFT: UnextractFrame with a non-zero shift is fused into the write-out.
-template <int LW2, bool FULL, bool SHIFT, int K0T = FPV_PAIR_K0, int G = 4>
+template <int LW2, bool FULL, bool SHIFT, int K0T = FPV_PAIR_K0, int G = 8>
 __global__ void __launch_bounds__(kPairThreads, 4) k_decode_pair(const PairParams p) {
   extern __shared__ __align__(128) uint8_t psm[];
   constexpr int L = 8 * LW2;
@@ -409,25 +406,7 @@ static cudaError_t launch_pair(const PairParams& p, bool full, int blocks, cudaS
     e = cudaFuncSetAttribute(k_decode_pair<LW2, F, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
     if (e == cudaSuccess) k_decode_pair<LW2, F, S><<<blocks, kPairThreads, smem, stream>>>(p);                    \
   } while (0)
-  if (LW2 == 5 && full && shift && getenv("FPV_PAIR_TUNE")) {
-    // tuning builds only: "K0,G"
-    int k0 = 16, g = 4;
-    sscanf(getenv("FPV_PAIR_TUNE"), "%d,%d", &k0, &g);
-#define FPV_LAUNCH_TUNE(K, GG)                                                                                        \
-  do {                                                                                                                \
-    e = cudaFuncSetAttribute(k_decode_pair<5, true, true, K, GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    if (e == cudaSuccess) k_decode_pair<5, true, true, K, GG><<<blocks, kPairThreads, smem, stream>>>(p);             \
-  } while (0)
-    if (k0 == 8 && g == 4) FPV_LAUNCH_TUNE(8, 4);
-    else if (k0 == 8 && g == 8) FPV_LAUNCH_TUNE(8, 8);
-    else if (k0 == 16 && g == 4) FPV_LAUNCH_TUNE(16, 4);
-    else if (k0 == 16 && g == 8) FPV_LAUNCH_TUNE(16, 8);
-    else if (k0 == 24 && g == 8) FPV_LAUNCH_TUNE(24, 8);
-    else if (k0 == 12 && g == 4) FPV_LAUNCH_TUNE(12, 4);
-    else if (k0 == 20 && g == 4) FPV_LAUNCH_TUNE(20, 4);
-    else FPV_LAUNCH_TUNE(24, 4);
-#undef FPV_LAUNCH_TUNE
-  } else if (full && shift) FPV_LAUNCH_PAIR(true, true);
+  if (full && shift) FPV_LAUNCH_PAIR(true, true);
   else if (full) FPV_LAUNCH_PAIR(true, false);
   else if (shift) FPV_LAUNCH_PAIR(false, true);
   else FPV_LAUNCH_PAIR(false, false);
