@@ -644,7 +644,7 @@ int enqueue_decode(const Geom& g, int num_sms, const uint8_t* high, const uint8_
     pp.unextract = unextract ? 1 : 0; pp.n = n;
     const int LW2 = (int)((g.W + 255) / 256);
     const bool full = g.W == 256u * (uint32_t)LW2;
-    const int blocks = (int)((n + 1) / 2);
+    const int blocks = (int)((n + 3) / 4);   // two pairs of frames per CTA
     cudaError_t e = cudaSuccess;
     if (hook) cudaEventRecord(hook->start, stream);
     switch (LW2) {

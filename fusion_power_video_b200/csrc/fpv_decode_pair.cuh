@@ -11,8 +11,8 @@
 // with a probability of only ~0.23 per pixel, so short segments pay a full
 // second pass; this kernel therefore uses
 //
-//   * ONE CTA PER PAIR OF FRAMES, three warps:
-//       warp 0      the chain warp.  Lane l owns the segment of L = 8*LW2 columns
+//   * TWO PAIRS OF FRAMES PER CTA, four warps; per pair:
+//       chain warp  Lane l owns  Lane l owns the segment of L = 8*LW2 columns
 //                   [l*L, (l+1)*L) of BOTH frames: frame A in the low 16-bit lane
 //                   of a register, frame B in the high one ("pair form", byte
 //                   values in [0,255]).  One step for both frames is
@@ -67,7 +67,7 @@ struct PairParams {
 #ifndef FPV_PAIR_K0
 #define FPV_PAIR_K0 16
 #endif
-constexpr int kPairThreads = 96;
+constexpr int kPairThreads = 192;   // per CTA: two pairs of frames x (chain, IO, helper) warps
 constexpr int kPairRing = 3;
 
 // Shared-memory plan (RB = 32 * L bytes = one padded byte row):
@@ -77,9 +77,17 @@ constexpr int kPairRing = 3;
 //   POST 2 x pair-form finished row                              4 RB each
 //   OUT  { output row A | output row B }  (uint16 pixels)        4 RB
 //   6 mbarriers
+// A CTA holds two such regions (two pairs of frames) and a 4-word role table.
 static inline size_t pair_smem_bytes(int LW2) {
   const size_t RB = 32 * 8 * (size_t)LW2;
-  return RB * (kPairRing * 2 + kPairRing * 6 + 8 + 8 + 4) + 2 * kPairRing * 8;
+  const size_t per_pair = RB * (kPairRing * 2 + kPairRing * 6 + 8 + 8 + 4) + 128;   // + mbarriers (padded)
+  return 2 * per_pair + 32;                                                      // + role table
+}
+
+__device__ __forceinline__ uint2 lds64(uint32_t a) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+  return v;
 }
 
 // (a & m) | (b & ~m) in one LOP3.
@@ -96,11 +104,12 @@ template <int LW2, bool FULL, int K0T, int G>
 __device__ __forceinline__ void pair_chain_row(const uint32_t (&n)[8 * LW2], uint32_t (&x)[8 * LW2], const uint32_t y,
                                                const uint32_t pre, const uint32_t post, const uint32_t cgmask,
                                                const uint32_t vmask, const int lane, const uint32_t last_lane,
-                                               const uint32_t last_t, uint32_t& last_prev, uint32_t& last_prev2) {
+                                               const uint32_t last_t, uint32_t& last_prev, uint32_t& last_prev2,
+                                               const int bar_id) {
   constexpr int L = 8 * LW2;
   constexpr int K0 = K0T < L ? K0T : L / 2;   // look-ahead pixels of pass 0
-  // word quad k of this lane sits at slot k*32 + lane (first half) / k*32 + (lane ^ 4) (second half)
-  const uint32_t a_lo = (uint32_t)lane * 16, a_hi = (uint32_t)(lane ^ 4) * 16;
+  // word quad k of this lane sits at 16-byte slot k*32 + lane
+  const uint32_t a_lo = (uint32_t)lane * 16, a_hi = a_lo;
 #pragma unroll
   for (int k = 0; k < 2 * LW2; k++) {
     const uint4 v = lds128(pre + k * 512 + (k < LW2 ? a_lo : a_hi));
@@ -193,14 +202,14 @@ __device__ __forceinline__ void pair_chain_row(const uint32_t (&n)[8 * LW2], uin
     last_prev2 = last_prev;
     last_prev = __shfl_sync(0xffffffffu, v, (int)last_lane);
   }
-  named_bar_sync(0, kPairThreads);
+  pair_bar_sync(bar_id);
 }
 
-// LW2:   words (4 px) per IO thread and frame row; the chain lane's segment is L = 8 LW2 px.
+// LW2:   the chain lane's segment is L = 8 LW2 px (LW2 = ceil(W / 256)).
 // FULL:  W == 32 L (every lane owns a complete segment).
 // SHIFT: UnextractFrame with a non-zero shift is fused into the write-out.
 template <int LW2, bool FULL, bool SHIFT, int K0T = FPV_PAIR_K0, int G = 8>
-__global__ void __launch_bounds__(kPairThreads, 4) k_decode_pair(const PairParams p) {
+__global__ void __launch_bounds__(kPairThreads, 2) k_decode_pair(const PairParams p) {
   extern __shared__ __align__(128) uint8_t psm[];
   constexpr int L = 8 * LW2;
   constexpr uint32_t RB = 32 * L;
@@ -210,35 +219,50 @@ __global__ void __launch_bounds__(kPairThreads, 4) k_decode_pair(const PairParam
   constexpr uint32_t kPost = kPre + 2 * kBuf;
   constexpr uint32_t kOut = kPost + 2 * kBuf;
   constexpr uint32_t kBars = kOut + 4 * RB;
-  const uint32_t sm0 = smem_u32(psm);
-  const uint32_t full1 = sm0 + kBars, full2 = full1 + 8 * kPairRing;
+  constexpr uint32_t kPairBytes = kBars + 128;      // per-pair region; the role table follows the two regions
   const uint32_t W = p.W, H = p.H;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  const uint32_t fA = 2 * blockIdx.x;
+  // ---- roles.  A latency-bound chain warp runs ~1.4x slower (measured) when it shares its SM
+  //      sub-partition with throughput warps, and two chain warps on one sub-partition do not
+  //      slow each other down.  The hardware gives the four warps of a CTA four consecutive warp
+  //      slots (rotated from CTA to CTA), sub-partition = slot % 4, so roles are taken from
+  //      %warpid: sub-partitions 0 / 1 run the chains of pair 0 / 1 of every resident CTA,
+  //      sub-partitions 2 / 3 their IO warps.  The claim table makes the assignment a bijection
+  //      whatever %warpid says (it is only a placement hint).
+  uint32_t* claim = reinterpret_cast<uint32_t*>(psm + 2 * kPairBytes);
+  if (threadIdx.x < 6) claim[threadIdx.x] = 0xffffffffu;
+  __syncthreads();
+  // roles: 0, 1 chain of pair 0 / 1 (sub-partitions 0 / 1); 2, 3 IO (sub-partitions 2 / 3); 4, 5 helper
+  uint32_t role = 0xffffffffu;
+  if (lane == 0) {
+    uint32_t slot;
+    asm volatile("mov.u32 %0, %%warpid;" : "=r"(slot));
+    if (atomicCAS(&claim[slot & 3u], 0xffffffffu, (uint32_t)warp) == 0xffffffffu) role = slot & 3u;
+  }
+  __syncthreads();
+  if (lane == 0 && role == 0xffffffffu) {
+    for (uint32_t r = 4; r < 10; r++)          // helpers first, then whatever is left
+      if (atomicCAS(&claim[r % 6], 0xffffffffu, (uint32_t)warp) == 0xffffffffu) { role = r % 6; break; }
+  }
+  role = __shfl_sync(0xffffffffu, role, 0);
+  const uint32_t pair = role & 1u;
+  const bool is_chain = role < 2, is_helper = role >= 4;
+  const int bar_id = 1 + (int)pair;                 // named barrier of this pair's three warps
+
+  const uint32_t sm0 = smem_u32(psm) + pair * kPairBytes;
+  const uint32_t full1 = sm0 + kBars, full2 = full1 + 8 * kPairRing;
+  const uint32_t fA = 4 * blockIdx.x + 2 * pair;
+  if (fA >= p.n) return;                            // odd number of pairs: this half of the CTA has nothing to do
   const uint32_t fB = fA + 1 < p.n ? fA + 1 : fA;   // odd tail: the pair is (A, A), B is not stored
   const uint32_t flA = p.flags[fA], flB = p.flags[fB];
   const bool lowA = !(flA & kFlagNoLow) && p.low != nullptr, lowB = !(flB & kFlagNoLow) && p.low != nullptr;
   const bool delA = (flA & kFlagDelta) && p.ddup != nullptr, delB = (flB & kFlagDelta) && p.ddup != nullptr;
   const uint32_t cgmask = ((flA & kFlagCG) ? 0x0000ffffu : 0u) | ((flB & kFlagCG) ? 0xffff0000u : 0u);
+  const uint32_t col0 = (uint32_t)lane * L;         // first column of this lane (both roles)
 
-  if (threadIdx.x == 32) {
-    for (int i = 0; i < 2 * kPairRing; i++) mbar_init(full1 + 8 * i, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (lowA != lowB) {
-    // only one frame of the pair has a low plane: the other one's ring rows are never written
-    // by TMA and must read as zero
-    for (uint32_t i = threadIdx.x; i < kPairRing * RB / 4; i += kPairThreads) {
-      const uint32_t s = i / (RB / 4), o = i % (RB / 4);
-      sts32(sm0 + kR2 + s * kR2Slot + (lowA ? RB : 0u) + 4 * o, 0u);
-    }
-  }
-  __syncthreads();
-
-  if (warp == 0) {
+  if (is_chain) {
     // =============================== chain warp ===================================
-    const uint32_t col0 = (uint32_t)lane * L;
     const bool lane_valid = FULL || col0 < W;
     const uint32_t vmask = lane_valid ? cgmask : 0u;
     const uint32_t last_lane = FULL ? 31u : (W - 1) / L, last_t = FULL ? (uint32_t)(L - 1) : (W - 1) % L;
@@ -247,34 +271,53 @@ __global__ void __launch_bounds__(kPairThreads, 4) k_decode_pair(const PairParam
     for (int t = 0; t < L; t++) rb[t] = 0;
     uint32_t last_prev = 0, last_prev2 = 0;   // h[y-1][W-1], h[y-2][W-1] of both frames
 
-    named_bar_sync(0, kPairThreads);          // row 0 is in PRE[0] (the IO warps' prologue)
+    pair_bar_sync(bar_id);               // mbarriers are initialised, the ring is zero-filled where needed
+    pair_bar_sync(bar_id);               // row 0 is in PRE[0] (the IO warp's prologue)
     for (uint32_t y = 0; y < H; y += 2) {
       pair_chain_row<LW2, FULL, K0T, G>(rb, ra, y, sm0 + kPre, sm0 + kPost, cgmask, vmask, lane, last_lane, last_t,
-                                last_prev, last_prev2);
+                                        last_prev, last_prev2, bar_id);
       if (y + 1 < H)
         pair_chain_row<LW2, FULL, K0T, G>(ra, rb, y + 1, sm0 + kPre + kBuf, sm0 + kPost + kBuf, cgmask, vmask, lane,
-                                  last_lane, last_t, last_prev, last_prev2);
+                                          last_lane, last_t, last_prev, last_prev2, bar_id);
     }
     return;
   }
 
-  // ================================= IO warps =====================================
-  const uint32_t i = threadIdx.x - 32;              // 0..63: columns [4 LW2 i, 4 LW2 (i+1))
-  const bool elected = i == 0;
-  const uint32_t wo = i * LW2;                      // first word (4 px) of this thread in a byte row
-  const uint32_t slot0 = ((i & 1u) * LW2 * 32 + ((i & 1u) ? ((i >> 1) ^ 4u) : (i >> 1))) * 16;
+  // ============================ IO warp and helper warp ==============================
+  // Lane l serves the chain lane l: columns [l L, (l+1) L) of both frames.  The helper issues
+  // the TMA loads and turns residual bytes into pair form (PRE); the IO warp turns finished
+  // rows (POST) into output pixels and issues the TMA stores.
+  const bool elected = lane == 0;
+  const uint32_t slot0 = (uint32_t)lane * 16;       // this lane's 16-byte slot in every quad row of PRE / POST
   const bool do_swap = p.unextract && p.big_endian;
   const uint32_t shmul = 1u << ((32 - p.shift) & 31), um = (0xffffu >> (p.shift & 31)) * 0x00010001u;
   // output words: two consecutive pixels of one frame out of two pair-form registers; the
   // UnextractFrame byte swap (.cc:857-860) is folded into the selector
   const uint32_t selA = do_swap ? 0x4501u : 0x5410u, selB = do_swap ? 0x6723u : 0x7632u;
-  const bool any_low = lowA || lowB;
   const uint32_t dmask = (delA ? 0x0000ffffu : 0u) | (delB ? 0xffff0000u : 0u);
   const uint32_t mh = kHiBytes & dmask, ml = kLoBytes & dmask;
   const uint32_t r2_bytes = (lowA ? W : 0u) + (lowB ? W : 0u) + (dmask ? 4 * W : 0u);
 
-  // ---- TMA issue state.  Every IO thread keeps it (it is warp-uniform, which lets the compiler
-  //      hold it in uniform registers); only the elected thread executes the copy instructions.
+  if (is_helper && elected) {
+    for (int i = 0; i < 2 * kPairRing; i++) mbar_init(full1 + 8 * i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // The write-out code is branch-free: a frame without a low plane reads zeros from ring rows that
+  // TMA never writes; without delta the delta words are masked off (mh = ml = 0).
+  if (is_helper && (!lowA || !lowB)) {
+    for (uint32_t i = lane; i < kPairRing * RB / 4; i += 32) {
+      const uint32_t s = i / (RB / 4), o = i % (RB / 4);
+      if (!lowA) sts32(sm0 + kR2 + s * kR2Slot + 4 * o, 0u);
+      if (!lowB) sts32(sm0 + kR2 + s * kR2Slot + RB + 4 * o, 0u);
+    }
+  }
+  if (is_helper && !dmask)
+    for (uint32_t i = lane; i < kPairRing * RB; i += 32)
+      sts32(sm0 + kR2 + (i / RB) * kR2Slot + 2 * RB + 4 * (i % RB), 0u);
+  pair_bar_sync(bar_id);
+
+  // ---- TMA issue state.  It is warp-uniform (which lets the compiler hold it in uniform
+  //      registers); only the elected lane executes the copy instructions.
   const uint8_t* s1A = p.high + (uint64_t)fA * p.P;   // next residual row to fetch
   const uint8_t* s1B = p.high + (uint64_t)fB * p.P;
   const uint8_t* s2A = p.low + (uint64_t)fA * p.P;    // next low row (dereferenced only if lowA / lowB)
@@ -313,52 +356,51 @@ __global__ void __launch_bounds__(kPairThreads, 4) k_decode_pair(const PairParam
   // residual bytes of the next row -> pair form for the chain warp, into PRE[buf]
   auto pre_row = [&](uint32_t buf) {
     mbar_wait(full1 + 8 * c1_slot, c1_par);
-    const uint32_t ra = sm0 + kR1 + c1_slot * kR1Slot + wo * 4, dst = sm0 + kPre + buf * kBuf + slot0;
+    const uint32_t ra = sm0 + kR1 + c1_slot * kR1Slot + col0, dst = sm0 + kPre + buf * kBuf + slot0;
     if (++c1_slot == kPairRing) { c1_slot = 0; c1_par ^= 1u; }
-    uint32_t A[LW2], B[LW2];
+    uint2 A[LW2], B[LW2];
 #pragma unroll
-    for (int kk = 0; kk < LW2; kk++) { A[kk] = lds32(ra + 4 * kk); B[kk] = lds32(ra + RB + 4 * kk); }
+    for (int k = 0; k < LW2; k++) { A[k] = lds64(ra + 8 * k); B[k] = lds64(ra + RB + 8 * k); }
 #pragma unroll
-    for (int kk = 0; kk < LW2; kk++) {
-      const uint32_t t = B[kk] << 16, u = B[kk] >> 16;
-      sts128(dst + kk * 512, __byte_perm(A[kk], t, 0x4640), __byte_perm(A[kk], t, 0x4741),
-             __byte_perm(A[kk], u, 0x6462), __byte_perm(A[kk], u, 0x6563));
+    for (int k = 0; k < LW2; k++) {
+      uint32_t t = B[k].x << 16, u = B[k].x >> 16;
+      sts128(dst + (2 * k) * 512, __byte_perm(A[k].x, t, 0x4640), __byte_perm(A[k].x, t, 0x4741),
+             __byte_perm(A[k].x, u, 0x6462), __byte_perm(A[k].x, u, 0x6563));
+      t = B[k].y << 16; u = B[k].y >> 16;
+      sts128(dst + (2 * k + 1) * 512, __byte_perm(A[k].y, t, 0x4640), __byte_perm(A[k].y, t, 0x4741),
+             __byte_perm(A[k].y, u, 0x6462), __byte_perm(A[k].y, u, 0x6563));
     }
   };
   // finished row in POST[buf] -> output pixels (.cc:335-344 and .cc:850-862), then one bulk store per frame
   auto post_row = [&](uint32_t buf) {
     if (r2_bytes) mbar_wait(full2 + 8 * c2_slot, c2_par);
     const uint32_t src = sm0 + kPost + buf * kBuf + slot0;
-    const uint32_t la = sm0 + kR2 + c2_slot * kR2Slot + wo * 4, da = la + 2 * RB + wo * 12;
+    const uint32_t la = sm0 + kR2 + c2_slot * kR2Slot + col0, da = sm0 + kR2 + c2_slot * kR2Slot + 2 * RB + col0 * 4;
     if (++c2_slot == kPairRing) { c2_slot = 0; c2_par ^= 1u; }
-    const uint32_t oa = sm0 + kOut + wo * 8;
-    uint4 X[LW2], D[LW2];
-    uint32_t A[LW2], B[LW2];
+    const uint32_t oa = sm0 + kOut + col0 * 2;
+    uint4 X[2 * LW2], D[2 * LW2];
+    uint2 A[LW2], B[LW2];
 #pragma unroll
-    for (int kk = 0; kk < LW2; kk++) X[kk] = lds128(src + kk * 512);
-    if (any_low) {
+    for (int k = 0; k < 2 * LW2; k++) X[k] = lds128(src + k * 512);
 #pragma unroll
-      for (int kk = 0; kk < LW2; kk++) { A[kk] = lds32(la + 4 * kk); B[kk] = lds32(la + RB + 4 * kk); }
-    }
-    if (dmask) {
+    for (int k = 0; k < LW2; k++) { A[k] = lds64(la + 8 * k); B[k] = lds64(la + RB + 8 * k); }
 #pragma unroll
-      for (int kk = 0; kk < LW2; kk++) D[kk] = lds128(da + kk * 16);
-    } else {
+    for (int k = 0; k < 2 * LW2; k++) D[k] = lds128(da + 16 * k);
 #pragma unroll
-      for (int kk = 0; kk < LW2; kk++) D[kk] = make_uint4(0, 0, 0, 0);
-    }
+    for (int k = 0; k < LW2; k++) {     // 8 columns per step
+      uint32_t Z[8], V[8];
+      uint32_t t = B[k].x << 16, u = B[k].x >> 16;
+      Z[0] = __byte_perm(A[k].x, t, 0x4640); Z[1] = __byte_perm(A[k].x, t, 0x4741);
+      Z[2] = __byte_perm(A[k].x, u, 0x6462); Z[3] = __byte_perm(A[k].x, u, 0x6563);
+      t = B[k].y << 16; u = B[k].y >> 16;
+      Z[4] = __byte_perm(A[k].y, t, 0x4640); Z[5] = __byte_perm(A[k].y, t, 0x4741);
+      Z[6] = __byte_perm(A[k].y, u, 0x6462); Z[7] = __byte_perm(A[k].y, u, 0x6563);
+      const uint32_t Xs[8] = {X[2 * k].x, X[2 * k].y, X[2 * k].z, X[2 * k].w,
+                              X[2 * k + 1].x, X[2 * k + 1].y, X[2 * k + 1].z, X[2 * k + 1].w};
+      const uint32_t Ds[8] = {D[2 * k].x, D[2 * k].y, D[2 * k].z, D[2 * k].w,
+                              D[2 * k + 1].x, D[2 * k + 1].y, D[2 * k + 1].z, D[2 * k + 1].w};
 #pragma unroll
-    for (int kk = 0; kk < LW2; kk++) {
-      uint32_t Z[4] = {0, 0, 0, 0};
-      if (any_low) {
-        const uint32_t t = B[kk] << 16, u = B[kk] >> 16;
-        Z[0] = __byte_perm(A[kk], t, 0x4640); Z[1] = __byte_perm(A[kk], t, 0x4741);
-        Z[2] = __byte_perm(A[kk], u, 0x6462); Z[3] = __byte_perm(A[kk], u, 0x6563);
-      }
-      const uint32_t Xs[4] = {X[kk].x, X[kk].y, X[kk].z, X[kk].w}, Ds[4] = {D[kk].x, D[kk].y, D[kk].z, D[kk].w};
-      uint32_t V[4];
-#pragma unroll
-      for (int j = 0; j < 4; j++) {
+      for (int j = 0; j < 8; j++) {
         // per 16-bit lane: ((x + dh) & 0xff) << 8 | ((l + dl) & 0xff).  The delta's high and low
         // bytes are added separately so that a carry out of one byte only ever lands in a bit the
         // final select drops (.cc:337-338: the bytes wrap independently); mh / ml also switch the
@@ -367,11 +409,13 @@ __global__ void __launch_bounds__(kPairThreads, 4) k_decode_pair(const PairParam
         V[j] = bitselect(hi, lo, kHiBytes);
         if (SHIFT) V[j] = __umulhi(V[j], shmul) & um;     // per lane: (pixel >> shift), .cc:855
       }
-      sts64(oa + kk * 8, __byte_perm(V[0], V[1], selA), __byte_perm(V[2], V[3], selA));            // frame A: px 0 1 | 2 3
-      sts64(oa + 2 * RB + kk * 8, __byte_perm(V[0], V[1], selB), __byte_perm(V[2], V[3], selB));   // frame B
+      sts128(oa + 16 * k, __byte_perm(V[0], V[1], selA), __byte_perm(V[2], V[3], selA),
+             __byte_perm(V[4], V[5], selA), __byte_perm(V[6], V[7], selA));               // frame A: 8 pixels
+      sts128(oa + 2 * RB + 16 * k, __byte_perm(V[0], V[1], selB), __byte_perm(V[2], V[3], selB),
+             __byte_perm(V[4], V[5], selB), __byte_perm(V[6], V[7], selB));               // frame B
     }
     fence_proxy_async();
-    named_bar_sync(1, 64);
+    __syncwarp();
     if (elected) {
       bulk_s2g(oA, sm0 + kOut, 2 * W);
       if (fB != fA) bulk_s2g(oB, sm0 + kOut + 2 * RB, 2 * W);
@@ -380,17 +424,24 @@ __global__ void __launch_bounds__(kPairThreads, 4) k_decode_pair(const PairParam
     oA += W; oB += W;
   };
 
-  issue_r1(); issue_r1(); issue_r1();
-  issue_r2();
-  pre_row(0);
-  named_bar_sync(0, kPairThreads);
+  if (is_helper) {
+    issue_r1(); issue_r1(); issue_r1();
+    issue_r2();
+    pre_row(0);
+    pair_bar_sync(bar_id);
+    for (uint32_t y = 0; y < H; y++) {
+      issue_r1();          // row y + 3 into slot y % 3: its row y was consumed in iteration y - 1
+      issue_r2();          // row y + 1 into slot (y + 1) % 3: its row y - 2 was consumed (by the IO warp) in iteration y - 1
+      if (y + 1 < H) pre_row((y + 1) & 1u);
+      pair_bar_sync(bar_id);
+    }
+    return;
+  }
+  pair_bar_sync(bar_id);
   for (uint32_t y = 0; y < H; y++) {
-    issue_r1();          // row y + 3 into slot y % 3: its row y was consumed in iteration y - 1
-    issue_r2();          // row y + 1 into slot (y + 1) % 3: its row y - 2 was consumed in iteration y - 1
     if (y >= 1) post_row((y - 1) & 1u);
-    if (y + 1 < H) pre_row((y + 1) & 1u);
     if (elected) bulk_wait_read0();   // the output row buffer may be rewritten after the barrier
-    named_bar_sync(0, kPairThreads);
+    pair_bar_sync(bar_id);
   }
   post_row((H - 1) & 1u);
   if (elected) bulk_wait0();

@@ -96,5 +96,11 @@ __device__ __forceinline__ void sts64(uint32_t a, uint32_t x, uint32_t y) {
 __device__ __forceinline__ void named_bar_sync(int id, int count) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
+// Barrier 1 or 2 over 96 threads (three warps), with immediate ids (a register id makes ptxas reserve all 16
+// hardware barriers for the CTA, and barriers are a per-SM resource).
+__device__ __forceinline__ void pair_bar_sync(int id) {
+  if (id == 1) asm volatile("bar.sync 1, 96;" ::: "memory");
+  else asm volatile("bar.sync 2, 96;" ::: "memory");
+}
 
 }  // namespace fpv
