@@ -115,15 +115,16 @@ __device__ __forceinline__ void pair_chain_row(const uint32_t (&n)[8 * LW2], uin
     const uint4 v = lds128(pre + k * 512 + (k < LW2 ? a_lo : a_hi));
     x[4 * k + 0] = v.x; x[4 * k + 1] = v.y; x[4 * k + 2] = v.z; x[4 * k + 3] = v.w;
   }
+  // PRE holds r + 256 per lane (see the helper's pre_row)
   if (cgmask != 0 && y > 0) {
     uint32_t c[L];
     uint32_t nw_in = __shfl_up_sync(0xffffffffu, n[L - 1], 1);
     if (lane == 0) nw_in = last_prev2;
     // flat index W (row 1, column 0) is not predicted (.cc:327 starts at W+1)
     const bool copy_first = (y == 1) && (lane == 0);
-    const uint32_t r_first = x[0];
+    const uint32_t r_first = x[0] - kLaneBias;
 #pragma unroll
-    for (int t = 0; t < L; t++) c[t] = x[t] + kLaneBias - (t == 0 ? nw_in : n[t - 1]);
+    for (int t = 0; t < L; t++) c[t] = x[t] - (t == 0 ? nw_in : n[t - 1]);
 
     // pass 0: estimate this segment's last pixel from a guess K0 pixels back
     uint32_t w_in;
@@ -182,12 +183,15 @@ __device__ __forceinline__ void pair_chain_row(const uint32_t (&n)[8 * LW2], uin
 #pragma unroll
       for (int k = 0; k < 2 * LW2; k++) {
         const uint4 v = lds128(pre + k * 512 + (k < LW2 ? a_lo : a_hi));
-        x[4 * k + 0] = (x[4 * k + 0] & cgmask) | (v.x & ~cgmask);
-        x[4 * k + 1] = (x[4 * k + 1] & cgmask) | (v.y & ~cgmask);
-        x[4 * k + 2] = (x[4 * k + 2] & cgmask) | (v.z & ~cgmask);
-        x[4 * k + 3] = (x[4 * k + 3] & cgmask) | (v.w & ~cgmask);
+        x[4 * k + 0] = (x[4 * k + 0] & cgmask) | ((v.x - kLaneBias) & ~cgmask);
+        x[4 * k + 1] = (x[4 * k + 1] & cgmask) | ((v.y - kLaneBias) & ~cgmask);
+        x[4 * k + 2] = (x[4 * k + 2] & cgmask) | ((v.z - kLaneBias) & ~cgmask);
+        x[4 * k + 3] = (x[4 * k + 3] & cgmask) | ((v.w - kLaneBias) & ~cgmask);
       }
     }
+  } else {
+#pragma unroll
+    for (int t = 0; t < L; t++) x[t] -= kLaneBias;
   }
 #pragma unroll
   for (int k = 0; k < 2 * LW2; k++)
@@ -361,14 +365,16 @@ __global__ void __launch_bounds__(kPairThreads, 2) k_decode_pair(const PairParam
     uint2 A[LW2], B[LW2];
 #pragma unroll
     for (int k = 0; k < LW2; k++) { A[k] = lds64(ra + 8 * k); B[k] = lds64(ra + RB + 8 * k); }
+    // PRE holds r + 256 per 16-bit lane (the chain's c = r + 256 - nw then is one subtraction): the
+    // 0x01 bytes come out of the shifts' addends, t = [0, 1, b0, b1] and u = [b2, b3, 0, 1]
 #pragma unroll
     for (int k = 0; k < LW2; k++) {
-      uint32_t t = B[k].x << 16, u = B[k].x >> 16;
-      sts128(dst + (2 * k) * 512, __byte_perm(A[k].x, t, 0x4640), __byte_perm(A[k].x, t, 0x4741),
-             __byte_perm(A[k].x, u, 0x6462), __byte_perm(A[k].x, u, 0x6563));
-      t = B[k].y << 16; u = B[k].y >> 16;
-      sts128(dst + (2 * k + 1) * 512, __byte_perm(A[k].y, t, 0x4640), __byte_perm(A[k].y, t, 0x4741),
-             __byte_perm(A[k].y, u, 0x6462), __byte_perm(A[k].y, u, 0x6563));
+      uint32_t t = B[k].x * 65536u + 0x0100u, u = __umulhi(B[k].x, 65536u) + 0x01000000u;
+      sts128(dst + (2 * k) * 512, __byte_perm(A[k].x, t, 0x5650), __byte_perm(A[k].x, t, 0x5751),
+             __byte_perm(A[k].x, u, 0x7472), __byte_perm(A[k].x, u, 0x7573));
+      t = B[k].y * 65536u + 0x0100u; u = __umulhi(B[k].y, 65536u) + 0x01000000u;
+      sts128(dst + (2 * k + 1) * 512, __byte_perm(A[k].y, t, 0x5650), __byte_perm(A[k].y, t, 0x5751),
+             __byte_perm(A[k].y, u, 0x7472), __byte_perm(A[k].y, u, 0x7573));
     }
   };
   // finished row in POST[buf] -> output pixels (.cc:335-344 and .cc:850-862), then one bulk store per frame
