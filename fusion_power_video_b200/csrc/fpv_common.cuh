@@ -155,6 +155,8 @@ __host__ __device__ inline QConst make_qconst(int mode, int s) {
   if (mode == kLE8 || mode == kLEs || mode == kLEbig) {
     c.sh_a = (uint32_t)s;                                      // q = (x << s) & m_a
     c.m_a = ((0xffffu << s) & 0xffffu) * 0x00010001u;
+    c.sh_b = s >= 32 ? 0u : 1u << s;                           // the same shift as a multiplier (make_hs_lo)
+    c.m_b = c.m_a & 0xff00ff00u;                               // mask of the high bytes of q
   } else if (mode == kBEs) {
     c.sh_a = (uint32_t)(s + 8);                                // ((x & m_a) << (s + 8))
     c.m_a = (0xffu >> s) * 0x00010001u;

@@ -458,6 +458,7 @@ int enqueue_encode(const Geom& g, const EncodeTuning& t, const EncodeScratch& s,
     fp.rows_per_stage = (uint32_t)rps;
     fp.stage_bytes = ((uint32_t)rps * g.W + kHaloPx) * 2;
     fp.compute_warps = (g.W + kStripPx - 1) / kStripPx;
+    fp.qc = make_qconst(g.mode, g.shift);
     // Band height: whole multiples of 4 rows; shrink for small batches so that
     // there are at least ~4 tasks per SM.
     uint32_t band = (uint32_t)t.band_rows;

@@ -63,6 +63,7 @@ struct FastParams {
   uint32_t rows_per_stage;      // 2 or 4
   uint32_t stage_bytes;         // bytes of one plane of one stage: (rows_per_stage * W + 8) * 2
   uint32_t compute_warps;       // ceil(W / 256)
+  QConst qc;                    // make_qconst(mode, shift)
 };
 
 // Walks the stage sequence of one CTA: tasks blockIdx.x, +gridDim.x, ...; per
@@ -110,54 +111,94 @@ struct StripState {
   uint32_t kc;      // offset (0..30) from this lane's first pixel to the next CG-decision sample
 };
 
+// Two raw pixels -> the two register forms a row is computed in, in as few ALU-pipe instructions
+// as the mode allows (the kernel is bound by the integer ALU pipe, so shifts are done as IMAD on
+// the FMA pipe and each mask is fused with the OR that follows it into one LOP3):
+//   hs1  S form of the RAW high bytes with bit 16 set: (q & 0xff00ff00) | 0x10000.  Bit 16 is the
+//        "+ 2^16" of the delta subtraction below; without delta it is junk <= 1 of lane 1.
+//   lof  q | 0x01000100: bytes 0 / 2 are the low bytes, every lane is >= 256.
+template <int MODE>
+__device__ __forceinline__ void make_hs_lo(uint32_t x, const QConst& c, uint32_t& hs1, uint32_t& lof) {
+  if (MODE == kLEs || MODE == kLE8 || MODE == kLEbig) {
+    const uint32_t sh = x * c.sh_b;                       // sh_b = 1 << shift (mod 2^32): IMAD
+    hs1 = (sh & c.m_b) | 0x00010000u;                     // m_b = m_a & 0xff00ff00
+    lof = (sh & c.m_a) | 0x01000100u;
+  } else {
+    const uint32_t q = make_q2<MODE>(x, c);
+    hs1 = (q & kHiBytes) | 0x00010000u;
+    lof = q | 0x01000100u;
+  }
+  // one LOP3 each; opaque so that later uses (OR of the low bytes, box sums) take the finished
+  // value instead of re-deriving it from the masks
+  asm("" : "+r"(hs1));
+  asm("" : "+r"(lof));
+}
+
+// a - b on the FMA pipe (IMAD); the compiler would pick the ALU pipe's IADD3.
+__device__ __forceinline__ uint32_t sub_fma(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("mad.lo.u32 %0, %1, 0xffffffff, %2;" : "=r"(r) : "r"(b), "r"(a));
+  return r;
+}
+
 // One row of one strip.  FIRSTROWS = true compiles the row-0 / row-1 special
 // cases and the halo (not-owned) row; the steady state uses FIRSTROWS = false.
-template <int MODE, bool FIRSTROWS, bool FULL>
+// DC = true: the frame is known to use delta and ClampedGradient (the common case), the two
+// flags are compile-time constants.
+template <int MODE, bool FIRSTROWS, bool FULL, bool DC>
 __device__ __forceinline__ void fast_row(
     StripState& st, const uint32_t raw_a /* shared addr of this lane's 8 px */, const uint32_t del_a,
-    const QConst qc, const bool use_delta, const bool use_cg, const bool active, const bool own,
+    const QConst qc, const bool use_delta_rt, const bool use_cg_rt, const bool active, const bool own,
     const uint32_t y, const bool emit_preview, const uint32_t c0, const uint32_t w31,
     uint8_t* __restrict__ out_high, uint8_t* __restrict__ out_low, uint8_t* __restrict__ out_prev,
     const uint32_t hist_a) {
-  uint32_t q[4], hs[4], lo[4], w[4];
+  const bool use_delta = DC || use_delta_rt, use_cg = DC || use_cg_rt;
+  uint32_t hr[4], hs[4], lo[4], w[4];
   uint32_t hw;  // S form of the two pixels west of this lane's first pixel
   {
     // lanes past the end of the row (FULL == false only) read whatever follows
     // in shared memory; nothing derived from it is ever stored
     const uint4 x = lds128(raw_a);
     const uint32_t xw = lds32(raw_a - 4);
-    q[0] = make_q2<MODE>(x.x, qc);
-    q[1] = make_q2<MODE>(x.y, qc);
-    q[2] = make_q2<MODE>(x.z, qc);
-    q[3] = make_q2<MODE>(x.w, qc);
-    hw = make_q2<MODE>(xw, qc) & kHiBytes;
+    uint32_t unused;
+    make_hs_lo<MODE>(x.x, qc, hr[0], lo[0]);
+    make_hs_lo<MODE>(x.y, qc, hr[1], lo[1]);
+    make_hs_lo<MODE>(x.z, qc, hr[2], lo[2]);
+    make_hs_lo<MODE>(x.w, qc, hr[3], lo[3]);
+    make_hs_lo<MODE>(xw, qc, hw, unused);
+  }
+  // statistics of the RAW planes: OR of the low bytes (bytes 0 / 2 of lof), 4x4 box sums of the
+  // high bytes (bytes 1 / 3 of hs1)
+  const bool counted = !FIRSTROWS || own;
+  if (counted) {
+    st.orl |= (lo[0] | lo[1]) | (lo[2] | lo[3]);
+    st.accA = __dp4a(hr[0], 0x01000100u, __dp4a(hr[1], 0x01000100u, st.accA));
+    st.accB = __dp4a(hr[2], 0x01000100u, __dp4a(hr[3], 0x01000100u, st.accB));
   }
   if (use_delta) {
     // Bytes wrap independently (.cc:534-537).  High: bits 8-15 / 24-31 of
     // (q & HI) + 2^16 - (d & HI); bit 16 is junk.  Low: bytes 0 / 2 of
-    // (q | 0x0100 per lane) - (d & LO); the rest is junk the packing drops.
+    // (q | 0x0100 per lane) - (d & LO) = lof - d + (d & HI); the rest is junk the packing drops.
     const uint4 d = lds128(del_a);
     const uint32_t dw = lds32(del_a - 4);
     const uint32_t dd[4] = {d.x, d.y, d.z, d.w};
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-      hs[j] = (q[j] & kHiBytes) + 0x00010000u - (dd[j] & kHiBytes);
-      lo[j] = (q[j] | 0x01000100u) - (dd[j] & kLoBytes);
+      const uint32_t dh = dd[j] & kHiBytes;
+      hs[j] = sub_fma(hr[j], dh);
+      lo[j] = lo[j] - dd[j] + dh;
     }
-    hw = hw + 0x00010000u - (dw & kHiBytes);
+    hw = sub_fma(hw, dw & kHiBytes);
   } else {
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-      hs[j] = q[j] & kHiBytes;
-      lo[j] = q[j];
-    }
+    for (int j = 0; j < 4; j++) hs[j] = hr[j];
   }
   w[0] = __funnelshift_l(hw, hs[0], 16);
   w[1] = __funnelshift_l(hs[0], hs[1], 16);
   w[2] = __funnelshift_l(hs[1], hs[2], 16);
   w[3] = __funnelshift_l(hs[2], hs[3], 16);
 
-  if (!FIRSTROWS || own) {
+  if (counted) {
     uint32_t res[4];
 #pragma unroll
     for (int j = 0; j < 4; j++) res[j] = cg_residual_s(hs[j], st.ph[j], w[j], st.pw[j]);
@@ -176,9 +217,6 @@ __device__ __forceinline__ void fast_row(
       stg64_cs(out_high, use_cg ? res8 : h8);
       if (mode_has_low(MODE)) stg64_cs(out_low, make_uint2(pack_lo(lo[0], lo[1]), pack_lo(lo[2], lo[3])));
     }
-    st.orl |= (q[0] | q[1]) | (q[2] | q[3]);
-    st.accA = __dp4a(q[0], 0x01000100u, __dp4a(q[1], 0x01000100u, st.accA));
-    st.accB = __dp4a(q[2], 0x01000100u, __dp4a(q[3], 0x01000100u, st.accB));
     // ---- ClampedGradient decision samples: flat index == W+1 (mod 31), >= W+1,
     //      a = post-delta high byte, b = a - CG (.cc:554-562).  A lane's 8 pixels
     //      hold at most one sample; it is picked out of the packed registers.
@@ -206,7 +244,7 @@ __device__ __forceinline__ void fast_row(
 // hist_a | hist_b] [full barriers] [empty barriers]
 // FULL: xsize is a multiple of 256, every lane of every consumer warp owns pixels.
 template <int MODE, bool FULL, int RPS>
-__global__ void __launch_bounds__(544, 1) k_encode_fast(const FastParams p) {
+__global__ void __maxnreg__(80) k_encode_fast(const FastParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t S = p.stages;
   const uint32_t slot_bytes = 2 * p.stage_bytes;
@@ -218,7 +256,7 @@ __global__ void __launch_bounds__(544, 1) k_encode_fast(const FastParams p) {
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t W = p.W;
-  const QConst qc = make_qconst(MODE, p.shift);
+  const QConst qc = p.qc;   // from the host: each mask is a constant-bank operand of its LOP3, not a derived register
 
   for (uint32_t i = threadIdx.x; i < (uint32_t)NW * kWarpScratchBytes / 4; i += blockDim.x)
     reinterpret_cast<uint32_t*>(scratch)[i] = 0;
@@ -350,20 +388,32 @@ __global__ void __launch_bounds__(544, 1) k_encode_fast(const FastParams p) {
         // steady state: RPS owned rows, none of them row 0 / row 1; stages start on even rows
         // (bands on multiples of 4), so a preview row group ends with the last row of a stage
         const bool group_end = RPS == 4 || (y & 2u);
+        if (use_delta && use_cg) {
 #pragma unroll
-        for (int r = 0; r < RPS; r++) {
-          fast_row<MODE, false, FULL>(st, raw_lane + r * rowb, raw_lane + r * rowb + p.stage_bytes, qc, use_delta,
-                                use_cg, active, true, y + r, r == RPS - 1 && group_end, c0, w31, oh, ol, op,
-                                hist_a);
-          oh += W;
-          if (mode_has_low(MODE)) ol += W;
+          for (int r = 0; r < RPS; r++) {
+            fast_row<MODE, false, FULL, true>(st, raw_lane + r * rowb, raw_lane + r * rowb + p.stage_bytes, qc, true,
+                                              true, active, true, y + r, r == RPS - 1 && group_end, c0, w31, oh, ol,
+                                              op, hist_a);
+            oh += W;
+            if (mode_has_low(MODE)) ol += W;
+          }
+        } else {
+#pragma unroll
+          for (int r = 0; r < RPS; r++) {
+            fast_row<MODE, false, FULL, false>(st, raw_lane + r * rowb, raw_lane + r * rowb + p.stage_bytes, qc,
+                                               use_delta, use_cg, active, true, y + r, r == RPS - 1 && group_end, c0,
+                                               w31, oh, ol, op, hist_a);
+            oh += W;
+            if (mode_has_low(MODE)) ol += W;
+          }
         }
         if (group_end) op += p.PW;
         y += RPS;
       } else {
         for (uint32_t r = 0; r < nrows; r++) {
-          fast_row<MODE, true, FULL>(st, raw_lane + r * rowb, raw_lane + r * rowb + p.stage_bytes, qc, use_delta,
-                               use_cg, active, own, y, (y & 3u) == 3u, c0, w31, oh, ol, op, hist_a);
+          fast_row<MODE, true, FULL, false>(st, raw_lane + r * rowb, raw_lane + r * rowb + p.stage_bytes, qc,
+                                            use_delta, use_cg, active, own, y, (y & 3u) == 3u, c0, w31, oh, ol, op,
+                                            hist_a);
           oh += W;
           if (mode_has_low(MODE)) ol += W;
           if ((y & 3u) == 3u) op += p.PW;
