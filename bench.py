@@ -315,7 +315,8 @@ def main():
         decode = {"metric": "decode_transform_raw_pixel_throughput", "value": world * F * P * 2 / (dms * 1e-3) / 1e9,
                   "unit": "GB/s", "frames_per_s": world * F / (dms * 1e-3), "ms_per_step": dms, "steps": dsteps,
                   "round_trip_exact": ok,
-                  "roofline": {"bound": "hbm (chain-latency limited, see DESIGN.md)", "kernel": "k_decode_simd",
+                  "roofline": {"bound": "hbm (chain-latency limited, see DESIGN.md)",
+                               "kernel": "k_decode_pair" if (W % 16 == 0 and 64 <= W <= 1280) else "k_decode_simd",
                                "achieved": dach, "peak": peak, "unit": "GB/s", "frac": dach / peak,
                                "traffic": ncu_traffic("decode", DEC_BYTES_PER_PX * F * P)}}
         del d_out

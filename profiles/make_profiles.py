@@ -7,7 +7,7 @@ summaries under profiles/ (run here, where ncu is installed but no GPU is):
   profiles/<round>_launches.csv      the launch list (gpu__time_duration.sum per launch) of one bench command
   profiles/<round>_launches.md       per-kernel share of that command
   profiles/<round>_encode.md         k_encode_fast main pass: ncu --set full metrics + SASS opcode mix + top stalls
-  profiles/<round>_decode.md         k_decode_simd: same
+  profiles/<round>_decode.md         k_decode_pair: same
 """
 import collections
 import csv
@@ -110,7 +110,7 @@ def launches_md(tag):
     main = [x for k, v in enc.items() if "k_encode_fast" in k for x in v if x > 100]
     lines += ["", f"Within the encode steps, the main pass of `k_encode_fast` (the {len(main)} launches > 100 us) is "
               f"{100 * sum(main) / etot:.1f} % of the listed encode time; bench.py's event timing of the same share "
-              "(`roofline.kernel_share_of_step`) is 0.87-0.88."]
+              "(`roofline.kernel_share_of_step`) is 0.85-0.86."]
     open(os.path.join(ROOT, "profiles", f"{tag}_launches.md"), "w").write("\n".join(lines) + "\n")
 
 
@@ -124,10 +124,10 @@ def main():
               512 * P / 256, "warp-row (256 px)", 512 * P * 4.0625,
               "`ncu --set full --clock-control none --import-source on -k regex:k_encode_fast -s 3 -c 1 python bench.py --steps 3 "
               "--warmup 3 --frames 512 --no-e2e --no-cpu --no-decode` (the 4th matching launch = the main pass of the 2nd step).")
-    traffic["decode"] = kernel_md(f"{tag}_decode", "k_decode_simd (C2, 1024 frames)", os.path.join(OUT, "prof_decode.ncu-rep"),
-              1024 * 800, "frame row (1280 px, one warp)", 1024 * P * 4.0,
-              "`ncu --set full --clock-control none --import-source on -k regex:k_decode_simd -s 1 -c 1 python bench.py --steps 3 "
-              "--warmup 3 --frames 1024 --no-e2e --no-cpu`.")
+    traffic["decode"] = kernel_md(f"{tag}_decode", "k_decode_pair (C2, 1024 frames)", os.path.join(OUT, "prof_decode.ncu-rep"),
+              1024 * 800, "frame row (1280 px)", 1024 * P * 4.0,
+              "`ncu --set full --clock-control none --import-source on -k regex:k_decode_pair -s 1 -c 1 python bench.py --steps 3 "
+              "--warmup 3 --frames 1024 --no-e2e --no-cpu --no-stream`.")
     json.dump(traffic, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
 
 
