@@ -188,7 +188,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--frames", type=int, default=1024, help="frames per GPU per step (device-resident)")
+    ap.add_argument("--frames", type=int, default=1184,
+                    help="frames per GPU per step (device-resident); 1184 = 148 SMs x 2 resident decode CTAs x 4 frames")
     ap.add_argument("--e2e-frames", type=int, default=256, help="frames per step of the host-buffer (e2e) leg")
     ap.add_argument("--e2e-batch", type=int, default=32)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
