@@ -84,6 +84,12 @@ def lib() -> C.CDLL:
     L.fpv_encode_submit.restype = i32
     L.fpv_wait.argtypes = [vp, u32]
     L.fpv_wait.restype = i32
+    L.fpv_stream_bound.argtypes = [vp, u32]
+    L.fpv_stream_bound.restype = sz
+    L.fpv_entropy_device.argtypes = [vp, vp, vp, vp, vp, u32, vp, sz, vp, vp]
+    L.fpv_entropy_device.restype = i32
+    L.fpv_encode_stream_submit.argtypes = [vp, u32, vp, u32, u32, vp, vp, vp, sz]
+    L.fpv_encode_stream_submit.restype = i32
     L.fpv_decode.argtypes = [vp, vp, vp, vp, u32, u32, vp]
     L.fpv_decode.restype = i32
     L.fpv_decode_device.argtypes = [vp, vp, vp, vp, u32, u32, vp, vp]
@@ -232,6 +238,35 @@ class Context:
 
     def wait(self, slot):
         self._check(self._L.fpv_wait(self._h, slot))
+
+    # -- GPU entropy coding ---------------------------------------------------
+    def stream_bound(self, n) -> int:
+        return int(self._L.fpv_stream_bound(self._h, n))
+
+    def entropy_device(self, flags_ptr, high_ptr, low_ptr, preview_ptr, n, out_ptr, capacity, frame_off_ptr, stream=0):
+        self._check(
+            self._L.fpv_entropy_device(
+                self._h, _ptr(flags_ptr), _ptr(high_ptr), _ptr(low_ptr) if low_ptr else None, _ptr(preview_ptr), n,
+                _ptr(out_ptr), capacity, _ptr(frame_off_ptr), C.c_void_p(stream),
+            )
+        )
+
+    def encode_stream_submit(self, slot, frames, n, flags, frame_off, out, capacity, options=ENC_DEFAULT):
+        self._check(self._L.fpv_encode_stream_submit(self._h, slot, _ptr(frames), n, options, _ptr(flags), _ptr(frame_off),
+                                                     _ptr(out), capacity))
+
+    def encode_stream(self, frames, options=ENC_DEFAULT):
+        """frames: uint16 [n, P] (host), n <= max_batch.  Returns flags and the list of the frames' container chunks
+        (bytes), entropy-coded on the GPU."""
+        frames = np.ascontiguousarray(frames, dtype=np.uint16).reshape(-1, self.P)
+        n = frames.shape[0]
+        cap = self.stream_bound(n)
+        flags = np.zeros(n, np.uint8)
+        off = np.zeros(n + 1, np.uint64)
+        out = np.zeros(cap, np.uint8)
+        self.encode_stream_submit(0, frames, n, flags, off, out, cap, options)
+        self.wait(0)
+        return flags, [out[int(off[i]):int(off[i + 1])].tobytes() for i in range(n)]
 
     # -- decode -------------------------------------------------------------
     def decode(self, high, low, flags, options=DEC_DEFAULT):

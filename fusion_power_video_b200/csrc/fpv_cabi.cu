@@ -37,6 +37,19 @@ struct Slot {
   uint8_t* d_preview = nullptr;
   uint8_t* d_flags = nullptr;
   bool allocated = false;
+  // a pending fpv_encode_stream_submit: fpv_wait fetches the coded bytes once their number is known
+  uint8_t* stream_out_host = nullptr;
+  uint64_t* stream_off_host = nullptr;
+  uint32_t stream_n = 0;
+};
+
+// Device buffers of the GPU entropy coder for up to max_batch frames.
+struct EntropyBuf {
+  uint8_t* scratch = nullptr;      // [cap * cpf][kEntropyChunkCap]
+  uint32_t* chunk_bytes = nullptr; // [cap * cpf]
+  uint64_t* frame_off = nullptr;   // [cap + 1]
+  uint8_t* out = nullptr;          // container chunks, stream_bound(cap) bytes (host-buffer entry points only)
+  uint32_t* overflow = nullptr;
 };
 
 }  // namespace
@@ -52,6 +65,7 @@ struct fpv_ctx {
   bool has_delta = false;
   EncodeScratch scratch[kNumSlots + 1];
   Slot slots[kNumSlots];
+  EntropyBuf entropy[kNumSlots + 1];
   uint8_t* d_serial_scratch = nullptr;
   size_t serial_scratch_bytes = 0;
   cudaStream_t aux_stream = nullptr;
@@ -121,6 +135,47 @@ int ensure_slot(fpv_ctx* c, int idx) {
   FPV_CUDA(cudaMalloc(&s.d_preview, B * PP));
   FPV_CUDA(cudaMalloc(&s.d_flags, B));
   s.allocated = true;
+  return FPV_OK;
+}
+
+uint32_t chunks_of(uint64_t bytes) { return (uint32_t)((bytes + kEntropyChunk - 1) / kEntropyChunk); }
+
+// Upper bound of the container chunks of n frames coded by the GPU entropy coder: per frame 11
+// container bytes and the three planes, per coded chunk at most 5 bytes of meta-block framing, per
+// plane stream the WBITS bit and the final 0x03.
+size_t stream_bound(const fpv_ctx* c, uint32_t n) {
+  const uint64_t cpf = chunks_of(c->g.PP) + 2ull * chunks_of(c->g.P);
+  return (size_t)n * (size_t)(11 + c->g.PP + 2 * c->g.P + 8 * cpf + 16);
+}
+
+int ensure_entropy(fpv_ctx* c, int idx, bool with_out) {
+  EntropyBuf& e = c->entropy[idx];
+  const uint64_t cap = c->max_batch, cpf = chunks_of(c->g.PP) + 2ull * chunks_of(c->g.P);
+  if (!e.scratch) {
+    FPV_CUDA(cudaMalloc(&e.scratch, cap * cpf * kEntropyChunkCap));
+    FPV_CUDA(cudaMalloc(&e.chunk_bytes, cap * cpf * sizeof(uint32_t)));
+    FPV_CUDA(cudaMalloc(&e.frame_off, (cap + 1) * sizeof(uint64_t)));
+    FPV_CUDA(cudaMalloc(&e.overflow, sizeof(uint32_t)));
+    FPV_CUDA(cudaMemset(e.overflow, 0, sizeof(uint32_t)));
+  }
+  if (with_out && !e.out) FPV_CUDA(cudaMalloc(&e.out, stream_bound(c, c->max_batch)));
+  return FPV_OK;
+}
+
+// Entropy-codes n <= max_batch frames whose planes are on the device.
+int entropy_device_impl(fpv_ctx* c, int idx, const uint8_t* flags, const uint8_t* high, const uint8_t* low,
+                        const uint8_t* preview, uint32_t n, uint8_t* out, uint64_t capacity, uint64_t* frame_off,
+                        cudaStream_t stream) {
+  EntropyBuf& e = c->entropy[idx];
+  EntropyParams p;
+  p.high = high; p.low = mode_has_low(c->g.mode) ? low : nullptr; p.preview = preview; p.flags = flags;
+  p.P = c->g.P; p.PP = c->g.PP; p.n = n;
+  p.cpl = chunks_of(c->g.P); p.cpp = chunks_of(c->g.PP); p.cpf = p.cpp + 2 * p.cpl;
+  p.scratch = e.scratch; p.chunk_bytes = e.chunk_bytes;
+  cudaError_t err = cudaSuccess;
+  int l = enqueue_entropy(p, frame_off, out, capacity, e.overflow, stream, &err);
+  if (l < 0) return cuda_fail(c, err, "entropy kernel launch");
+  c->launches += (uint64_t)l;
   return FPV_OK;
 }
 
@@ -266,6 +321,13 @@ void fpv_destroy(fpv_ctx* c) {
     if (s.d_flags) cudaFree(s.d_flags);
     if (s.done) cudaEventDestroy(s.done);
     if (s.stream) cudaStreamDestroy(s.stream);
+  }
+  for (auto& e : c->entropy) {
+    if (e.scratch) cudaFree(e.scratch);
+    if (e.chunk_bytes) cudaFree(e.chunk_bytes);
+    if (e.frame_off) cudaFree(e.frame_off);
+    if (e.out) cudaFree(e.out);
+    if (e.overflow) cudaFree(e.overflow);
   }
   for (auto& h : c->timing) {
     if (h.start) cudaEventDestroy(h.start);
@@ -456,6 +518,17 @@ int fpv_wait(fpv_ctx* c, uint32_t slot) {
   FPV_CUDA(cudaSetDevice(c->device));
   FPV_CUDA(cudaEventSynchronize(c->slots[slot].done));   // everything submitted on the slot so far
   FPV_CUDA(cudaStreamSynchronize(c->slots[slot].stream)); // (returns at once; surfaces stream errors)
+  Slot& s = c->slots[slot];
+  if (s.stream_n) {
+    // second half of fpv_encode_stream_submit: the coded size is known now, fetch exactly that many bytes
+    const uint64_t total = s.stream_off_host[s.stream_n];
+    const uint32_t n = s.stream_n;
+    s.stream_n = 0;
+    if (total > stream_bound(c, n)) return fail(c, FPV_ERR_CUDA, "entropy coder overflowed its output bound");
+    FPV_CUDA(cudaMemcpyAsync(s.stream_out_host, c->entropy[slot].out, (size_t)total, cudaMemcpyDeviceToHost, s.stream));
+    FPV_CUDA(cudaEventRecord(s.done, s.stream));
+    FPV_CUDA(cudaEventSynchronize(s.done));
+  }
   return FPV_OK;
 }
 
@@ -472,6 +545,63 @@ int fpv_encode(fpv_ctx* c, const uint16_t* frames_host, uint32_t n, uint32_t opt
     rc = fpv_wait(c, 0);
     if (rc != FPV_OK) return rc;
   }
+  return FPV_OK;
+}
+
+// ---- GPU entropy coding ---------------------------------------------------------
+
+size_t fpv_stream_bound(const fpv_ctx* c, uint32_t n) { return c ? stream_bound(c, n) : 0; }
+
+int fpv_entropy_device(fpv_ctx* c, const void* flags_dev, const void* high_dev, const void* low_dev,
+                       const void* preview_dev, uint32_t n, void* out_dev, size_t capacity, void* frame_off_dev,
+                       void* stream) {
+  if (!c) return FPV_ERR_INVALID_ARG;
+  if (n == 0) return FPV_OK;
+  if (n > c->max_batch) return fail(c, FPV_ERR_INVALID_ARG, "n exceeds max_batch");
+  if (!flags_dev || !high_dev || !preview_dev || !out_dev || !frame_off_dev)
+    return fail(c, FPV_ERR_INVALID_ARG, "NULL device buffer");
+  if (mode_has_low(c->g.mode) && !low_dev) return fail(c, FPV_ERR_INVALID_ARG, "low plane buffer is NULL");
+  if (capacity < stream_bound(c, n)) return fail(c, FPV_ERR_INVALID_ARG, "capacity below fpv_stream_bound(n)");
+  FPV_CUDA(cudaSetDevice(c->device));
+  int rc = ensure_entropy(c, kDeviceScratch, false);
+  if (rc != FPV_OK) return rc;
+  return entropy_device_impl(c, kDeviceScratch, static_cast<const uint8_t*>(flags_dev),
+                             static_cast<const uint8_t*>(high_dev), static_cast<const uint8_t*>(low_dev),
+                             static_cast<const uint8_t*>(preview_dev), n, static_cast<uint8_t*>(out_dev), capacity,
+                             static_cast<uint64_t*>(frame_off_dev), static_cast<cudaStream_t>(stream));
+}
+
+int fpv_encode_stream_submit(fpv_ctx* c, uint32_t slot, const uint16_t* frames_host, uint32_t n, uint32_t options,
+                             uint8_t* flags_host, uint64_t* frame_off_host, uint8_t* out_host, size_t capacity) {
+  if (!c) return FPV_ERR_INVALID_ARG;
+  if (slot >= kNumSlots) return fail(c, FPV_ERR_INVALID_ARG, "slot out of range");
+  if (n == 0) return FPV_OK;
+  if (n > c->max_batch) return fail(c, FPV_ERR_INVALID_ARG, "n exceeds max_batch");
+  if (!frames_host || !flags_host || !frame_off_host || !out_host)
+    return fail(c, FPV_ERR_INVALID_ARG, "NULL host buffer");
+  if (capacity < stream_bound(c, n)) return fail(c, FPV_ERR_INVALID_ARG, "capacity below fpv_stream_bound(n)");
+  FPV_CUDA(cudaSetDevice(c->device));
+  int rc = ensure_slot(c, (int)slot);
+  if (rc == FPV_OK) rc = ensure_entropy(c, (int)slot, true);
+  if (rc != FPV_OK) return rc;
+  Slot& s = c->slots[slot];
+  if (s.stream_n) return fail(c, FPV_ERR_INVALID_ARG, "slot has an unfinished stream submit: call fpv_wait first");
+  EntropyBuf& e = c->entropy[slot];
+  const size_t P = c->g.P;
+  FPV_CUDA(cudaMemcpyAsync(s.d_frames, frames_host, (size_t)n * P * 2, cudaMemcpyHostToDevice, s.stream));
+  rc = encode_device_chunked(c, (int)slot, s.d_frames, n, options, s.d_flags, s.d_high, s.d_low, s.d_preview,
+                             s.stream);
+  if (rc != FPV_OK) return rc;
+  rc = entropy_device_impl(c, (int)slot, s.d_flags, s.d_high, s.d_low, s.d_preview, n, e.out,
+                           stream_bound(c, c->max_batch), e.frame_off, s.stream);
+  if (rc != FPV_OK) return rc;
+  FPV_CUDA(cudaMemcpyAsync(flags_host, s.d_flags, (size_t)n, cudaMemcpyDeviceToHost, s.stream));
+  FPV_CUDA(cudaMemcpyAsync(frame_off_host, e.frame_off, (size_t)(n + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost,
+                           s.stream));
+  FPV_CUDA(cudaEventRecord(s.done, s.stream));
+  s.stream_out_host = out_host;
+  s.stream_off_host = frame_off_host;
+  s.stream_n = n;
   return FPV_OK;
 }
 

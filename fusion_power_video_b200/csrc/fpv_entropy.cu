@@ -1,0 +1,531 @@
+// fpv_entropy.cu -- chunk-parallel GPU entropy coder for the three byte planes of a frame.
+//
+// The reference hands each plane to libbrotli at quality 1 (fusion_power_video.cc:643-688,
+// BrotliEncoderCompress(1, 22, GENERIC)); its decoder accepts ANY valid RFC 7932 stream
+// (BrotliDecoderDecompressStream, .cc:186-214).  The reference notes that "only the entropy
+// coding matters, not the LZ77" (.cc:166-169), so this coder emits a brotli stream that uses the
+// format's entropy stage only:
+//
+//   plane stream := chunk* 0x03                       (0x03 = ISLAST, ISLASTEMPTY)
+//   chunk        := [WBITS bit, first chunk only]
+//                   compressed meta-block: MLEN = chunk size (<= 65536), one block type per
+//                     category, NTREES = 1, one literal prefix code (canonical Huffman from the
+//                     chunk's own histogram, max depth 15, stored as a "complex" code without
+//                     run-length symbols), a one-symbol insert-and-copy code whose only command
+//                     inserts the whole chunk, a one-symbol distance code, the literals
+//                   empty metadata meta-block, which pads the chunk to a byte boundary
+//                 | uncompressed meta-block when Huffman coding would not shrink the chunk
+//
+// Chunks are byte aligned and independent, so one CTA codes one chunk and a gather pass
+// concatenates them; the frame container bytes (.cc:820-846: total | 0 | 1+|bp| | pflags | bp |
+// flags | low? | high) are written on the device too, so the host only forwards pointers.
+// tests/huffcoder_ref.py states the same bitstream on the CPU; tests check it against libbrotlidec
+// and against this file byte for byte.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "fpv_internal.h"
+
+namespace fpv {
+
+namespace {
+
+constexpr int kET = 256;                       // threads per CTA
+constexpr uint32_t kOutWords = kEntropyChunkCap / 4;
+
+// RFC 7932 section 5: insert length code -> base, extra bits
+__constant__ uint32_t kInsBase[24] = {0, 1, 2, 3, 4, 5, 6, 8, 10, 14, 18, 26, 34, 50, 66, 98, 130, 194, 322, 578, 1090, 2114, 6210, 22594};
+__constant__ uint8_t kInsExtra[24] = {0, 0, 0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 7, 8, 9, 10, 12, 14, 24};
+// RFC 7932 section 3.5: storage order of the code length code lengths and their fixed code
+__constant__ uint8_t kClOrder[18] = {1, 2, 3, 4, 0, 5, 17, 6, 16, 7, 8, 9, 10, 11, 12, 13, 14, 15};
+__constant__ uint8_t kClclBits[6] = {0, 7, 3, 2, 1, 15};
+__constant__ uint8_t kClclLen[6] = {2, 4, 3, 2, 2, 4};
+
+struct Shared {
+  uint32_t out[kOutWords];       // the chunk's bit buffer
+  uint32_t hist[256];
+  uint32_t keys[256];            // sort keys (weight << 8 | symbol), then scratch
+  uint32_t wt[512];              // Huffman nodes: leaves in sorted order, then internal nodes
+  uint16_t parent[512];
+  uint32_t lc[256];              // per symbol: bit-reversed code | length << 16
+  uint8_t len[256];
+  uint32_t bl_count[16], next_code[16];
+  uint32_t cl_hist[18], cl_lc[18];
+  uint32_t warp_sum[8];
+  uint32_t pos;                  // running bit position of the serial writer
+  uint32_t maxd, lit_start, misc;
+};
+
+__device__ __forceinline__ void put_bits(Shared& s, uint32_t& pos, uint32_t value, uint32_t nbits) {
+  if (nbits == 0) return;
+  const uint32_t w = pos >> 5, sh = pos & 31;
+  atomicOr(&s.out[w], value << sh);
+  if (sh + nbits > 32) atomicOr(&s.out[w + 1], value >> (32 - sh));
+  pos += nbits;
+}
+
+// exclusive scan of one value per thread over the CTA; returns the prefix, *total = sum
+__device__ __forceinline__ uint32_t block_excl_scan(Shared& s, uint32_t v, uint32_t* total) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  uint32_t x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  __syncthreads();
+  if (lane == 31) s.warp_sum[w] = x;
+  __syncthreads();
+  uint32_t base = 0, tot = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const uint32_t t = s.warp_sum[i];
+    if (i < w) base += t;
+    tot += t;
+  }
+  *total = tot;
+  return base + x - v;
+}
+
+// Serial Huffman over <= 18 symbols with a depth limit (thread 0 only): the code length code.
+// Same construction as the 256-symbol one below: leaves sorted by (max(count, floor), symbol),
+// two queues, leaves win ties, the floor doubles until the tree is shallow enough.
+__device__ void small_huffman(const uint32_t* counts, int n, int max_bits, uint8_t* depth) {
+  uint32_t key[18], wt[36];
+  uint8_t par[36];
+  for (uint32_t floor_ = 1;; floor_ <<= 1) {
+    int m = 0;
+    for (int i = 0; i < n; i++)
+      if (counts[i]) {
+        const uint32_t w = counts[i] > floor_ ? counts[i] : floor_;
+        uint32_t k = (w << 8) | (uint32_t)i;
+        int j = m++;
+        while (j > 0 && key[j - 1] > k) { key[j] = key[j - 1]; j--; }
+        key[j] = k;
+      }
+    for (int i = 0; i < m; i++) wt[i] = key[i] >> 8;
+    int li = 0, ni = m, nn = m;
+    for (int k = 0; k + 1 < m; k++) {
+      int a, b;
+      if (li < m && (ni >= nn || wt[li] <= wt[ni])) a = li++; else a = ni++;
+      if (li < m && (ni >= nn || wt[li] <= wt[ni])) b = li++; else b = ni++;
+      wt[nn] = wt[a] + wt[b];
+      par[a] = par[b] = (uint8_t)nn;
+      nn++;
+    }
+    int maxd = 0;
+    for (int i = 0; i < n; i++) depth[i] = 0;
+    for (int i = 0; i < m; i++) {
+      int d = 0, k = i;
+      while (k != 2 * m - 2) { k = par[k]; d++; }
+      depth[key[i] & 255u] = (uint8_t)d;
+      if (d > maxd) maxd = d;
+    }
+    if (maxd <= max_bits) return;
+  }
+}
+
+// One byte of the chunk -> histogram
+__device__ __forceinline__ void hist4(Shared& s, uint32_t w) {
+  atomicAdd(&s.hist[w & 255u], 1u);
+  atomicAdd(&s.hist[(w >> 8) & 255u], 1u);
+  atomicAdd(&s.hist[(w >> 16) & 255u], 1u);
+  atomicAdd(&s.hist[w >> 24], 1u);
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(kET) k_entropy_chunk(const EntropyParams p) {
+  extern __shared__ __align__(16) uint8_t esm[];
+  Shared& s = *reinterpret_cast<Shared*>(esm);
+  const uint32_t tid = threadIdx.x;
+  const uint32_t c = blockIdx.x;
+  const uint32_t f = c / p.cpf, r = c % p.cpf;
+  const uint8_t* base;
+  uint64_t plen;
+  uint32_t ci;
+  if (r < p.cpp) { base = p.preview + (uint64_t)f * p.PP; plen = p.PP; ci = r; }
+  else if (r < p.cpp + p.cpl) { base = p.low ? p.low + (uint64_t)f * p.P : nullptr; plen = p.P; ci = r - p.cpp; }
+  else { base = p.high + (uint64_t)f * p.P; plen = p.P; ci = r - p.cpp - p.cpl; }
+  const bool is_low = r >= p.cpp && r < p.cpp + p.cpl;
+  if (is_low && (base == nullptr || (p.flags[f] & kFlagNoLow))) {
+    if (tid == 0) p.chunk_bytes[c] = 0;     // the low stream is absent (.cc:658-659)
+    return;
+  }
+  const uint64_t off = (uint64_t)ci * kEntropyChunk;
+  const uint32_t n = (uint32_t)(plen - off < kEntropyChunk ? plen - off : kEntropyChunk);
+  const bool first = ci == 0, last = off + n == plen;
+  const uint8_t* src = base + off;
+  const bool aligned = (reinterpret_cast<uintptr_t>(src) & 15u) == 0;
+
+  for (uint32_t i = tid; i < kOutWords; i += kET) s.out[i] = 0;
+  s.hist[tid] = 0;
+  if (tid < 18) s.cl_hist[tid] = 0;
+  if (tid < 16) s.bl_count[tid] = 0;
+  __syncthreads();
+
+  // ---- histogram -----------------------------------------------------------------------------
+  if (aligned) {
+    const uint32_t n16 = n / 16;
+    for (uint32_t i = tid; i < n16; i += kET) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(src) + i);
+      hist4(s, v.x); hist4(s, v.y); hist4(s, v.z); hist4(s, v.w);
+    }
+    for (uint32_t i = n16 * 16 + tid; i < n; i += kET) atomicAdd(&s.hist[src[i]], 1u);
+  } else {
+    for (uint32_t i = tid; i < n; i += kET) atomicAdd(&s.hist[src[i]], 1u);
+  }
+  __syncthreads();
+  const uint32_t cnt = s.hist[tid];
+  const int nz = __syncthreads_count(cnt != 0);
+
+  // ---- literal code lengths ------------------------------------------------------------------
+  if (nz >= 2) {
+    for (uint32_t floor_ = 1;; floor_ <<= 1) {
+      s.keys[tid] = cnt ? (((cnt > floor_ ? cnt : floor_) << 8) | tid) : 0xffffffffu;
+      if (tid == 0) s.maxd = 0;
+      __syncthreads();
+      // bitonic sort of 256 keys, ascending
+      for (uint32_t k = 2; k <= 256; k <<= 1)
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+          const uint32_t ixj = tid ^ j;
+          if (ixj > tid) {
+            const uint32_t a = s.keys[tid], b = s.keys[ixj];
+            const bool up = (tid & k) == 0;
+            if ((a > b) == up) { s.keys[tid] = b; s.keys[ixj] = a; }
+          }
+          __syncthreads();
+        }
+      if (tid < (uint32_t)nz) s.wt[tid] = s.keys[tid] >> 8;
+      __syncthreads();
+      if (tid == 0) {
+        const int m = nz;
+        int li = 0, ni = m, nn = m;
+        for (int k = 0; k + 1 < m; k++) {
+          int a, b;
+          if (li < m && (ni >= nn || s.wt[li] <= s.wt[ni])) a = li++; else a = ni++;
+          if (li < m && (ni >= nn || s.wt[li] <= s.wt[ni])) b = li++; else b = ni++;
+          s.wt[nn] = s.wt[a] + s.wt[b];
+          s.parent[a] = s.parent[b] = (uint16_t)nn;
+          nn++;
+        }
+      }
+      s.len[tid] = 0;
+      __syncthreads();
+      if (tid < (uint32_t)nz) {
+        uint32_t d = 0, k = tid;
+        const uint32_t root = 2 * (uint32_t)nz - 2;
+        while (k != root) { k = s.parent[k]; d++; }
+        s.len[s.keys[tid] & 255u] = (uint8_t)d;
+        atomicMax(&s.maxd, d);
+      }
+      __syncthreads();
+      const uint32_t maxd = s.maxd;
+      __syncthreads();
+      if (maxd <= 15) break;
+    }
+    // canonical code (RFC 7932 3.2), bit-reversed for the LSB-first writer
+    const uint32_t L = s.len[tid];
+    if (L) atomicAdd(&s.bl_count[L], 1u);
+    __syncthreads();
+    if (tid == 0) {
+      uint32_t code = 0;
+      s.next_code[0] = 0;
+      for (int b = 1; b <= 15; b++) {
+        code = (code + s.bl_count[b - 1]) << 1;
+        s.next_code[b] = code;
+      }
+    }
+    __syncthreads();
+    uint32_t rank = 0;
+    for (uint32_t j = 0; j < tid; j++) rank += (s.len[j] == L);
+    s.lc[tid] = L ? ((__brev(s.next_code[L] + rank) >> (32 - L)) | (L << 16)) : 0u;
+  } else {
+    s.len[tid] = 0;
+    s.lc[tid] = 0;
+  }
+  __syncthreads();
+
+  // ---- sizes: literal bits, last used symbol ---------------------------------------------------
+  uint32_t lit_bits;
+  block_excl_scan(s, cnt * s.len[tid], &lit_bits);
+  const uint32_t mylen = s.len[tid];
+  if (tid == 0) s.misc = 0;
+  __syncthreads();
+  if (cnt) atomicMax(&s.misc, tid);
+  __syncthreads();
+  const uint32_t last_sym = s.misc;     // largest used symbol
+  if (nz >= 2 && tid <= last_sym) atomicAdd(&s.cl_hist[mylen], 1u);
+  __syncthreads();
+
+  // ---- header, written by thread 0 up to the literal code lengths -----------------------------
+  uint32_t ic = 0;
+  for (int i = 23; i >= 0; i--)
+    if (kInsBase[i] <= n) { ic = (uint32_t)i; break; }
+  if (tid == 0) {
+    uint32_t pos = 0;
+    if (first) put_bits(s, pos, 0, 1);                 // WBITS = 16
+    put_bits(s, pos, 0, 1);                            // ISLAST = 0
+    const uint32_t nib = (n - 1) < (1u << 16) ? 4 : (n - 1) < (1u << 20) ? 5 : 6;
+    put_bits(s, pos, nib - 4, 2);
+    put_bits(s, pos, n - 1, 4 * nib);                  // MLEN - 1
+    s.misc = pos;                                      // position of the ISUNCOMPRESSED bit
+    put_bits(s, pos, 0, 1);                            // ISUNCOMPRESSED = 0
+    put_bits(s, pos, 0, 3);                            // NBLTYPESL = NBLTYPESI = NBLTYPESD = 1
+    put_bits(s, pos, 0, 6);                            // NPOSTFIX = 0, NDIRECT = 0
+    put_bits(s, pos, 0, 2);                            // context mode of literal block type 0
+    put_bits(s, pos, 0, 2);                            // NTREESL = NTREESD = 1
+    if (nz < 2) {
+      put_bits(s, pos, 1, 2); put_bits(s, pos, 0, 2); put_bits(s, pos, last_sym, 8);   // simple code, NSYM = 1
+    } else {
+      // the code length code: Huffman (depth <= 5) over the code lengths 0..15 in use
+      uint8_t cl_len[18];
+      uint32_t used = 0, only = 0;
+      for (int i = 0; i < 18; i++)
+        if (s.cl_hist[i]) { used++; only = (uint32_t)i; }
+      int to_store = 18;
+      if (used == 1) {
+        for (int i = 0; i < 18; i++) cl_len[i] = 0;
+        cl_len[only] = 1;        // stored as 1; a single code length costs 0 bits per symbol
+        for (int i = 0; i < 18; i++) s.cl_lc[i] = 0;
+      } else {
+        small_huffman(s.cl_hist, 18, 5, cl_len);
+        while (cl_len[kClOrder[to_store - 1]] == 0) to_store--;
+        uint32_t blc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, nc[8];
+        for (int i = 0; i < 18; i++) blc[cl_len[i]]++;
+        blc[0] = 0;
+        uint32_t code = 0;
+        nc[0] = 0;
+        for (int b = 1; b <= 5; b++) { code = (code + blc[b - 1]) << 1; nc[b] = code; }
+        for (int i = 0; i < 18; i++) {
+          const uint32_t l = cl_len[i];
+          s.cl_lc[i] = l ? ((__brev(nc[l]++) >> (32 - l)) | (l << 16)) : 0u;
+        }
+      }
+      uint32_t skip = 0;
+      if (cl_len[kClOrder[0]] == 0 && cl_len[kClOrder[1]] == 0) skip = cl_len[kClOrder[2]] == 0 ? 3 : 2;
+      put_bits(s, pos, skip, 2);
+      for (int i = (int)skip; i < to_store; i++) {
+        const uint32_t v = cl_len[kClOrder[i]];
+        put_bits(s, pos, kClclBits[v], kClclLen[v]);
+      }
+    }
+    s.pos = pos;
+  }
+  __syncthreads();
+  // the literal code lengths 0..last_sym, in parallel
+  {
+    const uint32_t e = (nz >= 2 && tid <= last_sym) ? s.cl_lc[mylen] : 0u;
+    uint32_t total;
+    const uint32_t o = block_excl_scan(s, e >> 16, &total);
+    uint32_t pos = s.pos + o;
+    put_bits(s, pos, e & 0xffffu, e >> 16);
+    __syncthreads();
+    if (tid == 0) {
+      pos = s.pos + total;
+      // insert-and-copy code: one symbol = (insert code ic, copy code 0); distance code: symbol 0 of 64
+      const uint32_t cell = ic < 8 ? 128u : ic < 16 ? 256u : 448u;
+      put_bits(s, pos, 1, 2); put_bits(s, pos, 0, 2); put_bits(s, pos, cell + ((ic & 7u) << 3), 10);
+      put_bits(s, pos, 1, 2); put_bits(s, pos, 0, 2); put_bits(s, pos, 0, 6);
+      put_bits(s, pos, n - kInsBase[ic], kInsExtra[ic]);     // the one command's insert extra bits
+      s.lit_start = pos;
+    }
+    __syncthreads();
+  }
+  const uint32_t lit_start = s.lit_start;
+  const uint32_t comp_bytes = (lit_start + lit_bits + 6 + 7) / 8;
+  const bool raw = comp_bytes > n + 4;       // Huffman coding does not pay: uncompressed meta-block
+
+  uint32_t bytes;
+  uint8_t* dst = p.scratch + (uint64_t)c * kEntropyChunkCap;
+  if (!raw) {
+    // ---- literals: thread t codes the bytes [t S, (t+1) S) ------------------------------------
+    const uint32_t S = (((n + kET - 1) / kET) + 15u) & ~15u;
+    const uint32_t b0 = tid * S < n ? tid * S : n, b1 = b0 + S < n ? b0 + S : n;
+    uint32_t mybits = 0;
+    if (aligned) {
+      uint32_t i = b0;
+      for (; i + 16 <= b1; i += 16) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + i));
+        const uint32_t ww[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+          mybits += s.len[ww[k] & 255u] + s.len[(ww[k] >> 8) & 255u] + s.len[(ww[k] >> 16) & 255u] + s.len[ww[k] >> 24];
+      }
+      for (; i < b1; i++) mybits += s.len[src[i]];
+    } else {
+      for (uint32_t i = b0; i < b1; i++) mybits += s.len[src[i]];
+    }
+    uint32_t total;
+    const uint32_t o = block_excl_scan(s, mybits, &total);
+    {
+      const uint32_t bitpos = lit_start + o;
+      uint32_t wi = bitpos >> 5, nb = bitpos & 31u;
+      unsigned long long acc = 0;
+      auto emit = [&](uint32_t byte) {
+        const uint32_t e = s.lc[byte];
+        acc |= (unsigned long long)(e & 0xffffu) << nb;
+        nb += e >> 16;
+        if (nb >= 32) {
+          atomicOr(&s.out[wi], (uint32_t)acc);
+          wi++;
+          acc >>= 32;
+          nb -= 32;
+        }
+      };
+      if (aligned) {
+        uint32_t i = b0;
+        for (; i + 16 <= b1; i += 16) {
+          const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + i));
+          const uint32_t ww[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            emit(ww[k] & 255u); emit((ww[k] >> 8) & 255u); emit((ww[k] >> 16) & 255u); emit(ww[k] >> 24);
+          }
+        }
+        for (; i < b1; i++) emit(src[i]);
+      } else {
+        for (uint32_t i = b0; i < b1; i++) emit(src[i]);
+      }
+      if (nb) atomicOr(&s.out[wi], (uint32_t)acc);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      uint32_t pos = lit_start + lit_bits;
+      // empty metadata meta-block: ISLAST = 0, MNIBBLES = 0 (coded 3), reserved 0, MSKIPBYTES = 0; pads to a byte
+      put_bits(s, pos, 0, 1); put_bits(s, pos, 3, 2); put_bits(s, pos, 0, 1); put_bits(s, pos, 0, 2);
+      uint32_t nbytes = (pos + 7) / 8;
+      if (last) {
+        reinterpret_cast<uint8_t*>(s.out)[nbytes] = 0x03;    // ISLAST, ISLASTEMPTY
+        nbytes++;
+      }
+      s.misc = nbytes;
+    }
+    __syncthreads();
+    bytes = s.misc;
+    for (uint32_t i = tid; i < (bytes + 3) / 4; i += kET) reinterpret_cast<uint32_t*>(dst)[i] = s.out[i];
+  } else {
+    // ---- uncompressed meta-block: header up to ISUNCOMPRESSED = 1, pad, raw bytes -------------
+    const uint32_t hdr_bits = s.misc + 1;
+    const uint32_t hb = (hdr_bits + 7) / 8;
+    __syncthreads();
+    if (tid == 0) {
+      uint32_t pos = s.misc;
+      // everything after the ISUNCOMPRESSED bit is dropped: rebuild the first bytes
+      uint32_t w0 = s.out[0] & ((pos >= 32) ? 0xffffffffu : ((1u << pos) - 1u));
+      w0 |= 1u << pos;                                    // hdr_bits <= 1 + 1 + 2 + 24 + 1 = 29
+      for (uint32_t i = 0; i < hb; i++) dst[i] = (uint8_t)(w0 >> (8 * i));
+      if (last) dst[hb + n] = 0x03;
+    }
+    for (uint32_t i = tid; i < n; i += kET) dst[hb + i] = src[i];
+    bytes = hb + n + (last ? 1u : 0u);
+  }
+  if (tid == 0) p.chunk_bytes[c] = bytes;
+}
+
+// Frame sizes -> frame offsets (exclusive scan); one CTA.  frame_off[n] = total bytes.
+__global__ void __launch_bounds__(1024) k_entropy_layout(const EntropyParams p, uint64_t* frame_off) {
+  __shared__ uint64_t wsum[32];
+  __shared__ uint64_t carry_s;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (uint32_t f0 = 0; f0 < p.n; f0 += blockDim.x) {
+    const uint32_t f = f0 + threadIdx.x;
+    uint64_t sz = 0;
+    if (f < p.n) {
+      sz = 11;     // total(4) kind(1) 1+|bp|(4) pflags(1) ... flags(1)
+      for (uint32_t k = 0; k < p.cpf; k++) sz += p.chunk_bytes[(uint64_t)f * p.cpf + k];
+    }
+    uint64_t x = sz;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint64_t y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) wsum[w] = x;
+    __syncthreads();
+    uint64_t base = carry_s;
+    for (int i = 0; i < w; i++) base += wsum[i];
+    if (f < p.n) frame_off[f] = base + x - sz;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry_s = base + x;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) frame_off[p.n] = carry_s;
+}
+
+// Copies every chunk to its place in the frame's container chunk and writes the container header
+// (fusion_power_video.cc:820-846).
+__global__ void __launch_bounds__(kET) k_entropy_gather(const EntropyParams p, const uint64_t* frame_off, uint8_t* out,
+                                                        uint64_t capacity, uint32_t* overflow) {
+  __shared__ uint64_t dst_s;
+  const uint32_t c = blockIdx.x, f = c / p.cpf, r = c % p.cpf;
+  const uint32_t* cb = p.chunk_bytes + (uint64_t)f * p.cpf;
+  if (frame_off[p.n] > capacity) {
+    if (c == 0 && threadIdx.x == 0) *overflow = 1;
+    return;
+  }
+  if (threadIdx.x == 0) {
+    uint64_t o = frame_off[f] + 10;
+    uint32_t bp = 0, core = 0;
+    for (uint32_t k = 0; k < p.cpf; k++) {
+      if (k < r) o += cb[k];
+      if (k < p.cpp) bp += cb[k]; else core += cb[k];
+    }
+    if (r >= p.cpp) o += 1;          // the core's flags byte sits between the preview stream and the low stream
+    dst_s = o;
+    if (r == 0) {
+      uint8_t* h = out + frame_off[f];
+      const uint32_t total = 11 + bp + core, fl = p.flags[f];
+      const uint32_t bp1 = bp + 1;
+      for (int i = 0; i < 4; i++) { h[i] = (uint8_t)(total >> (8 * i)); h[5 + i] = (uint8_t)(bp1 >> (8 * i)); }
+      h[4] = 0;                                          // frame chunk
+      h[9] = (uint8_t)((fl & kFlagCG) | kFlagNoLow);      // preview flags (.cc:842)
+      h[10 + bp] = (uint8_t)fl;                          // core := flags | low? | high
+    }
+  }
+  __syncthreads();
+  const uint32_t nb = cb[r];
+  const uint8_t* src = p.scratch + (uint64_t)c * kEntropyChunkCap;
+  uint8_t* dst = out + dst_s;
+  // destination alignment is arbitrary: bytes up to the first 4-byte boundary, then words assembled
+  // from two aligned source words
+  const uint32_t head = (uint32_t)((4 - (reinterpret_cast<uintptr_t>(dst) & 3u)) & 3u);
+  if (nb <= head + 8) {
+    for (uint32_t i = threadIdx.x; i < nb; i += kET) dst[i] = src[i];
+    return;
+  }
+  if (threadIdx.x < head) dst[threadIdx.x] = src[threadIdx.x];
+  const uint32_t words = (nb - head) / 4;
+  const uint32_t* s32 = reinterpret_cast<const uint32_t*>(src);
+  uint32_t* d32 = reinterpret_cast<uint32_t*>(dst + head);
+  const uint32_t sh = head * 8;
+  for (uint32_t i = threadIdx.x; i < words; i += kET) {
+    const uint32_t a = s32[i], b = sh ? s32[i + 1] : 0u;
+    d32[i] = sh ? __funnelshift_r(a, b, sh) : a;
+  }
+  for (uint32_t i = head + words * 4 + threadIdx.x; i < nb; i += kET) dst[i] = src[i];
+}
+
+size_t entropy_smem_bytes() { return sizeof(Shared); }
+
+int enqueue_entropy(const EntropyParams& p, uint64_t* frame_off, uint8_t* out, uint64_t capacity, uint32_t* overflow,
+                    cudaStream_t stream, cudaError_t* err) {
+  static bool attr_set[16] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 16 && !attr_set[dev]) {
+    *err = cudaFuncSetAttribute(k_entropy_chunk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Shared));
+    if (*err != cudaSuccess) return -1;
+    attr_set[dev] = true;
+  }
+  const uint32_t chunks = p.n * p.cpf;
+  k_entropy_chunk<<<chunks, kET, sizeof(Shared), stream>>>(p);
+  k_entropy_layout<<<1, 1024, 0, stream>>>(p, frame_off);
+  k_entropy_gather<<<chunks, kET, 0, stream>>>(p, frame_off, out, capacity, overflow);
+  *err = cudaGetLastError();
+  return *err == cudaSuccess ? 3 : -1;
+}
+
+}  // namespace fpv

@@ -55,6 +55,27 @@ int enqueue_encode(const Geom& g, const EncodeTuning& t, const EncodeScratch& s,
                    uint8_t* flags, uint8_t* high, uint8_t* low, uint8_t* preview,
                    cudaStream_t stream, cudaError_t* err, const TimingHook* hook = nullptr);
 
+// ---- GPU entropy coder (fpv_entropy.cu) -----------------------------------------------------
+constexpr uint32_t kEntropyChunk = 65536;                 // plane bytes per independently coded chunk
+constexpr uint32_t kEntropyChunkCap = kEntropyChunk + 128;  // scratch bytes per chunk (a coded chunk is <= n + 5 bytes)
+
+struct EntropyParams {
+  const uint8_t* high;      // [n][P]
+  const uint8_t* low;       // [n][P] or nullptr
+  const uint8_t* preview;   // [n][PP]
+  const uint8_t* flags;     // [n]
+  uint64_t P, PP;
+  uint32_t n;
+  uint32_t cpl, cpp, cpf;   // chunks per full plane, per preview plane, per frame (preview, low, high)
+  uint8_t* scratch;         // [n * cpf][kEntropyChunkCap]
+  uint32_t* chunk_bytes;    // [n * cpf]
+};
+
+// Enqueues chunk coding, layout and gather for n frames; frame_off: uint64[n + 1] (device), out: the
+// container chunks of the n frames back to back (device).  Returns kernels launched or -1.
+int enqueue_entropy(const EntropyParams& p, uint64_t* frame_off, uint8_t* out, uint64_t capacity, uint32_t* overflow,
+                    cudaStream_t stream, cudaError_t* err);
+
 // Splits a raw delta frame into image form ((high << 8) | low per pixel).
 int enqueue_delta_from_raw(const Geom& g, const uint16_t* raw, uint16_t* delta_image,
                            cudaStream_t stream, cudaError_t* err);

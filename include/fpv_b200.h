@@ -151,6 +151,30 @@ int fpv_encode_submit(fpv_ctx* ctx, uint32_t slot, const uint16_t* frames_host, 
                       uint8_t* low_host, uint8_t* preview_host);
 int fpv_wait(fpv_ctx* ctx, uint32_t slot);
 
+/* ---- optional GPU entropy coding ------------------------------------------------
+ * Replaces the reference's three BrotliEncoderCompress calls per frame
+ * (fusion_power_video.cc:643-688) and its OutputFull framing (.cc:830-846) by
+ * a chunk-parallel coder on the device.  Every plane becomes a valid RFC 7932
+ * (brotli) stream -- Huffman-coded literals only, independent byte-aligned
+ * chunks of 64 KiB -- so the reference's decoder (BrotliDecoderDecompressStream,
+ * .cc:186-214) reads the result unchanged; it is NOT byte-identical to what
+ * libbrotli's encoder writes.  The output of n frames is their container chunks
+ *   u32 total | u8 0 | u32 1+|bp| | u8 pflags | bp | u8 flags | low? | high
+ * back to back; frame_off[i] is the byte offset of frame i, frame_off[n] the
+ * total.  fpv_stream_bound(n) is the capacity the output buffer must have. */
+size_t fpv_stream_bound(const fpv_ctx* ctx, uint32_t n);
+/* planes already on the device (as fpv_encode_device leaves them); out_dev and
+ * frame_off_dev (uint64[n + 1]) are device buffers; enqueued on `stream`. */
+int fpv_entropy_device(fpv_ctx* ctx, const void* flags_dev, const void* high_dev, const void* low_dev,
+                       const void* preview_dev, uint32_t n, void* out_dev, size_t capacity,
+                       void* frame_off_dev, void* stream);
+/* Host-buffer form: raw frames in, container chunks out (pinned buffers).
+ * fpv_wait(slot) completes the call: it waits for the sizes, then fetches
+ * exactly frame_off_host[n] bytes into out_host. */
+int fpv_encode_stream_submit(fpv_ctx* ctx, uint32_t slot, const uint16_t* frames_host, uint32_t n,
+                             uint32_t options, uint8_t* flags_host, uint64_t* frame_off_host,
+                             uint8_t* out_host, size_t capacity);
+
 /* ---- decode (inverse) transform ---------------------------------------- */
 
 /* Replaces the post-brotli part of DecompressImage (.cc:326-344) for n frames

@@ -1,0 +1,118 @@
+"""GPU entropy coder (csrc/fpv_entropy.cu): its container chunks must (a) equal the CPU restatement of the
+bitstream (tests/huffcoder_ref.py) byte for byte and (b) decode with libbrotlidec -- the library the reference's
+decoder uses (fusion_power_video.cc:186-214) -- back to exactly the planes the transform produced."""
+import struct
+
+import numpy as np
+import pytest
+
+import huffcoder_ref as href
+
+pytestmark = pytest.mark.gpu
+
+
+def expected_chunk(flags, high, low, preview):
+    bp = href.encode_plane(preview)
+    core = bytes([flags]) + (b"" if (flags & 4) or low is None else href.encode_plane(low)) + href.encode_plane(high)
+    total = 10 + len(bp) + len(core)
+    return struct.pack("<IBIB", total, 0, len(bp) + 1, (flags & 2) | 4) + bp + core
+
+
+def split_chunk(chunk, P, PP, has_low):
+    """Container chunk -> flags, planes, using libbrotlidec the way the reference's DecompressImage does."""
+    total, kind, bp1, pflags = struct.unpack_from("<IBIB", chunk, 0)
+    assert total == len(chunk) and kind == 0
+    bp = chunk[10:10 + bp1 - 1]
+    preview = href.brotli_decode(bp, PP)
+    core = chunk[10 + bp1 - 1:]
+    flags = core[0]
+    rest = core[1:]
+    # the low and high streams are concatenated without a length: decode the first, find where it ended
+    streams = []
+    for _ in range(2 if (has_low and not flags & 4) else 1):
+        out, used = href.brotli_decode_prefix(rest, P)
+        streams.append(out)
+        rest = rest[used:]
+    assert len(rest) == 0
+    low = streams[0] if len(streams) == 2 else None
+    return flags, pflags, streams[-1], low, preview
+
+
+CASES = [
+    # W, H, bits, shift, big_endian, n
+    (1280, 160, 12, 4, False, 5),
+    (1024, 128, 16, 0, False, 3),
+    (256, 64, 8, 8, False, 3),      # no low plane
+    (520, 36, 16, 0, True, 2),      # ragged widths, unaligned preview planes
+    (12, 8, 16, 0, False, 4),       # tiny: preview of 6 bytes
+    (2048, 96, 16, 0, False, 2),
+]
+
+
+@pytest.mark.parametrize("W,H,bits,shift,be,n", CASES)
+def test_stream_matches_cpu_restatement_and_decodes(W, H, bits, shift, be, n):
+    import fusion_power_video_b200 as fpv
+    from fusion_power_video_b200 import synth
+
+    P, PP = W * H, (W // 4) * (H // 4)
+    frames = synth.plasma_frames(n, W, H, bits=bits, seed=7).reshape(n, -1)
+    if be:
+        frames = frames.byteswap()
+    with fpv.Context(W, H, shift, be, max_batch=n) as ctx:
+        ctx.set_delta_raw(frames[0])
+        flags, high, low, preview = ctx.encode(frames)
+        sflags, chunks = ctx.encode_stream(frames)
+    assert np.array_equal(flags, sflags)
+    for i in range(n):
+        exp = expected_chunk(int(flags[i]), high[i], None if low is None else low[i], preview[i])
+        assert chunks[i] == exp, f"frame {i}: GPU chunk ({len(chunks[i])} B) differs from the CPU restatement ({len(exp)} B)"
+        f2, pflags, h2, l2, p2 = split_chunk(chunks[i], P, PP, low is not None)
+        assert f2 == int(flags[i]) and pflags == ((f2 & 2) | 4)
+        assert h2 == high[i].tobytes() and p2 == preview[i].tobytes()
+        if l2 is not None:
+            assert l2 == low[i].tobytes()
+
+
+@pytest.mark.parametrize("kind", ["constant", "two_values", "noise", "zero_low"])
+def test_degenerate_planes(kind):
+    import fusion_power_video_b200 as fpv
+
+    W, H, n = 512, 256, 2
+    P, PP = W * H, (W // 4) * (H // 4)
+    rng = np.random.default_rng(3)
+    if kind == "constant":
+        frames = np.full((n, P), 0x1234, np.uint16)
+    elif kind == "two_values":
+        frames = rng.integers(0, 2, (n, P)).astype(np.uint16) * 0x0101
+    elif kind == "noise":
+        frames = rng.integers(0, 65536, (n, P)).astype(np.uint16)
+    else:
+        frames = (rng.integers(0, 256, (n, P)).astype(np.uint16) << 8)
+    with fpv.Context(W, H, 0, False, max_batch=n) as ctx:
+        flags, high, low, preview = ctx.encode(frames, fpv.ENC_NO_DELTA)
+        sflags, chunks = ctx.encode_stream(frames, fpv.ENC_NO_DELTA)
+    assert np.array_equal(flags, sflags)
+    for i in range(n):
+        assert chunks[i] == expected_chunk(int(flags[i]), high[i], low[i], preview[i])
+        f2, _, h2, l2, p2 = split_chunk(chunks[i], P, PP, True)
+        assert h2 == high[i].tobytes() and p2 == preview[i].tobytes()
+        assert (l2 is None) == bool(flags[i] & 4)
+
+
+def test_full_size_batch_round_trip():
+    """C2 geometry, a batch of 16: every plane stream decodes with libbrotlidec; sizes beat or match brotli q1 loosely."""
+    import fusion_power_video_b200 as fpv
+    from fusion_power_video_b200 import synth
+
+    W, H, n = 1280, 800, 16
+    P, PP = W * H, (W // 4) * (H // 4)
+    frames = synth.plasma_frames(n, W, H, bits=12, seed=1).reshape(n, -1)
+    with fpv.Context(W, H, 4, False, max_batch=n) as ctx:
+        ctx.set_delta_raw(frames[0])
+        flags, high, low, preview = ctx.encode(frames)
+        sflags, chunks = ctx.encode_stream(frames)
+    assert np.array_equal(flags, sflags)
+    for i in range(n):
+        f2, _, h2, l2, p2 = split_chunk(chunks[i], P, PP, True)
+        assert h2 == high[i].tobytes() and l2 == low[i].tobytes() and p2 == preview[i].tobytes()
+        assert len(chunks[i]) < 0.55 * 2 * P      # 12-bit frames: well under 9 bits per pixel
