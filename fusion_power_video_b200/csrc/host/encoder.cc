@@ -11,6 +11,7 @@
 //      (low plane; preview + high plane), the second to finish assembles the chunk,
 //   4. emits finished frames in submission order under one mutex, recording the
 //      frame offsets for the footer exactly as FinishTask does (.cc:1179-1183).
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -40,6 +41,8 @@ struct Encoder::Impl {
   size_t W = 0, H = 0, P = 0, PP = 0;
   bool has_low = true;
   uint32_t B = 1;
+  bool gpu_entropy = false;           // planes are entropy-coded and framed on the GPU (fpv_encode_stream_submit)
+  size_t stream_cap = 0;              // fpv_stream_bound(B)
 
   // Compressed pieces of one frame, filled by its two brotli tasks.
   struct Pieces {
@@ -49,6 +52,7 @@ struct Encoder::Impl {
   };
   struct Batch {
     Pinned frames, high, low, preview, flags;
+    Pinned coded, offs;               // gpu_entropy: container chunks back to back, uint64 offsets [B + 1]
     bool allocated = false;
     uint32_t n = 0;
     uint64_t first_id = 0;
@@ -123,8 +127,12 @@ struct Encoder::Impl {
 
   bool alloc_batch(Batch* b) {
     if (b->allocated) return true;
-    if (!b->frames.alloc((size_t)B * P * 2) || !b->high.alloc((size_t)B * P) || !b->low.alloc((size_t)B * P) ||
-        !b->preview.alloc((size_t)B * (PP ? PP : 1)) || !b->flags.alloc(B))
+    if (gpu_entropy) {
+      if (!b->frames.alloc((size_t)B * P * 2) || !b->flags.alloc(B) || !b->coded.alloc(stream_cap) ||
+          !b->offs.alloc(((size_t)B + 1) * sizeof(uint64_t)))
+        return fail("pinned allocation");
+    } else if (!b->frames.alloc((size_t)B * P * 2) || !b->high.alloc((size_t)B * P) || !b->low.alloc((size_t)B * P) ||
+               !b->preview.alloc((size_t)B * (PP ? PP : 1)) || !b->flags.alloc(B))
       return fail("pinned allocation");
     b->pieces = std::vector<Pieces>(B);
     b->allocated = true;
@@ -142,6 +150,24 @@ struct Encoder::Impl {
       done.erase(it);
       next_emit++;
     }
+  }
+
+  // gpu_entropy: the batch's chunks are complete and in order (the GPU thread lands batches in
+  // submission order), so they are emitted straight out of the pinned buffer, no copy.
+  void emit_coded(Batch* b) {
+    const uint64_t* off = b->offs.as<uint64_t>();
+    const uint8_t* bytes = b->coded.as<uint8_t>();
+    {
+      std::lock_guard<std::mutex> l(out_m);
+      for (uint32_t i = 0; i < b->n; i++) {
+        const size_t size = (size_t)(off[i + 1] - off[i]);
+        offsets.push_back(bytes_written);
+        bytes_written += size;
+        b->callbacks[i](bytes + off[i], size, b->payloads[i]);
+        next_emit++;
+      }
+    }
+    recycle(b);
   }
 
   void recycle(Batch* b) {
@@ -215,7 +241,8 @@ struct Encoder::Impl {
         std::lock_guard<std::mutex> l(m);
         gpu_busy--;
       }
-      compress_batch(b);
+      if (gpu_entropy) emit_coded(b);
+      else compress_batch(b);
     };
     for (;;) {
       Batch* b = nullptr;
@@ -233,9 +260,13 @@ struct Encoder::Impl {
         if (inflight.size() == 2) land();  // its slot is about to be reused
         b->slot = next_slot;
         next_slot ^= 1u;
-        int rc = fpv_encode_submit(ctx, b->slot, b->frames.as<uint16_t>(), b->n, FPV_ENC_DEFAULT,
-                                   b->flags.as<uint8_t>(), b->high.as<uint8_t>(),
-                                   has_low ? b->low.as<uint8_t>() : nullptr, b->preview.as<uint8_t>());
+        int rc = gpu_entropy
+                     ? fpv_encode_stream_submit(ctx, b->slot, b->frames.as<uint16_t>(), b->n, FPV_ENC_DEFAULT,
+                                                b->flags.as<uint8_t>(), b->offs.as<uint64_t>(),
+                                                b->coded.as<uint8_t>(), stream_cap)
+                     : fpv_encode_submit(ctx, b->slot, b->frames.as<uint16_t>(), b->n, FPV_ENC_DEFAULT,
+                                         b->flags.as<uint8_t>(), b->high.as<uint8_t>(),
+                                         has_low ? b->low.as<uint8_t>() : nullptr, b->preview.as<uint8_t>());
         if (rc != FPV_OK) fail("fpv_encode_submit");
         inflight.push_back(b);
       } else {
@@ -279,6 +310,11 @@ void Encoder::Init(const uint16_t* delta_frame, size_t xsize, size_t ysize, Call
     return;
   }
   s.ok = true;
+  {
+    const char* env = getenv("FPV_GPU_ENTROPY");
+    s.gpu_entropy = s.opt.gpu_entropy >= 0 ? s.opt.gpu_entropy != 0 : (env && atoi(env) != 0);
+    s.stream_cap = fpv_stream_bound(s.ctx, s.B);
+  }
   // enough batches that the brotli workers always have about two frames each queued
   // behind the (up to) three batches that are filling / on the GPU; pinned memory is
   // only allocated when a batch is first used
@@ -291,10 +327,11 @@ void Encoder::Init(const uint16_t* delta_frame, size_t xsize, size_t ysize, Call
   }
   // Header: the delta frame itself, predicted without a delta frame
   // (Frame df = delta_frame_; df.Compress(), reference .cc:1099-1101).
-  Impl::Batch& b = s.batches[0];
-  memcpy(b.frames.as<uint16_t>(), delta_frame, s.P * 2);
-  if (fpv_encode(s.ctx, b.frames.as<uint16_t>(), 1, FPV_ENC_NO_DELTA, b.flags.as<uint8_t>(), b.high.as<uint8_t>(),
-                 s.has_low ? b.low.as<uint8_t>() : nullptr, b.preview.as<uint8_t>()) != FPV_OK) {
+  // (once per stream, pageable buffers; the delta chunk's planes always go through libbrotli)
+  std::vector<uint8_t> dhigh(s.P), dlow(s.has_low ? s.P : 0), dprev(s.PP ? s.PP : 1);
+  uint8_t dflags = 0;
+  if (fpv_encode(s.ctx, delta_frame, 1, FPV_ENC_NO_DELTA, &dflags, dhigh.data(), s.has_low ? dlow.data() : nullptr,
+                 dprev.data()) != FPV_OK) {
     s.fail("fpv_encode (delta frame)");
     return;
   }
@@ -303,12 +340,11 @@ void Encoder::Init(const uint16_t* delta_frame, size_t xsize, size_t ysize, Call
   AppendU32((uint32_t)ysize, &header);
   AppendU32(0, &header);
   header.push_back(kChunkDelta);
-  AppendCore(b.flags.as<uint8_t>()[0], b.high.as<uint8_t>(), s.has_low ? b.low.as<uint8_t>() : nullptr, s.P,
-             &scratch, &header);
+  AppendCore(dflags, dhigh.data(), s.has_low ? dlow.data() : nullptr, s.P, &scratch, &header);
   StoreU32((uint32_t)(header.size() - 8), header.data() + 8);
   s.bytes_written = header.size();
   if (s.threads > 0) {
-    s.pool.reset(new Pool(s.threads));
+    if (!s.gpu_entropy) s.pool.reset(new Pool(s.threads));
     s.gpu_thread = std::thread([&s] { s.gpu_loop(); });
   }
   callback(header.data(), header.size(), payload);
@@ -321,6 +357,22 @@ void Encoder::CompressFrame(const uint16_t* img, Callback callback, void* payloa
     // synchronous: transform, brotli and the callback all happen here
     Impl::Batch& b = s.batches[0];
     memcpy(b.frames.as<uint16_t>(), img, s.P * 2);
+    if (s.gpu_entropy) {
+      if (fpv_encode_stream_submit(s.ctx, 0, b.frames.as<uint16_t>(), 1, FPV_ENC_DEFAULT, b.flags.as<uint8_t>(),
+                                   b.offs.as<uint64_t>(), b.coded.as<uint8_t>(), s.stream_cap) != FPV_OK ||
+          fpv_wait(s.ctx, 0) != FPV_OK) {
+        s.fail("fpv_encode_stream_submit");
+        return;
+      }
+      std::lock_guard<std::mutex> l(s.out_m);
+      const size_t size = (size_t)b.offs.as<uint64_t>()[1];
+      s.offsets.push_back(s.bytes_written);
+      s.bytes_written += size;
+      s.next_id++;
+      s.next_emit++;
+      callback(b.coded.as<uint8_t>(), size, payload);
+      return;
+    }
     if (fpv_encode(s.ctx, b.frames.as<uint16_t>(), 1, FPV_ENC_DEFAULT, b.flags.as<uint8_t>(),
                    b.high.as<uint8_t>(), s.has_low ? b.low.as<uint8_t>() : nullptr,
                    b.preview.as<uint8_t>()) != FPV_OK) {

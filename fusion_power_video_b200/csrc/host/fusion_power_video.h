@@ -52,6 +52,11 @@ const std::string& LastError();
 struct GpuOptions {
   int device = 0;
   uint32_t batch = 8;
+  // Entropy stage of the encoder: 0 = libbrotli quality 1 on host threads, byte-identical to the
+  // reference's stream; 1 = the chunk-parallel coder on the GPU (valid brotli streams any
+  // reference decoder reads, different bytes, no host brotli); -1 = 1 iff the environment
+  // variable FPV_GPU_ENTROPY is set to a non-zero value.
+  int gpu_entropy = -1;
 };
 
 class StreamingDecoder {

@@ -58,16 +58,37 @@ def last_error() -> str:
     return lib().fpvh_last_error().decode()
 
 
-def encode_stream(frames, xsize, ysize, shift=0, big_endian=False, threads=4, batch=8, delta=None, device=0):
-    """frames: uint16 [n, ysize*xsize]; delta defaults to frames[0].  Returns the stream as bytes."""
+class _entropy_mode:
+    """Selects the Encoder's entropy stage for the calls inside the block (GpuOptions::gpu_entropy = -1 reads the
+    environment variable FPV_GPU_ENTROPY in Encoder::Init)."""
+
+    def __init__(self, gpu_entropy):
+        self.value = "1" if gpu_entropy else "0"
+
+    def __enter__(self):
+        self.old = os.environ.get("FPV_GPU_ENTROPY")
+        os.environ["FPV_GPU_ENTROPY"] = self.value
+
+    def __exit__(self, *a):
+        if self.old is None:
+            del os.environ["FPV_GPU_ENTROPY"]
+        else:
+            os.environ["FPV_GPU_ENTROPY"] = self.old
+
+
+def encode_stream(frames, xsize, ysize, shift=0, big_endian=False, threads=4, batch=8, delta=None, device=0,
+                  gpu_entropy=False):
+    """frames: uint16 [n, ysize*xsize]; delta defaults to frames[0].  Returns the stream as bytes.
+    gpu_entropy: planes are entropy-coded on the GPU (valid brotli, not libbrotli's bytes) instead of host brotli."""
     L = lib()
     frames = np.ascontiguousarray(frames, dtype=np.uint16).reshape(-1, xsize * ysize)
     delta = frames[0] if delta is None else np.ascontiguousarray(delta, dtype=np.uint16).reshape(-1)
     n = frames.shape[0]
     cap = 64 + (n + 1) * (xsize * ysize * 5 // 2 + 4096)
     out = np.empty(cap, np.uint8)
-    size = L.fpvh_encode_stream(xsize, ysize, shift, int(big_endian), threads, batch, device, _p(delta), _p(frames), n,
-                                _p(out), cap)
+    with _entropy_mode(gpu_entropy):
+        size = L.fpvh_encode_stream(xsize, ysize, shift, int(big_endian), threads, batch, device, _p(delta), _p(frames),
+                                    n, _p(out), cap)
     if size == 0:
         raise HostError(f"encode failed: {last_error()}")
     if size > cap:
@@ -75,14 +96,16 @@ def encode_stream(frames, xsize, ysize, shift=0, big_endian=False, threads=4, ba
     return out[:size].tobytes()
 
 
-def time_encode(frames, xsize, ysize, shift=0, big_endian=False, threads=4, batch=8, delta=None, device=0):
+def time_encode(frames, xsize, ysize, shift=0, big_endian=False, threads=4, batch=8, delta=None, device=0,
+                gpu_entropy=False):
     """(seconds, stream bytes) of Encoder Init + CompressFrame x n + Finish (benchmark.cc's timing window)."""
     L = lib()
     frames = np.ascontiguousarray(frames, dtype=np.uint16).reshape(-1, xsize * ysize)
     delta = frames[0] if delta is None else np.ascontiguousarray(delta, dtype=np.uint16).reshape(-1)
     size = C.c_size_t(0)
-    t = L.fpvh_time_encode(xsize, ysize, shift, int(big_endian), threads, batch, device, _p(delta), _p(frames),
-                           frames.shape[0], C.byref(size))
+    with _entropy_mode(gpu_entropy):
+        t = L.fpvh_time_encode(xsize, ysize, shift, int(big_endian), threads, batch, device, _p(delta), _p(frames),
+                               frames.shape[0], C.byref(size))
     if t < 0:
         raise HostError(f"encode failed: {last_error()}")
     return t, size.value

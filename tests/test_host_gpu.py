@@ -105,3 +105,45 @@ def test_full_size_against_the_compiled_reference(W, H, bits, shift, n):
     assert np.array_equal(dec, dec_ref)
     raw = host.decode_stream(stream, n, W, H, batch=8, raw_shift=shift)
     assert np.array_equal(raw, frames), "round trip does not reproduce the input"
+
+
+# ---- Encoder with the GPU entropy coder (GpuOptions::gpu_entropy / FPV_GPU_ENTROPY) ---------------------------
+# The bytes differ from libbrotli's, so the checks are the north star's other two: the reference's own decoders
+# (decode.cc's StreamingDecoder, RandomAccessDecoder) read the stream, and the round trip reproduces the input.
+
+@pytest.mark.parametrize("threads,batch", [(0, 1), (2, 3), (4, 32)], ids=["sync", "t2b3", "t4b32"])
+@pytest.mark.parametrize("path", CASES, ids=[os.path.basename(p)[5:-4] for p in CASES])
+def test_gpu_entropy_stream_decodes_like_the_reference_stream(path, threads, batch):
+    g = np.load(path)
+    W, H, shift, be = int(g["W"]), int(g["H"]), int(g["shift"]), int(g["be"])
+    if W % 4 or H % 4:
+        pytest.skip("not encodable")
+    n = g["frames"].shape[0]
+    stream = host.encode_stream(g["frames"], W, H, shift, be, threads=threads, batch=batch, delta=g["delta"],
+                                gpu_entropy=True)
+    dec = host.decode_stream(stream, n + 2, W, H, block=4096, batch=3)
+    assert dec.shape[0] == n and np.array_equal(dec, g["decoded"])
+    nf, frames, preview = host.random_access(stream, n - 1, 1, W, H)
+    assert nf == n and np.array_equal(frames[0], g["decoded"][n - 1])
+    assert np.array_equal(preview, g["last_preview_decoded"])
+    if ref_available():
+        ref = Ref()
+        nd, dec_ref, wo, ho = ref.decode_stream(np.frombuffer(stream, np.uint8), n + 2, W, H)
+        assert nd == n and (wo, ho) == (W, H) and np.array_equal(dec_ref[:n], g["decoded"])
+        ok, img, prev, nf = ref.random_access_decode(np.frombuffer(stream, np.uint8), n - 1, W, H)
+        assert ok and nf == n and np.array_equal(img, g["decoded"][n - 1].reshape(-1))
+        assert np.array_equal(prev, g["last_preview_decoded"].reshape(-1))
+
+
+@pytest.mark.parametrize("W,H,bits,shift,n", [(1280, 800, 12, 4, 40), (1024, 1024, 16, 0, 9)])
+def test_gpu_entropy_full_size_round_trip(W, H, bits, shift, n):
+    frames = synth.plasma_frames(n, W, H, bits=bits, seed=78).reshape(n, -1)
+    stream = host.encode_stream(frames, W, H, shift, False, threads=4, batch=16, gpu_entropy=True)
+    brotli = host.encode_stream(frames, W, H, shift, False, threads=4, batch=16)
+    assert len(stream) < 1.03 * len(brotli), "GPU entropy coder much worse than brotli quality 1"
+    raw = host.decode_stream(stream, n, W, H, batch=8, raw_shift=shift)
+    assert np.array_equal(raw, frames), "round trip does not reproduce the input"
+    if ref_available():
+        nd, dec_ref, wo, ho = Ref().decode_stream(np.frombuffer(stream, np.uint8), n, W, H)
+        assert nd == n
+        assert np.array_equal(dec_ref[:n] >> shift if shift else dec_ref[:n], frames)
