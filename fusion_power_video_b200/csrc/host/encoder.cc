@@ -74,6 +74,9 @@ struct Encoder::Impl {
   uint64_t next_id = 0;
   std::thread gpu_thread;
   std::unique_ptr<Pool> pool;
+  // gpu_entropy: no brotli workers; a few helpers share the copy of each submitted frame into the
+  // pinned batch, which is otherwise the pipeline's bottleneck (one core copies ~8 GB/s).
+  std::unique_ptr<Pool> copy_pool;
 
   std::mutex out_m;                   // ordered emission
   struct Done {
@@ -102,6 +105,7 @@ struct Encoder::Impl {
       gpu_thread.join();
     }
     pool.reset();  // joins the brotli workers after their queue has drained
+    copy_pool.reset();
   }
 
   bool fail(const std::string& what) {
@@ -345,6 +349,7 @@ void Encoder::Init(const uint16_t* delta_frame, size_t xsize, size_t ysize, Call
   s.bytes_written = header.size();
   if (s.threads > 0) {
     if (!s.gpu_entropy) s.pool.reset(new Pool(s.threads));
+    else if (s.threads > 1 && s.P * 2 >= (1u << 19)) s.copy_pool.reset(new Pool(std::min<size_t>(s.threads - 1, 3)));
     s.gpu_thread = std::thread([&s] { s.gpu_loop(); });
   }
   callback(header.data(), header.size(), payload);
@@ -402,7 +407,25 @@ void Encoder::CompressFrame(const uint16_t* img, Callback callback, void* payloa
   }
   if (!b->allocated && !s.alloc_batch(b)) return;
   // only this (the submitting) thread touches a filling batch
-  memcpy(b->frames.as<uint16_t>() + (size_t)b->n * s.P, img, s.P * 2);
+  if (s.copy_pool) {
+    const size_t parts = s.copy_pool->size() + 1, bytes = s.P * 2, step = ((bytes + parts - 1) / parts + 4095) & ~(size_t)4095;
+    uint8_t* dst = reinterpret_cast<uint8_t*>(b->frames.as<uint16_t>() + (size_t)b->n * s.P);
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(img);
+    std::atomic<size_t> left{parts - 1};
+    auto copy_part = [&](size_t k) {
+      const size_t o = k * step;
+      if (o < bytes) memcpy(dst + o, src + o, std::min(step, bytes - o));
+    };
+    for (size_t k = 1; k < parts; k++)
+      s.copy_pool->run([&copy_part, &left, k] {
+        copy_part(k);
+        left.fetch_sub(1, std::memory_order_release);
+      });
+    copy_part(0);                                   // the caller copies its share too
+    while (left.load(std::memory_order_acquire)) std::this_thread::yield();
+  } else {
+    memcpy(b->frames.as<uint16_t>() + (size_t)b->n * s.P, img, s.P * 2);
+  }
   b->callbacks.push_back(callback);
   b->payloads.push_back(payload);
   b->n++;
