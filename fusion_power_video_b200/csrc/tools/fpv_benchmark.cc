@@ -20,7 +20,7 @@ static double Now() {
 
 int main(int argc, char* argv[]) {
   if (argc < 6) {
-    std::cerr << "usage: " << argv[0] << " file xsize ysize big_endian shift [maxframes] [threads=8] [batch=32]\n";
+    std::cerr << "usage: " << argv[0] << " file xsize ysize big_endian shift [maxframes] [threads=8] [batch=32] [gpu_entropy=0]\n";
     return 1;
   }
   const size_t xsize = strtoull(argv[2], nullptr, 10), ysize = strtoull(argv[3], nullptr, 10);
@@ -30,6 +30,7 @@ int main(int argc, char* argv[]) {
   const size_t threads = argc > 7 ? strtoull(argv[7], nullptr, 10) : 8;
   fpvc::GpuOptions opt;
   if (argc > 8) opt.batch = (uint32_t)atoi(argv[8]);
+  if (argc > 9) opt.gpu_entropy = atoi(argv[9]) != 0;
   const size_t px = xsize * ysize;
   if (px == 0) return 1;
 

@@ -12,7 +12,7 @@
 
 int main(int argc, char* argv[]) {
   if (argc < 5) {
-    std::cerr << "usage: " << argv[0] << " xsize ysize big_endian shift [threads=4] [batch=32] < raw > stream\n";
+    std::cerr << "usage: " << argv[0] << " xsize ysize big_endian shift [threads=4] [batch=32] [gpu_entropy=0] < raw > stream\n";
     return 1;
   }
   const size_t xsize = strtoull(argv[1], nullptr, 10), ysize = strtoull(argv[2], nullptr, 10);
@@ -21,6 +21,7 @@ int main(int argc, char* argv[]) {
   const size_t threads = argc > 5 ? strtoull(argv[5], nullptr, 10) : 4;
   fpvc::GpuOptions opt;
   if (argc > 6) opt.batch = (uint32_t)atoi(argv[6]);
+  if (argc > 7) opt.gpu_entropy = atoi(argv[7]) != 0;   // 1: entropy-code on the GPU (valid brotli, decodable by the reference)
   if (xsize == 0 || xsize > 65536 || ysize == 0 || ysize > 65536 || shift < 0 || shift > 16) {
     std::cerr << "invalid arguments\n";
     return 1;
