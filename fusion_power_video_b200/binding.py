@@ -11,7 +11,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "lib", "libfpv_b200.so")
+# FPV_B200_LIB: another build of the same library (tuning experiments: `make LIBDIR=../lib_x EXTRA=-D...`)
+_LIB_PATH = os.environ.get("FPV_B200_LIB") or os.path.join(_HERE, "lib", "libfpv_b200.so")
 
 ENC_DEFAULT, ENC_NO_DELTA, ENC_GENERIC = 0, 1, 2
 DEC_DEFAULT, DEC_UNEXTRACT = 0, 1

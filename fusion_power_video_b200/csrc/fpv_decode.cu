@@ -642,7 +642,13 @@ int enqueue_decode(const Geom& g, int num_sms, const uint8_t* high, const uint8_
     pp.high = high; pp.low = low; pp.flags = flags; pp.ddup = delta ? ddup : nullptr; pp.out = out;
     pp.W = g.W; pp.H = g.H; pp.P = g.P; pp.shift = g.shift; pp.big_endian = g.big_endian;
     pp.unextract = unextract ? 1 : 0; pp.n = n;
-    const int LW2 = (int)((g.W + 255) / 256);
+    // A lane owns L = 8 LW2 contiguous columns.  The IO warps walk the TMA-filled rows with a lane
+    // stride of L (residual, low), 2 L (output) and 4 L (duplicated delta) bytes: for L = 32 that is
+    // 8-way bank-conflicted, so widths of 769..1024 use L = 40 with the last lanes idle (measured on
+    // 1024x1024: 46 % -> see DESIGN.md).
+    int LW2 = (int)((g.W + 255) / 256);
+    if (LW2 == 4) LW2 = 5;
+    if (const char* v = getenv("FPV_PAIR_LW2")) { const int k = atoi(v); if (k >= LW2 && k <= 5) LW2 = k; }
     const bool full = g.W == 256u * (uint32_t)LW2;
     const int blocks = (int)((n + 3) / 4);   // two pairs of frames per CTA
     cudaError_t e = cudaSuccess;

@@ -212,7 +212,10 @@ __device__ __forceinline__ void pair_chain_row(const uint32_t (&n)[8 * LW2], uin
 // LW2:   the chain lane's segment is L = 8 LW2 px (LW2 = ceil(W / 256)).
 // FULL:  W == 32 L (every lane owns a complete segment).
 // SHIFT: UnextractFrame with a non-zero shift is fused into the write-out.
-template <int LW2, bool FULL, bool SHIFT, int K0T = FPV_PAIR_K0, int G = 8>
+#ifndef FPV_PAIR_G
+#define FPV_PAIR_G 8
+#endif
+template <int LW2, bool FULL, bool SHIFT, int K0T = FPV_PAIR_K0, int G = FPV_PAIR_G>
 __global__ void __launch_bounds__(kPairThreads, 2) k_decode_pair(const PairParams p) {
   extern __shared__ __align__(128) uint8_t psm[];
   constexpr int L = 8 * LW2;
