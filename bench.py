@@ -39,6 +39,10 @@ WORKLOADS = {
     "c2": (1280, 800, 12, 4, "12-bit 1280x800 camera stream, static delta frame, device-resident (BASELINE configs[1])"),
     "c1": (1024, 1024, 16, 0, "16-bit 1024x1024 (BASELINE configs[0] geometry)"),
     "c3": (2048, 2048, 16, 0, "16-bit 2048x2048, sharded by frame range (BASELINE configs[2] geometry)"),
+    # experiments: is a lower roofline fraction a matter of geometry (power-of-two strides) or of content (16-bit noise)?
+    "x1": (1024, 1000, 16, 0, "experiment: 16-bit 1024x1000 (frame size not a power of two)"),
+    "x2": (1280, 800, 16, 0, "experiment: 16-bit content at the C2 geometry"),
+    "x3": (1024, 1024, 12, 4, "experiment: 12-bit content at the C1 geometry"),
 }
 ENC_BYTES_PER_PX = 2 + 1 + 1 + 1.0 / 16  # raw in, high out, low out, preview out
 DEC_BYTES_PER_PX = 1 + 1 + 2             # planes in, uint16 out
@@ -319,7 +323,8 @@ def main():
                   "unit": "GB/s", "frames_per_s": world * F / (dms * 1e-3), "ms_per_step": dms, "steps": dsteps,
                   "round_trip_exact": ok,
                   "roofline": {"bound": "hbm (chain-latency limited, see DESIGN.md)",
-                               "kernel": "k_decode_pair" if (W % 16 == 0 and 64 <= W <= 1280) else "k_decode_simd",
+                               "kernel": ("k_decode_pair" if (W % 16 == 0 and 64 <= W <= 1280) else
+                                          "k_decode_pair (split mode)" if (W % 32 == 0 and W <= 2560) else "k_decode_simd"),
                                "achieved": dach, "peak": peak, "unit": "GB/s", "frac": dach / peak,
                                "traffic": ncu_traffic("decode", DEC_BYTES_PER_PX * F * P)}}
         del d_out

@@ -287,6 +287,7 @@ int fpv_create(fpv_ctx** out, int device, uint32_t xsize, uint32_t ysize, int sh
   if (const char* v = getenv("FPV_STAGES")) c->tune.stages = atoi(v);
   if (const char* v = getenv("FPV_BAND_ROWS")) c->tune.band_rows = atoi(v);
   if (const char* v = getenv("FPV_ROWS_PER_STAGE")) c->tune.rows_per_stage = atoi(v) == 2 ? 2 : 4;
+  if (const char* v = getenv("FPV_MAX_CTAS")) c->tune.max_ctas = atoi(v);
   if (c->tune.stages < 2) c->tune.stages = 2;
   if (c->tune.stages > 8) c->tune.stages = 8;
   if (c->tune.band_rows < 4) c->tune.band_rows = 4;

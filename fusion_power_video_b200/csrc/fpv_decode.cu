@@ -603,13 +603,30 @@ __global__ void k_delta_dup(const uint16_t* delta, uint32_t* ddup, uint64_t P) {
   }
 }
 
+// Split mode of the pair kernel (one frame, left half in the low lane, right half in the high lane):
+// word (row, c) = d[row][c] | d[row][c + W/2] << 16 for c < W/2.
+__global__ void k_delta_dup_split(const uint16_t* delta, uint32_t* ddup, uint32_t W, uint32_t H) {
+  const uint32_t Wh = W / 2;
+  const uint64_t total = (uint64_t)Wh * H;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t row = i / Wh, c = i % Wh;
+    ddup[i] = (uint32_t)delta[row * W + c] | ((uint32_t)delta[row * W + c + Wh] << 16);
+  }
+}
+
 }  // namespace
+
+// Widths the pair kernel takes two frames at a time / one frame as two halves.
+static bool pair_width_ok(uint32_t W) { return W % 16 == 0 && W >= 64 && W <= 1280; }
+static bool split_width_ok(uint32_t W) { return W % 32 == 0 && W > 1280 && W <= 2560; }
 
 int enqueue_delta_dup(const Geom& g, const uint16_t* delta_image, uint32_t* ddup, cudaStream_t stream,
                       cudaError_t* err) {
   unsigned gx = (unsigned)((g.P + 255) / 256);
   if (gx > 1184) gx = 1184;
-  k_delta_dup<<<gx, 256, 0, stream>>>(delta_image, ddup, g.P);
+  if (split_width_ok(g.W)) k_delta_dup_split<<<gx, 256, 0, stream>>>(delta_image, ddup, g.W, g.H);
+  else k_delta_dup<<<gx, 256, 0, stream>>>(delta_image, ddup, g.P);
   *err = cudaGetLastError();
   return *err == cudaSuccess ? 1 : -1;
 }
@@ -619,7 +636,7 @@ int enqueue_delta_dup(const Geom& g, const uint16_t* delta_image, uint32_t* ddup
 enum DecodeKernel { kDecPair, kDecSimd, kDecSpec };
 
 static DecodeKernel pick_decode_kernel(const Geom& g, const uint16_t* delta, const uint32_t* ddup) {
-  const bool pair_ok = g.W % 16 == 0 && g.W >= 64 && g.W <= 1280 && (delta == nullptr || ddup != nullptr);
+  const bool pair_ok = (pair_width_ok(g.W) || split_width_ok(g.W)) && (delta == nullptr || ddup != nullptr);
   const bool simd_ok = g.W % 4 == 0 && g.W <= 64 * 32 && g.W >= 64;
   if (const char* v = getenv("FPV_DECODE_KERNEL")) {
     if (!strcmp(v, "pair") && pair_ok) return kDecPair;
@@ -640,19 +657,27 @@ int enqueue_decode(const Geom& g, int num_sms, const uint8_t* high, const uint8_
   if (which == kDecPair) {
     PairParams pp;
     pp.high = high; pp.low = low; pp.flags = flags; pp.ddup = delta ? ddup : nullptr; pp.out = out;
-    pp.W = g.W; pp.H = g.H; pp.P = g.P; pp.shift = g.shift; pp.big_endian = g.big_endian;
+    const bool split = split_width_ok(g.W);
+    pp.W = split ? g.W / 2 : g.W; pp.stride = g.W; pp.H = g.H; pp.P = g.P; pp.shift = g.shift;
+    pp.big_endian = g.big_endian;
     pp.unextract = unextract ? 1 : 0; pp.n = n;
     // A lane owns L = 8 LW2 contiguous columns.  The IO warps walk the TMA-filled rows with a lane
     // stride of L (residual, low), 2 L (output) and 4 L (duplicated delta) bytes: for L = 32 that is
     // 8-way bank-conflicted, so widths of 769..1024 use L = 40 with the last lanes idle (measured on
     // 1024x1024: 46 % -> see DESIGN.md).
-    int LW2 = (int)((g.W + 255) / 256);
+    int LW2 = (int)((pp.W + 255) / 256);
     if (LW2 == 4) LW2 = 5;
-    if (const char* v = getenv("FPV_PAIR_LW2")) { const int k = atoi(v); if (k >= LW2 && k <= 5) LW2 = k; }
-    const bool full = g.W == 256u * (uint32_t)LW2;
-    const int blocks = (int)((n + 3) / 4);   // two pairs of frames per CTA
+    if (const char* v = getenv("FPV_PAIR_LW2")) { const int k = atoi(v); if (!split && k >= LW2 && k <= 5) LW2 = k; }
+    const bool full = pp.W == 256u * (uint32_t)LW2;
+    // two pairs of frames per CTA; split mode: two frames (each a pair of halves)
+    const int blocks = split ? (int)((n + 1) / 2) : (int)((n + 3) / 4);
     cudaError_t e = cudaSuccess;
     if (hook) cudaEventRecord(hook->start, stream);
+    if (split) {
+      // half widths of 641..1280 columns: LW2 is 3, 4 (run as 5) or 5
+      if (LW2 == 3) e = launch_pair<3, true>(pp, full, blocks, stream);
+      else e = launch_pair<5, true>(pp, full, blocks, stream);
+    } else
     switch (LW2) {
       case 1: e = launch_pair<1>(pp, full, blocks, stream); break;
       case 2: e = launch_pair<2>(pp, full, blocks, stream); break;

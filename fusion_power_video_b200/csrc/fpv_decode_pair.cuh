@@ -58,7 +58,8 @@ struct PairParams {
   const uint8_t* flags;
   const uint32_t* ddup;    // delta image, (d | d << 16) per pixel; may be nullptr
   uint16_t* out;
-  uint32_t W, H;
+  uint32_t W, H;           // W: columns of one "frame" of the pair (split mode: half the frame's width)
+  uint32_t stride;         // elements from one row to the next (== W, split mode: 2 W)
   uint64_t P;
   int shift, big_endian, unextract;
   uint32_t n;
@@ -100,7 +101,12 @@ __device__ __forceinline__ uint32_t bitselect(uint32_t a, uint32_t b, uint32_t m
 // One row of the chain warp: residual row (pair form, in PRE) -> finished row in x[] and in POST.
 // n[] is the finished previous row; the caller alternates two register arrays between rows so
 // that nothing is copied.
-template <int LW2, bool FULL, int K0T, int G>
+// SPLIT: the two 16-bit lanes are not two frames but the left and the right half of ONE frame (widths
+// up to 2560).  The chain then runs through the low lane's 32 segments and on through the high
+// lane's: segment 0 of the right half takes its incoming values from the last segment of the left
+// half of the same row (speculated and repaired like every other segment boundary), segment 0 of the
+// left half from the right half of the previous row (exact).
+template <int LW2, bool FULL, int K0T, int G, bool SPLIT>
 __device__ __forceinline__ void pair_chain_row(const uint32_t (&n)[8 * LW2], uint32_t (&x)[8 * LW2], const uint32_t y,
                                                const uint32_t pre, const uint32_t post, const uint32_t cgmask,
                                                const uint32_t vmask, const int lane, const uint32_t last_lane,
@@ -119,9 +125,13 @@ __device__ __forceinline__ void pair_chain_row(const uint32_t (&n)[8 * LW2], uin
   if (cgmask != 0 && y > 0) {
     uint32_t c[L];
     uint32_t nw_in = __shfl_up_sync(0xffffffffu, n[L - 1], 1);
-    if (lane == 0) nw_in = last_prev2;
+    // lane 0: the pixel before column 0 in flat order.  Pair mode: the last pixel of row y-2 of each
+    // frame.  Split mode: left half <- last pixel of row y-2 (right half), right half <- the left
+    // half's last pixel of row y-1.
+    if (lane == 0) nw_in = SPLIT ? ((last_prev2 >> 16) | (last_prev << 16)) : last_prev2;
     // flat index W (row 1, column 0) is not predicted (.cc:327 starts at W+1)
     const bool copy_first = (y == 1) && (lane == 0);
+    const uint32_t copy_mask = SPLIT ? 0x0000ffffu : 0xffffffffu;   // split: only the left half has a column 0
     const uint32_t r_first = x[0] - kLaneBias;
 #pragma unroll
     for (int t = 0; t < L; t++) c[t] = x[t] - (t == 0 ? nw_in : n[t - 1]);
@@ -137,7 +147,13 @@ __device__ __forceinline__ void pair_chain_row(const uint32_t (&n)[8 * LW2], uin
         nw = nn;
       }
       w_in = __shfl_up_sync(0xffffffffu, w, 1);
-      if (lane == 0) w_in = last_prev;              // exact for segment 0
+      if (SPLIT) {
+        // the left half's last segment feeds the right half's first (a guess, repaired below)
+        const uint32_t wl = __shfl_sync(0xffffffffu, w, (int)last_lane);
+        if (lane == 0) w_in = (last_prev >> 16) | (wl << 16);
+      } else if (lane == 0) {
+        w_in = last_prev;                           // exact for segment 0
+      }
     }
     // pass 1: every segment in full
     {
@@ -146,7 +162,7 @@ __device__ __forceinline__ void pair_chain_row(const uint32_t (&n)[8 * LW2], uin
       for (int t = 0; t < L; t++) {
         const uint32_t nn = n[t];
         uint32_t v = (c[t] + __vimin3_u16x2(nn, w, nw) + __vimax3_u16x2(nn, w, nw)) & kLaneMask;
-        if (t == 0 && copy_first) v = r_first;
+        if (t == 0 && copy_first) v = (r_first & copy_mask) | (v & ~copy_mask);
         x[t] = v;
         w = v;
         nw = nn;
@@ -155,7 +171,18 @@ __device__ __forceinline__ void pair_chain_row(const uint32_t (&n)[8 * LW2], uin
     // repair: re-run segments whose incoming value was wrong until nothing changes
     for (;;) {
       uint32_t w_new = __shfl_up_sync(0xffffffffu, x[L - 1], 1);
-      if (lane == 0) w_new = last_prev;
+      if (SPLIT) {
+        uint32_t xl = x[L - 1];
+        if (!FULL) {
+#pragma unroll
+          for (int k = 0; k < 2 * LW2; k++)
+            if ((uint32_t)(4 * k + 3) == last_t) xl = x[4 * k + 3];
+        }
+        xl = __shfl_sync(0xffffffffu, xl, (int)last_lane);
+        if (lane == 0) w_new = (last_prev >> 16) | (xl << 16);
+      } else if (lane == 0) {
+        w_new = last_prev;
+      }
       const bool changed = ((w_new ^ w_in) & vmask) != 0;
       if (!__any_sync(0xffffffffu, changed)) break;
       w_in = w_new;
@@ -168,7 +195,7 @@ __device__ __forceinline__ void pair_chain_row(const uint32_t (&n)[8 * LW2], uin
           const int t = G * k + j;
           const uint32_t nn = n[t];
           uint32_t v = (c[t] + __vimin3_u16x2(nn, w, nw) + __vimax3_u16x2(nn, w, nw)) & kLaneMask;
-          if (t == 0 && copy_first) v = r_first;
+          if (t == 0 && copy_first) v = (r_first & copy_mask) | (v & ~copy_mask);
           if (j == G - 1) same = ((v ^ x[t]) & vmask) == 0;
           x[t] = v;
           w = v;
@@ -215,7 +242,7 @@ __device__ __forceinline__ void pair_chain_row(const uint32_t (&n)[8 * LW2], uin
 #ifndef FPV_PAIR_G
 #define FPV_PAIR_G 8
 #endif
-template <int LW2, bool FULL, bool SHIFT, int K0T = FPV_PAIR_K0, int G = FPV_PAIR_G>
+template <int LW2, bool FULL, bool SHIFT, bool SPLIT = false, int K0T = FPV_PAIR_K0, int G = FPV_PAIR_G>
 __global__ void __launch_bounds__(kPairThreads, 2) k_decode_pair(const PairParams p) {
   extern __shared__ __align__(128) uint8_t psm[];
   constexpr int L = 8 * LW2;
@@ -259,9 +286,11 @@ __global__ void __launch_bounds__(kPairThreads, 2) k_decode_pair(const PairParam
 
   const uint32_t sm0 = smem_u32(psm) + pair * kPairBytes;
   const uint32_t full1 = sm0 + kBars, full2 = full1 + 8 * kPairRing;
-  const uint32_t fA = 4 * blockIdx.x + 2 * pair;
+  // pair mode: frames (fA, fA + 1); split mode: the two halves of frame fA
+  const uint32_t fA = SPLIT ? 2 * blockIdx.x + pair : 4 * blockIdx.x + 2 * pair;
   if (fA >= p.n) return;                            // odd number of pairs: this half of the CTA has nothing to do
-  const uint32_t fB = fA + 1 < p.n ? fA + 1 : fA;   // odd tail: the pair is (A, A), B is not stored
+  const uint32_t fB = SPLIT ? fA : (fA + 1 < p.n ? fA + 1 : fA);   // odd tail: the pair is (A, A), B is not stored
+  const uint32_t offB = SPLIT ? W : 0u;             // split mode: "frame B" starts W columns into the row
   const uint32_t flA = p.flags[fA], flB = p.flags[fB];
   const bool lowA = !(flA & kFlagNoLow) && p.low != nullptr, lowB = !(flB & kFlagNoLow) && p.low != nullptr;
   const bool delA = (flA & kFlagDelta) && p.ddup != nullptr, delB = (flB & kFlagDelta) && p.ddup != nullptr;
@@ -281,10 +310,10 @@ __global__ void __launch_bounds__(kPairThreads, 2) k_decode_pair(const PairParam
     pair_bar_sync(bar_id);               // mbarriers are initialised, the ring is zero-filled where needed
     pair_bar_sync(bar_id);               // row 0 is in PRE[0] (the IO warp's prologue)
     for (uint32_t y = 0; y < H; y += 2) {
-      pair_chain_row<LW2, FULL, K0T, G>(rb, ra, y, sm0 + kPre, sm0 + kPost, cgmask, vmask, lane, last_lane, last_t,
+      pair_chain_row<LW2, FULL, K0T, G, SPLIT>(rb, ra, y, sm0 + kPre, sm0 + kPost, cgmask, vmask, lane, last_lane, last_t,
                                         last_prev, last_prev2, bar_id);
       if (y + 1 < H)
-        pair_chain_row<LW2, FULL, K0T, G>(ra, rb, y + 1, sm0 + kPre + kBuf, sm0 + kPost + kBuf, cgmask, vmask, lane,
+        pair_chain_row<LW2, FULL, K0T, G, SPLIT>(ra, rb, y + 1, sm0 + kPre + kBuf, sm0 + kPost + kBuf, cgmask, vmask, lane,
                                           last_lane, last_t, last_prev, last_prev2, bar_id);
     }
     return;
@@ -325,11 +354,12 @@ __global__ void __launch_bounds__(kPairThreads, 2) k_decode_pair(const PairParam
 
   // ---- TMA issue state.  It is warp-uniform (which lets the compiler hold it in uniform
   //      registers); only the elected lane executes the copy instructions.
+  const uint32_t stride = p.stride;
   const uint8_t* s1A = p.high + (uint64_t)fA * p.P;   // next residual row to fetch
-  const uint8_t* s1B = p.high + (uint64_t)fB * p.P;
+  const uint8_t* s1B = p.high + (uint64_t)fB * p.P + offB;
   const uint8_t* s2A = p.low + (uint64_t)fA * p.P;    // next low row (dereferenced only if lowA / lowB)
-  const uint8_t* s2B = p.low + (uint64_t)fB * p.P;
-  const uint32_t* s2D = p.ddup;
+  const uint8_t* s2B = p.low + (uint64_t)fB * p.P + offB;
+  const uint32_t* s2D = p.ddup;                       // W words per row in either mode
   uint32_t i1_row = 0, i1_slot = 0, i2_row = 0, i2_slot = 0;
   auto issue_r1 = [&]() {     // residual rows of both frames
     if (i1_row < H && elected) {
@@ -338,7 +368,7 @@ __global__ void __launch_bounds__(kPairThreads, 2) k_decode_pair(const PairParam
       bulk_g2s(dst, s1A, W, bar);
       bulk_g2s(dst + RB, s1B, W, bar);
     }
-    s1A += W; s1B += W;
+    s1A += stride; s1B += stride;
     i1_row++;
     if (++i1_slot == kPairRing) i1_slot = 0;
   };
@@ -350,7 +380,7 @@ __global__ void __launch_bounds__(kPairThreads, 2) k_decode_pair(const PairParam
       if (lowB) bulk_g2s(dst + RB, s2B, W, bar);
       if (dmask) bulk_g2s(dst + 2 * RB, s2D, 4 * W, bar);
     }
-    s2A += W; s2B += W; s2D += W;
+    s2A += stride; s2B += stride; s2D += W;
     i2_row++;
     if (++i2_slot == kPairRing) i2_slot = 0;
   };
@@ -358,7 +388,7 @@ __global__ void __launch_bounds__(kPairThreads, 2) k_decode_pair(const PairParam
   // ---- consumer state: ring slot and mbarrier parity of the next row of each kind ------------
   uint32_t c1_slot = 0, c1_par = 0, c2_slot = 0, c2_par = 0;
   uint16_t* oA = p.out + (uint64_t)fA * p.P;        // next output row
-  uint16_t* oB = p.out + (uint64_t)fB * p.P;
+  uint16_t* oB = p.out + (uint64_t)fB * p.P + offB;
 
   // residual bytes of the next row -> pair form for the chain warp, into PRE[buf]
   auto pre_row = [&](uint32_t buf) {
@@ -427,10 +457,10 @@ __global__ void __launch_bounds__(kPairThreads, 2) k_decode_pair(const PairParam
     __syncwarp();
     if (elected) {
       bulk_s2g(oA, sm0 + kOut, 2 * W);
-      if (fB != fA) bulk_s2g(oB, sm0 + kOut + 2 * RB, 2 * W);
+      if (SPLIT || fB != fA) bulk_s2g(oB, sm0 + kOut + 2 * RB, 2 * W);
       bulk_commit();
     }
-    oA += W; oB += W;
+    oA += stride; oB += stride;
   };
 
   if (is_helper) {
@@ -456,15 +486,15 @@ __global__ void __launch_bounds__(kPairThreads, 2) k_decode_pair(const PairParam
   if (elected) bulk_wait0();
 }
 
-template <int LW2>
+template <int LW2, bool SPLIT = false>
 static cudaError_t launch_pair(const PairParams& p, bool full, int blocks, cudaStream_t stream) {
   const size_t smem = pair_smem_bytes(LW2);
   const bool shift = p.unextract && p.shift != 0;
   cudaError_t e = cudaSuccess;
-#define FPV_LAUNCH_PAIR(F, S)                                                                                     \
-  do {                                                                                                            \
-    e = cudaFuncSetAttribute(k_decode_pair<LW2, F, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
-    if (e == cudaSuccess) k_decode_pair<LW2, F, S><<<blocks, kPairThreads, smem, stream>>>(p);                    \
+#define FPV_LAUNCH_PAIR(F, S)                                                                                            \
+  do {                                                                                                                   \
+    e = cudaFuncSetAttribute(k_decode_pair<LW2, F, S, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
+    if (e == cudaSuccess) k_decode_pair<LW2, F, S, SPLIT><<<blocks, kPairThreads, smem, stream>>>(p);                    \
   } while (0)
   if (full && shift) FPV_LAUNCH_PAIR(true, true);
   else if (full) FPV_LAUNCH_PAIR(true, false);

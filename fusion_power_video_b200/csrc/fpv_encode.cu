@@ -523,6 +523,7 @@ int enqueue_encode(const Geom& g, const EncodeTuning& t, const EncodeScratch& s,
     if (ctas_per_sm < 1) ctas_per_sm = 1;
     int by_threads = 2048 / threads; if (by_threads < 1) by_threads = 1;
     if (ctas_per_sm > by_threads) ctas_per_sm = by_threads;
+    if (t.max_ctas > 0 && ctas_per_sm > t.max_ctas) ctas_per_sm = t.max_ctas;
     uint64_t max_tasks = (uint64_t)n * fp.bands;
     int grid = t.num_sms * ctas_per_sm;
     if ((uint64_t)grid > max_tasks) grid = (int)max_tasks;

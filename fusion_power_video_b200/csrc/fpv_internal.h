@@ -32,7 +32,8 @@ struct EncodeTuning {
   int num_sms = 148;
   int stages = 2;          // smem ring depth of the fast kernel (2 measured best: occupancy wins)
   int rows_per_stage = 4;  // 4 or 2
-  int band_rows = 64;      // rows per task (multiple of 4)
+  int band_rows = 128;     // rows per task (multiple of 4)
+  int max_ctas = 4;        // cap on resident CTAs per SM of the fast kernel (0 = what fits); a fifth CTA costs 8 points at W = 1024
   int max_smem_optin = 0;  // bytes
 };
 

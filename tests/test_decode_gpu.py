@@ -92,7 +92,9 @@ def test_speculation_adversarial(oracle, W, H, kind, kernel, monkeypatch):
 
 
 PAIR_GEOMS = [(64, 5), (80, 7), (128, 3), (256, 9), (320, 6), (512, 4), (768, 5), (1024, 6), (1040, 3),
-              (1280, 1), (1280, 2), (1280, 9)]
+              (1280, 1), (1280, 2), (1280, 9),
+              # wider than 1280: the pair kernel's split mode (one frame as a left and a right half)
+              (1312, 5), (1536, 4), (1920, 7), (2016, 2), (2048, 1), (2048, 6), (2560, 3)]
 
 
 @pytest.mark.parametrize("kernel", ["pair", "simd", "spec"])
