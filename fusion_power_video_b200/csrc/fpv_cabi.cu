@@ -293,7 +293,7 @@ int fpv_create(fpv_ctx** out, int device, uint32_t xsize, uint32_t ysize, int sh
   if (c->tune.band_rows < 4) c->tune.band_rows = 4;
   c->force_generic = getenv("FPV_FORCE_GENERIC") != nullptr;
   cudaError_t e2 = cudaMalloc(&c->d_delta, c->g.P * 2);
-  if (e2 == cudaSuccess) e2 = cudaMalloc(&c->d_delta_dup, c->g.P * 4);
+  if (e2 == cudaSuccess) e2 = cudaMalloc(&c->d_delta_dup, delta_dup_bytes(c->g));
   if (e2 == cudaSuccess) e2 = cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking);
   if (e2 != cudaSuccess) {
     int rc = cuda_fail(nullptr, e2, "fpv_create allocation");

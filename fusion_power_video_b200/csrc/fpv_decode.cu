@@ -593,25 +593,18 @@ __global__ void k_planes_add_delta(uint8_t* high, uint8_t* low, const uint8_t* f
   }
 }
 
-// delta image -> (d | d << 16) per pixel: the form k_decode_pair adds to the same
-// column of two frames at once.
-__global__ void k_delta_dup(const uint16_t* delta, uint32_t* ddup, uint64_t P) {
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P;
-       i += (uint64_t)gridDim.x * blockDim.x) {
-    const uint32_t d = delta[i];
-    ddup[i] = d | (d << 16);
-  }
-}
-
-// Split mode of the pair kernel (one frame, left half in the low lane, right half in the high lane):
-// word (row, c) = d[row][c] | d[row][c + W/2] << 16 for c < W/2.
-__global__ void k_delta_dup_split(const uint16_t* delta, uint32_t* ddup, uint32_t W, uint32_t H) {
-  const uint32_t Wh = W / 2;
-  const uint64_t total = (uint64_t)Wh * H;
+// delta image -> pair form for k_decode_pair, one padded and permuted row of 32 L words per image row
+// (pair_ddup_word).  Pair mode: (d | d << 16), the same column of two frames.  Split mode (one frame,
+// left half in the low lane, right half in the high lane): d[row][c] | d[row][c + W/2] << 16.
+__global__ void k_delta_dup(const uint16_t* delta, uint32_t* ddup, uint32_t W, uint32_t H, uint32_t L, int split) {
+  const uint32_t Wp = split ? W / 2 : W;          // columns of the pair kernel's "frame"
+  const uint64_t total = (uint64_t)Wp * H;
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (uint64_t)gridDim.x * blockDim.x) {
-    const uint64_t row = i / Wh, c = i % Wh;
-    ddup[i] = (uint32_t)delta[row * W + c] | ((uint32_t)delta[row * W + c + Wh] << 16);
+    const uint64_t row = i / Wp;
+    const uint32_t c = (uint32_t)(i % Wp);
+    const uint32_t a = delta[row * W + c], b = split ? delta[row * W + c + Wp] : a;
+    ddup[row * 32u * L + pair_ddup_word(c, L)] = a | (b << 16);
   }
 }
 
@@ -621,12 +614,28 @@ __global__ void k_delta_dup_split(const uint16_t* delta, uint32_t* ddup, uint32_
 static bool pair_width_ok(uint32_t W) { return W % 16 == 0 && W >= 64 && W <= 1280; }
 static bool split_width_ok(uint32_t W) { return W % 32 == 0 && W > 1280 && W <= 2560; }
 
+// Columns per lane / 8 of the pair kernel for a geometry (the duplicated delta image depends on it).
+static int pair_lw2(const Geom& g, bool* split_out) {
+  const bool split = split_width_ok(g.W);
+  const uint32_t Wp = split ? g.W / 2 : g.W;
+  int LW2 = (int)((Wp + 255) / 256);
+  if (const char* v = getenv("FPV_PAIR_LW2")) { const int k = atoi(v); if (k >= LW2 && k <= 5) LW2 = k; }
+  if (split_out) *split_out = split;
+  return LW2;
+}
+
+size_t delta_dup_bytes(const Geom& g) { return ((size_t)g.W + 256) * g.H * 4; }
+
 int enqueue_delta_dup(const Geom& g, const uint16_t* delta_image, uint32_t* ddup, cudaStream_t stream,
                       cudaError_t* err) {
+  if (!pair_width_ok(g.W) && !split_width_ok(g.W)) { *err = cudaSuccess; return 0; }   // the pair kernel is not used
+  bool split = false;
+  const uint32_t L = 8u * (uint32_t)pair_lw2(g, &split);
   unsigned gx = (unsigned)((g.P + 255) / 256);
   if (gx > 1184) gx = 1184;
-  if (split_width_ok(g.W)) k_delta_dup_split<<<gx, 256, 0, stream>>>(delta_image, ddup, g.W, g.H);
-  else k_delta_dup<<<gx, 256, 0, stream>>>(delta_image, ddup, g.P);
+  *err = cudaMemsetAsync(ddup, 0, (size_t)32 * L * g.H * 4, stream);      // padding columns
+  if (*err != cudaSuccess) return -1;
+  k_delta_dup<<<gx, 256, 0, stream>>>(delta_image, ddup, g.W, g.H, L, split ? 1 : 0);
   *err = cudaGetLastError();
   return *err == cudaSuccess ? 1 : -1;
 }
@@ -661,21 +670,17 @@ int enqueue_decode(const Geom& g, int num_sms, const uint8_t* high, const uint8_
     pp.W = split ? g.W / 2 : g.W; pp.stride = g.W; pp.H = g.H; pp.P = g.P; pp.shift = g.shift;
     pp.big_endian = g.big_endian;
     pp.unextract = unextract ? 1 : 0; pp.n = n;
-    // A lane owns L = 8 LW2 contiguous columns.  The IO warps walk the TMA-filled rows with a lane
-    // stride of L (residual, low), 2 L (output) and 4 L (duplicated delta) bytes: for L = 32 that is
-    // 8-way bank-conflicted, so widths of 769..1024 use L = 40 with the last lanes idle (measured on
-    // 1024x1024: 46 % -> see DESIGN.md).
-    int LW2 = (int)((pp.W + 255) / 256);
-    if (LW2 == 4) LW2 = 5;
-    if (const char* v = getenv("FPV_PAIR_LW2")) { const int k = atoi(v); if (!split && k >= LW2 && k <= 5) LW2 = k; }
+    // A lane owns L = 8 LW2 contiguous columns.
+    const int LW2 = pair_lw2(g, nullptr);
     const bool full = pp.W == 256u * (uint32_t)LW2;
     // two pairs of frames per CTA; split mode: two frames (each a pair of halves)
     const int blocks = split ? (int)((n + 1) / 2) : (int)((n + 3) / 4);
     cudaError_t e = cudaSuccess;
     if (hook) cudaEventRecord(hook->start, stream);
     if (split) {
-      // half widths of 641..1280 columns: LW2 is 3, 4 (run as 5) or 5
+      // half widths of 641..1280 columns
       if (LW2 == 3) e = launch_pair<3, true>(pp, full, blocks, stream);
+      else if (LW2 == 4) e = launch_pair<4, true>(pp, full, blocks, stream);
       else e = launch_pair<5, true>(pp, full, blocks, stream);
     } else
     switch (LW2) {

@@ -56,7 +56,7 @@ struct PairParams {
   const uint8_t* high;
   const uint8_t* low;      // may be nullptr
   const uint8_t* flags;
-  const uint32_t* ddup;    // delta image, (d | d << 16) per pixel; may be nullptr
+  const uint32_t* ddup;    // delta image in pair form, rows permuted and padded (pair_ddup_word); may be nullptr
   uint16_t* out;
   uint32_t W, H;           // W: columns of one "frame" of the pair (split mode: half the frame's width)
   uint32_t stride;         // elements from one row to the next (== W, split mode: 2 W)
@@ -83,6 +83,16 @@ static inline size_t pair_smem_bytes(int LW2) {
   const size_t RB = 32 * 8 * (size_t)LW2;
   const size_t per_pair = RB * (kPairRing * 2 + kPairRing * 6 + 8 + 8 + 4) + 128;   // + mbarriers (padded)
   return 2 * per_pair + 32;                                                      // + role table
+}
+
+// Layout of one row of the duplicated delta image (global memory and, copied verbatim by TMA, shared
+// memory): 32 L words, the word of column c = lane L + 8 chunk + 4 half + j (lane = c / L) sits at
+//     ((2 chunk + half) 32 + lane) 4 + j
+// so that the 32 lanes of an LDS.128 read 32 consecutive 16-byte slots (conflict free), like the
+// PRE / POST buffers.  A linear row would put the lanes 4 L bytes apart: 8-way conflicts for L = 32.
+__host__ __device__ inline uint32_t pair_ddup_word(uint32_t c, uint32_t L) {
+  const uint32_t lane = c / L, r = c % L;
+  return ((r >> 2) * 32u + lane) * 4u + (r & 3u);
 }
 
 __device__ __forceinline__ uint2 lds64(uint32_t a) {
@@ -332,7 +342,7 @@ __global__ void __launch_bounds__(kPairThreads, 2) k_decode_pair(const PairParam
   const uint32_t selA = do_swap ? 0x4501u : 0x5410u, selB = do_swap ? 0x6723u : 0x7632u;
   const uint32_t dmask = (delA ? 0x0000ffffu : 0u) | (delB ? 0xffff0000u : 0u);
   const uint32_t mh = kHiBytes & dmask, ml = kLoBytes & dmask;
-  const uint32_t r2_bytes = (lowA ? W : 0u) + (lowB ? W : 0u) + (dmask ? 4 * W : 0u);
+  const uint32_t r2_bytes = (lowA ? W : 0u) + (lowB ? W : 0u) + (dmask ? 4 * RB : 0u);
 
   if (is_helper && elected) {
     for (int i = 0; i < 2 * kPairRing; i++) mbar_init(full1 + 8 * i, 1);
@@ -359,7 +369,7 @@ __global__ void __launch_bounds__(kPairThreads, 2) k_decode_pair(const PairParam
   const uint8_t* s1B = p.high + (uint64_t)fB * p.P + offB;
   const uint8_t* s2A = p.low + (uint64_t)fA * p.P;    // next low row (dereferenced only if lowA / lowB)
   const uint8_t* s2B = p.low + (uint64_t)fB * p.P + offB;
-  const uint32_t* s2D = p.ddup;                       // W words per row in either mode
+  const uint32_t* s2D = p.ddup;                       // 32 L words per row (pair_ddup_word)
   uint32_t i1_row = 0, i1_slot = 0, i2_row = 0, i2_slot = 0;
   auto issue_r1 = [&]() {     // residual rows of both frames
     if (i1_row < H && elected) {
@@ -378,9 +388,9 @@ __global__ void __launch_bounds__(kPairThreads, 2) k_decode_pair(const PairParam
       mbar_arrive_expect_tx(bar, r2_bytes);
       if (lowA) bulk_g2s(dst, s2A, W, bar);
       if (lowB) bulk_g2s(dst + RB, s2B, W, bar);
-      if (dmask) bulk_g2s(dst + 2 * RB, s2D, 4 * W, bar);
+      if (dmask) bulk_g2s(dst + 2 * RB, s2D, 4 * RB, bar);    // a whole permuted row: 32 L words
     }
-    s2A += stride; s2B += stride; s2D += W;
+    s2A += stride; s2B += stride; s2D += RB;
     i2_row++;
     if (++i2_slot == kPairRing) i2_slot = 0;
   };
@@ -390,6 +400,16 @@ __global__ void __launch_bounds__(kPairThreads, 2) k_decode_pair(const PairParam
   uint16_t* oA = p.out + (uint64_t)fA * p.P;        // next output row
   uint16_t* oB = p.out + (uint64_t)fB * p.P + offB;
 
+  // Order in which a lane walks its LW2 chunks of 8 columns.  With L = 32 (LW2 = 4) the lanes sit
+  // 32 / 64 bytes apart in the TMA-filled rows and in the output row: taking the chunks in a
+  // lane-dependent rotation makes the 64-bit loads of a half-warp and the 128-bit stores of a
+  // quarter-warp hit distinct banks ((l & 3, chunk) resp. (l & 1, chunk) are then all different).
+  // Only addresses depend on it; register arrays stay indexed by the loop counter.
+  const uint32_t rot = ((uint32_t)lane >> 2) + 2u * (((uint32_t)lane >> 1) & 1u);
+  auto chunk = [&](int k) -> uint32_t {
+    if constexpr (LW2 == 4) return ((uint32_t)k + rot) & 3u;
+    else return (uint32_t)k;
+  };
   // residual bytes of the next row -> pair form for the chain warp, into PRE[buf]
   auto pre_row = [&](uint32_t buf) {
     mbar_wait(full1 + 8 * c1_slot, c1_par);
@@ -397,16 +417,16 @@ __global__ void __launch_bounds__(kPairThreads, 2) k_decode_pair(const PairParam
     if (++c1_slot == kPairRing) { c1_slot = 0; c1_par ^= 1u; }
     uint2 A[LW2], B[LW2];
 #pragma unroll
-    for (int k = 0; k < LW2; k++) { A[k] = lds64(ra + 8 * k); B[k] = lds64(ra + RB + 8 * k); }
+    for (int k = 0; k < LW2; k++) { A[k] = lds64(ra + 8 * chunk(k)); B[k] = lds64(ra + RB + 8 * chunk(k)); }
     // PRE holds r + 256 per 16-bit lane (the chain's c = r + 256 - nw then is one subtraction): the
     // 0x01 bytes come out of the shifts' addends, t = [0, 1, b0, b1] and u = [b2, b3, 0, 1]
 #pragma unroll
     for (int k = 0; k < LW2; k++) {
       uint32_t t = B[k].x * 65536u + 0x0100u, u = __umulhi(B[k].x, 65536u) + 0x01000000u;
-      sts128(dst + (2 * k) * 512, __byte_perm(A[k].x, t, 0x5650), __byte_perm(A[k].x, t, 0x5751),
+      sts128(dst + (2 * chunk(k)) * 512, __byte_perm(A[k].x, t, 0x5650), __byte_perm(A[k].x, t, 0x5751),
              __byte_perm(A[k].x, u, 0x7472), __byte_perm(A[k].x, u, 0x7573));
       t = B[k].y * 65536u + 0x0100u; u = __umulhi(B[k].y, 65536u) + 0x01000000u;
-      sts128(dst + (2 * k + 1) * 512, __byte_perm(A[k].y, t, 0x5650), __byte_perm(A[k].y, t, 0x5751),
+      sts128(dst + (2 * chunk(k) + 1) * 512, __byte_perm(A[k].y, t, 0x5650), __byte_perm(A[k].y, t, 0x5751),
              __byte_perm(A[k].y, u, 0x7472), __byte_perm(A[k].y, u, 0x7573));
     }
   };
@@ -414,17 +434,23 @@ __global__ void __launch_bounds__(kPairThreads, 2) k_decode_pair(const PairParam
   auto post_row = [&](uint32_t buf) {
     if (r2_bytes) mbar_wait(full2 + 8 * c2_slot, c2_par);
     const uint32_t src = sm0 + kPost + buf * kBuf + slot0;
-    const uint32_t la = sm0 + kR2 + c2_slot * kR2Slot + col0, da = sm0 + kR2 + c2_slot * kR2Slot + 2 * RB + col0 * 4;
+    const uint32_t la = sm0 + kR2 + c2_slot * kR2Slot + col0, da = sm0 + kR2 + c2_slot * kR2Slot + 2 * RB + slot0;
     if (++c2_slot == kPairRing) { c2_slot = 0; c2_par ^= 1u; }
     const uint32_t oa = sm0 + kOut + col0 * 2;
     uint4 X[2 * LW2], D[2 * LW2];
     uint2 A[LW2], B[LW2];
 #pragma unroll
-    for (int k = 0; k < 2 * LW2; k++) X[k] = lds128(src + k * 512);
+    for (int k = 0; k < LW2; k++) {
+      X[2 * k] = lds128(src + (2 * chunk(k)) * 512);
+      X[2 * k + 1] = lds128(src + (2 * chunk(k) + 1) * 512);
+    }
 #pragma unroll
-    for (int k = 0; k < LW2; k++) { A[k] = lds64(la + 8 * k); B[k] = lds64(la + RB + 8 * k); }
+    for (int k = 0; k < LW2; k++) { A[k] = lds64(la + 8 * chunk(k)); B[k] = lds64(la + RB + 8 * chunk(k)); }
 #pragma unroll
-    for (int k = 0; k < 2 * LW2; k++) D[k] = lds128(da + 16 * k);
+    for (int k = 0; k < LW2; k++) {
+      D[2 * k] = lds128(da + (2 * chunk(k)) * 512);          // pair_ddup_word: slot (2 chunk + half) 32 + lane
+      D[2 * k + 1] = lds128(da + (2 * chunk(k) + 1) * 512);
+    }
 #pragma unroll
     for (int k = 0; k < LW2; k++) {     // 8 columns per step
       uint32_t Z[8], V[8];
@@ -448,9 +474,9 @@ __global__ void __launch_bounds__(kPairThreads, 2) k_decode_pair(const PairParam
         V[j] = bitselect(hi, lo, kHiBytes);
         if (SHIFT) V[j] = __umulhi(V[j], shmul) & um;     // per lane: (pixel >> shift), .cc:855
       }
-      sts128(oa + 16 * k, __byte_perm(V[0], V[1], selA), __byte_perm(V[2], V[3], selA),
+      sts128(oa + 16 * chunk(k), __byte_perm(V[0], V[1], selA), __byte_perm(V[2], V[3], selA),
              __byte_perm(V[4], V[5], selA), __byte_perm(V[6], V[7], selA));               // frame A: 8 pixels
-      sts128(oa + 2 * RB + 16 * k, __byte_perm(V[0], V[1], selB), __byte_perm(V[2], V[3], selB),
+      sts128(oa + 2 * RB + 16 * chunk(k), __byte_perm(V[0], V[1], selB), __byte_perm(V[2], V[3], selB),
              __byte_perm(V[4], V[5], selB), __byte_perm(V[6], V[7], selB));               // frame B
     }
     fence_proxy_async();

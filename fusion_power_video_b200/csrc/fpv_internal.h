@@ -90,7 +90,8 @@ int enqueue_decode(const Geom& g, int num_sms, const uint8_t* high, const uint8_
                    bool unextract, uint16_t* out, cudaStream_t stream, cudaError_t* err,
                    const TimingHook* hook = nullptr);
 
-// delta image -> uint32[P] duplicated form for the pair decode kernel.
+// delta image -> pair form for the pair decode kernel (padded, permuted rows; delta_dup_bytes(g) bytes).
+size_t delta_dup_bytes(const Geom& g);
 int enqueue_delta_dup(const Geom& g, const uint16_t* delta_image, uint32_t* ddup, cudaStream_t stream,
                       cudaError_t* err);
 
