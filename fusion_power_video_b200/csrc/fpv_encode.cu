@@ -531,7 +531,7 @@ int enqueue_encode(const Geom& g, const EncodeTuning& t, const EncodeScratch& s,
       fp.list = s.lists + (size_t)pass * s.cap;
       fp.count = s.counts + pass;
       // redo passes are almost always empty: a small grid is enough
-      int gpass = pass == 0 ? grid : (grid < t.num_sms ? grid : t.num_sms);
+      int gpass = pass == 0 ? grid : (grid < 2 * t.num_sms ? grid : 2 * t.num_sms);
       cudaError_t e = cudaSuccess;
       if (hook && pass == 0) cudaEventRecord(hook->start, stream);
       const bool full = g.W % kStripPx == 0;

@@ -72,12 +72,13 @@ struct FastParams {
 // running stage number.
 struct StageCursor {
   uint32_t t, f, y0, y1, ys, rps;
+  uint32_t band_rows, bands;    // of this launch (short frame lists use shorter bands, see the kernel)
   __device__ __forceinline__ bool load_task(const FastParams& p, uint32_t total) {
     if (t >= total) return false;
-    f = p.list[t / p.bands];
-    const uint32_t b = t % p.bands;
-    y0 = b * p.band_rows;
-    y1 = min(p.H, y0 + p.band_rows);
+    f = p.list[t / bands];
+    const uint32_t b = t % bands;
+    y0 = b * band_rows;
+    y1 = min(p.H, y0 + band_rows);
     ys = y0 > 0 ? y0 - 1 : 0;
     return true;
   }
@@ -269,8 +270,14 @@ __global__ void __maxnreg__(80) k_encode_fast(const FastParams p) {
   }
   __syncthreads();
 
-  const uint32_t total_tasks = (*p.count) * p.bands;
+  // A short frame list (the redo passes: the few frames whose flags were guessed wrong) would leave
+  // most CTAs without a task and the rest with one long one; it is cut into 32-row bands instead.
+  const uint32_t nframes = *p.count;
+  const bool short_list = nframes * p.bands < gridDim.x && p.band_rows > 32;
   StageCursor cur;
+  cur.band_rows = short_list ? 32u : p.band_rows;
+  cur.bands = short_list ? (p.H + 31u) / 32u : p.bands;
+  const uint32_t total_tasks = nframes * cur.bands;
   cur.t = blockIdx.x;
   cur.rps = RPS;
   bool more = cur.load_task(p, total_tasks);

@@ -99,18 +99,19 @@ def launches_md(tag):
         per.setdefault(r[ik].split("(")[0], []).append(float(r[iv]) / 1000)
     tot = sum(sum(v) for v in per.values())
     lines = [f"# Launch list ({tag})", "",
-             "`ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k_... -c 80 python bench.py --steps 3 --warmup 3 "
-             "--frames 512 --no-e2e --no-cpu` on one B200 (C2: 12-bit 1280x800, 512 frames per step; encode steps then "
-             "decode steps).  Per-launch times are cold-cache and serialised: compare shares, not absolutes.", "",
+             "`ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k_... -c 120 python bench.py --steps 3 --warmup 3 "
+             "--no-e2e --no-cpu --no-stream` on one B200 (the bench's default workload, C2: 12-bit 1280x800, 1184 frames per step; "
+             "encode steps, then decode steps, then the entropy coder on 256 frames).  Per-launch times are cold-cache and "
+             "serialised: compare shares, not absolutes.", "",
              "| kernel | launches | avg us | min us | max us | share of all listed time |", "|---|---|---|---|---|---|"]
     for k, v in per.items():
         lines.append(f"| `{k}` | {len(v)} | {sum(v) / len(v):.1f} | {min(v):.1f} | {max(v):.1f} | {100 * sum(v) / tot:.1f} % |")
-    enc = {k: v for k, v in per.items() if "decode" not in k and "delta_from_raw" not in k}
+    enc = {k: v for k, v in per.items() if "decode" not in k and "delta_" not in k and "entropy" not in k}
     etot = sum(sum(v) for v in enc.values())
     main = [x for k, v in enc.items() if "k_encode_fast" in k for x in v if x > 100]
     lines += ["", f"Within the encode steps, the main pass of `k_encode_fast` (the {len(main)} launches > 100 us) is "
               f"{100 * sum(main) / etot:.1f} % of the listed encode time; bench.py's event timing of the same share "
-              "(`roofline.kernel_share_of_step`) is 0.85-0.86."]
+              "(`roofline.kernel_share_of_step`) is 0.89-0.91."]
     open(os.path.join(ROOT, "profiles", f"{tag}_launches.md"), "w").write("\n".join(lines) + "\n")
 
 
@@ -120,14 +121,23 @@ def main():
     launches_md(tag)
     import json
     traffic = {}
-    traffic["encode"] = kernel_md(f"{tag}_encode", "k_encode_fast, main pass (C2, 512 frames)", os.path.join(OUT, "prof_encode_main.ncu-rep"),
-              512 * P / 256, "warp-row (256 px)", 512 * P * 4.0625,
+    F = 1184
+    traffic["encode"] = kernel_md(f"{tag}_encode", f"k_encode_fast, main pass (C2, {F} frames)", os.path.join(OUT, "prof_encode_main.ncu-rep"),
+              F * P / 256, "warp-row (256 px)", F * P * 4.0625,
               "`ncu --set full --clock-control none --import-source on -k regex:k_encode_fast -s 3 -c 1 python bench.py --steps 3 "
-              "--warmup 3 --frames 512 --no-e2e --no-cpu --no-decode` (the 4th matching launch = the main pass of the 2nd step).")
-    traffic["decode"] = kernel_md(f"{tag}_decode", "k_decode_pair (C2, 1024 frames)", os.path.join(OUT, "prof_decode.ncu-rep"),
-              1024 * 800, "frame row (1280 px)", 1024 * P * 4.0,
+              "--warmup 3 --no-e2e --no-cpu --no-stream --no-decode --no-entropy` (the 4th matching launch = the main pass of the 2nd step).")
+    traffic["decode"] = kernel_md(f"{tag}_decode", f"k_decode_pair (C2, {F} frames)", os.path.join(OUT, "prof_decode.ncu-rep"),
+              F * 800, "frame row (1280 px)", F * P * 4.0,
               "`ncu --set full --clock-control none --import-source on -k regex:k_decode_pair -s 1 -c 1 python bench.py --steps 3 "
-              "--warmup 3 --frames 1024 --no-e2e --no-cpu --no-stream`.")
+              "--warmup 3 --no-e2e --no-cpu --no-stream --no-entropy`.")
+    if os.path.exists(os.path.join(OUT, "prof_entropy.ncu-rep")):
+        Fe = 256
+        traffic["entropy"] = kernel_md(f"{tag}_entropy", f"k_entropy_chunk (C2 planes, {Fe} frames = {Fe * 33} chunks of 64 KiB)",
+              os.path.join(OUT, "prof_entropy.ncu-rep"), Fe * 33, "chunk (<= 64 KiB)", Fe * P * (2 + 1 / 16) * 1.5,
+              "`ncu --set full --clock-control none --import-source on -k regex:k_entropy_chunk -s 1 -c 1 python bench.py --steps 3 "
+              "--warmup 3 --no-e2e --no-cpu --no-stream --no-decode`.  Algorithmic bytes here = planes read once + coded bytes "
+              "written to the scratch (about half the plane bytes); the kernel reads each chunk three times (histogram, sizes, "
+              "packing), the second and third time from L1/L2.  It is not HBM bound: the serial Huffman construction per chunk dominates.")
     json.dump(traffic, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
 
 
