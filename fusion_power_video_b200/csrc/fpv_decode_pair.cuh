@@ -108,6 +108,25 @@ __device__ __forceinline__ uint32_t bitselect(uint32_t a, uint32_t b, uint32_t m
   return r;
 }
 
+// One step of the chain for two pixels: x = (c + min3(n,w,nw) + max3(n,w,nw)) & 0x00ff00ff.
+// FPV_CHAIN_FMA: the two additions go to the FMA pipe (IMAD) instead of one IADD3 on the ALU pipe --
+// the sub-partitions that run the chain warps are bound by the ALU pipe's issue rate; c + min3 can
+// issue while max3 is still in flight, so the dependent depth stays max3 -> add -> and.
+#ifndef FPV_CHAIN_FMA
+#define FPV_CHAIN_FMA 0
+#endif
+__device__ __forceinline__ uint32_t chain_step(uint32_t c, uint32_t n, uint32_t w, uint32_t nw) {
+  const uint32_t mn = __vimin3_u16x2(n, w, nw), mx = __vimax3_u16x2(n, w, nw);
+#if FPV_CHAIN_FMA
+  uint32_t t, v;
+  asm("mad.lo.u32 %0, %1, 1, %2;" : "=r"(t) : "r"(mn), "r"(c));
+  asm("mad.lo.u32 %0, %1, 1, %2;" : "=r"(v) : "r"(mx), "r"(t));
+  return v & kLaneMask;
+#else
+  return (c + mn + mx) & kLaneMask;
+#endif
+}
+
 // One row of the chain warp: residual row (pair form, in PRE) -> finished row in x[] and in POST.
 // n[] is the finished previous row; the caller alternates two register arrays between rows so
 // that nothing is copied.
@@ -148,12 +167,17 @@ __device__ __forceinline__ void pair_chain_row(const uint32_t (&n)[8 * LW2], uin
 
     // pass 0: estimate this segment's last pixel from a guess K0 pixels back
     uint32_t w_in;
+#ifdef FPV_ABL_NO_PASS0
+    w_in = __shfl_up_sync(0xffffffffu, n[L - 1], 1);
+    if (lane == 0) w_in = last_prev;
+    if (false)
+#endif
     {
       uint32_t nw = n[L - K0 - 1], w = nw;          // the guess: west == north-west
 #pragma unroll
       for (int t = L - K0; t < L; t++) {
         const uint32_t nn = n[t];
-        w = (c[t] + __vimin3_u16x2(nn, w, nw) + __vimax3_u16x2(nn, w, nw)) & kLaneMask;
+        w = chain_step(c[t], nn, w, nw);
         nw = nn;
       }
       w_in = __shfl_up_sync(0xffffffffu, w, 1);
@@ -171,7 +195,7 @@ __device__ __forceinline__ void pair_chain_row(const uint32_t (&n)[8 * LW2], uin
 #pragma unroll
       for (int t = 0; t < L; t++) {
         const uint32_t nn = n[t];
-        uint32_t v = (c[t] + __vimin3_u16x2(nn, w, nw) + __vimax3_u16x2(nn, w, nw)) & kLaneMask;
+        uint32_t v = chain_step(c[t], nn, w, nw);
         if (t == 0 && copy_first) v = (r_first & copy_mask) | (v & ~copy_mask);
         x[t] = v;
         w = v;
@@ -179,6 +203,9 @@ __device__ __forceinline__ void pair_chain_row(const uint32_t (&n)[8 * LW2], uin
       }
     }
     // repair: re-run segments whose incoming value was wrong until nothing changes
+#ifdef FPV_ABL_NO_REPAIR
+    if (false)
+#endif
     for (;;) {
       uint32_t w_new = __shfl_up_sync(0xffffffffu, x[L - 1], 1);
       if (SPLIT) {
@@ -197,6 +224,7 @@ __device__ __forceinline__ void pair_chain_row(const uint32_t (&n)[8 * LW2], uin
       if (!__any_sync(0xffffffffu, changed)) break;
       w_in = w_new;
       uint32_t w = w_in, nw = nw_in;
+      bool settled = false;     // the chains met their old values before the segment ends: no end changed
 #pragma unroll
       for (int k = 0; k < L / G; k++) {
         bool same = true;
@@ -204,7 +232,7 @@ __device__ __forceinline__ void pair_chain_row(const uint32_t (&n)[8 * LW2], uin
         for (int j = 0; j < G; j++) {
           const int t = G * k + j;
           const uint32_t nn = n[t];
-          uint32_t v = (c[t] + __vimin3_u16x2(nn, w, nw) + __vimax3_u16x2(nn, w, nw)) & kLaneMask;
+          uint32_t v = chain_step(c[t], nn, w, nw);
           if (t == 0 && copy_first) v = (r_first & copy_mask) | (v & ~copy_mask);
           if (j == G - 1) same = ((v ^ x[t]) & vmask) == 0;
           x[t] = v;
@@ -212,8 +240,9 @@ __device__ __forceinline__ void pair_chain_row(const uint32_t (&n)[8 * LW2], uin
           nw = nn;
         }
         // every chain met its previous values: the rest of the segment is unchanged
-        if (k + 1 < L / G && __all_sync(0xffffffffu, same)) break;
+        if (k + 1 < L / G && __all_sync(0xffffffffu, same)) { settled = true; break; }
       }
+      if (settled) break;       // nothing to hand on: skip the exchange and the vote of another round
     }
     if (cgmask != 0xffffffffu) {
       // one of the two frames is not ClampedGradient-predicted: its row is the residual row
@@ -470,9 +499,13 @@ __global__ void __launch_bounds__(kPairThreads, 2) k_decode_pair(const PairParam
         // bytes are added separately so that a carry out of one byte only ever lands in a bit the
         // final select drops (.cc:337-338: the bytes wrap independently); mh / ml also switch the
         // delta off for a frame of the pair that does not use it.
+#ifdef FPV_ABL_IO_LIGHT
+        V[j] = Xs[j] ^ Ds[j] ^ Z[j];
+#else
         const uint32_t hi = Xs[j] * 256u + (Ds[j] & mh), lo = Z[j] + (Ds[j] & ml);
         V[j] = bitselect(hi, lo, kHiBytes);
         if (SHIFT) V[j] = __umulhi(V[j], shmul) & um;     // per lane: (pixel >> shift), .cc:855
+#endif
       }
       sts128(oa + 16 * chunk(k), __byte_perm(V[0], V[1], selA), __byte_perm(V[2], V[3], selA),
              __byte_perm(V[4], V[5], selA), __byte_perm(V[6], V[7], selA));               // frame A: 8 pixels
