@@ -446,6 +446,24 @@ def main():
             "stream_bytes": int(sizeg), "bpp": sizeg * 8.0 / (ns * P), "batch": 32,
             "bound": "PCIe: 2 B/px in, about 1 B/px out"}
 
+        # decode side of the codec: StreamingDecoder (host brotli decode on all cores + GPU inverse transform +
+        # UnextractFrame on the GPU) on the stream just described, both entropy variants
+        nd = min(ns, 256)
+        dec = {}
+        for name, ge in (("brotli_stream", False), ("gpu_entropy_stream", True)):
+            st = fpv_host.encode_stream(fr[:nd], W, H, shift, False, threads=ncpu, batch=32, gpu_entropy=ge)
+            fpv_host.decode_stream(st, nd, W, H, block=1 << 24, batch=32, raw_shift=shift)
+            t_a = time.perf_counter()
+            bestd, okd = None, False
+            for _ in range(2):
+                out, sec = fpv_host.decode_stream(st, nd, W, H, block=1 << 24, batch=32, raw_shift=shift, return_time=True)
+                bestd = sec if bestd is None else min(bestd, sec)
+                okd = bool(np.array_equal(out, fr[:nd]))
+            windows.append((t_a, time.perf_counter()))
+            dec[name] = {"value": nd * P * 2 / bestd / 1e9, "unit": "GB/s", "frames_per_s": nd / bestd, "frames": nd,
+                         "round_trip_exact": okd, "stream_bytes": len(st)}
+        stream_leg["decode"] = dec
+
     clocks = sampler.stop(windows) if rank == 0 else None
 
     # ---- CPU baseline: the reference's own code on this box's host cores (rank 0, N == 1 only) -----
@@ -465,6 +483,15 @@ def main():
                 nsr = min(stream_leg["frames"], 16 * ncpu)
                 frs = np.ascontiguousarray(np.tile(hin.array, ((nsr + Fe - 1) // Fe, 1))[:nsr])
                 t, size = Ref().time_encode(frs, W, H, shift, 0, frs[0], ncpu)
+                if "decode" in stream_leg:
+                    ndr = min(64, nsr)
+                    stb = Ref().encode_stream(frs[:ndr], W, H, shift, 0, frs[0], ncpu)
+                    t0 = time.perf_counter()
+                    nrd, _, _, _ = Ref().decode_stream(stb, ndr, W, H)
+                    tdr = time.perf_counter() - t0
+                    stream_leg["decode"]["reference_cpu"] = {
+                        "value": ndr * P * 2 / tdr / 1e9, "unit": "GB/s", "frames_per_s": ndr / tdr, "frames": int(nrd),
+                        "what": "unmodified reference StreamingDecoder (single-threaded by design) on the reference's stream"}
                 stream_leg["reference_cpu"] = {"value": nsr * P * 2 / t / 1e9, "unit": "GB/s", "frames_per_s": nsr / t,
                                                "mp_per_s": nsr * P / t / 1e6, "frames": nsr, "threads": ncpu,
                                                "what": "unmodified reference Encoder (transform + brotli) on the same host"}

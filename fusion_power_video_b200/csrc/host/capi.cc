@@ -3,8 +3,11 @@
 #include <string.h>
 
 #include <chrono>
+#include <future>
+#include <memory>
 #include <vector>
 
+#include "columnar_batch.h"
 #include "fusion_power_video.h"
 
 namespace {
@@ -126,6 +129,56 @@ int fpvh_random_access(const uint8_t* bytes, size_t size, uint32_t batch, int de
   if (frames && count && !dec.DecodeFrames(first, count, frames)) return 0;
   if (preview && !dec.DecodePreview(first, preview)) return 0;
   return 1;
+}
+
+// Pushes `n` frames through a ColumnarBatchEncoder whose batch processor feeds a ColumnarBatchDecoder
+// (the wiring of the reference's columnar_batch_decoder_test.cc) and collects the decoded images back to
+// back in `out` (bytes_per_image each) with their timestamps.  Returns the number of images, -1 on failure.
+long fpvh_columnar_roundtrip(size_t xsize, size_t ysize, int shift, int big_endian, int frames_per_batch, int type,
+                             int unshift, const uint16_t* frames, const int64_t* timestamps, size_t n, uint8_t* out,
+                             int64_t* out_timestamps, size_t capacity, size_t* bytes_per_image, long* batches,
+                             int64_t* encoder_close, int64_t* decoder_close, size_t* compressed_bytes) {
+  namespace cb = fpvc::columnarbatch;
+  struct State {
+    uint8_t* out;
+    int64_t* ts;
+    size_t capacity, used = 0, count = 0, per = 0, compressed = 0;
+    long batches = 0;
+    bool failed = false;
+  } st;
+  st.out = out;
+  st.ts = out_timestamps;
+  st.capacity = capacity;
+  std::unique_ptr<cb::ColumnarBatchEncoder> enc;
+  std::unique_ptr<cb::ColumnarBatchDecoder> dec;
+  dec.reset(new cb::ColumnarBatchDecoder((cb::Image::Type)type, unshift != 0, [&st](cb::Image img) {
+    const size_t bytes = img.xsize() * img.ysize() * (img.type() == cb::Image::Type::FULL ? 2 : 1);   // FULL is always 16 bit
+    st.per = bytes;
+    if (st.used + bytes <= st.capacity) {
+      memcpy(st.out + st.used, img.data8(), bytes);
+      st.ts[st.count] = img.timestamp();
+      st.used += bytes;
+    }
+    st.count++;
+  }));
+  enc.reset(new cb::ColumnarBatchEncoder(xsize, ysize, shift, big_endian != 0, [&](cb::BatchPtr batch) {
+    if (!batch) return;
+    st.batches++;
+    st.compressed += batch->preview_column().size() + batch->high_plane_column().size() + batch->low_plane_column().size();
+    std::future<cb::BatchPtr> f = dec->PushBatch(batch);
+    if (!f.valid()) { st.failed = true; return; }
+    enc->ReturnProcessedBatch(f.get());
+  }, frames_per_batch));
+  for (size_t i = 0; i < n; i++)
+    enc->PushFrame((uint64_t)timestamps[i], const_cast<uint16_t*>(frames + i * xsize * ysize), nullptr).wait();
+  const int64_t ec = enc->Close().get();
+  const int64_t dc = dec->Close().get();
+  if (encoder_close) *encoder_close = ec;
+  if (decoder_close) *decoder_close = dc;
+  if (bytes_per_image) *bytes_per_image = st.per;
+  if (batches) *batches = st.batches;
+  if (compressed_bytes) *compressed_bytes = st.compressed;
+  return (st.failed || !enc->ok()) ? -1 : (long)st.count;
 }
 
 void fpvh_unextract(const uint16_t* img, size_t xsize, size_t ysize, int shift, int big_endian, uint8_t* out) {

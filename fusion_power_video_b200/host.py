@@ -33,6 +33,9 @@ def lib() -> C.CDLL:
     L.fpvh_last_error.restype = C.c_char_p
     L.fpvh_encode_stream.argtypes = [sz, sz, i32, i32, sz, u32, i32, vp, vp, sz, vp, sz]
     L.fpvh_encode_stream.restype = sz
+    L.fpvh_columnar_roundtrip.argtypes = [sz, sz, i32, i32, i32, i32, i32, vp, vp, sz, vp, vp, sz, C.POINTER(sz),
+                                          C.POINTER(C.c_long), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(sz)]
+    L.fpvh_columnar_roundtrip.restype = C.c_long
     L.fpvh_time_encode.argtypes = [sz, sz, i32, i32, sz, u32, i32, vp, vp, sz, C.POINTER(sz)]
     L.fpvh_time_encode.restype = C.c_double
     L.fpvh_decode_stream.argtypes = [vp, sz, sz, u32, i32, i32, i32, vp, sz, C.POINTER(sz), C.POINTER(sz),
@@ -147,3 +150,31 @@ def unextract(img, xsize, ysize, shift, big_endian):
     out = np.empty(xsize * ysize * 2, np.uint8)
     lib().fpvh_unextract(_p(img), xsize, ysize, shift, int(big_endian), _p(out))
     return out
+
+
+IMAGE_PREVIEW, IMAGE_MSB8, IMAGE_FULL = 0, 1, 2
+
+
+def columnar_roundtrip(frames, timestamps, xsize, ysize, shift=0, big_endian=False, frames_per_batch=10, image_type=IMAGE_FULL,
+                       unshift=False):
+    """frames -> ColumnarBatchEncoder -> Batches -> ColumnarBatchDecoder -> images (the reference's
+    columnar_batch_decoder_test.cc wiring).  Returns (images, timestamps, info)."""
+    L = lib()
+    frames = np.ascontiguousarray(frames, dtype=np.uint16).reshape(-1, xsize * ysize)
+    ts = np.ascontiguousarray(timestamps, dtype=np.int64)
+    n = frames.shape[0]
+    per = {IMAGE_PREVIEW: (xsize // 4) * (ysize // 4), IMAGE_MSB8: xsize * ysize, IMAGE_FULL: 2 * xsize * ysize}[image_type]
+    out = np.zeros(max(n * per, 1), np.uint8)
+    out_ts = np.zeros(max(n, 1), np.int64)
+    bpi, batches, comp = C.c_size_t(0), C.c_long(0), C.c_size_t(0)
+    ec, dc = C.c_int64(0), C.c_int64(0)
+    cnt = L.fpvh_columnar_roundtrip(xsize, ysize, shift, int(big_endian), frames_per_batch, image_type, int(unshift), _p(frames),
+                                    _p(ts), n, _p(out), _p(out_ts), out.size, C.byref(bpi), C.byref(batches), C.byref(ec),
+                                    C.byref(dc), C.byref(comp))
+    if cnt < 0:
+        raise HostError(f"columnar batch round trip failed: {last_error()}")
+    images = out[:cnt * per].reshape(cnt, per)
+    if image_type == IMAGE_FULL:
+        images = images.view(np.uint16)
+    return images, out_ts[:cnt], {"batches": batches.value, "encoder_close": ec.value, "decoder_close": dc.value,
+                                  "compressed_bytes": comp.value, "bytes_per_image": bpi.value}
