@@ -452,11 +452,11 @@ def main():
         dec = {}
         for name, ge in (("brotli_stream", False), ("gpu_entropy_stream", True)):
             st = fpv_host.encode_stream(fr[:nd], W, H, shift, False, threads=ncpu, batch=32, gpu_entropy=ge)
-            fpv_host.decode_stream(st, nd, W, H, block=1 << 24, batch=32, raw_shift=shift)
+            fpv_host.decode_stream(st, nd, W, H, block=0, batch=32, raw_shift=shift)
             t_a = time.perf_counter()
             bestd, okd = None, False
             for _ in range(2):
-                out, sec = fpv_host.decode_stream(st, nd, W, H, block=1 << 24, batch=32, raw_shift=shift, return_time=True)
+                out, sec = fpv_host.decode_stream(st, nd, W, H, block=0, batch=32, raw_shift=shift, return_time=True)
                 bestd = sec if bestd is None else min(bestd, sec)
                 okd = bool(np.array_equal(out, fr[:nd]))
             windows.append((t_a, time.perf_counter()))

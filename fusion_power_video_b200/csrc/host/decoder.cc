@@ -20,16 +20,32 @@ using namespace internal;
 
 namespace {
 
-// Everything a decoder needs on the GPU side for one geometry.
+// Everything a decoder needs on the GPU side for one geometry.  Two sets of plane buffers: while the GPU
+// inverts batch k and the caller's callbacks consume it, the pool already brotli-decodes batch k + 1.
 struct GpuDecoder {
   fpv_ctx* ctx = nullptr;
   size_t W = 0, H = 0, P = 0;
   uint32_t B = 1;
-  Pinned high, low, flags, out;
+  struct Set {
+    Pinned high, low, flags;
+    std::vector<char> good;
+    size_t n = 0, left = 0;
+    std::mutex m;
+    std::condition_variable cv;
+  } sets[2];
+  Pinned out;
   std::unique_ptr<Pool> pool;
 
   ~GpuDecoder() {
+    pool.reset();   // no parse task may outlive the buffers
     if (ctx) fpv_destroy(ctx);
+  }
+
+  bool alloc_set(Set& st) {
+    if (st.high.bytes()) return true;
+    if (!st.high.alloc((size_t)B * P) || !st.low.alloc((size_t)B * P) || !st.flags.alloc(B))
+      return FPV_FAIL("pinned allocation failed");
+    return true;
   }
 
   bool open(const GpuOptions& opt, size_t xsize, size_t ysize, int shift, bool big_endian, uint32_t batch) {
@@ -39,35 +55,61 @@ struct GpuDecoder {
     B = batch ? batch : 1;
     if (fpv_create(&ctx, opt.device, (uint32_t)xsize, (uint32_t)ysize, shift, big_endian ? 1 : 0, B) != FPV_OK)
       return FPV_FAIL(std::string("fpv_create: ") + fpv_last_error(nullptr));
-    if (!high.alloc((size_t)B * P) || !low.alloc((size_t)B * P) || !flags.alloc(B) || !out.alloc((size_t)B * P * 2))
-      return FPV_FAIL("pinned allocation failed");
+    if (!alloc_set(sets[0]) || !out.alloc((size_t)B * P * 2)) return false;
     size_t t = std::thread::hardware_concurrency();
     t = std::min<size_t>(t ? t : 1, 32);
     if (B > 1 && t > 1) pool.reset(new Pool(std::min<size_t>(t, B)));
     return true;
   }
 
-  // cores[i] / sizes[i]: the core chunk of frame i.  Decodes n <= B frames into
-  // `out` (uint16 images, or raw file bytes with FPV_DEC_UNEXTRACT).  Returns the
-  // number of leading frames that decoded correctly (n on success).
-  size_t decode(const uint8_t* const* cores, const size_t* sizes, size_t n, uint32_t options, bool allow_delta) {
-    std::vector<char> good(n, 0);
-    ParallelFor(pool.get(), n, [&](size_t i) {
-      uint8_t f = 0;
-      bool ok = ParseCore(cores[i], sizes[i], P, &f, high.as<uint8_t>() + i * P, low.as<uint8_t>() + i * P);
-      if (ok && (f & FPV_FLAG_USE_DELTA) && !allow_delta) ok = FPV_FAIL("delta frame not given");
-      flags.as<uint8_t>()[i] = f;
-      good[i] = ok ? 1 : 0;
-    });
+  // Starts the brotli decoding of n <= B core chunks into buffer set `which` (returns at once when there is
+  // a pool).  cores / sizes must stay valid until finish().
+  bool start(int which, const uint8_t* const* cores, const size_t* sizes, size_t n, bool allow_delta) {
+    Set& st = sets[which];
+    if (!alloc_set(st)) return false;
+    st.good.assign(n, 0);
+    st.n = n;
+    st.left = n;
+    for (size_t i = 0; i < n; i++) {
+      const uint8_t* core = cores[i];
+      const size_t size = sizes[i];
+      auto task = [this, &st, core, size, i, allow_delta] {
+        uint8_t f = 0;
+        bool ok = ParseCore(core, size, P, &f, st.high.as<uint8_t>() + i * P, st.low.as<uint8_t>() + i * P);
+        if (ok && (f & FPV_FLAG_USE_DELTA) && !allow_delta) ok = FPV_FAIL("delta frame not given");
+        st.flags.as<uint8_t>()[i] = f;
+        st.good[i] = ok ? 1 : 0;
+        std::lock_guard<std::mutex> l(st.m);
+        if (--st.left == 0) st.cv.notify_all();
+      };
+      if (pool) pool->run(task);
+      else task();
+    }
+    return true;
+  }
+
+  // Waits for start(which), then inverts the leading frames that parsed correctly into `out` (uint16 images,
+  // or raw file bytes with FPV_DEC_UNEXTRACT).  Returns their number (n on success).
+  size_t finish(int which, uint32_t options) {
+    Set& st = sets[which];
+    {
+      std::unique_lock<std::mutex> l(st.m);
+      st.cv.wait(l, [&] { return st.left == 0; });
+    }
     size_t k = 0;
-    while (k < n && good[k]) k++;
+    while (k < st.n && st.good[k]) k++;
     if (k == 0) return 0;
-    if (fpv_decode(ctx, high.as<uint8_t>(), low.as<uint8_t>(), flags.as<uint8_t>(), (uint32_t)k, options,
+    if (fpv_decode(ctx, st.high.as<uint8_t>(), st.low.as<uint8_t>(), st.flags.as<uint8_t>(), (uint32_t)k, options,
                    out.as<uint8_t>()) != FPV_OK) {
       FPV_FAIL(std::string("fpv_decode: ") + fpv_last_error(ctx));
       return 0;
     }
     return k;
+  }
+
+  size_t decode(const uint8_t* const* cores, const size_t* sizes, size_t n, uint32_t options, bool allow_delta) {
+    if (!start(0, cores, sizes, n, allow_delta)) return 0;
+    return finish(0, options);
   }
 };
 
@@ -136,16 +178,16 @@ void StreamingDecoder::Decode(
   }
 
   const uint32_t options = s.raw_output ? FPV_DEC_UNEXTRACT : FPV_DEC_DEFAULT;
-  std::vector<const uint8_t*> cores;
-  std::vector<size_t> sizes;
+  std::vector<const uint8_t*> cores[2];
+  std::vector<size_t> sizes[2];
   bool stream_bad = false;
   const char* bad_what = nullptr;
-  while (s.have_delta && !stream_bad) {
-    // gather the frames that are complete in the buffer, up to one GPU batch
-    cores.clear();
-    sizes.clear();
-    size_t scan = pos;
-    while (cores.size() < s.gpu.B) {
+  size_t scan = pos;
+  // the frames that are complete in the buffer from `scan` on, up to one GPU batch; their parsing starts at once
+  auto gather = [&](int set) {
+    cores[set].clear();
+    sizes[set].clear();
+    while (cores[set].size() < s.gpu.B && !stream_bad) {
       if (scan + 9 > insize) break;
       const size_t frame_size = LoadU32(in + scan);
       const uint8_t flag = in[scan + 4];
@@ -158,18 +200,32 @@ void StreamingDecoder::Decode(
         bad_what = "preview size too large";
         break;
       }
-      cores.push_back(in + scan + 9 + preview_size);
-      sizes.push_back(frame_size - preview_size - 9);
+      cores[set].push_back(in + scan + 9 + preview_size);
+      sizes[set].push_back(frame_size - preview_size - 9);
       scan += frame_size;
     }
-    if (cores.empty()) break;
-    const size_t good = s.gpu.decode(cores.data(), sizes.data(), cores.size(), options, true);
+    if (!cores[set].empty() && !s.gpu.start(set, cores[set].data(), sizes[set].data(), cores[set].size(), true))
+      cores[set].clear();
+    return !cores[set].empty();
+  };
+  int cur = 0;
+  bool have = s.have_delta && gather(cur);
+  while (have) {
+    const size_t end_of_cur = scan;
+    // batch k + 1 is brotli-decoded on the pool while the GPU inverts batch k and the callbacks consume it
+    const bool have_next = !stream_bad && gather(cur ^ 1);
+    const size_t good = s.gpu.finish(cur, options);
     for (size_t i = 0; i < good; i++) {
       callback(true, s.gpu.out.as<uint16_t>() + i * s.gpu.P, s.gpu.W, s.gpu.H, payload);
       s.id++;
     }
-    if (good != cores.size()) return fail("decompressing frame failed");
-    pos = scan;
+    if (good != cores[cur].size()) {
+      if (have_next) s.gpu.finish(cur ^ 1, options);   // let the started tasks drain before the buffers go away
+      return fail("decompressing frame failed");
+    }
+    pos = end_of_cur;
+    cur ^= 1;
+    have = have_next;
   }
   if (stream_bad) return fail(bad_what);
 
