@@ -190,3 +190,20 @@ def test_device_pointer_decode(oracle):
             ctx.decode_device(d_high.data_ptr(), d_low.data_ptr(), d_flags.data_ptr(), n, d_out.data_ptr(), stream=s.cuda_stream)
         s.synchronize()
         assert np.array_equal(d_out.cpu().numpy().view(np.uint16), frames)
+
+
+@pytest.mark.parametrize("W,H,bits,shift,n", [(1280, 800, 12, 4, 5), (1024, 1024, 16, 0, 5), (2048, 2048, 16, 0, 3)])
+def test_benchmark_geometries_decode_vs_oracle(oracle, W, H, bits, shift, n):
+    """BASELINE.json's frame sizes through encode -> decode: decoded images equal the oracle's DecompressImage
+    (pair kernel, its L = 32 layout at 1024, its split mode at 2048) and the round trip reproduces the raw file."""
+    frames = synth.plasma_frames(n, W, H, bits=bits, seed=W ^ H).reshape(n, -1)
+    with fpv.Context(W, H, shift, 0, max_batch=8) as ctx:
+        ctx.set_delta_raw(frames[0])
+        flags, high, low, _ = ctx.encode(frames)
+        out = ctx.decode(high, low, flags)
+        raw = ctx.decode(high, low, flags, fpv.DEC_UNEXTRACT)
+    delta = oracle.delta_image(frames[0], shift, 0)
+    for i in range(n):
+        exp = oracle.inverse(high[i], None if flags[i] & 4 else low[i], delta, W, H, int(flags[i]))
+        assert np.array_equal(out[i], exp), f"frame {i}: first diff at {np.flatnonzero(out[i] != exp)[:8]}"
+    assert np.array_equal(raw, frames), "encode -> decode does not reproduce the input"
