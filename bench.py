@@ -196,6 +196,7 @@ def main():
                     help="frames per GPU per step (device-resident); 1184 = 148 SMs x 2 resident decode CTAs x 4 frames")
     ap.add_argument("--e2e-frames", type=int, default=256, help="frames per step of the host-buffer (e2e) leg")
     ap.add_argument("--e2e-batch", type=int, default=32)
+    ap.add_argument("--e2e-slots", type=int, default=3, help="overlapped submit slots of the host-buffer legs (<= 4)")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-decode", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
@@ -379,16 +380,18 @@ def main():
         hin.array[:] = frames[:Fe].cpu().numpy()
         e2e_bufs = (hin, hh, hl, hp, hf)
 
+        NS = args.e2e_slots
+
         def e2e_pass():
             nb = Fe // B
             for b in range(nb):
-                slot = b & 1
+                slot = b % NS
                 ectx.wait(slot)
                 o = b * B
                 ectx.encode_submit(slot, hin.array[o:o + B], B, hf.array[o:o + B], hh.array[o:o + B], hl.array[o:o + B],
                                    hp.array[o:o + B])
-            ectx.wait(0)
-            ectx.wait(1)
+            for sl in range(NS):
+                ectx.wait(sl)
 
         esteps = max(3, min(args.steps, 20))
         for _ in range(2):
@@ -408,7 +411,43 @@ def main():
         e2e = {"value": world * Fe * P * 2 / e2e_s / 1e9, "unit": "GB/s", "h2d_bytes_per_step": Fe * P * 2,
                "d2h_bytes_per_step": Fe * (2 * P + P // 16 + 1), "frames_per_step": Fe, "batch": B,
                "frames_per_s": world * Fe / e2e_s, "matches_device_path": e2e_ok,
-               "what": "fpv_encode_submit/fpv_wait on pinned host buffers, two slots overlapped (no brotli)"}
+               "slots": NS,
+               "what": "fpv_encode_submit/fpv_wait on pinned host buffers, slots overlapped (no brotli)"}
+
+    # ---- decode e2e: planes in pinned host memory -> fpv_decode_submit / fpv_wait -> raw frames in host memory ----
+    decode_e2e = None
+    if not args.no_e2e and not args.no_decode:
+        ho = PinnedArray((Fe, P), np.uint16)
+
+        def dec_pass():
+            nb = Fe // B
+            for b in range(nb):
+                slot = b % NS
+                ectx.wait(slot)
+                o = b * B
+                ectx.decode_submit(slot, hh.array[o:o + B], hl.array[o:o + B], hf.array[o:o + B], B, ho.array[o:o + B],
+                                   options=fpv.DEC_UNEXTRACT)
+            for sl in range(NS):
+                ectx.wait(sl)
+
+        for _ in range(2):
+            dec_pass()
+        if world > 1:
+            dist.barrier()
+        t_a = time.perf_counter()
+        for _ in range(esteps):
+            dec_pass()
+        t_b = time.perf_counter()
+        windows.append((t_a, t_b))
+        td2 = torch.tensor([(t_b - t_a) / esteps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(td2, op=dist.ReduceOp.MAX)
+        dsec = float(td2.item())
+        decode_e2e = {"value": world * Fe * P * 2 / dsec / 1e9, "unit": "GB/s", "frames_per_s": world * Fe / dsec,
+                      "h2d_bytes_per_step": Fe * (2 * P + 1), "d2h_bytes_per_step": Fe * P * 2, "frames_per_step": Fe, "batch": B,
+                      "round_trip_exact": bool(np.array_equal(ho.array, hin.array)),
+                      "what": "fpv_decode_submit/fpv_wait on pinned host buffers (planes in, raw file words out), slots overlapped (a batch's kernel alone takes 1 ms: the chain)"}
+        ho.free()
 
     # ---- whole codec: fpvc::Encoder (GPU transform + host brotli + framing) on host frames ----------
     stream_leg = None
@@ -510,7 +549,7 @@ def main():
                        "l2": f"inputs larger than L2: {F * P * 2 / 1e6:.0f} MB raw + {F * P * 2.0625 / 1e6:.0f} MB out per step vs 126 MB L2",
                        "flags_histogram": {int(u): int(c) for u, c in zip(uniq, cnt)}},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": clocks, "decode": decode, "entropy": entropy, "stream": stream_leg,
+            "clocks": clocks, "decode": decode, "decode_e2e": decode_e2e, "entropy": entropy, "stream": stream_leg,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -22,8 +22,8 @@ using namespace fpv;
 
 namespace {
 
-constexpr int kNumSlots = 2;       // host-pipeline slots
-constexpr int kDeviceScratch = 2;  // scratch index used by the *_device entry points
+constexpr int kNumSlots = 4;       // host-pipeline slots (FPV_NUM_SLOTS in the header); staging is allocated on first use
+constexpr int kDeviceScratch = kNumSlots;  // scratch index used by the *_device entry points
 
 std::mutex g_err_mutex;
 std::string g_create_error = "no error";

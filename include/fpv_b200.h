@@ -142,10 +142,11 @@ int fpv_encode_device(fpv_ctx* ctx, const void* frames_dev, uint32_t n, uint32_t
                       void* flags_dev, void* high_dev, void* low_dev, void* preview_dev,
                       void* stream);
 
-/* Overlapped form for the Encoder pipeline: `slot` (0 or 1) selects one of
- * two staging sets with its own stream; submit returns after enqueueing
+/* Overlapped form for the Encoder pipeline: `slot` (0 .. FPV_NUM_SLOTS - 1) selects one of
+ * the staging sets with its own stream; submit returns after enqueueing
  * H2D copy + kernels + D2H copies, wait blocks until that slot's outputs
  * have landed in the (pinned) host buffers. */
+#define FPV_NUM_SLOTS 4
 int fpv_encode_submit(fpv_ctx* ctx, uint32_t slot, const uint16_t* frames_host, uint32_t n,
                       uint32_t options, uint8_t* flags_host, uint8_t* high_host,
                       uint8_t* low_host, uint8_t* preview_host);
