@@ -75,7 +75,8 @@ struct Encoder::Impl {
   std::thread gpu_thread;
   std::unique_ptr<Pool> pool;
   // gpu_entropy: no brotli workers; a few helpers share the copy of each submitted frame into the
-  // pinned batch, which is otherwise the pipeline's bottleneck (one core copies ~8 GB/s).
+  // pinned batch, which is otherwise the pipeline's bottleneck (one core copies ~8 GB/s; measured
+  // 12 / 18 / 22 / 24 GB/s of frames with 1 / 3 / 5 / 11 helpers).
   std::unique_ptr<Pool> copy_pool;
 
   std::mutex out_m;                   // ordered emission
@@ -322,7 +323,8 @@ void Encoder::Init(const uint16_t* delta_frame, size_t xsize, size_t ysize, Call
   // enough batches that the brotli workers always have about two frames each queued
   // behind the (up to) three batches that are filling / on the GPU; pinned memory is
   // only allocated when a batch is first used
-  s.num_batches = s.threads == 0 ? 1 : (int)std::min<size_t>(kMaxBatches, 3 + (2 * s.threads + s.B - 1) / s.B);
+  // (GPU entropy stage: one filling, two on the GPU, one being emitted)
+  s.num_batches = s.threads == 0 ? 1 : s.gpu_entropy ? 4 : (int)std::min<size_t>(kMaxBatches, 3 + (2 * s.threads + s.B - 1) / s.B);
   for (int i = 0; i < s.num_batches; i++) s.free_.push_back(&s.batches[i]);
   if (!s.alloc_batch(&s.batches[0])) return;
   if (fpv_set_delta_raw(s.ctx, delta_frame) != FPV_OK) {
@@ -349,7 +351,11 @@ void Encoder::Init(const uint16_t* delta_frame, size_t xsize, size_t ysize, Call
   s.bytes_written = header.size();
   if (s.threads > 0) {
     if (!s.gpu_entropy) s.pool.reset(new Pool(s.threads));
-    else if (s.threads > 1 && s.P * 2 >= (1u << 19)) s.copy_pool.reset(new Pool(std::min<size_t>(s.threads - 1, 3)));
+    else if (s.threads > 1 && s.P * 2 >= (1u << 19)) {
+      size_t helpers = 5;
+      if (const char* v = getenv("FPV_COPY_THREADS")) helpers = (size_t)std::max(1, atoi(v));
+      s.copy_pool.reset(new Pool(std::min<size_t>(s.threads - 1, helpers)));
+    }
     s.gpu_thread = std::thread([&s] { s.gpu_loop(); });
   }
   callback(header.data(), header.size(), payload);

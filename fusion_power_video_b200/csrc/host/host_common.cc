@@ -94,7 +94,7 @@ namespace {
 std::mutex g_pin_m;
 std::multimap<size_t, void*> g_pin_cache;
 size_t g_pin_cached_bytes = 0;
-constexpr size_t kPinCacheLimit = (size_t)1 << 30;
+constexpr size_t kPinCacheLimit = (size_t)3 << 30;
 }  // namespace
 
 void* PinnedAcquire(size_t bytes) {
