@@ -242,7 +242,10 @@ __device__ __forceinline__ void pair_chain_row(const uint32_t (&n)[8 * LW2], uin
         // every chain met its previous values: the rest of the segment is unchanged
         if (k + 1 < L / G && __all_sync(0xffffffffu, same)) { settled = true; break; }
       }
-      if (settled) break;       // nothing to hand on: skip the exchange and the vote of another round
+      // Nothing to hand on: skip the exchange and the vote of another round.  Not in split mode with a
+      // partial last lane: its hand-over pixel x[last_t] lies before the point where the chains met
+      // again and may have changed.
+      if (settled && !(SPLIT && !FULL)) break;
     }
     if (cgmask != 0xffffffffu) {
       // one of the two frames is not ClampedGradient-predicted: its row is the residual row

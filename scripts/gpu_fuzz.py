@@ -1,0 +1,92 @@
+#!/usr/bin/env python
+"""Randomised parity sweep (not part of the pytest suite): random geometries, split modes and contents through
+encode / decode / the GPU entropy coder, every result compared with the oracle (tests/oracle_binding.py) or the
+CPU restatement of the bitstream.  Usage: python scripts/gpu_fuzz.py [seconds] [seed]"""
+import os
+import struct
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np
+
+import fusion_power_video_b200 as fpv
+from fusion_power_video_b200 import synth
+from oracle_binding import Oracle
+import huffcoder_ref as href
+
+
+def content(rng, kind, n, W, H, bits):
+    P = W * H
+    if kind == 0:
+        return synth.plasma_frames(n, W, H, bits=bits, seed=int(rng.integers(1 << 30))).reshape(n, -1)
+    if kind == 1:
+        return rng.integers(0, 1 << bits, (n, P)).astype(np.uint16)
+    if kind == 2:
+        base = rng.integers(0, 1 << bits, P).astype(np.uint16)
+        return np.stack([(base + rng.integers(0, 3, P)).astype(np.uint16) & ((1 << bits) - 1) for _ in range(n)])
+    if kind == 3:
+        v = rng.integers(0, 1 << bits)
+        f = np.full((n, P), v, np.uint16)
+        f[:, :: max(1, P // 7)] ^= 1
+        return f
+    yy, xx = np.meshgrid(np.arange(H), np.arange(W), indexing="ij")
+    return np.stack([(((xx * (3 + k) + yy * (5 + 2 * k)) & ((1 << bits) - 1))).astype(np.uint16).reshape(-1) for k in range(n)])
+
+
+def main():
+    budget = float(sys.argv[1]) if len(sys.argv) > 1 else 120.0
+    seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+    rng = np.random.default_rng(seed)
+    oracle = Oracle()
+    t0 = time.time()
+    cases = fails = 0
+    while time.time() - t0 < budget:
+        W = int(rng.choice([4 * int(rng.integers(1, 80)), 8 * int(rng.integers(8, 330)), 32 * int(rng.integers(41, 81)),
+                            256 * int(rng.integers(1, 9)), 16 * int(rng.integers(4, 81))]))
+        H = 4 * int(rng.integers(1, 24))
+        shift, be = [(0, 0), (4, 0), (8, 0), (0, 1), (3, 1), (8, 1), (6, 0), (12, 0)][int(rng.integers(8))]
+        bits = 16 - shift if shift <= 8 else 4
+        n = int(rng.integers(1, 7))
+        kind = int(rng.integers(5))
+        frames = content(rng, kind, n, W, H, bits)
+        delta = frames[0] if rng.integers(2) else content(rng, int(rng.integers(5)), 1, W, H, bits)[0]
+        if be:
+            frames, delta = frames.byteswap(), delta.byteswap()
+        P, PP = W * H, (W // 4) * (H // 4)
+        tag = f"W={W} H={H} shift={shift} be={be} n={n} kind={kind}"
+        try:
+            with fpv.Context(W, H, shift, bool(be), max_batch=4) as ctx:
+                ctx.set_delta_raw(delta)
+                flags, high, low, prev = ctx.encode(frames)
+                out = ctx.decode(high, low, flags)
+                raw = ctx.decode(high, low, flags, fpv.DEC_UNEXTRACT)
+                sflags, chunks = ctx.encode_stream(frames[:4])
+            dimg = oracle.delta_image(delta, shift, be)
+            for i in range(n):
+                fl, h, l, p = oracle.predict(frames[i], W, H, shift, be, delta)
+                assert fl == int(flags[i]), f"flags {fl} vs {int(flags[i])}"
+                assert np.array_equal(h, high[i]) and np.array_equal(p, prev[i]), "high / preview plane"
+                if low is not None and not (fl & 4):
+                    assert np.array_equal(l, low[i]), "low plane"
+                exp = oracle.inverse(high[i], None if (fl & 4) or low is None else low[i], dimg, W, H, fl)
+                assert np.array_equal(out[i], exp), "decoded image"
+                assert np.array_equal(raw[i].view(np.uint8), oracle.unextract(exp, shift, be)), "unextract"
+            for i in range(min(n, 4)):
+                fl = int(flags[i])
+                bp = href.encode_plane(prev[i])
+                core = bytes([fl]) + (b"" if (fl & 4) or low is None else href.encode_plane(low[i])) + href.encode_plane(high[i])
+                exp_chunk = struct.pack("<IBIB", 10 + len(bp) + len(core), 0, len(bp) + 1, (fl & 2) | 4) + bp + core
+                assert chunks[i] == exp_chunk, "entropy coder chunk"
+        except Exception as e:  # noqa: BLE001
+            fails += 1
+            print("FAIL", tag, "->", repr(e)[:200], flush=True)
+        cases += 1
+    print(f"fuzz: {cases} cases, {fails} failures, seed {seed}, {time.time() - t0:.0f} s")
+    return 1 if fails else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
