@@ -46,7 +46,7 @@ def main():
     while time.time() - t0 < budget:
         W = int(rng.choice([4 * int(rng.integers(1, 80)), 8 * int(rng.integers(8, 330)), 32 * int(rng.integers(41, 81)),
                             256 * int(rng.integers(1, 9)), 16 * int(rng.integers(4, 81))]))
-        H = 4 * int(rng.integers(1, 24))
+        H = 4 * int(rng.integers(1, 24)) if rng.integers(4) else 4 * int(rng.integers(24, 90))   # tall: several bands
         shift, be = [(0, 0), (4, 0), (8, 0), (0, 1), (3, 1), (8, 1), (6, 0), (12, 0)][int(rng.integers(8))]
         bits = 16 - shift if shift <= 8 else 4
         n = int(rng.integers(1, 7))
@@ -74,6 +74,18 @@ def main():
                 exp = oracle.inverse(high[i], None if (fl & 4) or low is None else low[i], dimg, W, H, fl)
                 assert np.array_equal(out[i], exp), "decoded image"
                 assert np.array_equal(raw[i].view(np.uint8), oracle.unextract(exp, shift, be)), "unextract"
+            if W % 4 == 0 and cases % 5 == 0:
+                # host layer: Encoder (both entropy stages) -> StreamingDecoder must reproduce the raw file
+                from fusion_power_video_b200 import host
+                for ge in (False, True):
+                    st = host.encode_stream(frames, W, H, shift, bool(be), threads=3, batch=int(rng.integers(1, 5)), delta=delta,
+                                            gpu_entropy=ge)
+                    back = host.decode_stream(st, n + 1, W, H, block=int(rng.choice([0, 4096, 1 << 20])), batch=3,
+                                              raw_shift=shift, big_endian=bool(be))
+                    expect = frames if shift == 0 else None
+                    dec_img = host.decode_stream(st, n + 1, W, H, batch=2)
+                    assert dec_img.shape[0] == n and np.array_equal(dec_img, out), f"host decode (gpu_entropy={ge})"
+                    assert back.shape[0] == n and np.array_equal(back, raw), f"host raw decode (gpu_entropy={ge})"
             for i in range(min(n, 4)):
                 fl = int(flags[i])
                 bp = href.encode_plane(prev[i])
