@@ -11,10 +11,9 @@
 // with a probability of only ~0.23 per pixel, so short segments pay a full
 // second pass; this kernel therefore uses
 //
-//   * TWO PAIRS OF FRAMES PER CTA, four warps; per pair:
-//       chain warp  Lane l owns  Lane l owns the segment of L = 8*LW2 columns
-//                   [l*L, (l+1)*L) of BOTH frames: frame A in the low 16-bit lane
-//                   of a register, frame B in the high one ("pair form", byte
+//   * TWO PAIRS OF FRAMES PER CTA, six warps; per pair:
+//       chain warp  Lane l owns the segment of L = 8*LW2 columns [l*L, (l+1)*L) of BOTH frames: frame A
+//                   in the low 16-bit lane of a register, frame B in the high one ("pair form", byte
 //                   values in [0,255]).  One step for both frames is
 //                       x = (c + min3(n,w,nw) + max3(n,w,nw)) & 0x00ff00ff
 //                   with c = r + 256 - nw, because CG = n + w - median(n,w,nw)
@@ -28,23 +27,27 @@
 //                   until nothing changes.  Lane 0's input is exact (last pixel
 //                   of the previous row: flat indexing, .cc:327-332), so by
 //                   induction over lanes the fixed point is the serial result.
-//       warps 1, 2  the IO warps.  They turn the residual bytes of row y+1 into
-//                   pair form for the chain warp, and turn the finished row y-1
-//                   into output pixels: delta add with independent byte wrap
-//                   (.cc:337-338), high/low recombination, UnextractFrame shift
-//                   and byte swap -- all on two pixels per register, the delta
-//                   image coming in a pre-duplicated form (d | d << 16) so that
-//                   one word serves the same column of both frames.
+//       helper warp issues the TMA row loads and turns the residual bytes of row y+1 into pair form (PRE).
+//       IO warp     turns the finished row y-1 (POST) into output pixels: delta add with independent
+//                   byte wrap (.cc:337-338), high/low recombination, UnextractFrame shift and byte
+//                   swap -- all on two pixels per register, the delta image coming in pair form
+//                   (d | d << 16) so that one word serves the same column of both frames -- and
+//                   issues the TMA row stores.
+//     Roles are placed by SM sub-partition (%warpid): chains on 0 / 1, IO and helper warps on 2 / 3.
+//   * SPLIT MODE (widths 1281..2560): the two 16-bit lanes hold the left and the right half of ONE
+//     frame; see pair_chain_row.
 //   * TMA both ways: rows are fetched with 1-D cp.async.bulk into 3-deep rings
 //     signalled by mbarriers (one elected thread issues), finished rows leave
 //     through a shared-memory row buffer and cp.async.bulk stores, so global
 //     traffic is fully coalesced and costs no LSU instructions.
-//   * one CTA barrier per row couples the two roles; pre/post buffers are
+//   * Shared-memory accesses of the IO / helper warps are bank-conflict free for every L: lane-rotated
+//     chunk order (chunk()) and a permuted delta row (pair_ddup_word).
+//   * one named barrier per row couples the three warps of a pair; pre/post buffers are
 //     double-buffered so the chain warp never waits for the IO warps' work of
 //     the same row.
 //
-// Algorithmic traffic 4 B/px (1 + 1 in, 2 out); the duplicated delta (4 B per
-// column for two frames) is L2-resident.
+// Algorithmic traffic 4 B/px (1 + 1 in, 2 out); the pair-form delta image (4 B per column for two
+// frames) is L2-resident.
 #pragma once
 
 #include "fpv_internal.h"
@@ -108,23 +111,11 @@ __device__ __forceinline__ uint32_t bitselect(uint32_t a, uint32_t b, uint32_t m
   return r;
 }
 
-// One step of the chain for two pixels: x = (c + min3(n,w,nw) + max3(n,w,nw)) & 0x00ff00ff.
-// FPV_CHAIN_FMA: the two additions go to the FMA pipe (IMAD) instead of one IADD3 on the ALU pipe --
-// the sub-partitions that run the chain warps are bound by the ALU pipe's issue rate; c + min3 can
-// issue while max3 is still in flight, so the dependent depth stays max3 -> add -> and.
-#ifndef FPV_CHAIN_FMA
-#define FPV_CHAIN_FMA 0
-#endif
+// One step of the chain for two pixels: x = (c + min3(n,w,nw) + max3(n,w,nw)) & 0x00ff00ff.  (Doing the two
+// additions as IMADs on the FMA pipe instead of one IADD3 measured no different: the chain is bound by the
+// dependent latency max3 -> add -> and, not by the ALU pipe's issue rate.)
 __device__ __forceinline__ uint32_t chain_step(uint32_t c, uint32_t n, uint32_t w, uint32_t nw) {
-  const uint32_t mn = __vimin3_u16x2(n, w, nw), mx = __vimax3_u16x2(n, w, nw);
-#if FPV_CHAIN_FMA
-  uint32_t t, v;
-  asm("mad.lo.u32 %0, %1, 1, %2;" : "=r"(t) : "r"(mn), "r"(c));
-  asm("mad.lo.u32 %0, %1, 1, %2;" : "=r"(v) : "r"(mx), "r"(t));
-  return v & kLaneMask;
-#else
-  return (c + mn + mx) & kLaneMask;
-#endif
+  return (c + __vimin3_u16x2(n, w, nw) + __vimax3_u16x2(n, w, nw)) & kLaneMask;
 }
 
 // One row of the chain warp: residual row (pair form, in PRE) -> finished row in x[] and in POST.

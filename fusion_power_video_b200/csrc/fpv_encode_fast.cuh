@@ -6,8 +6,8 @@
 // :550-562).
 //
 // Work decomposition
-//   task   = (frame, band of `band_rows` rows); persistent CTAs take tasks
-//            round-robin.
+//   task   = (frame, band of `band_rows` rows; 32 rows for short frame lists); persistent CTAs (at most
+//            4 per SM) take tasks round-robin.
 //   stage  = up to 4 (or 2) consecutive rows of the band = ONE contiguous flat range
 //            of the raw frame (and of the delta image), fetched with
 //            cp.async.bulk (TMA, 1-D) into a shared-memory ring and signalled
@@ -26,9 +26,9 @@
 //            consumer warps never see them.
 //
 // Arithmetic is done on two pixels per register ("q form" / "S form", see
-// fpv_common.cuh).  Per row and lane: LDS.128 + LDS.32 of raw and of delta,
-// ~70 integer ops, 2x STG.64 (+ 1 STG.16 of preview every 4th row) and two
-// predicated shared atomics for the ClampedGradient decision histograms.
+// fpv_common.cuh) and balanced over the ALU and the FMA pipe (make_hs_lo, sub_fma).  Per row and lane:
+// LDS.128 + LDS.32 of raw and of delta, ~54 ALU-pipe and ~24 FMA-pipe instructions, 2x STG.64 (+ 1 STG.16
+// of preview every 4th row) and two predicated shared atomics for the ClampedGradient decision histograms.
 // The delta decision needs no histogram in the common case: only 8 bit
 // counters per frame (see k_decide).
 #pragma once
