@@ -116,3 +116,42 @@ def test_full_size_batch_round_trip():
         f2, _, h2, l2, p2 = split_chunk(chunks[i], P, PP, True)
         assert h2 == high[i].tobytes() and l2 == low[i].tobytes() and p2 == preview[i].tobytes()
         assert len(chunks[i]) < 0.55 * 2 * P      # 12-bit frames: well under 9 bits per pixel
+
+
+def test_crafted_planes_depth_limit_and_ragged_chunks():
+    """Planes uploaded as they are (fpv_entropy_device): Fibonacci symbol counts force the depth-limit loop of the
+    Huffman construction (an unlimited tree would be 21 deep), a plane size that is not a multiple of the chunk
+    size leaves a ragged last chunk, a two-symbol preview uses a one-bit code."""
+    import torch
+    import fusion_power_video_b200 as fpv
+
+    W, H, n = 1280, 68, 3          # P = 87040 = 65536 + 21504
+    P, PP = W * H, (W // 4) * (H // 4)
+    rng = np.random.default_rng(21)
+    fib = [1, 1, 2, 3, 5, 8, 13, 21, 34, 55, 89, 144, 233, 377, 610, 987, 1597, 2584, 4181, 6765, 10946, 17711]
+    deep = np.concatenate([np.full(v, i * 7 % 256, np.uint8) for i, v in enumerate(fib)])
+    high = np.zeros((n, P), np.uint8)
+    for i in range(n):
+        rng.shuffle(deep)
+        high[i, :deep.size] = deep                      # first chunk: 46367 skewed symbols + zeros
+        high[i, 65536:] = rng.integers(0, 256, P - 65536)
+    low = np.minimum(rng.geometric(0.05, (n, P)) - 1, 255).astype(np.uint8)
+    preview = rng.integers(0, 2, (n, PP)).astype(np.uint8) * 254
+    flags = np.array([3, 4, 0], np.uint8)               # frame 1 has no low plane
+    dev = torch.device("cuda", 0)
+    t = {k: torch.from_numpy(v).to(dev) for k, v in dict(high=high, low=low, preview=preview, flags=flags).items()}
+    with fpv.Context(W, H, 0, False, max_batch=n) as ctx:
+        cap = ctx.stream_bound(n)
+        out = torch.zeros(cap, dtype=torch.uint8, device=dev)
+        off = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+        ctx.entropy_device(t["flags"].data_ptr(), t["high"].data_ptr(), t["low"].data_ptr(), t["preview"].data_ptr(), n,
+                           out.data_ptr(), cap, off.data_ptr())
+        torch.cuda.synchronize()
+    off = off.cpu().numpy()
+    out = out.cpu().numpy()
+    assert max(href.huffman_lengths(np.bincount(high[0, :65536], minlength=256).tolist(), 30)) > 15
+    for i in range(n):
+        chunk = out[off[i]:off[i + 1]].tobytes()
+        assert chunk == expected_chunk(int(flags[i]), high[i], low[i], preview[i]), f"frame {i}"
+        f2, _, h2, l2, p2 = split_chunk(chunk, P, PP, True)
+        assert h2 == high[i].tobytes() and p2 == preview[i].tobytes() and (l2 is None) == bool(flags[i] & 4)
