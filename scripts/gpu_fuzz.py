@@ -36,6 +36,52 @@ def content(rng, kind, n, W, H, bits):
     return np.stack([(((xx * (3 + k) + yy * (5 + 2 * k)) & ((1 << bits) - 1))).astype(np.uint16).reshape(-1) for k in range(n)])
 
 
+def entropy_case(rng):
+    """Random symbol distributions straight into the entropy coder (fpv_entropy_device), vs the CPU restatement."""
+    import torch
+
+    W = 16 * int(rng.integers(4, 120))
+    H = 4 * int(rng.integers(1, 40))
+    n = int(rng.integers(1, 4))
+    P, PP = W * H, (W // 4) * (H // 4)
+
+    def plane(size):
+        k = int(rng.integers(6))
+        if k == 0:
+            return np.full(size, rng.integers(256), np.uint8)
+        if k == 1:
+            return rng.choice(rng.integers(0, 256, int(rng.integers(2, 6))), size).astype(np.uint8)
+        if k == 2:
+            return np.minimum(rng.geometric(float(rng.uniform(0.01, 0.9)), size) - 1, 255).astype(np.uint8)
+        if k == 3:
+            return rng.integers(0, 256, size).astype(np.uint8)
+        if k == 4:   # exponentially spaced counts: deep trees
+            w = 1.6 ** -np.arange(int(rng.integers(8, 40)))
+            return rng.choice(len(w), size, p=w / w.sum()).astype(np.uint8)
+        return (np.cumsum(rng.integers(-2, 3, size)) & 255).astype(np.uint8)
+
+    high = np.stack([plane(P) for _ in range(n)])
+    low = np.stack([plane(P) for _ in range(n)])
+    prev = np.stack([plane(PP) for _ in range(n)])
+    flags = rng.integers(0, 8, n).astype(np.uint8)
+    dev = torch.device("cuda", 0)
+    th, tl, tp, tf = (torch.from_numpy(a).to(dev) for a in (high, low, prev, flags))
+    with fpv.Context(W, H, 0, False, max_batch=n) as ctx:
+        cap = ctx.stream_bound(n)
+        out = torch.zeros(cap, dtype=torch.uint8, device=dev)
+        off = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+        ctx.entropy_device(tf.data_ptr(), th.data_ptr(), tl.data_ptr(), tp.data_ptr(), n, out.data_ptr(), cap, off.data_ptr())
+        torch.cuda.synchronize()
+    off, out = off.cpu().numpy(), out.cpu().numpy()
+    for i in range(n):
+        fl = int(flags[i])
+        bp = href.encode_plane(prev[i])
+        core = bytes([fl]) + (b"" if fl & 4 else href.encode_plane(low[i])) + href.encode_plane(high[i])
+        exp = struct.pack("<IBIB", 10 + len(bp) + len(core), 0, len(bp) + 1, (fl & 2) | 4) + bp + core
+        assert out[off[i]:off[i + 1]].tobytes() == exp, f"entropy_device W={W} H={H} frame {i} flags {fl}"
+        assert href.brotli_decode(href.encode_plane(high[i]), P) == high[i].tobytes()
+
+
 def main():
     budget = float(sys.argv[1]) if len(sys.argv) > 1 else 120.0
     seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1
@@ -58,6 +104,8 @@ def main():
         P, PP = W * H, (W // 4) * (H // 4)
         tag = f"W={W} H={H} shift={shift} be={be} n={n} kind={kind}"
         try:
+            if cases % 7 == 3:
+                entropy_case(rng)
             with fpv.Context(W, H, shift, bool(be), max_batch=4) as ctx:
                 ctx.set_delta_raw(delta)
                 flags, high, low, prev = ctx.encode(frames)
