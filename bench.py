@@ -414,6 +414,51 @@ def main():
                "slots": NS,
                "what": "fpv_encode_submit/fpv_wait on pinned host buffers, slots overlapped (no brotli)"}
 
+    # ---- e2e with the entropy stage on the GPU: raw frames in, container chunks (coded streams) out ----------------
+    e2e_stream = None
+    if not args.no_e2e and not args.no_entropy:
+        capb = ectx.stream_bound(B)
+        hc = [PinnedArray((capb,), np.uint8) for _ in range(NS)]
+        hoff = [PinnedArray((B + 1,), np.uint64) for _ in range(NS)]
+        coded = [0]
+
+        def st_pass():
+            nb = Fe // B
+            tot = 0
+            for b in range(nb):
+                slot = b % NS
+                ectx.wait(slot)
+                if b >= NS:
+                    tot += int(hoff[slot].array[B])
+                o = b * B
+                ectx.encode_stream_submit(slot, hin.array[o:o + B], B, hf.array[o:o + B], hoff[slot].array, hc[slot].array, capb)
+            for sl in range(NS):
+                ectx.wait(sl)
+            for b in range(max(0, nb - NS), nb):
+                tot += int(hoff[b % NS].array[B])
+            coded[0] = tot
+
+        for _ in range(2):
+            st_pass()
+        if world > 1:
+            dist.barrier()
+        t_a = time.perf_counter()
+        for _ in range(esteps):
+            st_pass()
+        t_b = time.perf_counter()
+        windows.append((t_a, t_b))
+        ts2 = torch.tensor([(t_b - t_a) / esteps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ts2, op=dist.ReduceOp.MAX)
+        ssec = float(ts2.item())
+        e2e_stream = {"value": world * Fe * P * 2 / ssec / 1e9, "unit": "GB/s", "frames_per_s": world * Fe / ssec,
+                      "h2d_bytes_per_step": Fe * P * 2, "d2h_bytes_per_step": int(coded[0]) + Fe * (1 + 8), "frames_per_step": Fe,
+                      "batch": B, "slots": NS, "bpp": coded[0] * 8.0 / (Fe * P),
+                      "what": "fpv_encode_stream_submit/fpv_wait on pinned host buffers: transform + GPU entropy coding + "
+                              "container framing; only the coded bytes come back (about half the plane bytes)"}
+        for a in hc + hoff:
+            a.free()
+
     # ---- decode e2e: planes in pinned host memory -> fpv_decode_submit / fpv_wait -> raw frames in host memory ----
     decode_e2e = None
     if not args.no_e2e and not args.no_decode:
@@ -549,7 +594,7 @@ def main():
                        "l2": f"inputs larger than L2: {F * P * 2 / 1e6:.0f} MB raw + {F * P * 2.0625 / 1e6:.0f} MB out per step vs 126 MB L2",
                        "flags_histogram": {int(u): int(c) for u, c in zip(uniq, cnt)}},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": clocks, "decode": decode, "decode_e2e": decode_e2e, "entropy": entropy, "stream": stream_leg,
+            "clocks": clocks, "decode": decode, "e2e_stream": e2e_stream, "decode_e2e": decode_e2e, "entropy": entropy, "stream": stream_leg,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
