@@ -194,8 +194,8 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--frames", type=int, default=1184,
                     help="frames per GPU per step (device-resident); 1184 = 148 SMs x 2 resident decode CTAs x 4 frames")
-    ap.add_argument("--e2e-frames", type=int, default=256, help="frames per step of the host-buffer (e2e) leg")
-    ap.add_argument("--e2e-batch", type=int, default=32)
+    ap.add_argument("--e2e-frames", type=int, default=512, help="frames per step of the host-buffer (e2e) legs")
+    ap.add_argument("--e2e-batch", type=int, default=64)
     ap.add_argument("--e2e-slots", type=int, default=3, help="overlapped submit slots of the host-buffer legs (<= 4)")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-decode", action="store_true")
