@@ -18,11 +18,14 @@ int main(int argc, char* argv[]) {
   const bool big_endian = atoi(argv[3]) != 0;
   const int shift = atoi(argv[4]);
   fpvc::GpuOptions opt;
+  opt.batch = 32;
   if (argc > 5) opt.batch = (uint32_t)atoi(argv[5]);
   fpvc::StreamingDecoder decoder(opt);
   decoder.SetRawOutput(shift, big_endian);
   bool failed = false;
-  std::vector<uint8_t> block(1 << 20);
+  // decode.cc reads 1 MiB at a time (decode.cc:67-77); the GPU decoder wants several batches of frames per call,
+  // so that brotli decoding of one batch overlaps the inverse transform of the previous one
+  std::vector<uint8_t> block((size_t)128 << 20);
   size_t n;
   while (!failed && (n = fread(block.data(), 1, block.size(), stdin)) > 0) {
     decoder.Decode(block.data(), n,
