@@ -272,10 +272,13 @@ __device__ __forceinline__ void pair_chain_row(const uint32_t (&n)[8 * LW2], uin
 // LW2:   the chain lane's segment is L = 8 LW2 px (LW2 = ceil(W / 256)).
 // FULL:  W == 32 L (every lane owns a complete segment).
 // SHIFT: UnextractFrame with a non-zero shift is fused into the write-out.
+// Repair groups: the chains are re-run G pixels at a time with a vote in between.  8 measured best for
+// L = 40 (4 and 16 do not even divide it evenly), 16 for L = 32 (2048x2048: 69.9 -> 71.5 %).
 #ifndef FPV_PAIR_G
-#define FPV_PAIR_G 8
+#define FPV_PAIR_G 0
 #endif
-template <int LW2, bool FULL, bool SHIFT, bool SPLIT = false, int K0T = FPV_PAIR_K0, int G = FPV_PAIR_G>
+template <int LW2, bool FULL, bool SHIFT, bool SPLIT = false, int K0T = FPV_PAIR_K0,
+          int G = (FPV_PAIR_G ? FPV_PAIR_G : (LW2 == 4 ? 16 : 8))>
 __global__ void __launch_bounds__(kPairThreads, 2) k_decode_pair(const PairParams p) {
   extern __shared__ __align__(128) uint8_t psm[];
   constexpr int L = 8 * LW2;
