@@ -155,3 +155,21 @@ def test_crafted_planes_depth_limit_and_ragged_chunks():
         assert chunk == expected_chunk(int(flags[i]), high[i], low[i], preview[i]), f"frame {i}"
         f2, _, h2, l2, p2 = split_chunk(chunk, P, PP, True)
         assert h2 == high[i].tobytes() and p2 == preview[i].tobytes() and (l2 is None) == bool(flags[i] & 4)
+
+
+def test_more_frames_than_layout_threads():
+    """More than 1024 frames in one call: k_entropy_layout scans them in passes with a carry."""
+    import fusion_power_video_b200 as fpv
+    from fusion_power_video_b200 import synth
+
+    W, H, n = 64, 16, 1100
+    frames = synth.plasma_frames(n, W, H, bits=12, seed=3).reshape(n, -1)
+    with fpv.Context(W, H, 4, False, max_batch=n) as ctx:
+        ctx.set_delta_raw(frames[0])
+        flags, high, low, preview = ctx.encode(frames)
+        sflags, chunks = ctx.encode_stream(frames)
+    assert np.array_equal(flags, sflags) and len(chunks) == n
+    for i in range(n):
+        assert int.from_bytes(chunks[i][:4], "little") == len(chunks[i]), f"frame {i}: container size field"
+    for i in (0, 1, 511, 1023, 1024, 1025, n - 1):
+        assert chunks[i] == expected_chunk(int(flags[i]), high[i], low[i], preview[i]), f"frame {i}"
