@@ -138,6 +138,18 @@ def main():
               "--warmup 3 --no-e2e --no-cpu --no-stream --no-decode`.  Algorithmic bytes here = planes read once + coded bytes "
               "written to the scratch (about half the plane bytes); the kernel reads each chunk three times (histogram, sizes, "
               "packing), the second and third time from L1/L2.  It is not HBM bound: the serial Huffman construction per chunk dominates.")
+    if os.path.exists(os.path.join(OUT, "prof_decode_c3.ncu-rep")):
+        F3, P3 = 592, 2048 * 2048
+        traffic["decode_c3"] = kernel_md(f"{tag}_decode_c3", f"k_decode_pair in split mode (C3: 16-bit 2048x2048, {F3} frames = one wave)",
+              os.path.join(OUT, "prof_decode_c3.ncu-rep"), F3 * 2048, "frame row (2048 px)", F3 * P3 * 4.0,
+              "`ncu --set full --clock-control none --import-source on -k regex:k_decode_pair -s 1 -c 1 python bench.py --workload c3 "
+              "--frames 592 --steps 3 --warmup 3 --no-e2e --no-cpu --no-stream --no-entropy`.")
+    if os.path.exists(os.path.join(OUT, "prof_encode_c3.ncu-rep")):
+        F3, P3 = 592, 2048 * 2048
+        traffic["encode_c3"] = kernel_md(f"{tag}_encode_c3", f"k_encode_fast, main pass (C3: 16-bit 2048x2048, {F3} frames)",
+              os.path.join(OUT, "prof_encode_c3.ncu-rep"), F3 * P3 / 256, "warp-row (256 px)", F3 * P3 * 4.0625,
+              "`ncu ... -k regex:k_encode_fast -s 3 -c 1 python bench.py --workload c3 --frames 592 --steps 3 --warmup 3 --no-e2e "
+              "--no-cpu --no-stream --no-entropy --no-decode`.")
     json.dump(traffic, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
 
 
