@@ -17,6 +17,7 @@ _LIB_PATH = os.environ.get("FPV_B200_LIB") or os.path.join(_HERE, "lib", "libfpv
 ENC_DEFAULT, ENC_NO_DELTA, ENC_GENERIC = 0, 1, 2
 DEC_DEFAULT, DEC_UNEXTRACT = 0, 1
 FLAG_USE_DELTA, FLAG_USE_CG, FLAG_NO_LOW_BYTES = 1, 2, 4
+IPC_HANDLE_BYTES = 64
 
 _lib = None
 
@@ -77,6 +78,14 @@ def lib() -> C.CDLL:
     L.fpv_set_delta_image_device.restype = i32
     L.fpv_copy_delta_peer.argtypes = [vp, vp]
     L.fpv_copy_delta_peer.restype = i32
+    L.fpv_delta_ipc_export.argtypes = [vp, vp]
+    L.fpv_delta_ipc_export.restype = i32
+    L.fpv_delta_ipc_import.argtypes = [vp, vp]
+    L.fpv_delta_ipc_import.restype = i32
+    L.fpv_bind_thread.argtypes = [vp]
+    L.fpv_bind_thread.restype = i32
+    L.fpv_device_of.argtypes = [vp]
+    L.fpv_device_of.restype = i32
     L.fpv_encode.argtypes = [vp, vp, u32, u32, vp, vp, vp, vp]
     L.fpv_encode.restype = i32
     L.fpv_encode_device.argtypes = [vp, vp, u32, u32, vp, vp, vp, vp, vp]
@@ -213,6 +222,21 @@ class Context:
 
     def copy_delta_from(self, other: "Context"):
         self._check(self._L.fpv_copy_delta_peer(self._h, other._h))
+
+    def delta_ipc_export(self) -> bytes:
+        """CUDA IPC handle (64 bytes) of the resident delta image, for fpv_delta_ipc_import in ANOTHER process."""
+        buf = C.create_string_buffer(IPC_HANDLE_BYTES)
+        self._check(self._L.fpv_delta_ipc_export(self._h, buf))
+        return buf.raw
+
+    def delta_ipc_import(self, handle: bytes):
+        """Maps the exporting process's delta image and copies it device to device (peer copy over NVLink / PCIe)."""
+        assert len(handle) == IPC_HANDLE_BYTES
+        buf = C.create_string_buffer(bytes(handle), IPC_HANDLE_BYTES)
+        self._check(self._L.fpv_delta_ipc_import(self._h, buf))
+
+    def bind_thread(self):
+        self._check(self._L.fpv_bind_thread(self._h))
 
     # -- encode -------------------------------------------------------------
     def encode(self, frames, options=ENC_DEFAULT):

@@ -25,8 +25,9 @@ namespace {
 constexpr int kNumSlots = 4;       // host-pipeline slots (FPV_NUM_SLOTS in the header); staging is allocated on first use
 constexpr int kDeviceScratch = kNumSlots;  // scratch index used by the *_device entry points
 
-std::mutex g_err_mutex;
-std::string g_create_error = "no error";
+// Last failure of the calling thread (fpv_last_error): per thread, so that threads sharing a context
+// never read each other's half-written message.
+thread_local std::string tl_error = "no error";
 
 struct Slot {
   cudaStream_t stream = nullptr;
@@ -74,17 +75,18 @@ struct fpv_ctx {
   bool timing_on = false;
   std::vector<TimingHook> timing;   // event pairs, reused
   size_t timing_used = 0;
-  std::string err = "no error";
+  // Every entry point holds this while it touches the context; fpv_wait drops it while it sleeps.
+  // Recursive: the synchronous entry points are built from submit + wait.
+  std::recursive_mutex mu;
 };
+
+#define FPV_LOCK(c) std::lock_guard<std::recursive_mutex> lock__((c)->mu)
 
 namespace {
 
 int fail(fpv_ctx* c, int code, const std::string& msg) {
-  if (c) c->err = msg;
-  else {
-    std::lock_guard<std::mutex> l(g_err_mutex);
-    g_create_error = msg;
-  }
+  (void)c;
+  tl_error = msg;
   return code;
 }
 
@@ -211,10 +213,11 @@ int decode_device_impl(fpv_ctx* c, const uint8_t* high, const uint8_t* low, cons
   cudaError_t e = cudaSuccess;
   const uint16_t* delta = c->has_delta ? c->d_delta : nullptr;
   const bool unextract = (options & FPV_DEC_UNEXTRACT) != 0;
-  int l = -1;
+  int l = -2;
   if (!getenv("FPV_DECODE_SERIAL"))
     l = enqueue_decode(c->g, c->tune.num_sms, high, low, flags, delta, c->d_delta_dup, n, unextract, out,
                        stream, &e, next_hook(c));
+  if (l == -1) return cuda_fail(c, e, "decode kernel launch");
   if (l < 0) {
     // rows too wide for the shared-memory row pipeline (or forced): serial chain
     uint8_t* scratch = const_cast<uint8_t*>(high);
@@ -261,7 +264,8 @@ int fpv_create(fpv_ctx** out, int device, uint32_t xsize, uint32_t ysize, int sh
   if (mode < 0)
     return fail(nullptr, FPV_ERR_UNSUPPORTED,
                 "shift must be 0..16 (0..8 for big-endian data: the reference shifts by 8 - shift)");
-  if (max_batch == 0) return fail(nullptr, FPV_ERR_INVALID_ARG, "max_batch must be >= 1");
+  if (max_batch == 0 || max_batch > 65535)
+    return fail(nullptr, FPV_ERR_INVALID_ARG, "max_batch must be 1..65535 (frames are a grid dimension of the small kernels)");
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0)
@@ -342,19 +346,28 @@ void fpv_destroy(fpv_ctx* c) {
 }
 
 const char* fpv_last_error(const fpv_ctx* c) {
-  if (c) return c->err.c_str();
-  std::lock_guard<std::mutex> l(g_err_mutex);
-  static thread_local std::string copy;
-  copy = g_create_error;
-  return copy.c_str();
+  (void)c;
+  return tl_error.c_str();
 }
+
+int fpv_bind_thread(const fpv_ctx* c) {
+  if (!c) return FPV_ERR_INVALID_ARG;
+  return cudaSetDevice(c->device) == cudaSuccess ? FPV_OK : FPV_ERR_CUDA;
+}
+
+int fpv_device_of(const fpv_ctx* c) { return c ? c->device : -1; }
 
 size_t fpv_plane_bytes(const fpv_ctx* c) { return c ? (size_t)c->g.P : 0; }
 size_t fpv_preview_bytes(const fpv_ctx* c) { return c ? (size_t)c->g.PP : 0; }
-uint64_t fpv_kernel_launches(const fpv_ctx* c) { return c ? c->launches : 0; }
+uint64_t fpv_kernel_launches(const fpv_ctx* c) {
+  if (!c) return 0;
+  std::lock_guard<std::recursive_mutex> l(const_cast<fpv_ctx*>(c)->mu);
+  return c->launches;
+}
 
 int fpv_enable_kernel_timing(fpv_ctx* c, int on) {
   if (!c) return FPV_ERR_INVALID_ARG;
+  FPV_LOCK(c);
   c->timing_on = on != 0;
   c->timing_used = 0;
   return FPV_OK;
@@ -362,6 +375,7 @@ int fpv_enable_kernel_timing(fpv_ctx* c, int on) {
 
 int fpv_read_kernel_timing(fpv_ctx* c, double* total_ms, uint32_t* launches) {
   if (!c || !total_ms || !launches) return FPV_ERR_INVALID_ARG;
+  FPV_LOCK(c);
   FPV_CUDA(cudaSetDevice(c->device));
   double total = 0;
   for (size_t i = 0; i < c->timing_used; i++) {
@@ -398,6 +412,7 @@ static int refresh_delta_dup(fpv_ctx* c, cudaStream_t stream) {
 
 int fpv_set_delta_raw_device(fpv_ctx* c, const void* raw_dev, void* stream) {
   if (!c) return FPV_ERR_INVALID_ARG;
+  FPV_LOCK(c);
   FPV_CUDA(cudaSetDevice(c->device));
   if (!raw_dev) { c->has_delta = false; return FPV_OK; }
   cudaError_t e = cudaSuccess;
@@ -413,6 +428,7 @@ int fpv_set_delta_raw_device(fpv_ctx* c, const void* raw_dev, void* stream) {
 
 int fpv_set_delta_raw(fpv_ctx* c, const uint16_t* raw_host) {
   if (!c) return FPV_ERR_INVALID_ARG;
+  FPV_LOCK(c);
   FPV_CUDA(cudaSetDevice(c->device));
   if (!raw_host) { c->has_delta = false; return FPV_OK; }
   uint16_t* tmp = nullptr;
@@ -429,6 +445,7 @@ int fpv_set_delta_raw(fpv_ctx* c, const uint16_t* raw_host) {
 
 int fpv_set_delta_image_device(fpv_ctx* c, const void* image_dev, void* stream) {
   if (!c) return FPV_ERR_INVALID_ARG;
+  FPV_LOCK(c);
   FPV_CUDA(cudaSetDevice(c->device));
   if (!image_dev) { c->has_delta = false; return FPV_OK; }
   FPV_CUDA(cudaMemcpyAsync(c->d_delta, image_dev, c->g.P * 2, cudaMemcpyDeviceToDevice,
@@ -441,6 +458,7 @@ int fpv_set_delta_image_device(fpv_ctx* c, const void* image_dev, void* stream) 
 
 int fpv_set_delta_image(fpv_ctx* c, const uint16_t* image_host) {
   if (!c) return FPV_ERR_INVALID_ARG;
+  FPV_LOCK(c);
   FPV_CUDA(cudaSetDevice(c->device));
   if (!image_host) { c->has_delta = false; return FPV_OK; }
   FPV_CUDA(cudaMemcpy(c->d_delta, image_host, c->g.P * 2, cudaMemcpyHostToDevice));
@@ -454,6 +472,12 @@ int fpv_set_delta_image(fpv_ctx* c, const uint16_t* image_host) {
 int fpv_copy_delta_peer(fpv_ctx* dst, const fpv_ctx* src) {
   fpv_ctx* c = dst;
   if (!dst || !src) return FPV_ERR_INVALID_ARG;
+  if (dst == src) return FPV_OK;
+  // both contexts are touched; lock in address order so that two opposite copies cannot deadlock
+  fpv_ctx* first = dst < src ? dst : const_cast<fpv_ctx*>(src);
+  fpv_ctx* second = dst < src ? const_cast<fpv_ctx*>(src) : dst;
+  std::lock_guard<std::recursive_mutex> l1(first->mu);
+  std::lock_guard<std::recursive_mutex> l2(second->mu);
   if (dst->g.P != src->g.P) return fail(dst, FPV_ERR_INVALID_ARG, "geometry mismatch between contexts");
   if (!src->has_delta) { dst->has_delta = false; return FPV_OK; }
   FPV_CUDA(cudaSetDevice(dst->device));
@@ -466,11 +490,45 @@ int fpv_copy_delta_peer(fpv_ctx* dst, const fpv_ctx* src) {
   return FPV_OK;
 }
 
+int fpv_delta_ipc_export(fpv_ctx* c, void* handle_out) {
+  if (!c || !handle_out) return FPV_ERR_INVALID_ARG;
+  FPV_LOCK(c);
+  static_assert(sizeof(cudaIpcMemHandle_t) == FPV_IPC_HANDLE_BYTES, "IPC handle size");
+  if (!c->has_delta) return fail(c, FPV_ERR_NO_DELTA, "no delta frame to export");
+  FPV_CUDA(cudaSetDevice(c->device));
+  FPV_CUDA(cudaStreamSynchronize(c->aux_stream));   // the image is complete before anyone maps it
+  cudaIpcMemHandle_t h;
+  FPV_CUDA(cudaIpcGetMemHandle(&h, c->d_delta));
+  memcpy(handle_out, &h, sizeof h);
+  return FPV_OK;
+}
+
+int fpv_delta_ipc_import(fpv_ctx* c, const void* handle) {
+  if (!c || !handle) return FPV_ERR_INVALID_ARG;
+  FPV_LOCK(c);
+  FPV_CUDA(cudaSetDevice(c->device));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof h);
+  void* peer = nullptr;
+  FPV_CUDA(cudaIpcOpenMemHandle(&peer, h, cudaIpcMemLazyEnablePeerAccess));
+  // device-to-device over NVLink / PCIe peer access; the owner keeps its copy
+  cudaError_t e = cudaMemcpyAsync(c->d_delta, peer, c->g.P * 2, cudaMemcpyDefault, c->aux_stream);
+  int rc = FPV_OK;
+  if (e != cudaSuccess) rc = cuda_fail(c, e, "delta peer copy (IPC)");
+  if (rc == FPV_OK) rc = refresh_delta_dup(c, c->aux_stream);
+  cudaError_t es = cudaStreamSynchronize(c->aux_stream);
+  cudaIpcCloseMemHandle(peer);
+  if (rc == FPV_OK && es != cudaSuccess) rc = cuda_fail(c, es, "delta peer copy (IPC)");
+  if (rc == FPV_OK) c->has_delta = true;
+  return rc;
+}
+
 // ---- encode -------------------------------------------------------------------
 
 int fpv_encode_device(fpv_ctx* c, const void* frames_dev, uint32_t n, uint32_t options, void* flags_dev,
                       void* high_dev, void* low_dev, void* preview_dev, void* stream) {
   if (!c) return FPV_ERR_INVALID_ARG;
+  FPV_LOCK(c);
   if (n == 0) return FPV_OK;
   if (!frames_dev || !flags_dev || !high_dev || !preview_dev)
     return fail(c, FPV_ERR_INVALID_ARG, "NULL device buffer");
@@ -487,6 +545,7 @@ int fpv_encode_device(fpv_ctx* c, const void* frames_dev, uint32_t n, uint32_t o
 int fpv_encode_submit(fpv_ctx* c, uint32_t slot, const uint16_t* frames_host, uint32_t n, uint32_t options,
                       uint8_t* flags_host, uint8_t* high_host, uint8_t* low_host, uint8_t* preview_host) {
   if (!c) return FPV_ERR_INVALID_ARG;
+  FPV_LOCK(c);
   if (slot >= kNumSlots) return fail(c, FPV_ERR_INVALID_ARG, "slot out of range");
   if (n == 0) return FPV_OK;
   if (n > c->max_batch) return fail(c, FPV_ERR_INVALID_ARG, "n exceeds max_batch");
@@ -515,11 +574,18 @@ int fpv_encode_submit(fpv_ctx* c, uint32_t slot, const uint16_t* frames_host, ui
 int fpv_wait(fpv_ctx* c, uint32_t slot) {
   if (!c) return FPV_ERR_INVALID_ARG;
   if (slot >= kNumSlots) return fail(c, FPV_ERR_INVALID_ARG, "slot out of range");
-  if (!c->slots[slot].allocated) return FPV_OK;
-  FPV_CUDA(cudaSetDevice(c->device));
-  FPV_CUDA(cudaEventSynchronize(c->slots[slot].done));   // everything submitted on the slot so far
-  FPV_CUDA(cudaStreamSynchronize(c->slots[slot].stream)); // (returns at once; surfaces stream errors)
+  std::unique_lock<std::recursive_mutex> lk(c->mu);
   Slot& s = c->slots[slot];
+  if (!s.allocated) return FPV_OK;
+  FPV_CUDA(cudaSetDevice(c->device));
+  // Sleep WITHOUT the context lock: another thread may submit into a different slot meanwhile.  (When the
+  // caller is one of the synchronous entry points the lock is held once more further up; that is fine,
+  // those calls are blocking by contract.)
+  lk.unlock();
+  cudaError_t e = cudaEventSynchronize(s.done);                    // everything submitted on the slot so far
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s.stream);       // (returns at once; surfaces stream errors)
+  lk.lock();
+  if (e != cudaSuccess) return cuda_fail(c, e, "fpv_wait");
   if (s.stream_n) {
     // second half of fpv_encode_stream_submit: the coded size is known now, fetch exactly that many bytes
     const uint64_t total = s.stream_off_host[s.stream_n];
@@ -528,7 +594,10 @@ int fpv_wait(fpv_ctx* c, uint32_t slot) {
     if (total > stream_bound(c, n)) return fail(c, FPV_ERR_CUDA, "entropy coder overflowed its output bound");
     FPV_CUDA(cudaMemcpyAsync(s.stream_out_host, c->entropy[slot].out, (size_t)total, cudaMemcpyDeviceToHost, s.stream));
     FPV_CUDA(cudaEventRecord(s.done, s.stream));
-    FPV_CUDA(cudaEventSynchronize(s.done));
+    lk.unlock();
+    e = cudaEventSynchronize(s.done);
+    lk.lock();
+    if (e != cudaSuccess) return cuda_fail(c, e, "fpv_wait (coded bytes)");
   }
   return FPV_OK;
 }
@@ -536,6 +605,7 @@ int fpv_wait(fpv_ctx* c, uint32_t slot) {
 int fpv_encode(fpv_ctx* c, const uint16_t* frames_host, uint32_t n, uint32_t options, uint8_t* flags_host,
                uint8_t* high_host, uint8_t* low_host, uint8_t* preview_host) {
   if (!c) return FPV_ERR_INVALID_ARG;
+  FPV_LOCK(c);
   const size_t P = c->g.P, PP = c->g.PP;
   for (uint32_t off = 0; off < n; off += c->max_batch) {
     uint32_t m = n - off < c->max_batch ? n - off : c->max_batch;
@@ -549,6 +619,43 @@ int fpv_encode(fpv_ctx* c, const uint16_t* frames_host, uint32_t n, uint32_t opt
   return FPV_OK;
 }
 
+int fpv_split(fpv_ctx* c, const uint16_t* frames_host, uint32_t n, uint8_t* flags_host, uint8_t* high_host,
+              uint8_t* low_host) {
+  if (!c) return FPV_ERR_INVALID_ARG;
+  FPV_LOCK(c);
+  if (n == 0) return FPV_OK;
+  if (!frames_host || !flags_host || !high_host) return fail(c, FPV_ERR_INVALID_ARG, "NULL host buffer");
+  const bool has_low = mode_has_low(c->g.mode);
+  if (has_low && !low_host) return fail(c, FPV_ERR_INVALID_ARG, "low plane buffer is NULL");
+  FPV_CUDA(cudaSetDevice(c->device));
+  int rc = ensure_slot(c, 0);
+  if (rc != FPV_OK) return rc;
+  Slot& s = c->slots[0];
+  const size_t P = c->g.P;
+  std::vector<uint32_t> lor(c->max_batch);
+  for (uint32_t off = 0; off < n; off += c->max_batch) {
+    const uint32_t m = n - off < c->max_batch ? n - off : c->max_batch;
+    FPV_CUDA(cudaMemcpyAsync(s.d_frames, frames_host + (size_t)off * P, (size_t)m * P * 2, cudaMemcpyHostToDevice, s.stream));
+    cudaError_t e = cudaSuccess;
+    // the preview staging buffer doubles as the per-frame OR words (4 bytes per frame; it holds >= 1 byte per frame only
+    // for tiny geometries, so use the flags + a dedicated allocation instead)
+    uint32_t* d_or = nullptr;
+    FPV_CUDA(cudaMallocAsync(&d_or, sizeof(uint32_t) * m, s.stream));
+    int l = enqueue_split(c->g, s.d_frames, m, s.d_high, has_low ? s.d_low : nullptr, d_or, s.stream, &e);
+    if (l < 0) { cudaFreeAsync(d_or, s.stream); return cuda_fail(c, e, "split kernel launch"); }
+    c->launches += (uint64_t)l;
+    FPV_CUDA(cudaMemcpyAsync(high_host + (size_t)off * P, s.d_high, (size_t)m * P, cudaMemcpyDeviceToHost, s.stream));
+    if (has_low)
+      FPV_CUDA(cudaMemcpyAsync(low_host + (size_t)off * P, s.d_low, (size_t)m * P, cudaMemcpyDeviceToHost, s.stream));
+    FPV_CUDA(cudaMemcpyAsync(lor.data(), d_or, sizeof(uint32_t) * m, cudaMemcpyDeviceToHost, s.stream));
+    FPV_CUDA(cudaFreeAsync(d_or, s.stream));
+    FPV_CUDA(cudaStreamSynchronize(s.stream));
+    for (uint32_t i = 0; i < m; i++)
+      flags_host[off + i] = (!has_low || (lor[i] & 0xffu) == 0) ? FPV_FLAG_NO_LOW_BYTES : 0;
+  }
+  return FPV_OK;
+}
+
 // ---- GPU entropy coding ---------------------------------------------------------
 
 size_t fpv_stream_bound(const fpv_ctx* c, uint32_t n) { return c ? stream_bound(c, n) : 0; }
@@ -557,6 +664,7 @@ int fpv_entropy_device(fpv_ctx* c, const void* flags_dev, const void* high_dev, 
                        const void* preview_dev, uint32_t n, void* out_dev, size_t capacity, void* frame_off_dev,
                        void* stream) {
   if (!c) return FPV_ERR_INVALID_ARG;
+  FPV_LOCK(c);
   if (n == 0) return FPV_OK;
   if (n > c->max_batch) return fail(c, FPV_ERR_INVALID_ARG, "n exceeds max_batch");
   if (!flags_dev || !high_dev || !preview_dev || !out_dev || !frame_off_dev)
@@ -575,6 +683,7 @@ int fpv_entropy_device(fpv_ctx* c, const void* flags_dev, const void* high_dev, 
 int fpv_encode_stream_submit(fpv_ctx* c, uint32_t slot, const uint16_t* frames_host, uint32_t n, uint32_t options,
                              uint8_t* flags_host, uint64_t* frame_off_host, uint8_t* out_host, size_t capacity) {
   if (!c) return FPV_ERR_INVALID_ARG;
+  FPV_LOCK(c);
   if (slot >= kNumSlots) return fail(c, FPV_ERR_INVALID_ARG, "slot out of range");
   if (n == 0) return FPV_OK;
   if (n > c->max_batch) return fail(c, FPV_ERR_INVALID_ARG, "n exceeds max_batch");
@@ -611,6 +720,7 @@ int fpv_encode_stream_submit(fpv_ctx* c, uint32_t slot, const uint16_t* frames_h
 int fpv_decode_device(fpv_ctx* c, const void* high_dev, const void* low_dev, const void* flags_dev,
                       uint32_t n, uint32_t options, void* out_dev, void* stream) {
   if (!c) return FPV_ERR_INVALID_ARG;
+  FPV_LOCK(c);
   if (n == 0) return FPV_OK;
   if (!high_dev || !flags_dev || !out_dev) return fail(c, FPV_ERR_INVALID_ARG, "NULL device buffer");
   if ((reinterpret_cast<uintptr_t>(high_dev) & 15) || (reinterpret_cast<uintptr_t>(low_dev) & 15) ||
@@ -625,6 +735,7 @@ int fpv_decode_device(fpv_ctx* c, const void* high_dev, const void* low_dev, con
 int fpv_decode_submit(fpv_ctx* c, uint32_t slot, const uint8_t* high_host, const uint8_t* low_host,
                       const uint8_t* flags_host, uint32_t n, uint32_t options, void* out_host) {
   if (!c) return FPV_ERR_INVALID_ARG;
+  FPV_LOCK(c);
   if (slot >= kNumSlots) return fail(c, FPV_ERR_INVALID_ARG, "slot out of range");
   if (n == 0) return FPV_OK;
   if (n > c->max_batch) return fail(c, FPV_ERR_INVALID_ARG, "n exceeds max_batch");
@@ -657,6 +768,7 @@ int fpv_decode_submit(fpv_ctx* c, uint32_t slot, const uint8_t* high_host, const
 int fpv_decode(fpv_ctx* c, const uint8_t* high_host, const uint8_t* low_host, const uint8_t* flags_host,
                uint32_t n, uint32_t options, void* out_host) {
   if (!c) return FPV_ERR_INVALID_ARG;
+  FPV_LOCK(c);
   const size_t P = c->g.P;
   for (uint32_t off = 0; off < n; off += c->max_batch) {
     uint32_t m = n - off < c->max_batch ? n - off : c->max_batch;
@@ -672,6 +784,7 @@ int fpv_decode(fpv_ctx* c, const uint8_t* high_host, const uint8_t* low_host, co
 int fpv_unpredict_planes(fpv_ctx* c, uint8_t* high_host, uint8_t* low_host, uint8_t* preview_host,
                          const uint8_t* flags_host, uint32_t n) {
   if (!c) return FPV_ERR_INVALID_ARG;
+  FPV_LOCK(c);
   if (n == 0) return FPV_OK;
   if (!high_host || !flags_host) return fail(c, FPV_ERR_INVALID_ARG, "NULL host buffer");
   FPV_CUDA(cudaSetDevice(c->device));

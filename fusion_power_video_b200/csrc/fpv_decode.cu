@@ -748,8 +748,8 @@ int enqueue_decode(const Geom& g, int num_sms, const uint8_t* high, const uint8_
   p.warp_smem_words = 2 * slot_words + nst * stage_words;
   size_t smem = (size_t)p.warp_smem_words * 4 * wpb;
   if (smem > limit) {
-    *err = cudaErrorInvalidConfiguration;  // caller falls back to enqueue_decode_serial
-    return -1;
+    *err = cudaErrorInvalidConfiguration;  // geometry not supported: the caller falls back to enqueue_decode_serial
+    return -2;
   }
   int blocks = (int)((n + wpb - 1) / wpb);
   int max_blocks = num_sms * 16;
@@ -808,3 +808,13 @@ int enqueue_unpredict_planes(const Geom& g, int num_sms, uint8_t* high, uint8_t*
 }
 
 }  // namespace fpv
+
+#ifdef FPV_PAIR_PROF
+// Profiling builds only: reads and clears the per-role cycle counters of k_decode_pair.
+extern "C" int fpv_debug_pair_prof(unsigned long long* out16) {
+  cudaDeviceSynchronize();
+  if (cudaMemcpyFromSymbol(out16, fpv::g_pair_prof, 16 * sizeof(unsigned long long)) != cudaSuccess) return 1;
+  unsigned long long zero[16] = {};
+  return cudaMemcpyToSymbol(fpv::g_pair_prof, zero, sizeof zero) == cudaSuccess ? 0 : 1;
+}
+#endif

@@ -74,6 +74,27 @@ struct PairParams {
 constexpr int kPairThreads = 192;   // per CTA: two pairs of frames x (chain, IO, helper) warps
 constexpr int kPairRing = 3;
 
+// -DFPV_PAIR_PROF: per-role cycle accounting (profiling builds only, see scripts/gpu_pair_prof.py).
+// g_pair_prof: [0..6] chain: load+c, pass 0, pass 1, repair, store, barrier wait, repair rounds;
+// [8..10] IO: work, TMA-store read wait, barrier wait; [12..14] helper: issue, pre_row (incl. TMA wait), barrier wait;
+// [15] rows counted (chain warps).
+#ifdef FPV_PAIR_PROF
+__device__ unsigned long long g_pair_prof[16];
+#define PROF_DECL(n) uint32_t prof_acc[n] = {}; uint32_t prof_t = (uint32_t)clock()
+#define PROF_MARK(i) do { const uint32_t t__ = (uint32_t)clock(); prof_acc[i] += t__ - prof_t; prof_t = t__; } while (0)
+#define PROF_FLUSH(base, n) do { if (lane == 0) for (int i__ = 0; i__ < (n); i__++) atomicAdd(&g_pair_prof[(base) + i__], (unsigned long long)prof_acc[i__]); } while (0)
+#define PROF_PARAMS , uint32_t (&prof_acc)[8], uint32_t& prof_t
+#define PROF_ARGS , prof_acc, prof_t
+#define PROF_COUNT(i) prof_acc[i]++
+#else
+#define PROF_PARAMS
+#define PROF_ARGS
+#define PROF_COUNT(i)
+#define PROF_DECL(n)
+#define PROF_MARK(i)
+#define PROF_FLUSH(base, n)
+#endif
+
 // Shared-memory plan (RB = 32 * L bytes = one padded byte row):
 //   R1   ring x { residual A | residual B }                      2 RB each
 //   R2   ring x { low A | low B | duplicated delta (4 B/col) }   6 RB each
@@ -131,7 +152,7 @@ __device__ __forceinline__ void pair_chain_row(const uint32_t (&n)[8 * LW2], uin
                                                const uint32_t pre, const uint32_t post, const uint32_t cgmask,
                                                const uint32_t vmask, const int lane, const uint32_t last_lane,
                                                const uint32_t last_t, uint32_t& last_prev, uint32_t& last_prev2,
-                                               const int bar_id) {
+                                               const int bar_id PROF_PARAMS) {
   constexpr int L = 8 * LW2;
   constexpr int K0 = K0T < L ? K0T : L / 2;   // look-ahead pixels of pass 0
   // word quad k of this lane sits at 16-byte slot k*32 + lane
@@ -155,6 +176,7 @@ __device__ __forceinline__ void pair_chain_row(const uint32_t (&n)[8 * LW2], uin
     const uint32_t r_first = x[0] - kLaneBias;
 #pragma unroll
     for (int t = 0; t < L; t++) c[t] = x[t] - (t == 0 ? nw_in : n[t - 1]);
+    PROF_MARK(0);
 
     // pass 0: estimate this segment's last pixel from a guess K0 pixels back
     uint32_t w_in;
@@ -180,6 +202,7 @@ __device__ __forceinline__ void pair_chain_row(const uint32_t (&n)[8 * LW2], uin
         w_in = last_prev;                           // exact for segment 0
       }
     }
+    PROF_MARK(1);
     // pass 1: every segment in full
     {
       uint32_t w = w_in, nw = nw_in;
@@ -193,6 +216,7 @@ __device__ __forceinline__ void pair_chain_row(const uint32_t (&n)[8 * LW2], uin
         nw = nn;
       }
     }
+    PROF_MARK(2);
     // repair: re-run segments whose incoming value was wrong until nothing changes
 #ifdef FPV_ABL_NO_REPAIR
     if (false)
@@ -213,6 +237,7 @@ __device__ __forceinline__ void pair_chain_row(const uint32_t (&n)[8 * LW2], uin
       }
       const bool changed = ((w_new ^ w_in) & vmask) != 0;
       if (!__any_sync(0xffffffffu, changed)) break;
+      PROF_COUNT(6);
       w_in = w_new;
       uint32_t w = w_in, nw = nw_in;
       bool settled = false;     // the chains met their old values before the segment ends: no end changed
@@ -238,6 +263,7 @@ __device__ __forceinline__ void pair_chain_row(const uint32_t (&n)[8 * LW2], uin
       // again and may have changed.
       if (settled && !(SPLIT && !FULL)) break;
     }
+    PROF_MARK(3);
     if (cgmask != 0xffffffffu) {
       // one of the two frames is not ClampedGradient-predicted: its row is the residual row
 #pragma unroll
@@ -266,7 +292,10 @@ __device__ __forceinline__ void pair_chain_row(const uint32_t (&n)[8 * LW2], uin
     last_prev2 = last_prev;
     last_prev = __shfl_sync(0xffffffffu, v, (int)last_lane);
   }
+  PROF_MARK(4);
   pair_bar_sync(bar_id);
+  PROF_MARK(5);
+  PROF_COUNT(7);
 }
 
 // LW2:   the chain lane's segment is L = 8 LW2 px (LW2 = ceil(W / 256)).
@@ -345,13 +374,20 @@ __global__ void __launch_bounds__(kPairThreads, 2) k_decode_pair(const PairParam
 
     pair_bar_sync(bar_id);               // mbarriers are initialised, the ring is zero-filled where needed
     pair_bar_sync(bar_id);               // row 0 is in PRE[0] (the IO warp's prologue)
+    PROF_DECL(8);
     for (uint32_t y = 0; y < H; y += 2) {
       pair_chain_row<LW2, FULL, K0T, G, SPLIT>(rb, ra, y, sm0 + kPre, sm0 + kPost, cgmask, vmask, lane, last_lane, last_t,
-                                        last_prev, last_prev2, bar_id);
+                                        last_prev, last_prev2, bar_id PROF_ARGS);
       if (y + 1 < H)
         pair_chain_row<LW2, FULL, K0T, G, SPLIT>(ra, rb, y + 1, sm0 + kPre + kBuf, sm0 + kPost + kBuf, cgmask, vmask, lane,
-                                          last_lane, last_t, last_prev, last_prev2, bar_id);
+                                          last_lane, last_t, last_prev, last_prev2, bar_id PROF_ARGS);
     }
+#ifdef FPV_PAIR_PROF
+    if (lane == 0) {
+      for (int i = 0; i < 7; i++) atomicAdd(&g_pair_prof[i], (unsigned long long)prof_acc[i]);
+      atomicAdd(&g_pair_prof[15], (unsigned long long)prof_acc[7]);
+    }
+#endif
     return;
   }
 
@@ -524,20 +560,30 @@ __global__ void __launch_bounds__(kPairThreads, 2) k_decode_pair(const PairParam
     issue_r2();
     pre_row(0);
     pair_bar_sync(bar_id);
+    PROF_DECL(3);
     for (uint32_t y = 0; y < H; y++) {
       issue_r1();          // row y + 3 into slot y % 3: its row y was consumed in iteration y - 1
       issue_r2();          // row y + 1 into slot (y + 1) % 3: its row y - 2 was consumed (by the IO warp) in iteration y - 1
+      PROF_MARK(0);
       if (y + 1 < H) pre_row((y + 1) & 1u);
+      PROF_MARK(1);
       pair_bar_sync(bar_id);
+      PROF_MARK(2);
     }
+    PROF_FLUSH(12, 3);
     return;
   }
   pair_bar_sync(bar_id);
+  PROF_DECL(3);
   for (uint32_t y = 0; y < H; y++) {
     if (y >= 1) post_row((y - 1) & 1u);
+    PROF_MARK(0);
     if (elected) bulk_wait_read0();   // the output row buffer may be rewritten after the barrier
+    PROF_MARK(1);
     pair_bar_sync(bar_id);
+    PROF_MARK(2);
   }
+  PROF_FLUSH(8, 3);
   post_row((H - 1) & 1u);
   if (elected) bulk_wait0();
 }

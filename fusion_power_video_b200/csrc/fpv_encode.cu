@@ -431,17 +431,29 @@ k_delta_from_raw(const uint16_t* __restrict__ raw, uint16_t* __restrict__ image,
   }
 }
 
+// Frame ctor alone (.cc:388-449): split into byte planes + OR of the low bytes, no prediction.  Serves the
+// fpvc::Frame facade (planes of a frame that is never predicted, e.g. one that becomes a delta frame).
+template <int MODE>
+__global__ void __launch_bounds__(256)
+k_split_planes(const uint16_t* __restrict__ frames, uint8_t* __restrict__ high, uint8_t* __restrict__ low,
+               uint32_t* __restrict__ low_or, uint64_t P, int s) {
+  const uint32_t f = blockIdx.y;
+  const uint16_t* img = frames + (uint64_t)f * P;
+  uint32_t lor = 0;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += (uint64_t)gridDim.x * blockDim.x) {
+    uint32_t h, l;
+    split1<MODE>(img[i], s, h, l);
+    high[(uint64_t)f * P + i] = (uint8_t)h;
+    if (mode_has_low(MODE)) low[(uint64_t)f * P + i] = (uint8_t)l;
+    lor |= l;
+  }
+  lor = __reduce_or_sync(0xffffffffu, lor);
+  if ((threadIdx.x & 31) == 0 && lor) atomicOr(&low_or[f], lor);
+}
+
 // =====================================================================================
 // Host-side launch logic
 // =====================================================================================
-
-bool encode_fast_supported(const Geom& g, const EncodeTuning& t) {
-  if (g.W % 8 != 0 || g.W < 8) return false;
-  if (g.W > 32 * 31 * 8) return false;  // at most 31 compute warps + 1 producer
-  if (g.W > 4096) return false;
-  int stages = t.stages < 2 ? 2 : t.stages;
-  return fast_smem_bytes(g.W, stages, t.rows_per_stage == 2 ? 2 : 4) <= (size_t)t.max_smem_optin;
-}
 
 #define FPV_DISPATCH_MODE(mode, CALL)                       \
   switch (mode) {                                           \
@@ -454,18 +466,33 @@ bool encode_fast_supported(const Geom& g, const EncodeTuning& t) {
     default:   { constexpr int M = kLEbig; CALL; } break;   \
   }
 
+int enqueue_split(const Geom& g, const uint16_t* frames, uint32_t n, uint8_t* high, uint8_t* low, uint32_t* low_or,
+                  cudaStream_t stream, cudaError_t* err) {
+  *err = cudaMemsetAsync(low_or, 0, sizeof(uint32_t) * n, stream);
+  if (*err != cudaSuccess) return -1;
+  unsigned gx = (unsigned)((g.P + 255) / 256);
+  if (gx > 1024) gx = 1024;
+  FPV_DISPATCH_MODE(g.mode, (k_split_planes<M><<<dim3(gx, n), 256, 0, stream>>>(frames, high, low, low_or, g.P, g.shift)));
+  *err = cudaGetLastError();
+  return *err == cudaSuccess ? 1 : -1;
+}
+
+bool encode_fast_supported(const Geom& g, const EncodeTuning& t) {
+  if (g.W % 8 != 0 || g.W < 8) return false;
+  if (g.W > 32 * 31 * 8) return false;  // at most 31 compute warps + 1 producer
+  if (g.W > 4096) return false;
+  int stages = t.stages < 2 ? 2 : t.stages;
+  return fast_smem_bytes(g.W, stages, t.rows_per_stage == 2 ? 2 : 4) <= (size_t)t.max_smem_optin;
+}
+
+
 template <int MODE, bool FULL, int RPS>
 static cudaError_t launch_fast(const FastParams& fp, int grid, int threads, size_t smem,
                                cudaStream_t stream) {
-  static bool attr_set[16] = {};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 16 && !attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(k_encode_fast<MODE, FULL, RPS>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024);
-    if (e != cudaSuccess) return e;
-    attr_set[dev] = true;
-  }
+  // per launch: the attribute is per device and is lost by cudaDeviceReset; the call costs about a microsecond
+  cudaError_t ea = cudaFuncSetAttribute(k_encode_fast<MODE, FULL, RPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        232448 - 1024);
+  if (ea != cudaSuccess) return ea;
   k_encode_fast<MODE, FULL, RPS><<<grid, threads, smem, stream>>>(fp);
   return cudaGetLastError();
 }

@@ -512,14 +512,9 @@ size_t entropy_smem_bytes() { return sizeof(Shared); }
 
 int enqueue_entropy(const EntropyParams& p, uint64_t* frame_off, uint8_t* out, uint64_t capacity, uint32_t* overflow,
                     cudaStream_t stream, cudaError_t* err) {
-  static bool attr_set[16] = {};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 16 && !attr_set[dev]) {
-    *err = cudaFuncSetAttribute(k_entropy_chunk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Shared));
-    if (*err != cudaSuccess) return -1;
-    attr_set[dev] = true;
-  }
+  // per launch: the attribute is per device and does not survive cudaDeviceReset
+  *err = cudaFuncSetAttribute(k_entropy_chunk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Shared));
+  if (*err != cudaSuccess) return -1;
   const uint32_t chunks = p.n * p.cpf;
   k_entropy_chunk<<<chunks, kET, sizeof(Shared), stream>>>(p);
   k_entropy_layout<<<1, 1024, 0, stream>>>(p, frame_off);

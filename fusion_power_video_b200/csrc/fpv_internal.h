@@ -77,6 +77,10 @@ struct EntropyParams {
 int enqueue_entropy(const EntropyParams& p, uint64_t* frame_off, uint8_t* out, uint64_t capacity, uint32_t* overflow,
                     cudaStream_t stream, cudaError_t* err);
 
+// Frame ctor only: byte planes of n raw frames, low_or[f] = OR of frame f's low bytes (uint32[n], device).
+int enqueue_split(const Geom& g, const uint16_t* frames, uint32_t n, uint8_t* high, uint8_t* low, uint32_t* low_or,
+                  cudaStream_t stream, cudaError_t* err);
+
 // Splits a raw delta frame into image form ((high << 8) | low per pixel).
 int enqueue_delta_from_raw(const Geom& g, const uint16_t* raw, uint16_t* delta_image,
                            cudaStream_t stream, cudaError_t* err);
@@ -85,6 +89,8 @@ int enqueue_delta_from_raw(const Geom& g, const uint16_t* raw, uint16_t* delta_i
 // file bytes when `unextract`.
 // `ddup` is the delta image in duplicated form ((d | d << 16) per pixel, see
 // enqueue_delta_dup); without it the pair kernel is not used for delta streams.
+// Returns the number of kernels launched, -1 on a CUDA error (*err), -2 if no row-pipelined kernel
+// takes this geometry (rows too wide for shared memory: the caller uses enqueue_decode_serial).
 int enqueue_decode(const Geom& g, int num_sms, const uint8_t* high, const uint8_t* low,
                    const uint8_t* flags, const uint16_t* delta, const uint32_t* ddup, uint32_t n,
                    bool unextract, uint16_t* out, cudaStream_t stream, cudaError_t* err,

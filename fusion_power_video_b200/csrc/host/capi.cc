@@ -48,6 +48,29 @@ size_t fpvh_encode_stream(size_t xsize, size_t ysize, int shift, int big_endian,
   return stream.size();
 }
 
+// The same with one Encoder over several GPUs (GpuOptions::devices); gpu_entropy as in GpuOptions (-1: environment).
+size_t fpvh_encode_stream_multi(size_t xsize, size_t ysize, int shift, int big_endian, size_t threads, uint32_t batch,
+                                const int* devices, int ndevices, int gpu_entropy, const uint16_t* delta,
+                                const uint16_t* frames, size_t nframes, uint8_t* out, size_t cap, double* seconds) {
+  std::vector<uint8_t> stream;
+  fpvc::GpuOptions opt;
+  if (batch) opt.batch = batch;
+  opt.gpu_entropy = gpu_entropy;
+  for (int i = 0; i < ndevices; i++) opt.devices.push_back(devices[i]);
+  const double t0 = Now();
+  {
+    fpvc::Encoder enc(threads, shift, big_endian != 0, opt);
+    enc.Init(delta, xsize, ysize, Append, &stream);
+    if (!enc.ok()) return 0;
+    for (size_t i = 0; i < nframes; i++) enc.CompressFrame(frames + i * xsize * ysize, Append, &stream);
+    enc.Finish(Append, &stream);
+    if (!enc.ok()) return 0;
+  }
+  if (seconds) *seconds = Now() - t0;
+  if (out && stream.size() <= cap) memcpy(out, stream.data(), stream.size());
+  return stream.size();
+}
+
 // Same work, timed like the reference's benchmark (benchmark.cc:153-180: from
 // before Encoder construction to after Finish); compressed bytes are counted,
 // not kept.  Returns seconds, < 0 on failure.

@@ -11,6 +11,17 @@
 //      (low plane; preview + high plane), the second to finish assembles the chunk,
 //   4. emits finished frames in submission order under one mutex, recording the
 //      frame offsets for the footer exactly as FinishTask does (.cc:1179-1183).
+//
+// Several GPUs (GpuOptions::devices): where the reference feeds ONE queue to a pool of worker threads
+// (.cc:1076-1084, :1199-1230), this encoder feeds one stream of batches to a pool of GPUs: batch k goes to
+// device k mod G, each device has its own context, GPU thread and two submit slots, the delta frame is
+// uploaded to the first device and reaches the others by peer copy (fpv_copy_delta_peer).  Emission order
+// is the submission order whatever device a batch ran on, so the stream is byte-identical to the
+// single-GPU one.
+//
+// Failures (a CUDA error in submit / wait): the batch is dropped, ok() turns false, every later frame is
+// dropped as well (fail-stop: nothing that was not produced by the GPU is ever emitted), Finish still
+// writes a footer for the frames that did go out, so the stream stays decodable up to the failure.
 #include <stdlib.h>
 #include <string.h>
 
@@ -36,8 +47,8 @@ struct Encoder::Impl {
   bool big_endian = false;
   GpuOptions opt;
 
-  fpv_ctx* ctx = nullptr;
-  bool ok = false;
+  fpv_ctx* ctx = nullptr;             // lanes[0]->ctx: header encoding, the synchronous path, size queries
+  std::atomic<bool> ok{false};
   size_t W = 0, H = 0, P = 0, PP = 0;
   bool has_low = true;
   uint32_t B = 1;
@@ -56,6 +67,7 @@ struct Encoder::Impl {
     bool allocated = false;
     uint32_t n = 0;
     uint64_t first_id = 0;
+    uint64_t seq = 0;                 // batch number in submission order (device = seq % G; emission order of coded batches)
     std::vector<Callback> callbacks;
     std::vector<void*> payloads;
     std::vector<Pieces> pieces;
@@ -63,16 +75,24 @@ struct Encoder::Impl {
     uint32_t slot = 0;
   };
   Batch batches[kMaxBatches];
+  // One per GPU: context, GPU thread, its queue of batches that are ready to be submitted.
+  struct Lane {
+    int device = 0;
+    fpv_ctx* ctx = nullptr;
+    std::thread thread;
+    std::deque<Batch*> ready;
+  };
+  std::vector<std::unique_ptr<Lane>> lanes;
   int num_batches = 1;   // one filling, up to two on the GPU, the rest feeding brotli
 
   std::mutex m;                       // batch lists, ids, stop flag
   std::condition_variable cv_free, cv_ready, cv_drained;
-  std::deque<Batch*> free_, ready_;
+  std::deque<Batch*> free_;
   Batch* filling = nullptr;
-  size_t gpu_busy = 0;                // batches handed to the GPU thread, not yet landed
+  size_t gpu_busy = 0;                // batches handed to a GPU thread, not yet landed
   bool stop = false;
   uint64_t next_id = 0;
-  std::thread gpu_thread;
+  uint64_t next_seq = 0;
   std::unique_ptr<Pool> pool;
   // gpu_entropy: no brotli workers; a few helpers share the copy of each submitted frame into the
   // pinned batch, which is otherwise the pipeline's bottleneck (one core copies ~8 GB/s; measured
@@ -80,6 +100,8 @@ struct Encoder::Impl {
   std::unique_ptr<Pool> copy_pool;
 
   std::mutex out_m;                   // ordered emission
+  std::condition_variable cv_emit;    // gpu_entropy with several GPUs: batches take turns by seq
+  uint64_t emit_seq = 0;
   struct Done {
     std::vector<uint8_t> bytes;
     Callback callback;
@@ -93,25 +115,34 @@ struct Encoder::Impl {
 
   ~Impl() {
     shutdown();
-    if (ctx) fpv_destroy(ctx);
+    for (auto& l : lanes)
+      if (l->ctx) fpv_destroy(l->ctx);
   }
 
   void shutdown() {
-    if (gpu_thread.joinable()) {
-      {
-        std::lock_guard<std::mutex> l(m);
-        stop = true;
-      }
-      cv_ready.notify_all();
-      gpu_thread.join();
+    {
+      std::lock_guard<std::mutex> l(m);
+      stop = true;
     }
+    cv_ready.notify_all();
+    for (auto& l : lanes)
+      if (l->thread.joinable()) l->thread.join();
     pool.reset();  // joins the brotli workers after their queue has drained
     copy_pool.reset();
   }
 
+  // Records the failure (message of the calling thread's last C-ABI error) and stops the encoder.
   bool fail(const std::string& what) {
-    ok = false;
-    return FPV_FAIL(what + (ctx ? std::string(": ") + fpv_last_error(ctx) : std::string()));
+    ok.store(false);
+    cv_emit.notify_all();
+    return FPV_FAIL(what + std::string(": ") + fpv_last_error(ctx));
+  }
+
+  // Queues a filled batch for its GPU (caller holds m).
+  void hand_over_locked(Batch* b) {
+    b->seq = next_seq++;
+    lanes[b->seq % lanes.size()]->ready.push_back(b);
+    gpu_busy++;
   }
 
   // frame -> chunk bytes (frame := total | 0 | 1+|bp| | pflags | bp | core)
@@ -157,21 +188,34 @@ struct Encoder::Impl {
     }
   }
 
-  // gpu_entropy: the batch's chunks are complete and in order (the GPU thread lands batches in
-  // submission order), so they are emitted straight out of the pinned buffer, no copy.
+  // gpu_entropy: the batch's chunks are complete; they are emitted straight out of the pinned buffer, no
+  // copy.  One GPU thread lands its batches in submission order; with several GPUs the batches take turns.
   void emit_coded(Batch* b) {
     const uint64_t* off = b->offs.as<uint64_t>();
     const uint8_t* bytes = b->coded.as<uint8_t>();
+    // what came back must be a monotonic offset table inside the buffer before any pointer is formed from it
+    bool sane = off[0] == 0 && off[b->n] <= stream_cap;
+    for (uint32_t i = 0; sane && i < b->n; i++) sane = off[i + 1] >= off[i] + 11;
     {
-      std::lock_guard<std::mutex> l(out_m);
-      for (uint32_t i = 0; i < b->n; i++) {
-        const size_t size = (size_t)(off[i + 1] - off[i]);
-        offsets.push_back(bytes_written);
-        bytes_written += size;
-        b->callbacks[i](bytes + off[i], size, b->payloads[i]);
-        next_emit++;
+      std::unique_lock<std::mutex> l(out_m);
+      cv_emit.wait(l, [&] { return emit_seq == b->seq || !ok.load(); });
+      if (ok.load() && !sane) {
+        l.unlock();
+        fail("GPU entropy stage returned an inconsistent offset table");
+        l.lock();
       }
+      if (ok.load()) {
+        for (uint32_t i = 0; i < b->n; i++) {
+          const size_t size = (size_t)(off[i + 1] - off[i]);
+          offsets.push_back(bytes_written);
+          bytes_written += size;
+          b->callbacks[i](bytes + off[i], size, b->payloads[i]);
+          next_emit++;
+        }
+      }
+      emit_seq = b->seq + 1;
     }
+    cv_emit.notify_all();
     recycle(b);
   }
 
@@ -235,28 +279,41 @@ struct Encoder::Impl {
     }
   }
 
-  void gpu_loop() {
+  void gpu_loop(Lane& lane) {
+    fpv_bind_thread(lane.ctx);
     std::deque<Batch*> inflight;
     uint32_t next_slot = 0;
+    // A batch whose submit or wait failed -- or that lands after another one failed -- is dropped: its
+    // buffers hold stale or partial data and must never reach brotli or a callback.
+    auto drop = [&](Batch* b) {
+      if (gpu_entropy) {
+        std::lock_guard<std::mutex> l(out_m);
+        if (emit_seq <= b->seq) emit_seq = b->seq + 1;
+      }
+      cv_emit.notify_all();
+      recycle(b);
+    };
     auto land = [&] {
       Batch* b = inflight.front();
       inflight.pop_front();
-      if (fpv_wait(ctx, b->slot) != FPV_OK) fail("fpv_wait");
+      const bool good = fpv_wait(lane.ctx, b->slot) == FPV_OK;
+      if (!good) fail("fpv_wait");
       {
         std::lock_guard<std::mutex> l(m);
         gpu_busy--;
       }
-      if (gpu_entropy) emit_coded(b);
+      if (!good || !ok.load()) drop(b);
+      else if (gpu_entropy) emit_coded(b);
       else compress_batch(b);
     };
     for (;;) {
       Batch* b = nullptr;
       {
         std::unique_lock<std::mutex> l(m);
-        if (inflight.empty()) cv_ready.wait(l, [&] { return stop || !ready_.empty(); });
-        if (!ready_.empty()) {
-          b = ready_.front();
-          ready_.pop_front();
+        if (inflight.empty()) cv_ready.wait(l, [&] { return stop || !lane.ready.empty(); });
+        if (!lane.ready.empty()) {
+          b = lane.ready.front();
+          lane.ready.pop_front();
         } else if (inflight.empty()) {
           return;  // stop requested and nothing left
         }
@@ -265,15 +322,24 @@ struct Encoder::Impl {
         if (inflight.size() == 2) land();  // its slot is about to be reused
         b->slot = next_slot;
         next_slot ^= 1u;
-        int rc = gpu_entropy
-                     ? fpv_encode_stream_submit(ctx, b->slot, b->frames.as<uint16_t>(), b->n, FPV_ENC_DEFAULT,
+        int rc = !ok.load() ? FPV_ERR_INVALID_ARG
+                 : gpu_entropy
+                     ? fpv_encode_stream_submit(lane.ctx, b->slot, b->frames.as<uint16_t>(), b->n, FPV_ENC_DEFAULT,
                                                 b->flags.as<uint8_t>(), b->offs.as<uint64_t>(),
                                                 b->coded.as<uint8_t>(), stream_cap)
-                     : fpv_encode_submit(ctx, b->slot, b->frames.as<uint16_t>(), b->n, FPV_ENC_DEFAULT,
+                     : fpv_encode_submit(lane.ctx, b->slot, b->frames.as<uint16_t>(), b->n, FPV_ENC_DEFAULT,
                                          b->flags.as<uint8_t>(), b->high.as<uint8_t>(),
                                          has_low ? b->low.as<uint8_t>() : nullptr, b->preview.as<uint8_t>());
-        if (rc != FPV_OK) fail("fpv_encode_submit");
-        inflight.push_back(b);
+        if (rc != FPV_OK) {
+          if (ok.load()) fail("fpv_encode_submit");
+          {
+            std::lock_guard<std::mutex> l(m);
+            gpu_busy--;
+          }
+          drop(b);
+        } else {
+          inflight.push_back(b);
+        }
       } else {
         land();  // nothing new to submit: collect the oldest batch
       }
@@ -309,11 +375,36 @@ void Encoder::Init(const uint16_t* delta_frame, size_t xsize, size_t ysize, Call
   s.PP = (xsize / 4) * (ysize / 4);
   s.has_low = s.shift != 8;
   s.B = s.threads == 0 ? 1 : (s.opt.batch ? s.opt.batch : 1);
-  if (fpv_create(&s.ctx, s.opt.device, (uint32_t)xsize, (uint32_t)ysize, s.shift, s.big_endian ? 1 : 0, s.B) !=
-      FPV_OK) {
-    FPV_FAIL(std::string("fpv_create: ") + fpv_last_error(nullptr));
-    return;
+  // one context per GPU; without worker threads everything runs synchronously on the first device
+  std::vector<int> devices = s.opt.devices;
+  if (devices.empty()) {
+    // unmodified callers (the reference's encode.cc / benchmark.cc) pick GPUs through the environment:
+    // FPV_DEVICES=0,2,3 or FPV_GPUS=4 (devices 0..3)
+    if (const char* v = getenv("FPV_DEVICES")) {
+      for (const char* p = v; *p;) {
+        char* end = nullptr;
+        const long d = strtol(p, &end, 10);
+        if (end == p) break;
+        devices.push_back((int)d);
+        p = *end == ',' ? end + 1 : end;
+      }
+    } else if (const char* g = getenv("FPV_GPUS")) {
+      for (int d = 0; d < atoi(g); d++) devices.push_back(d);
+    }
+    if (devices.empty()) devices.push_back(s.opt.device);
   }
+  if (s.threads == 0) devices.resize(1);
+  for (int dev : devices) {
+    std::unique_ptr<Impl::Lane> lane(new Impl::Lane);
+    lane->device = dev;
+    if (fpv_create(&lane->ctx, dev, (uint32_t)xsize, (uint32_t)ysize, s.shift, s.big_endian ? 1 : 0, s.B) != FPV_OK) {
+      FPV_FAIL(std::string("fpv_create (device ") + std::to_string(dev) + "): " + fpv_last_error(nullptr));
+      return;
+    }
+    s.lanes.push_back(std::move(lane));
+  }
+  s.ctx = s.lanes[0]->ctx;
+  fpv_bind_thread(s.ctx);   // pinned allocations below belong to the first device's context, not to device 0's
   s.ok = true;
   {
     const char* env = getenv("FPV_GPU_ENTROPY");
@@ -324,13 +415,23 @@ void Encoder::Init(const uint16_t* delta_frame, size_t xsize, size_t ysize, Call
   // behind the (up to) three batches that are filling / on the GPU; pinned memory is
   // only allocated when a batch is first used
   // (GPU entropy stage: one filling, two on the GPU, one being emitted)
-  s.num_batches = s.threads == 0 ? 1 : s.gpu_entropy ? 4 : (int)std::min<size_t>(kMaxBatches, 3 + (2 * s.threads + s.B - 1) / s.B);
+  // (several GPUs: two more in flight per additional device)
+  const size_t extra = 2 * (s.lanes.size() - 1);
+  s.num_batches = s.threads == 0 ? 1
+                  : s.gpu_entropy ? (int)std::min<size_t>(kMaxBatches, 4 + extra)
+                                  : (int)std::min<size_t>(kMaxBatches, 3 + extra + (2 * s.threads + s.B - 1) / s.B);
   for (int i = 0; i < s.num_batches; i++) s.free_.push_back(&s.batches[i]);
   if (!s.alloc_batch(&s.batches[0])) return;
   if (fpv_set_delta_raw(s.ctx, delta_frame) != FPV_OK) {
     s.fail("fpv_set_delta_raw");
     return;
   }
+  // the other GPUs get the split delta planes by peer copy: the only inter-GPU traffic of a stream
+  for (size_t k = 1; k < s.lanes.size(); k++)
+    if (fpv_copy_delta_peer(s.lanes[k]->ctx, s.ctx) != FPV_OK) {
+      s.fail("fpv_copy_delta_peer");
+      return;
+    }
   // Header: the delta frame itself, predicted without a delta frame
   // (Frame df = delta_frame_; df.Compress(), reference .cc:1099-1101).
   // (once per stream, pageable buffers; the delta chunk's planes always go through libbrotli)
@@ -356,7 +457,10 @@ void Encoder::Init(const uint16_t* delta_frame, size_t xsize, size_t ysize, Call
       if (const char* v = getenv("FPV_COPY_THREADS")) helpers = (size_t)std::max(1, atoi(v));
       s.copy_pool.reset(new Pool(std::min<size_t>(s.threads - 1, helpers)));
     }
-    s.gpu_thread = std::thread([&s] { s.gpu_loop(); });
+    for (auto& lane : s.lanes) {
+      Impl::Lane* lp = lane.get();
+      lp->thread = std::thread([&s, lp] { s.gpu_loop(*lp); });
+    }
   }
   callback(header.data(), header.size(), payload);
 }
@@ -411,7 +515,10 @@ void Encoder::CompressFrame(const uint16_t* img, Callback callback, void* payloa
     b = s.filling;
     s.next_id++;
   }
-  if (!b->allocated && !s.alloc_batch(b)) return;
+  if (!b->allocated) {
+    fpv_bind_thread(s.ctx);
+    if (!s.alloc_batch(b)) return;
+  }
   // only this (the submitting) thread touches a filling batch
   if (s.copy_pool) {
     const size_t parts = s.copy_pool->size() + 1, bytes = s.P * 2, step = ((bytes + parts - 1) / parts + 4095) & ~(size_t)4095;
@@ -438,10 +545,9 @@ void Encoder::CompressFrame(const uint16_t* img, Callback callback, void* payloa
   bool hand_over = b->n == s.B;
   {
     std::lock_guard<std::mutex> l(s.m);
-    if (!hand_over && s.gpu_busy == 0 && s.ready_.empty()) hand_over = true;  // idle pipeline: go now
+    if (!hand_over && s.gpu_busy == 0) hand_over = true;  // idle pipeline: go now
     if (hand_over) {
-      s.ready_.push_back(b);
-      s.gpu_busy++;
+      s.hand_over_locked(b);
       s.filling = nullptr;
     }
   }
@@ -452,12 +558,11 @@ void Encoder::Finish(Callback callback, void* payload) {
   Impl& s = *impl_;
   if (s.finished) return;
   s.finished = true;
-  if (s.ok && s.threads > 0) {
+  if (!s.lanes.empty() && s.threads > 0 && (s.lanes[0]->thread.joinable())) {
     {
       std::unique_lock<std::mutex> l(s.m);
       if (s.filling && s.filling->n > 0) {
-        s.ready_.push_back(s.filling);
-        s.gpu_busy++;
+        s.hand_over_locked(s.filling);
         s.filling = nullptr;
       }
     }
@@ -475,6 +580,7 @@ void Encoder::Finish(Callback callback, void* payload) {
   for (size_t i = 0; i < s.offsets.size(); i++) StoreU64(s.offsets[i], footer.data() + 5 + 8 * i);
   StoreU64(s.offsets.size(), footer.data() + 5 + 8 * s.offsets.size());
   callback(footer.data(), footer.size(), payload);
+  if (!s.ok.load()) FPV_FAIL("Encoder: the stream is incomplete, a GPU call failed (see above); the footer indexes the frames that were written");
 }
 
 }  // namespace fpvc

@@ -57,6 +57,10 @@ struct GpuOptions {
   // reference decoder reads, different bytes, no host brotli); -1 = 1 iff the environment
   // variable FPV_GPU_ENTROPY is set to a non-zero value.
   int gpu_entropy = -1;
+  // Encoder only: several GPUs of one box behind ONE Encoder, the counterpart of the reference's one pool of
+  // worker threads (reference .cc:1076-1084).  Batches go to the devices round-robin, the delta frame crosses
+  // GPUs once by peer copy, emission order and stream bytes are those of a single GPU.  Empty = {device}.
+  std::vector<int> devices;
 };
 
 class StreamingDecoder {

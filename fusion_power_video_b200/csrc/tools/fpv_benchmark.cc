@@ -20,7 +20,7 @@ static double Now() {
 
 int main(int argc, char* argv[]) {
   if (argc < 6) {
-    std::cerr << "usage: " << argv[0] << " file xsize ysize big_endian shift [maxframes] [threads=8] [batch=32] [gpu_entropy=0]\n";
+    std::cerr << "usage: " << argv[0] << " file xsize ysize big_endian shift [maxframes] [threads=8] [batch=32] [gpu_entropy=0] [gpus=1]\n";
     return 1;
   }
   const size_t xsize = strtoull(argv[2], nullptr, 10), ysize = strtoull(argv[3], nullptr, 10);
@@ -31,6 +31,8 @@ int main(int argc, char* argv[]) {
   fpvc::GpuOptions opt;
   if (argc > 8) opt.batch = (uint32_t)atoi(argv[8]);
   if (argc > 9) opt.gpu_entropy = atoi(argv[9]) != 0;
+  if (argc > 10)
+    for (int d = 0; d < atoi(argv[10]); d++) opt.devices.push_back(d);
   const size_t px = xsize * ysize;
   if (px == 0) return 1;
 

@@ -36,6 +36,8 @@ def lib() -> C.CDLL:
     L.fpvh_columnar_roundtrip.argtypes = [sz, sz, i32, i32, i32, i32, i32, vp, vp, sz, vp, vp, sz, C.POINTER(sz),
                                           C.POINTER(C.c_long), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(sz)]
     L.fpvh_columnar_roundtrip.restype = C.c_long
+    L.fpvh_encode_stream_multi.argtypes = [sz, sz, i32, i32, sz, u32, vp, i32, i32, vp, vp, sz, vp, sz, C.POINTER(C.c_double)]
+    L.fpvh_encode_stream_multi.restype = sz
     L.fpvh_time_encode.argtypes = [sz, sz, i32, i32, sz, u32, i32, vp, vp, sz, C.POINTER(sz)]
     L.fpvh_time_encode.restype = C.c_double
     L.fpvh_decode_stream.argtypes = [vp, sz, sz, u32, i32, i32, i32, vp, sz, C.POINTER(sz), C.POINTER(sz),
@@ -97,6 +99,28 @@ def encode_stream(frames, xsize, ysize, shift=0, big_endian=False, threads=4, ba
     if size > cap:
         raise HostError("stream larger than the output buffer")
     return out[:size].tobytes()
+
+
+def encode_stream_multi(frames, xsize, ysize, shift=0, big_endian=False, threads=4, batch=8, delta=None, devices=(0,),
+                        gpu_entropy=False, return_time=False):
+    """One fpvc::Encoder over several GPUs (GpuOptions::devices): batches round-robin over `devices`, the delta frame
+    reaches devices[1:] by peer copy, the stream is the single-GPU stream byte for byte."""
+    L = lib()
+    frames = np.ascontiguousarray(frames, dtype=np.uint16).reshape(-1, xsize * ysize)
+    delta = frames[0] if delta is None else np.ascontiguousarray(delta, dtype=np.uint16).reshape(-1)
+    n = frames.shape[0]
+    cap = 64 + (n + 1) * (xsize * ysize * 5 // 2 + 4096)
+    out = np.empty(cap, np.uint8)
+    devs = np.ascontiguousarray(list(devices), dtype=np.int32)
+    sec = C.c_double(0)
+    size = L.fpvh_encode_stream_multi(xsize, ysize, shift, int(big_endian), threads, batch, _p(devs), devs.size,
+                                      int(bool(gpu_entropy)), _p(delta), _p(frames), n, _p(out), cap, C.byref(sec))
+    if size == 0:
+        raise HostError(f"encode failed: {last_error()}")
+    if size > cap:
+        raise HostError("stream larger than the output buffer")
+    stream = out[:size].tobytes()
+    return (stream, sec.value) if return_time else stream
 
 
 def time_encode(frames, xsize, ysize, shift=0, big_endian=False, threads=4, batch=8, delta=None, device=0,

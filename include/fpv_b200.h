@@ -10,9 +10,14 @@
  *
  * Conventions: extern "C", opaque handle, plain pointers and sizes, int status
  * (0 = FPV_OK).  No C++ types, no exceptions, no torch types cross this
- * boundary.  A context is bound to one CUDA device and one frame geometry;
- * calls on one context must be serialised by the caller (one context per
- * worker / per GPU), different contexts are independent.
+ * boundary.  A context is bound to one CUDA device and one frame geometry.
+ * Thread safety: every entry point takes the context's lock, so any number of
+ * threads may share one context; the one blocking call, fpv_wait, releases the
+ * lock while it sleeps on the slot's event, so one thread can submit into a
+ * slot while another waits for a different slot (the Encoder's pipeline).  A
+ * SLOT, however, belongs to one submit/wait sequence at a time: two threads
+ * must not submit into the same slot without a wait in between.  Different
+ * contexts are independent.  fpv_last_error is per calling thread.
  *
  * Layout of all buffers: frames are dense, frame-major.
  *   raw frames   uint16[n][ysize*xsize]   as read from the raw file (native
@@ -73,9 +78,17 @@ int fpv_create(fpv_ctx** ctx, int device, uint32_t xsize, uint32_t ysize,
                int shift_to_left_align, int big_endian, uint32_t max_batch);
 void fpv_destroy(fpv_ctx* ctx);
 
-/* Human-readable description of the last failure on this context (or of the
- * last failed fpv_create when ctx is NULL).  Never NULL. */
+/* Human-readable description of the last failure of the CALLING THREAD (on any
+ * context, or in fpv_create).  The argument is accepted for symmetry and may
+ * be NULL.  Never returns NULL; valid until the thread's next failing call. */
 const char* fpv_last_error(const fpv_ctx* ctx);
+
+/* Makes the context's device the calling thread's current CUDA device
+ * (cudaSetDevice).  Host threads that allocate pinned memory with
+ * fpv_host_alloc for a context on a device other than 0 call this first, so
+ * that no primary context is created on device 0 behind their back. */
+int fpv_bind_thread(const fpv_ctx* ctx);
+int fpv_device_of(const fpv_ctx* ctx);
 
 /* Library / device introspection. */
 int fpv_device_count(void);
@@ -115,8 +128,21 @@ int fpv_set_delta_image_device(fpv_ctx* ctx, const void* image_dev, void* stream
 
 /* Multi-GPU: copies the resident delta planes of `src` (another device) into
  * `dst` by peer copy -- the only inter-GPU traffic of the path (frames are
- * independent given the delta frame, .cc:36-38). */
+ * independent given the delta frame, .cc:36-38; the reference shares one
+ * delta_frame_ between its pool threads, .cc:1097, :1164). */
 int fpv_copy_delta_peer(fpv_ctx* dst, const fpv_ctx* src);
+
+/* The same across PROCESSES (one process per GPU, e.g. torchrun): the owner
+ * exports a CUDA IPC handle of its resident delta image, the handle bytes
+ * travel over any control plane (a file, a pipe, torch.distributed), and each
+ * importer maps the owner's memory and copies it device to device over
+ * NVLink / PCIe peer access.  The owner's context must stay alive until every
+ * importer has returned.  Fails with FPV_ERR_NO_DELTA if the owner has no
+ * delta frame, FPV_ERR_CUDA if the handle is opened in the exporting process
+ * (use fpv_copy_delta_peer there). */
+#define FPV_IPC_HANDLE_BYTES 64
+int fpv_delta_ipc_export(fpv_ctx* ctx, void* handle_out);
+int fpv_delta_ipc_import(fpv_ctx* ctx, const void* handle);
 
 /* ---- encode transform --------------------------------------------------- */
 
@@ -151,6 +177,13 @@ int fpv_encode_submit(fpv_ctx* ctx, uint32_t slot, const uint16_t* frames_host, 
                       uint32_t options, uint8_t* flags_host, uint8_t* high_host,
                       uint8_t* low_host, uint8_t* preview_host);
 int fpv_wait(fpv_ctx* ctx, uint32_t slot);
+
+/* Frame constructor alone, for n frames: replaces `Frame(xsize, ysize, img, shift, big_endian)`
+ * (.cc:370-451) without Predict -- the byte planes as Frame::high() / low() hold them in state RAW,
+ * flags[i] = NO_LOW_BYTES iff every low byte of frame i is zero (always for shift 8, where `low` may be
+ * NULL).  Host buffers, synchronous.  Any xsize, ysize >= 1. */
+int fpv_split(fpv_ctx* ctx, const uint16_t* frames_host, uint32_t n, uint8_t* flags_host, uint8_t* high_host,
+              uint8_t* low_host);
 
 /* ---- optional GPU entropy coding ------------------------------------------------
  * Replaces the reference's three BrotliEncoderCompress calls per frame
@@ -188,6 +221,11 @@ int fpv_encode_stream_submit(fpv_ctx* ctx, uint32_t slot, const uint16_t* frames
  * Any xsize, ysize >= 1. */
 int fpv_decode(fpv_ctx* ctx, const uint8_t* high_host, const uint8_t* low_host,
                const uint8_t* flags_host, uint32_t n, uint32_t options, void* out_host);
+/* Device-pointer form.  The flags live on the device, so this form cannot
+ * refuse a USE_DELTA frame when no delta frame is set (FPV_ERR_NO_DELTA is
+ * reported by the host-buffer forms only): such a frame is decoded WITHOUT
+ * the delta add.  Callers that build flags themselves must set the delta
+ * frame first, as the reference's decoders do (.cc:902-906). */
 int fpv_decode_device(fpv_ctx* ctx, const void* high_dev, const void* low_dev,
                       const void* flags_dev, uint32_t n, uint32_t options, void* out_dev,
                       void* stream);
