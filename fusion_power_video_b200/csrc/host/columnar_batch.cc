@@ -50,6 +50,37 @@ PreviewContexts& previews() {
 
 // ---- BatchSchema ---------------------------------------------------------------------------------
 
+// reference columnar_batch.cc:6-24 (which compresses into zero-sized vectors; this does what was meant)
+BatchSchema::BatchSchema(size_t xsize, size_t ysize, size_t shifted_left, Frame& uncompressed_delta_frame)
+    : xsize_(xsize), ysize_(ysize), shifted_left_(shifted_left), big_endian_(false), device_(0) {
+  delta_frame_ = uncompressed_delta_frame;
+  const size_t P = xsize * ysize;
+  if (delta_frame_.high().size() != P) {
+    FPV_FAIL("BatchSchema: the delta frame must be un-compressed and of the schema's size");
+    return;
+  }
+  if (fpv_create(&ctx_, device_, (uint32_t)xsize, (uint32_t)ysize, (int)shifted_left, 0, (uint32_t)kMaxBatch) != FPV_OK) {
+    FPV_FAIL(std::string("fpv_create: ") + fpv_last_error(nullptr));
+    return;
+  }
+  // the context's delta frame in image form: (high << 8) | low per pixel (reference .cc:337-338)
+  std::vector<uint16_t> image(P);
+  const std::vector<uint8_t>& h = delta_frame_.high();
+  const std::vector<uint8_t>& l = delta_frame_.low();
+  for (size_t i = 0; i < P; i++) image[i] = (uint16_t)((h[i] << 8) | (l.size() == P ? l[i] : 0));
+  if (fpv_set_delta_image(ctx_, image.data()) != FPV_OK) {
+    FPV_FAIL(std::string("fpv_set_delta_image: ") + fpv_last_error(ctx_));
+    return;
+  }
+  compressed_high_.resize(Frame::MaxCompressedPlaneSize(xsize, ysize));
+  compressed_low_.resize(Frame::MaxCompressedPlaneSize(xsize, ysize));
+  size_t hs = compressed_high_.size(), ls = compressed_low_.size(), ps = 0;
+  uncompressed_delta_frame.CompressPredicted(&hs, compressed_high_.data(), &ls, compressed_low_.data(), &ps, nullptr);
+  compressed_high_.resize(hs);
+  compressed_low_.resize(ls);
+  ok_ = hs > 0;
+}
+
 BatchSchema::BatchSchema(size_t xsize, size_t ysize, size_t shifted_left, bool big_endian, const uint16_t* delta_frame,
                          int device)
     : xsize_(xsize), ysize_(ysize), shifted_left_(shifted_left), big_endian_(big_endian), device_(device) {
@@ -76,6 +107,10 @@ BatchSchema::BatchSchema(size_t xsize, size_t ysize, size_t shifted_left, bool b
   }
   ok_ = BrotliPlane(high.data(), P, &scratch, &compressed_high_);
   if (ok_ && has_low && !(flags & FPV_FLAG_NO_LOW_BYTES)) ok_ = BrotliPlane(low.data(), P, &scratch, &compressed_low_);
+  // the same planes as a Frame, for callers of the reference's delta_frame() accessor
+  if (ok_)
+    delta_frame_ = Frame(xsize, ysize, (uint8_t)(flags & FPV_FLAG_NO_LOW_BYTES), (uint8_t)FrameState::RAW, std::move(high),
+                         std::move(low), std::vector<uint8_t>());
 }
 
 BatchSchema::~BatchSchema() {
@@ -97,6 +132,20 @@ void Batch::Reset() {
   std::fill(preview_offsets_.begin(), preview_offsets_.end(), 0u);
   std::fill(high_offsets_.begin(), high_offsets_.end(), 0u);
   std::fill(low_offsets_.begin(), low_offsets_.end(), 0u);
+}
+
+// reference columnar_batch.cc:65-90
+bool Batch::AppendPredicted(Frame predicted_frame) {
+  if (length_ >= batch_size_) return false;
+  const size_t x = schema_->xsize(), y = schema_->ysize();
+  std::vector<uint8_t> high(Frame::MaxCompressedPlaneSize(x, y)), low(Frame::MaxCompressedPlaneSize(x, y)),
+      preview(Frame::MaxCompressedPreviewSize(x, y));
+  size_t hs = high.size(), ls = low.size(), ps = preview.size();
+  predicted_frame.CompressPredicted(&hs, high.data(), &ls, low.data(), &ps, preview.data());
+  high.resize(hs);
+  low.resize(ls);
+  preview.resize(ps);
+  return AppendPredicted(predicted_frame.timestamp(), predicted_frame.flags(), preview, high, low);
 }
 
 bool Batch::AppendPredicted(int64_t timestamp, uint8_t flags, const std::vector<uint8_t>& preview,

@@ -6,9 +6,10 @@
 // planes); the first pushed frame doubles as the delta frame and defines the BatchSchema; a
 // ColumnarBatchDecoder turns Batches back into Images (PREVIEW, MSB8 or FULL).  Differences: the frame
 // transform (Frame ctor + Predict, reference columnar_batch_encoder.cc:61-71) and its inverse
-// (Frame::Uncompress, columnar_batch.cc:110) run on the GPU one batch at a time through the C ABI; there
-// is no public fpvc::Frame, so Batch::AppendPredicted takes planes instead of a Frame and BatchSchema is
-// built from the raw delta frame.  Where the reference has defects (compressing into a zero-sized vector,
+// (Frame::Uncompress, columnar_batch.cc:110) run on the GPU one batch at a time through the C ABI.  The
+// reference's Frame-based entry points (BatchSchema from an uncompressed delta Frame, delta_frame(),
+// Batch::AppendPredicted(Frame)) are kept next to the batched ones this file's encoder uses (BatchSchema from
+// the raw delta frame, AppendPredicted of compressed planes).  Where the reference has defects (compressing into a zero-sized vector,
 // columnar_batch.cc:10-22; passing the high plane as the low plane, columnar_batch_decoder.cc:73-74) this
 // file implements what was meant.
 #ifndef FPV_B200_COLUMNAR_BATCH_H_
@@ -35,7 +36,9 @@ namespace columnarbatch {
 
 class BatchSchema {
  public:
-  // delta_frame: the raw uint16 frame as the camera delivers it (same meaning as the encoders' frames)
+  // As the reference (columnar_batch.h:11): from an un-predicted, un-compressed delta Frame.
+  BatchSchema(size_t xsize, size_t ysize, size_t shifted_left, Frame& uncompressed_delta_frame);
+  // Extension: from the raw uint16 frame as the camera delivers it (same meaning as the encoders' frames)
   BatchSchema(size_t xsize, size_t ysize, size_t shifted_left, bool big_endian, const uint16_t* delta_frame,
               int device = 0);
   ~BatchSchema();
@@ -47,6 +50,7 @@ class BatchSchema {
   size_t shiftedLeft() const { return shifted_left_; }
   bool bigEndian() const { return big_endian_; }
   bool ok() const { return ok_; }
+  Frame& delta_frame() { return delta_frame_; }
   // Delta frame is _not_ CG predicted (reference columnar_batch.h:17)
   const std::vector<uint8_t>& compressedDeltaFrameHighPlane() const { return compressed_high_; }
   const std::vector<uint8_t>& compressedDeltaFrameLowPlane() const { return compressed_low_; }
@@ -63,6 +67,7 @@ class BatchSchema {
   bool big_endian_, ok_ = false;
   int device_ = 0;
   std::vector<uint8_t> compressed_high_, compressed_low_;
+  Frame delta_frame_;
   fpv_ctx* ctx_ = nullptr;
   std::mutex ctx_mutex_;
 };
@@ -100,7 +105,10 @@ class Batch {
   Batch(size_t batch_size, SchemaPtr schema);
 
   void Reset();
-  // one predicted frame: flags and the brotli streams of its three planes (low may be empty)
+  // As the reference (columnar_batch.h:73, columnar_batch.cc:65-90): compresses the predicted frame's planes
+  // (Frame::CompressPredicted) into the columns.
+  bool AppendPredicted(Frame predicted_frame);
+  // Extension: one predicted frame given as flags and the brotli streams of its three planes (low may be empty)
   bool AppendPredicted(int64_t timestamp, uint8_t flags, const std::vector<uint8_t>& preview,
                        const std::vector<uint8_t>& high, const std::vector<uint8_t>& low);
 

@@ -63,6 +63,101 @@ struct GpuOptions {
   std::vector<int> devices;
 };
 
+// ---- fpvc::Frame ---------------------------------------------------------------------------------
+// The reference's frame object (reference fusion_power_video.h:59-139): same enums, constructors, accessors and
+// methods, so that code written against it -- the reference's columnar_batch/*.cc and arrow/*.cc wrappers --
+// recompiles unchanged.  What differs is where the arithmetic runs:
+//   * the u16 constructor splits the image into byte planes on the GPU (fpv_split; reference .cc:370-451),
+//   * Predict() is ONE fused GPU call (fpv_encode: preview + delta + ClampedGradient with the reference's
+//     integer heuristics; reference .cc:777-785),
+//   * Uncompress() undoes the predictions on the GPU (fpv_unpredict_planes; reference .cc:595-641, :773-774),
+//   * brotli (Compress / CompressPredicted / Uncompress) stays on the host, as in the Encoder.
+// This is the single-frame compatibility surface: every call is a synchronous round trip of one frame over
+// PCIe.  The batched, overlapped path is fpvc::Encoder / the decoders / columnarbatch::ColumnarBatchEncoder.
+// There is no CPU implementation: without a CUDA device the GPU-backed methods report failure (LastError)
+// and leave the frame unchanged.
+// Restriction: Predict() needs a frame on which none of its three steps has run yet (the state every
+// constructor and Uncompress() leave behind when all predictions were undone) or one on which all have
+// (no-op, as in the reference); a frame with only some of the steps applied is refused.
+enum FrameState {
+  EMPTY = 0,
+  RAW = 1,
+  PREVIEW_GENERATED = 2,
+  DELTA_PREDICTED = 4,
+  CG_PREDICTED = 8,
+  COMPRESSED = 16,
+};
+
+enum FrameFlags {
+  NONE = 0,
+  USE_DELTA = 1,
+  USE_CG = 2,
+  NO_LOW_BYTES = 4,
+};
+
+class Frame {
+  size_t xsize_ = 0;
+  size_t ysize_ = 0;
+  size_t size_ = 0;
+  uint8_t flags_ = FrameFlags::NONE;   // FrameFlags
+  uint8_t state_ = FrameState::EMPTY;  // FrameState
+  int64_t timestamp_ = -1;
+
+ protected:
+  std::vector<uint8_t> preview_;
+  std::vector<uint8_t> high_;
+  std::vector<uint8_t> low_;
+
+ public:
+  static Frame EMPTY;
+
+  size_t xsize() const { return xsize_; }
+  size_t ysize() const { return ysize_; }
+  uint8_t flags() const { return flags_; }
+  uint8_t state() const { return state_; }
+  int64_t timestamp() const { return timestamp_; }
+  const std::vector<uint8_t>& high() { return high_; }
+  const std::vector<uint8_t>& low() { return low_; }
+  const std::vector<uint8_t>& preview() { return preview_; }
+  std::vector<uint8_t>&& MoveOutHigh() { Touch(); return std::move(high_); }
+  std::vector<uint8_t>&& MoveOutLow() { Touch(); return std::move(low_); }
+  std::vector<uint8_t>&& MoveOutPreview() { return std::move(preview_); }
+
+  Frame(size_t xsize = 0, size_t ysize = 0, const uint16_t* image = nullptr, int shift_to_left_align = 0,
+        bool big_endian = false, int64_t timestamp = -1);
+  Frame(size_t xsize, size_t ysize, const uint8_t* image, int64_t timestamp = -1);
+  Frame(size_t xsize, size_t ysize, uint8_t flags, uint8_t state, std::vector<uint8_t>&& high,
+        std::vector<uint8_t>&& low, std::vector<uint8_t>&& preview, int64_t timestamp = -1);
+
+  static size_t MaxCompressedPlaneSize(size_t xsize, size_t ysize);
+  static size_t MaxCompressedPreviewSize(size_t xsize, size_t ysize);
+  size_t MaxCompressedPlaneSize();
+  size_t MaxCompressedPreviewSize();
+
+  void Compress(Frame& delta_frame = EMPTY);
+  void Uncompress(Frame& delta_frame = EMPTY);
+  void Predict(Frame& delta_frame = EMPTY);
+  void CompressPredicted(size_t* encoded_high_size, uint8_t* encoded_high_buffer, size_t* encoded_low_size,
+                         uint8_t* encoded_low_buffer, size_t* encoded_preview_size, uint8_t* encoded_preview_buffer,
+                         bool parallel = true);
+  void OutputCore(std::vector<uint8_t>* out);
+  void OutputFull(std::vector<uint8_t>* out);
+
+  // Extension: CUDA device the Frame methods of this process run on (default 0).
+  static void SetDevice(int device);
+
+ private:
+  void ApplyBrotliCompression();
+  void Touch();   // the planes changed: a GPU context holding them as its delta frame must reload them
+  // the image the u16 constructor received, kept until Predict() so that Predict is one fused GPU call on
+  // the raw pixels (shared between copies of the frame)
+  std::shared_ptr<const std::vector<uint16_t>> raw_;
+  int shift_ = 0;
+  bool big_endian_ = false;
+  uint64_t generation_ = 0;   // identity of the current plane contents (see Touch)
+  friend struct FrameGpu;
+};
+
 class StreamingDecoder {
  public:
   StreamingDecoder();

@@ -111,6 +111,16 @@ int fpv_encode(fpv_ctx* c, const uint16_t* frames, uint32_t n, uint32_t options,
   }
   return FPV_OK;
 }
+int fpv_split(fpv_ctx* c, const uint16_t* frames, uint32_t n, uint8_t* flags, uint8_t* high, uint8_t* low) {
+  if (!c) return FPV_ERR_INVALID_ARG;
+  if (n == 0) return FPV_OK;
+  if (!frames || !flags || !high) return fail(FPV_ERR_INVALID_ARG, "NULL host buffer");
+  if (c->has_low && !low) return fail(FPV_ERR_INVALID_ARG, "low plane buffer is NULL");
+  for (uint32_t i = 0; i < n; i++)
+    flags[i] = fpvo_split(frames + (size_t)i * c->P, c->P, c->shift, c->big_endian, high + (size_t)i * c->P,
+                          low ? low + (size_t)i * c->P : NULL);
+  return FPV_OK;
+}
 int fpv_encode_device(fpv_ctx* c, const void* frames, uint32_t n, uint32_t options, void* flags, void* high, void* low,
                       void* preview, void* stream) {
   (void)stream;
