@@ -2,9 +2,12 @@
 // bindings (tests/ and bench.py reach the host layer through these).
 #include <string.h>
 
+#include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <future>
 #include <memory>
+#include <thread>
 #include <vector>
 
 #include "columnar_batch.h"
@@ -202,6 +205,86 @@ long fpvh_columnar_roundtrip(size_t xsize, size_t ysize, int shift, int big_endi
   if (batches) *batches = st.batches;
   if (compressed_bytes) *compressed_bytes = st.compressed;
   return (st.failed || !enc->ok()) ? -1 : (long)st.count;
+}
+
+// Real-time ingest (BASELINE configs[4]; the loop of reference encode.cc:63-96 driven by a camera clock instead of
+// stdin): frames ARRIVE at `fps` for `seconds`, whether or not the encoder keeps up.  The camera side owns a ring of
+// `ring_frames` buffers; the feeder thread hands arrived frames to Encoder::CompressFrame in order, and a frame whose
+// turn comes more than ring_frames / fps after its arrival has been overwritten by then: it is DROPPED (counted, not
+// encoded).  Latency of an encoded frame = time its compressed bytes reach the callback - its arrival time.
+// frames: pool of `npool` distinct frames cycled through (frame 0 is also the delta frame).
+// out[0..9] = offered, encoded, dropped, p50 ms, p99 ms, max ms, mean ms, achieved frames/s, stream bytes, wall seconds.
+// Returns 0, or -1 if the encoder failed.
+int fpvh_ingest(size_t xsize, size_t ysize, int shift, int big_endian, size_t threads, uint32_t batch, int device,
+                int gpu_entropy, const uint16_t* frames, size_t npool, double fps, double seconds, size_t ring_frames,
+                double* out) {
+  const size_t P = xsize * ysize;
+  const size_t total = (size_t)(fps * seconds);
+  if (total == 0 || npool == 0 || !out) return -1;
+  struct State {
+    std::vector<double> arrival, latency;
+    std::atomic<size_t> bytes{0};
+    double t0 = 0;
+  } st;
+  st.arrival.assign(total, 0.0);
+  st.latency.assign(total, -1.0);
+  fpvc::GpuOptions opt;
+  opt.device = device;
+  if (batch) opt.batch = batch;
+  opt.gpu_entropy = gpu_entropy;
+  size_t dropped = 0, encoded = 0;
+  double wall = 0;
+  {
+    fpvc::Encoder enc(threads, shift, big_endian != 0, opt);
+    auto sink = [&st](const uint8_t*, size_t size, void* payload) {
+      const size_t idx = (size_t)(uintptr_t)payload;
+      st.bytes += size;
+      if (idx != (size_t)-1) st.latency[idx] = Now() - st.arrival[idx];
+    };
+    enc.Init(frames, xsize, ysize, sink, (void*)(uintptr_t)(size_t)-1);
+    if (!enc.ok()) return -1;
+    // warm the pipeline (contexts, pinned batches, worker threads) before the camera starts
+    for (size_t i = 0; i < std::min<size_t>(npool, 2 * (batch ? batch : 8)); i++)
+      enc.CompressFrame(frames + (i % npool) * P, sink, (void*)(uintptr_t)(size_t)-1);
+    std::this_thread::sleep_for(std::chrono::milliseconds(300));
+    const double period = 1.0 / fps, patience = (double)ring_frames / fps;
+    st.t0 = Now();
+    for (size_t i = 0; i < total; i++) {
+      const double due = st.t0 + (double)i * period;
+      double now = Now();
+      if (now < due) {
+        if (due - now > 200e-6) std::this_thread::sleep_for(std::chrono::duration<double>(due - now - 100e-6));
+        while ((now = Now()) < due) {}
+      }
+      st.arrival[i] = due;
+      if (now - due > patience) {   // its ring slot has been overwritten by a newer frame
+        dropped++;
+        continue;
+      }
+      enc.CompressFrame(frames + (i % npool) * P, sink, (void*)(uintptr_t)i);
+      encoded++;
+    }
+    enc.Finish(sink, (void*)(uintptr_t)(size_t)-1);
+    wall = Now() - st.t0;
+    if (!enc.ok()) return -1;
+  }
+  std::vector<double> lat;
+  for (double v : st.latency)
+    if (v >= 0) lat.push_back(v * 1e3);
+  std::sort(lat.begin(), lat.end());
+  double mean = 0;
+  for (double v : lat) mean += v;
+  out[0] = (double)total;
+  out[1] = (double)encoded;
+  out[2] = (double)dropped;
+  out[3] = lat.empty() ? 0 : lat[lat.size() / 2];
+  out[4] = lat.empty() ? 0 : lat[std::min(lat.size() - 1, (size_t)(lat.size() * 0.99))];
+  out[5] = lat.empty() ? 0 : lat.back();
+  out[6] = lat.empty() ? 0 : mean / (double)lat.size();
+  out[7] = wall > 0 ? (double)encoded / wall : 0;
+  out[8] = (double)st.bytes.load();
+  out[9] = wall;
+  return 0;
 }
 
 void fpvh_unextract(const uint16_t* img, size_t xsize, size_t ysize, int shift, int big_endian, uint8_t* out) {

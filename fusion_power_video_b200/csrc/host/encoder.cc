@@ -256,8 +256,11 @@ struct Encoder::Impl {
   }
 
   void compress_batch(Batch* b) {
-    b->pending.store(b->n);
-    for (uint32_t i = 0; i < b->n; i++) {
+    // n is read ONCE: the moment the last task of the batch finishes, the batch is recycled and may already be
+    // filling again (b->n counting the next frames) while this loop is still on its way out
+    const uint32_t n = b->n;
+    b->pending.store(n);
+    for (uint32_t i = 0; i < n; i++) {
       Pieces& pc = b->pieces[i];
       pc.parts.store(0);
       pc.low.clear();

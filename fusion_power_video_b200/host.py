@@ -18,6 +18,12 @@ def lib_path() -> str:
     return _LIB_PATH
 
 
+def _preload_cabi():
+    from . import binding
+
+    binding.lib()  # the C ABI first, so the dependency resolves from lib/
+
+
 def lib() -> C.CDLL:
     """Loads the host library (which links libfpv_b200.so).  Raises if missing."""
     global _lib
@@ -25,9 +31,7 @@ def lib() -> C.CDLL:
         return _lib
     if not os.path.exists(_LIB_PATH):
         raise ImportError(f"{_LIB_PATH} not found: run `make -C fusion_power_video_b200/csrc all`")
-    from . import binding
-
-    binding.lib()  # the C ABI first, so the dependency resolves from lib/
+    _preload_cabi()
     L = C.CDLL(_LIB_PATH)
     vp, sz, i32, u32 = C.c_void_p, C.c_size_t, C.c_int, C.c_uint32
     L.fpvh_last_error.restype = C.c_char_p
@@ -38,6 +42,8 @@ def lib() -> C.CDLL:
     L.fpvh_columnar_roundtrip.restype = C.c_long
     L.fpvh_encode_stream_multi.argtypes = [sz, sz, i32, i32, sz, u32, vp, i32, i32, vp, vp, sz, vp, sz, C.POINTER(C.c_double)]
     L.fpvh_encode_stream_multi.restype = sz
+    L.fpvh_ingest.argtypes = [sz, sz, i32, i32, sz, u32, i32, i32, vp, sz, C.c_double, C.c_double, sz, C.POINTER(C.c_double)]
+    L.fpvh_ingest.restype = i32
     L.fpvh_time_encode.argtypes = [sz, sz, i32, i32, sz, u32, i32, vp, vp, sz, C.POINTER(sz)]
     L.fpvh_time_encode.restype = C.c_double
     L.fpvh_decode_stream.argtypes = [vp, sz, sz, u32, i32, i32, i32, vp, sz, C.POINTER(sz), C.POINTER(sz),
@@ -121,6 +127,25 @@ def encode_stream_multi(frames, xsize, ysize, shift=0, big_endian=False, threads
         raise HostError("stream larger than the output buffer")
     stream = out[:size].tobytes()
     return (stream, sec.value) if return_time else stream
+
+
+def ingest(frames, xsize, ysize, fps, seconds, shift=0, big_endian=False, threads=4, batch=8, device=0, gpu_entropy=False,
+           ring_frames=64):
+    """Paced real-time ingest into fpvc::Encoder (capi.cc fpvh_ingest): frames arrive at `fps` for `seconds`; returns a
+    dict with offered / encoded / dropped counts and the arrival-to-callback latency distribution (ms)."""
+    L = lib()
+    frames = np.ascontiguousarray(frames, dtype=np.uint16).reshape(-1, xsize * ysize)
+    out = (C.c_double * 10)()
+    rc = L.fpvh_ingest(xsize, ysize, shift, int(big_endian), threads, batch, device, int(bool(gpu_entropy)), _p(frames),
+                       frames.shape[0], float(fps), float(seconds), ring_frames, out)
+    if rc != 0:
+        raise HostError(f"ingest failed: {last_error()}")
+    keys = ["offered", "encoded", "dropped", "p50_ms", "p99_ms", "max_ms", "mean_ms", "achieved_fps", "stream_bytes", "wall_s"]
+    d = dict(zip(keys, [float(v) for v in out]))
+    for k in ("offered", "encoded", "dropped", "stream_bytes"):
+        d[k] = int(d[k])
+    d.update(offered_fps=float(fps), batch=batch, threads=threads, gpu_entropy=bool(gpu_entropy), ring_frames=ring_frames)
+    return d
 
 
 def time_encode(frames, xsize, ysize, shift=0, big_endian=False, threads=4, batch=8, delta=None, device=0,

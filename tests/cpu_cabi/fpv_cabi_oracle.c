@@ -48,7 +48,7 @@ void fpv_host_free(void* p) { free(p); }
 int fpv_create(fpv_ctx** out, int device, uint32_t xsize, uint32_t ysize, int shift, int big_endian, uint32_t max_batch) {
   if (!out) return fail(FPV_ERR_INVALID_ARG, "ctx out pointer is NULL");
   *out = NULL;
-  if (device != 0) return fail(FPV_ERR_INVALID_ARG, "device index out of range");
+  if (device < 0 || device >= 8) return fail(FPV_ERR_INVALID_ARG, "device index out of range");   /* pretend 8 devices: multi-GPU host logic */
   if (xsize == 0 || ysize == 0 || xsize > 65536 || ysize > 65536 || (uint64_t)xsize * ysize > 1000000000ull)
     return fail(FPV_ERR_INVALID_ARG, "invalid image dimensions");
   if (shift < 0 || shift > 16 || (big_endian && shift > 8)) return fail(FPV_ERR_UNSUPPORTED, "shift");

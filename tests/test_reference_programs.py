@@ -141,6 +141,13 @@ def test_cpu_reference_encode_decode_on_mirror(cpu_programs, tmp_path, cfg):
     check_encode_decode(cpu_programs, tmp_path, *cfg)
 
 
+@pytest.mark.parametrize("gpus", [2, 3])
+def test_cpu_one_encoder_over_several_devices_writes_the_same_stream(cpu_programs, tmp_path, gpus):
+    """GpuOptions::devices (here through FPV_GPUS, which the unmodified encode.cc cannot set any other way): batches
+    go round-robin to per-device contexts and GPU threads, emission stays in submission order."""
+    check_encode_decode(cpu_programs, tmp_path, 256, 128, 12, 4, 0, 37, 6, env={"FPV_GPUS": str(gpus)})
+
+
 def test_cpu_reference_benchmark_on_mirror(cpu_programs, tmp_path):
     check_benchmark(cpu_programs, tmp_path)
 
