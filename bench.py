@@ -3,12 +3,23 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-Workload (BASELINE.json configs[1]): 12-bit 1280x800 high-speed-camera frames
+N = 1 (BASELINE.json configs[1]): 12-bit 1280x800 high-speed-camera frames
 stored as uint16 (shift 4), static delta frame = frame 0, one GPU holding a
 contiguous range of the sequence resident in HBM.  A *step* is one pass of the
 encode transform (Frame ctor + Frame::Predict of the reference) over that
-range.  With N GPUs every rank owns its own contiguous frame range (weak
-scaling, no data-path collective; the delta frame is uploaded to each GPU).
+range.  The line also carries `configs` (the same measurement on configs[0] and
+configs[2] geometry) and `ingest` (configs[4]: paced real-time ingest).
+
+N > 1 (BASELINE.json configs[2]): ONE 16-bit 2048x2048 sequence of 10 000 frames
+cut into contiguous frame ranges, one rank / GPU each (sharding.frame_range), no
+data-path collective.  The only thing that crosses GPUs is the delta frame: rank
+0 splits it and every other rank copies the planes device to device through a
+CUDA IPC handle (fpv_delta_ipc_export / _import).  A step is one pass over the
+whole sequence (every rank over its shard, resident in HBM); the total work is
+fixed, so "scaling" is "strong".  The run ends with a merged-stream check: a
+subsample of the sequence is encoded shard by shard with fpvc::Encoder, the
+shard streams are merged on rank 0 (sharding.merge_shards) and compared with
+the stream ONE GPU writes for the same frames.
 
 Prints ONE JSON line (rank 0).  `value` is device-resident raw-pixel GB/s
 (2 bytes x pixels / s) over all GPUs; `e2e` is the same metric through the
@@ -38,7 +49,7 @@ WORKLOADS = {
     # name: (xsize, ysize, bits, shift, description)
     "c2": (1280, 800, 12, 4, "12-bit 1280x800 camera stream, static delta frame, device-resident (BASELINE configs[1])"),
     "c1": (1024, 1024, 16, 0, "16-bit 1024x1024 (BASELINE configs[0] geometry)"),
-    "c3": (2048, 2048, 16, 0, "16-bit 2048x2048, sharded by frame range (BASELINE configs[2] geometry)"),
+    "c3": (2048, 2048, 16, 0, "16-bit 2048x2048 x 10k frames, encode sharded by frame range across the GPUs with a one-frame (delta frame) halo (BASELINE configs[2])"),
     # experiments: is a lower roofline fraction a matter of geometry (power-of-two strides) or of content (16-bit noise)?
     "x1": (1024, 1000, 16, 0, "experiment: 16-bit 1024x1000 (frame size not a power of two)"),
     "x2": (1280, 800, 16, 0, "experiment: 16-bit content at the C2 geometry"),
@@ -114,6 +125,41 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def pin_rank_cpus(local, rank, world):
+    """Gives every rank of a multi-GPU run its own slice of the host cores -- inside the GPU's NUMA node where the
+    platform reports one (sysfs), else of all cores -- BEFORE any pinned buffer is allocated, so that first-touch puts
+    the staging memory next to the threads that fill it and the ranks' brotli / copy threads do not migrate onto each
+    other.  Returns the cpu list (also used as the rank's thread budget)."""
+    cpus = sorted(os.sched_getaffinity(0))
+    if world <= 1:
+        return cpus
+    node_cpus = None
+    try:
+        bus = subprocess.check_output(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(local)],
+                                      text=True).strip().lower()
+        if bus.startswith("00000000:"):
+            bus = bus[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip())
+        if node >= 0:
+            node_cpus = []
+            for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+                a, _, b = part.partition("-")
+                node_cpus.extend(range(int(a), int(b or a) + 1))
+            node_cpus = sorted(set(node_cpus) & set(cpus))
+    except Exception:
+        node_cpus = None
+    per = max(1, len(cpus) // world)
+    mine = cpus[(rank * per) % len(cpus):(rank * per) % len(cpus) + per]
+    if node_cpus:
+        # ranks that share a node split that node's cores among themselves
+        mine = [c for c in mine if c in node_cpus] or node_cpus[:per]
+    try:
+        os.sched_setaffinity(0, mine)
+    except Exception:
+        return cpus
+    return mine
+
+
 def cpu_reference_rate(frames_np, W, H, shift, delta_np, budget_s, threads=None):
     """raw-pixel GB/s of the reference's CPU transform (Frame ctor + Predict) on `threads` host threads."""
     from oracle_binding import Oracle, Ref, ref_available
@@ -185,13 +231,95 @@ def run_reference_arm(args, W, H, bits, shift, desc):
     print(json.dumps(line), flush=True)
 
 
+def geometry_leg(fpv, synth, torch, dev, local, name, peak, steps=10):
+    """Device-resident encode + decode of another BASELINE geometry, measured like the headline (CUDA events around
+    the dominant kernel, inputs far larger than L2): roofline fractions for the `configs` entry of the N = 1 line."""
+    W, H, bits, shift, desc = WORKLOADS[name]
+    P = W * H
+    F = 1184 if P < 4000000 else 592
+    frames = torch.empty((F, P), dtype=torch.uint16, device=dev)
+    for c in range(0, F, 64):
+        m = min(64, F - c)
+        frames[c:c + m] = synth.plasma_frames_torch(m, W, H, bits=bits, seed=1, first=c, device=dev).reshape(m, P)
+    hi = torch.empty((F, P), dtype=torch.uint8, device=dev)
+    lo = torch.empty((F, P), dtype=torch.uint8, device=dev)
+    pv = torch.empty((F, P // 16), dtype=torch.uint8, device=dev)
+    fl = torch.empty(F, dtype=torch.uint8, device=dev)
+    out = torch.empty((F, P), dtype=torch.int16, device=dev)
+    sp = torch.cuda.current_stream().cuda_stream
+    ctx = fpv.Context(W, H, shift, False, max_batch=F, device=local)
+    ctx.set_delta_raw_device(frames[0].data_ptr(), sp)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    res = {"workload": desc, "xsize": W, "ysize": H, "bits": bits, "shift": shift, "frames": F}
+
+    def enc():
+        ctx.encode_device(frames.data_ptr(), F, fl.data_ptr(), hi.data_ptr(), lo.data_ptr(), pv.data_ptr(), stream=sp)
+
+    def dec():
+        ctx.decode_device(hi.data_ptr(), lo.data_ptr(), fl.data_ptr(), F, out.data_ptr(), options=fpv.DEC_UNEXTRACT, stream=sp)
+
+    t_a = time.perf_counter()
+    for what, fn, bpp in (("encode", enc, ENC_BYTES_PER_PX), ("decode", dec, DEC_BYTES_PER_PX)):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        ctx.enable_kernel_timing(True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        kms, kcnt = ctx.read_kernel_timing()
+        ctx.enable_kernel_timing(False)
+        ach = bpp * F * P / (kms / max(kcnt, 1) * 1e-3) / 1e9
+        res[what] = {"value": F * P * 2 / (ms * 1e-3) / 1e9, "unit": "GB/s", "frames_per_s": F / (ms * 1e-3), "ms_per_step": ms,
+                     "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                                  "step_frac": bpp * F * P / (ms * 1e-3) / 1e9 / peak}}
+    res["decode"]["round_trip_exact"] = bool(torch.equal(out.view(torch.uint16), frames))
+    window = (t_a, time.perf_counter())
+    del frames, hi, lo, pv, fl, out, ctx
+    torch.cuda.empty_cache()
+    return res, window
+
+
+def ingest_leg(fpv_host, synth, ncpu, local, seconds):
+    """BASELINE configs[4]: 16-bit 1024x1024 frames ARRIVING at a camera rate (the reference states none, so
+    the offered load is swept) into fpvc::Encoder; a frame that waits longer than the camera ring holds it is dropped.
+    Reports, per entropy stage, every sweep point and the highest offered rate without a drop."""
+    W, H, bits, shift, _ = WORKLOADS["c1"]
+    pool = synth.plasma_frames(64, W, H, bits=bits, seed=1).reshape(64, -1)
+    out = {"geometry": "16-bit 1024x1024 (BASELINE configs[4])", "ring_frames": 64, "seconds_per_point": seconds,
+           "latency": "frame arrival (camera clock) -> its compressed bytes reach the Encoder callback",
+           "drop_rule": "a frame whose turn comes more than ring_frames / fps after its arrival is dropped, never waited for"}
+    for mode, ge, batch, rates in (("host_brotli", False, 8, (500, 1000, 1500, 2000, 3000)),
+                                   ("gpu_entropy", True, 16, (2000, 5000, 8000, 10000, 15000, 20000))):
+        pts, best = [], None
+        for fps in rates:
+            r = fpv_host.ingest(pool, W, H, fps, seconds, shift=shift, threads=ncpu, batch=batch, device=local, gpu_entropy=ge,
+                                ring_frames=64)
+            pts.append({k: r[k] for k in ("offered_fps", "offered", "encoded", "dropped", "p50_ms", "p99_ms", "max_ms", "achieved_fps")})
+            if r["dropped"] == 0:
+                best = r
+        out[mode] = {"batch": batch, "threads": ncpu, "sweep": pts,
+                     "max_zero_drop_fps": best["offered_fps"] if best else None,
+                     "max_zero_drop_raw_gbs": best["offered_fps"] * W * H * 2 / 1e9 if best else None,
+                     "p50_ms_at_max": best["p50_ms"] if best else None, "p99_ms_at_max": best["p99_ms"] if best else None}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS),
+                    help="default: c2 on one GPU, c3 (the 10 000-frame sequence, sharded) on several")
+    ap.add_argument("--sequence-frames", type=int, default=10000, help="frames of the sharded sequence (N > 1)")
+    ap.add_argument("--no-ingest", action="store_true", help="skip the paced real-time ingest leg")
+    ap.add_argument("--no-configs", action="store_true", help="skip the configs[0] / configs[2] geometry legs (N = 1)")
+    ap.add_argument("--ingest-seconds", type=float, default=1.5)
     ap.add_argument("--frames", type=int, default=1184,
                     help="frames per GPU per step (device-resident); 1184 = 148 SMs x 2 resident decode CTAs x 4 frames")
     ap.add_argument("--e2e-frames", type=int, default=512, help="frames per step of the host-buffer (e2e) legs")
@@ -206,6 +334,10 @@ def main():
     ap.add_argument("--no-entropy", action="store_true", help="skip the device-resident GPU entropy coder leg")
     ap.add_argument("--entropy-frames", type=int, default=256)
     args = ap.parse_args()
+    world_env = int(os.environ.get("WORLD_SIZE", "1"))
+    explicit_workload = args.workload is not None
+    if args.workload is None:
+        args.workload = "c2" if max(world_env, args.gpus) == 1 else "c3"
     W, H, bits, shift, desc = WORKLOADS[args.workload]
     P = W * H
 
@@ -230,19 +362,79 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    F = args.frames
-    # rank r owns frames [r*F, (r+1)*F) of the sequence; the delta frame is frame 0 (encode.cc:87-90)
-    frames = synth.plasma_frames_torch(F, W, H, bits=bits, seed=1, first=rank * F, device=dev).reshape(F, P)
-    delta = synth.plasma_frames_torch(1, W, H, bits=bits, seed=1, first=0, device=dev).reshape(P)
+    from fusion_power_video_b200 import sharding
+
+    # control-plane collectives (IPC handle, shard streams) go over gloo: no data-path collective exists
+    ctl = dist.new_group(backend="gloo") if world > 1 else None
+    cpus = pin_rank_cpus(local, rank, world)
+    sharded = world > 1 and args.workload == "c3"
+    stream = torch.cuda.current_stream()
+    sp = stream.cuda_stream
+    multi = None
+
+    def gen(first, n):
+        return synth.plasma_frames_torch(n, W, H, bits=bits, seed=1, first=first, device=dev).reshape(n, P)
+
+    if sharded:
+        # ONE sequence of --sequence-frames frames, cut into contiguous ranges; this rank's shard stays resident
+        seq_total = args.sequence_frames
+        f0, f1 = sharding.frame_range(seq_total, world, rank)
+        F = f1 - f0
+        free_b, _ = torch.cuda.mem_get_info()
+        per_frame = P * 2 + 2 * P + P // 16 + 1
+        fit = int(0.80 * free_b // per_frame)
+        if F > fit:
+            raise SystemExit(f"shard of {F} frames ({F * per_frame / 1e9:.0f} GB in + out) does not fit {free_b / 1e9:.0f} GB of HBM: "
+                             "use more GPUs or a shorter --sequence-frames")
+        frames = torch.empty((F, P), dtype=torch.uint16, device=dev)
+        for c in range(0, F, 64):
+            m = min(64, F - c)
+            frames[c:c + m] = gen(f0 + c, m)
+        delta = gen(0, 1).reshape(P)
+        ctx = fpv.Context(W, H, shift, False, max_batch=min(F, 8192), device=local)
+        # the one-frame halo: rank 0 splits the delta frame, every other rank copies the planes device to device
+        t_ipc = time.perf_counter()
+        if rank == 0:
+            ctx.set_delta_raw_device(delta.data_ptr(), sp)
+            torch.cuda.synchronize()
+            box = [ctx.delta_ipc_export()]
+        else:
+            box = [None]
+        dist.broadcast_object_list(box, src=0, group=ctl)
+        if rank != 0:
+            ctx.delta_ipc_import(box[0])
+        dist.barrier(group=ctl)          # rank 0 keeps the exported image alive until everyone has copied it
+        t_ipc = time.perf_counter() - t_ipc
+        # proof that the halo arrived: frame 0 encoded against it is all zeros on every rank (frame == delta frame)
+        z = [torch.empty((1, P), dtype=torch.uint8, device=dev) for _ in range(2)]
+        zp = torch.empty((1, P // 16), dtype=torch.uint8, device=dev)
+        zf = torch.empty(1, dtype=torch.uint8, device=dev)
+        ctx.encode_device(delta.data_ptr(), 1, zf.data_ptr(), z[0].data_ptr(), z[1].data_ptr(), zp.data_ptr(), stream=sp)
+        torch.cuda.synchronize()
+        halo_ok = bool(int(zf.item()) & 1) and int(z[0].max().item()) == 0 and int(z[1].max().item()) == 0
+        oks = [None] * world
+        dist.all_gather_object(oks, halo_ok, group=ctl)
+        multi = {"sequence_frames": seq_total, "frame_range_rank0": [f0, f1], "frames_per_gpu": F,
+                 "delta_halo": {"how": "fpv_delta_ipc_export on rank 0 -> 64-byte handle over gloo -> fpv_delta_ipc_import "
+                                       "(cudaIpcOpenMemHandle + device-to-device copy) on every other rank",
+                                "bytes_per_gpu": P * 2, "seconds_incl_handshake": t_ipc,
+                                "frame0_encodes_to_zero_on_every_rank": all(oks)}}
+        del z, zp, zf
+    else:
+        F = args.frames
+        seq_total = world * F
+        # rank r owns frames [r*F, (r+1)*F) of the sequence; the delta frame is frame 0 (encode.cc:87-90)
+        frames = torch.empty((F, P), dtype=torch.uint16, device=dev)
+        for c in range(0, F, 64):
+            m = min(64, F - c)
+            frames[c:c + m] = gen(rank * F + c, m)
+        delta = gen(0, 1).reshape(P)
+        ctx = fpv.Context(W, H, shift, False, max_batch=F, device=local)
+        ctx.set_delta_raw_device(delta.data_ptr(), sp)
     d_high = torch.empty((F, P), dtype=torch.uint8, device=dev)
     d_low = torch.empty((F, P), dtype=torch.uint8, device=dev)
     d_prev = torch.empty((F, P // 16), dtype=torch.uint8, device=dev)
     d_flags = torch.empty(F, dtype=torch.uint8, device=dev)
-    stream = torch.cuda.current_stream()
-    sp = stream.cuda_stream
-
-    ctx = fpv.Context(W, H, shift, False, max_batch=F, device=local)
-    ctx.set_delta_raw_device(delta.data_ptr(), sp)
 
     def step():
         ctx.encode_device(frames.data_ptr(), F, d_flags.data_ptr(), d_high.data_ptr(), d_low.data_ptr(),
@@ -280,34 +472,38 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step = float(t.item()) / args.steps
-    value = world * F * P * 2 / (ms_step * 1e-3) / 1e9
+    value = seq_total * P * 2 / (ms_step * 1e-3) / 1e9
     flags_host = d_flags.cpu().numpy()
 
     peak, peak_src = measured_peak()
+    # one step = ceil(F / max_batch) launches of the fused kernel; their summed time covers F frames per step
+    k_step_ms = kms / args.steps
     k_avg_ms = kms / max(kcnt, 1)
-    achieved = ENC_BYTES_PER_PX * F * P / (k_avg_ms * 1e-3) / 1e9
+    achieved = ENC_BYTES_PER_PX * F * P / (k_step_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "k_encode_fast", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": ncu_traffic("encode", ENC_BYTES_PER_PX * F * P),
                 "traffic_source": "profiles/traffic.json (ncu --set full dram__bytes_read.sum + dram__bytes_write.sum, scaled per byte)",
                 "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": ENC_BYTES_PER_PX * F * P, "kernel_ms": k_avg_ms,
-                "kernel_share_of_step": k_avg_ms / ms_step if world == 1 else None}
+                "algorithmic_bytes_per_launch": ENC_BYTES_PER_PX * F * P * args.steps / max(kcnt, 1), "kernel_ms": k_avg_ms,
+                "launches_per_step": kcnt / args.steps, "kernel_ms_per_step": k_step_ms,
+                "kernel_share_of_step": k_step_ms / ms_step if world == 1 else None}
 
     # ---- decode (inverse transform) on the planes just produced: extra, device-resident -------------
     decode = None
+    Fd = min(F, 1184 if P < 4000000 else 592)     # decode legs: one full wave of the decode kernel
     if not args.no_decode:
-        d_out = torch.empty((F, P), dtype=torch.int16, device=dev)
+        d_out = torch.empty((Fd, P), dtype=torch.int16, device=dev)
         dsteps = max(3, min(args.steps, 20))
         for _ in range(2):
-            ctx.decode_device(d_high.data_ptr(), d_low.data_ptr(), d_flags.data_ptr(), F, d_out.data_ptr(),
+            ctx.decode_device(d_high.data_ptr(), d_low.data_ptr(), d_flags.data_ptr(), Fd, d_out.data_ptr(),
                               options=fpv.DEC_UNEXTRACT, stream=sp)
         torch.cuda.synchronize()
-        ok = bool(torch.equal(d_out.view(torch.uint16), frames))
+        ok = bool(torch.equal(d_out.view(torch.uint16), frames[:Fd]))
         ctx.enable_kernel_timing(True)
         t_a = time.perf_counter()
         e0.record(stream)
         for _ in range(dsteps):
-            ctx.decode_device(d_high.data_ptr(), d_low.data_ptr(), d_flags.data_ptr(), F, d_out.data_ptr(),
+            ctx.decode_device(d_high.data_ptr(), d_low.data_ptr(), d_flags.data_ptr(), Fd, d_out.data_ptr(),
                               options=fpv.DEC_UNEXTRACT, stream=sp)
         e1.record(stream)
         torch.cuda.synchronize()
@@ -319,15 +515,15 @@ def main():
         if world > 1:
             dist.all_reduce(td, op=dist.ReduceOp.MAX)
         dms = float(td.item())
-        dach = DEC_BYTES_PER_PX * F * P / (dk / max(dc, 1) * 1e-3) / 1e9
-        decode = {"metric": "decode_transform_raw_pixel_throughput", "value": world * F * P * 2 / (dms * 1e-3) / 1e9,
-                  "unit": "GB/s", "frames_per_s": world * F / (dms * 1e-3), "ms_per_step": dms, "steps": dsteps,
+        dach = DEC_BYTES_PER_PX * Fd * P / (dk / max(dc, 1) * 1e-3) / 1e9
+        decode = {"metric": "decode_transform_raw_pixel_throughput", "value": world * Fd * P * 2 / (dms * 1e-3) / 1e9,
+                  "unit": "GB/s", "frames_per_s": world * Fd / (dms * 1e-3), "frames_per_gpu": Fd, "ms_per_step": dms, "steps": dsteps,
                   "round_trip_exact": ok,
                   "roofline": {"bound": "hbm (chain-latency limited, see DESIGN.md)",
                                "kernel": ("k_decode_pair" if (W % 16 == 0 and 64 <= W <= 1280) else
                                           "k_decode_pair (split mode)" if (W % 32 == 0 and W <= 2560) else "k_decode_simd"),
                                "achieved": dach, "peak": peak, "unit": "GB/s", "frac": dach / peak,
-                               "traffic": ncu_traffic("decode", DEC_BYTES_PER_PX * F * P)}}
+                               "traffic": ncu_traffic("decode", DEC_BYTES_PER_PX * Fd * P)}}
         del d_out
 
     # ---- GPU entropy coder on the planes just produced: extra, device-resident ----------------------
@@ -367,7 +563,8 @@ def main():
     # ---- e2e: host buffers through the C ABI, copies inside the timed region -----------------------
     e2e, e2e_bufs = None, ()
     if not args.no_e2e:
-        Fe, B = min(args.e2e_frames, F), args.e2e_batch
+        big = P >= 4000000                      # 2048x2048: 8.4 MB per frame, keep the pinned staging per rank modest
+        Fe, B = min(args.e2e_frames if not big else 128, F), (args.e2e_batch if not big else 16)
         Fe = (Fe // B) * B or B
         ectx = fpv.Context(W, H, shift, False, max_batch=B, device=local)
         ectx.set_delta_raw_device(delta.data_ptr(), sp)
@@ -494,59 +691,114 @@ def main():
                       "what": "fpv_decode_submit/fpv_wait on pinned host buffers (planes in, raw file words out), slots overlapped (a batch's kernel alone takes 1 ms: the chain)"}
         ho.free()
 
-    # ---- whole codec: fpvc::Encoder (GPU transform + host brotli + framing) on host frames ----------
+    # ---- whole codec: fpvc::Encoder (GPU transform + host brotli + framing) on host frames, every rank at once ------
     stream_leg = None
-    if not args.no_e2e and rank == 0 and world == 1 and not args.no_stream:
+    if not args.no_e2e and not args.no_stream:
         from fusion_power_video_b200 import host as fpv_host
 
-        ncpu = os.cpu_count() or 1
-        ns = args.stream_frames
+        ncpu = len(cpus)                      # this rank's share of the host cores (all of them at N = 1)
+        big = P >= 4000000
+        ns = args.stream_frames if not big else 96
+        if world > 1:
+            ns = max(32, ns // world)
         fr = np.ascontiguousarray(np.tile(hin.array, ((ns + Fe - 1) // Fe, 1))[:ns])   # the stream repeats the e2e frames
-        fpv_host.time_encode(fr[:2], W, H, shift, False, threads=ncpu, batch=8)   # warm-up: context, pinned pools
+
+        def timed_encode(n_rep, **kw):
+            """best-of-n_rep seconds of Init + CompressFrame x ns + Finish, all ranks started together; max over ranks"""
+            best, size = None, 0
+            for _ in range(n_rep):
+                if world > 1:
+                    dist.barrier(group=ctl)
+                t, size = fpv_host.time_encode(fr, W, H, shift, False, threads=ncpu, device=local, **kw)
+                tt = [None] * world
+                if world > 1:
+                    dist.all_gather_object(tt, t, group=ctl)
+                    t = max(tt)
+                best = t if best is None else min(best, t)
+            return best, size
+
+        fpv_host.time_encode(fr[:2], W, H, shift, False, threads=ncpu, batch=8, device=local)   # warm-up: context, pinned pools
         t_a = time.perf_counter()
-        best, size = None, 0
-        for _ in range(3):
-            t, size = fpv_host.time_encode(fr, W, H, shift, False, threads=ncpu, batch=8)
-            best = t if best is None else min(best, t)
+        best, size = timed_encode(3 if world == 1 else 2, batch=8)
         windows.append((t_a, time.perf_counter()))
         stream_leg = {"what": "fpvc::Encoder Init + CompressFrame x n + Finish (benchmark.cc:153-180 window): pinned H2D, "
-                              "GPU transform, D2H, brotli q1 on host threads, framing",
-                      "value": ns * P * 2 / best / 1e9, "unit": "GB/s", "frames_per_s": ns / best, "mp_per_s": ns * P / best / 1e6,
-                      "frames": ns, "host_threads": ncpu, "stream_bytes": int(size), "bpp": size * 8.0 / (ns * P),
+                              "GPU transform, D2H, brotli q1 on host threads, framing; one Encoder per rank / GPU, all at once",
+                      "value": world * ns * P * 2 / best / 1e9, "unit": "GB/s", "frames_per_s": world * ns / best,
+                      "mp_per_s": world * ns * P / best / 1e6, "frames": world * ns, "host_threads": ncpu * world,
+                      "stream_bytes_rank0": int(size), "bpp": size * 8.0 / (ns * P),
                       "bound": "host brotli (about 70 MP/s per core) -- the transform is off the critical path"}
 
         # the same codec with the entropy stage on the GPU (brotli-compatible streams, no host brotli)
-        fpv_host.time_encode(fr[:64], W, H, shift, False, threads=ncpu, batch=32, gpu_entropy=True)
+        fpv_host.time_encode(fr[:32], W, H, shift, False, threads=ncpu, batch=32 if not big else 8, gpu_entropy=True, device=local)
         t_a = time.perf_counter()
-        bestg, sizeg = None, 0
-        for _ in range(3):
-            t, sizeg = fpv_host.time_encode(fr, W, H, shift, False, threads=ncpu, batch=32, gpu_entropy=True)
-            bestg = t if bestg is None else min(bestg, t)
+        bestg, sizeg = timed_encode(3 if world == 1 else 2, batch=32 if not big else 8, gpu_entropy=True)
         windows.append((t_a, time.perf_counter()))
         stream_leg["gpu_entropy"] = {
             "what": "same Encoder with GpuOptions::gpu_entropy: transform + chunk-parallel Huffman coding (valid RFC 7932 "
                     "streams the reference decoder reads) + framing on the GPU; D2H carries only the coded bytes",
-            "value": ns * P * 2 / bestg / 1e9, "unit": "GB/s", "frames_per_s": ns / bestg, "mp_per_s": ns * P / bestg / 1e6,
-            "stream_bytes": int(sizeg), "bpp": sizeg * 8.0 / (ns * P), "batch": 32,
-            "bound": "PCIe: 2 B/px in, about 1 B/px out"}
+            "value": world * ns * P * 2 / bestg / 1e9, "unit": "GB/s", "frames_per_s": world * ns / bestg,
+            "mp_per_s": world * ns * P / bestg / 1e6, "stream_bytes_rank0": int(sizeg), "bpp": sizeg * 8.0 / (ns * P),
+            "batch": 32 if not big else 8, "bound": "PCIe: 2 B/px in, about 1 B/px out"}
 
         # decode side of the codec: StreamingDecoder (host brotli decode on all cores + GPU inverse transform +
-        # UnextractFrame on the GPU) on the stream just described, both entropy variants
-        nd = min(ns, 256)
-        dec = {}
-        for name, ge in (("brotli_stream", False), ("gpu_entropy_stream", True)):
-            st = fpv_host.encode_stream(fr[:nd], W, H, shift, False, threads=ncpu, batch=32, gpu_entropy=ge)
-            fpv_host.decode_stream(st, nd, W, H, block=0, batch=32, raw_shift=shift)
-            t_a = time.perf_counter()
-            bestd, okd = None, False
-            for _ in range(2):
-                out, sec = fpv_host.decode_stream(st, nd, W, H, block=0, batch=32, raw_shift=shift, return_time=True)
-                bestd = sec if bestd is None else min(bestd, sec)
-                okd = bool(np.array_equal(out, fr[:nd]))
-            windows.append((t_a, time.perf_counter()))
-            dec[name] = {"value": nd * P * 2 / bestd / 1e9, "unit": "GB/s", "frames_per_s": nd / bestd, "frames": nd,
-                         "round_trip_exact": okd, "stream_bytes": len(st)}
-        stream_leg["decode"] = dec
+        # UnextractFrame on the GPU) on the stream just described, both entropy variants (rank 0, N = 1)
+        if world == 1:
+            nd = min(ns, 256 if not big else 32)
+            dec = {}
+            for name, ge in (("brotli_stream", False), ("gpu_entropy_stream", True)):
+                st = fpv_host.encode_stream(fr[:nd], W, H, shift, False, threads=ncpu, batch=32, gpu_entropy=ge)
+                fpv_host.decode_stream(st, nd, W, H, block=0, batch=32, raw_shift=shift)
+                t_a = time.perf_counter()
+                bestd, okd = None, False
+                for _ in range(2):
+                    out, sec = fpv_host.decode_stream(st, nd, W, H, block=0, batch=32, raw_shift=shift, return_time=True)
+                    bestd = sec if bestd is None else min(bestd, sec)
+                    okd = bool(np.array_equal(out, fr[:nd]))
+                windows.append((t_a, time.perf_counter()))
+                dec[name] = {"value": nd * P * 2 / bestd / 1e9, "unit": "GB/s", "frames_per_s": nd / bestd, "frames": nd,
+                             "round_trip_exact": okd, "stream_bytes": len(st)}
+            stream_leg["decode"] = dec
+
+    # ---- merged-stream check (N > 1): shards of a subsample of the sequence, encoded per rank, merge to the stream
+    #      one GPU writes for the same frames ------------------------------------------------------------------------
+    if sharded and not args.no_e2e:
+        import hashlib
+        from fusion_power_video_b200 import host as fpv_host
+
+        n_sub = 4 * world
+        idx = [k * (seq_total // n_sub) for k in range(n_sub)]            # spread over the whole sequence; idx[0] = the delta frame
+        sa, sb = sharding.frame_range(n_sub, world, rank)
+        mine = torch.cat([gen(idx[j], 1) for j in range(sa, sb)]).cpu().numpy()
+        delta_np = delta.cpu().numpy()
+        local_stream = fpv_host.encode_stream(mine, W, H, shift, False, threads=len(cpus), batch=4, delta=delta_np, device=local)
+        merged = sharding.gather_stream(local_stream, group=ctl)
+        if rank == 0:
+            every = torch.cat([gen(i, 1) for i in idx]).cpu().numpy()
+            single = fpv_host.encode_stream(every, W, H, shift, False, threads=len(cpus), batch=4, delta=delta_np, device=local)
+            back = fpv_host.decode_stream(merged, n_sub, W, H, block=0, batch=4, raw_shift=shift)
+            multi["merged_stream"] = {
+                "frames": n_sub, "sequence_indices": idx, "bytes": len(merged),
+                "sha256_merged": hashlib.sha256(merged).hexdigest(), "sha256_single_gpu": hashlib.sha256(single).hexdigest(),
+                "matches_single_gpu_stream": merged == single, "round_trip_exact": bool(np.array_equal(back, every)),
+                "what": "every rank encodes its range of the subsample with fpvc::Encoder (host brotli), rank 0 merges the "
+                        "shard streams (sharding.merge_shards: chunks in rank order, footer offsets = prefix sum) and compares "
+                        "with the stream its own single GPU writes for all of the subsample"}
+
+    # ---- the other BASELINE geometries, same measurement (N = 1 line only) -------------------------------------------
+    configs = None
+    if world == 1 and not args.no_configs and not explicit_workload:
+        peak_c, _ = measured_peak()
+        configs = {}
+        for nm in ("c1", "c3"):
+            configs[nm], wnd = geometry_leg(fpv, synth, torch, dev, local, nm, peak_c)
+            windows.append(wnd)
+
+    # ---- BASELINE configs[4]: paced real-time ingest (N = 1 line only) ------------------------------------------------
+    ingest = None
+    if world == 1 and not args.no_ingest and not args.no_e2e and not explicit_workload:
+        from fusion_power_video_b200 import host as fpv_host
+
+        ingest = ingest_leg(fpv_host, synth, len(cpus), local, args.ingest_seconds)
 
     clocks = sampler.stop(windows) if rank == 0 else None
 
@@ -587,14 +839,18 @@ def main():
         line = {
             "metric": "encode_transform_raw_pixel_throughput", "value": value, "unit": "GB/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "frames_per_s": world * F / (ms_step * 1e-3),
+            "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "frames_per_s": seq_total / (ms_step * 1e-3),
             "config": {"workload": desc, "xsize": W, "ysize": H, "bits": bits, "shift": shift,
-                       "frames_per_gpu_per_step": F, "parallelism": f"frame-range x{world}, no collective",
+                       "frames_per_gpu_per_step": F, "frames_per_step": seq_total,
+                       "parallelism": (f"one {seq_total}-frame sequence cut into {world} contiguous frame ranges, delta frame by peer copy (CUDA IPC), no collective"
+                                       if sharded else f"frame-range x{world}, no collective"),
                        "l2": f"inputs larger than L2: {F * P * 2 / 1e6:.0f} MB raw + {F * P * 2.0625 / 1e6:.0f} MB out per step vs 126 MB L2",
                        "flags_histogram": {int(u): int(c) for u, c in zip(uniq, cnt)}},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clocks, "decode": decode, "e2e_stream": e2e_stream, "decode_e2e": decode_e2e, "entropy": entropy, "stream": stream_leg,
+            "multi_gpu": multi, "configs": configs, "ingest": ingest,
+            "host": {"cpus_per_rank": len(cpus), "cpu_count": os.cpu_count()},
         }
         print(json.dumps(line), flush=True)
     if world > 1:

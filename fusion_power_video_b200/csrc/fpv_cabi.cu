@@ -187,7 +187,7 @@ int encode_device_chunked(fpv_ctx* c, int scratch_idx, const uint16_t* frames, u
   if (!c->encode_ok)
     return fail(c, FPV_ERR_UNSUPPORTED,
                 "encode requires xsize % 4 == 0 and ysize % 4 == 0 (the reference reads out of "
-                "bounds otherwise, fusion_power_video.cc:577-578)");
+                "bounds otherwise, fusion_power_video.cc:577-578) and shift <= 8 for big-endian data");
   if (mode_has_low(c->g.mode) && !low) return fail(c, FPV_ERR_INVALID_ARG, "low plane buffer is NULL");
   int rc = ensure_scratch(c, scratch_idx);
   if (rc != FPV_OK) return rc;
@@ -261,9 +261,13 @@ int fpv_create(fpv_ctx** out, int device, uint32_t xsize, uint32_t ysize, int sh
       (uint64_t)xsize * ysize > 1000000000ull)
     return fail(nullptr, FPV_ERR_INVALID_ARG, "invalid image dimensions");  // .cc:891-895
   int mode = pick_split_mode(shift, big_endian);
+  // Big-endian data with shift > 8: the reference's Frame constructor shifts by 8 - shift there (undefined), but its
+  // UnextractFrame (.cc:850-862) is fine, so such a context decodes and refuses to encode.
+  const bool decode_only = mode < 0 && big_endian && shift > 8 && shift <= 16;
+  if (decode_only) mode = kBE0;
   if (mode < 0)
     return fail(nullptr, FPV_ERR_UNSUPPORTED,
-                "shift must be 0..16 (0..8 for big-endian data: the reference shifts by 8 - shift)");
+                "shift must be 0..16 (0..8 to ENCODE big-endian data: the reference shifts by 8 - shift)");
   if (max_batch == 0 || max_batch > 65535)
     return fail(nullptr, FPV_ERR_INVALID_ARG, "max_batch must be 1..65535 (frames are a grid dimension of the small kernels)");
   int ndev = 0;
@@ -285,7 +289,7 @@ int fpv_create(fpv_ctx** out, int device, uint32_t xsize, uint32_t ysize, int sh
   c->g.PW = xsize / 4; c->g.PP = (uint64_t)(xsize / 4) * (ysize / 4);
   c->g.shift = shift; c->g.big_endian = big_endian ? 1 : 0; c->g.mode = mode;
   c->max_batch = max_batch;
-  c->encode_ok = (xsize % 4 == 0) && (ysize % 4 == 0);
+  c->encode_ok = (xsize % 4 == 0) && (ysize % 4 == 0) && !decode_only;
   c->tune.num_sms = prop.multiProcessorCount;
   c->tune.max_smem_optin = (int)prop.sharedMemPerBlockOptin;
   if (const char* v = getenv("FPV_STAGES")) c->tune.stages = atoi(v);

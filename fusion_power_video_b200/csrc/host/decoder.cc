@@ -36,9 +36,19 @@ struct GpuDecoder {
   Pinned out;
   std::unique_ptr<Pool> pool;
 
-  ~GpuDecoder() {
+  ~GpuDecoder() { close(); }
+
+  // Back to the unopened state (a decoder that is re-initialised with another geometry starts over).
+  void close() {
     pool.reset();   // no parse task may outlive the buffers
     if (ctx) fpv_destroy(ctx);
+    ctx = nullptr;
+    for (Set& st : sets) {
+      st.high.reset();
+      st.low.reset();
+      st.flags.reset();
+    }
+    out.reset();
   }
 
   bool alloc_set(Set& st) {
@@ -141,6 +151,11 @@ StreamingDecoder::StreamingDecoder(const GpuOptions& options) : impl_(new Impl) 
 StreamingDecoder::~StreamingDecoder() = default;
 
 void StreamingDecoder::SetRawOutput(int shift, bool big_endian) {
+  if (impl_->gpu.ctx && (shift != impl_->shift || big_endian != impl_->big_endian || !impl_->raw_output)) {
+    // shift and endianness are properties of the GPU context, which exists (and holds the delta frame) by now
+    FPV_FAIL("StreamingDecoder::SetRawOutput must be called before the first Decode(); ignored");
+    return;
+  }
   impl_->raw_output = true;
   impl_->shift = shift;
   impl_->big_endian = big_endian;
@@ -288,6 +303,12 @@ bool RandomAccessDecoder::Init(const uint8_t* data, size_t size) {
   if (chunk > size - 8) return FPV_FAIL("out of bounds");
   if (chunk < 5) return FPV_FAIL("delta frame too small");
   if (data[12] != kChunkDelta) return FPV_FAIL("must begin with delta frame");
+  if (s.gpu.ctx && (s.gpu.W != s.xsize || s.gpu.H != s.ysize)) {
+    // re-initialised on a stream of another geometry: the contexts and staging buffers start over
+    s.gpu.close();
+    s.preview_gpu.close();
+  }
+  s.offsets.clear();
   if (!s.gpu.ctx && !s.gpu.open(s.opt, s.xsize, s.ysize, 0, false, s.opt.batch)) return false;
   const uint8_t* core = data + 13;
   const size_t core_size = chunk - 5;

@@ -47,6 +47,11 @@ void UnextractFrame(const uint16_t* img, size_t xsize, size_t ysize, int shift, 
 // Extension: the reference only prints to stderr (which this library does too).
 const std::string& LastError();
 
+// Extension: the encoders / decoders recycle their page-locked staging buffers through a process-wide cache (pinning
+// memory costs about a millisecond per few MB), bounded by FPV_PIN_CACHE_MB (default 2048).  Long-lived processes
+// that are done with a geometry call this to hand the cached blocks back to the driver; returns the bytes released.
+size_t TrimPinnedCache();
+
 // Tuning knobs (extension).  device: CUDA device index; batch: frames per GPU
 // submission (the encoder submits earlier when its pipeline is idle).
 struct GpuOptions {

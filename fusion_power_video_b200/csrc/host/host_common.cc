@@ -1,6 +1,7 @@
 // host_common.cc -- error reporting, brotli glue, worker pool, UnextractFrame.
 #include <brotli/decode.h>
 #include <brotli/encode.h>
+#include <stdlib.h>
 #include <string.h>
 #include <sys/resource.h>
 #include <sys/syscall.h>
@@ -94,7 +95,15 @@ namespace {
 std::mutex g_pin_m;
 std::multimap<size_t, void*> g_pin_cache;
 size_t g_pin_cached_bytes = 0;
-constexpr size_t kPinCacheLimit = (size_t)3 << 30;
+// Bound of the cache: FPV_PIN_CACHE_MB (default 2048; 0 disables caching).  Cached blocks are returned to the driver
+// by fpvc::TrimPinnedCache() or when the limit is exceeded, never silently kept beyond it.
+size_t PinCacheLimit() {
+  static const size_t limit = [] {
+    const char* v = getenv("FPV_PIN_CACHE_MB");
+    return (size_t)(v ? strtoull(v, nullptr, 10) : 2048) << 20;
+  }();
+  return limit;
+}
 }  // namespace
 
 void* PinnedAcquire(size_t bytes) {
@@ -117,13 +126,26 @@ void PinnedRelease(void* p, size_t bytes) {
   if (bytes == 0) bytes = 1;
   {
     std::lock_guard<std::mutex> l(g_pin_m);
-    if (g_pin_cached_bytes + bytes <= kPinCacheLimit) {
+    if (g_pin_cached_bytes + bytes <= PinCacheLimit()) {
       g_pin_cache.emplace(bytes, p);
       g_pin_cached_bytes += bytes;
       return;
     }
   }
   fpv_host_free(p);
+}
+
+size_t PinnedTrim() {
+  std::multimap<size_t, void*> drop;
+  size_t bytes = 0;
+  {
+    std::lock_guard<std::mutex> l(g_pin_m);
+    drop.swap(g_pin_cache);
+    bytes = g_pin_cached_bytes;
+    g_pin_cached_bytes = 0;
+  }
+  for (auto& e : drop) fpv_host_free(e.second);
+  return bytes;
 }
 
 // ---- Pool ----------------------------------------------------------------------------
@@ -200,6 +222,8 @@ void ParallelFor(Pool* pool, size_t n, const std::function<void(size_t)>& body) 
 }
 
 }  // namespace internal
+
+size_t TrimPinnedCache() { return internal::PinnedTrim(); }
 
 void UnextractFrame(const uint16_t* img, size_t xsize, size_t ysize, int shift, bool big_endian, uint8_t* out) {
   const size_t n = xsize * ysize;

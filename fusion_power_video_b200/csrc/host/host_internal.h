@@ -72,6 +72,7 @@ bool ParseCore(const uint8_t* in, size_t size, size_t plane_bytes, uint8_t* flag
 // blocks go to a small process-wide cache and are handed out again by size.
 void* PinnedAcquire(size_t bytes);
 void PinnedRelease(void* p, size_t bytes);
+size_t PinnedTrim();   // frees every cached block; returns the bytes released
 
 class Pinned {
  public:

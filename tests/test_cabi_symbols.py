@@ -30,8 +30,9 @@ def test_version_and_error_paths_without_device():
     # invalid geometry is rejected before any CUDA call
     assert L.fpv_create(C.byref(h), 0, 0, 16, 0, 0, 1) == 1
     assert b"dimensions" in L.fpv_last_error(None)
-    # big-endian shift > 8 is undefined in the reference (shift by 8 - shift)
-    assert L.fpv_create(C.byref(h), 0, 16, 16, 9, 1, 1) == 3
+    # a shift beyond 16 bits is refused outright (big-endian shift 9..16 gives a decode-only context, see the GPU tests)
+    assert L.fpv_create(C.byref(h), 0, 16, 16, 17, 1, 1) == 3
+    assert L.fpv_create(C.byref(h), 0, 16, 16, 3, 0, 70000) == 1   # max_batch is a grid dimension: <= 65535
     # NULL context is handled
     assert L.fpv_wait(None, 0) == 1
     assert L.fpv_plane_bytes(None) == 0

@@ -148,6 +148,25 @@ def test_big_endian_unextract(oracle):
             assert np.array_equal(raw[i].view(np.uint8), exp)
 
 
+@pytest.mark.parametrize("shift", [9, 12, 16])
+def test_big_endian_shift_above_8_is_a_decode_only_context(oracle, shift):
+    """The reference's Frame constructor is undefined for big-endian data with shift > 8 (it shifts by 8 - shift,
+    .cc:407-412) but UnextractFrame (.cc:850-862) is not: such a context decodes and refuses to encode."""
+    W, H, n = 96, 8, 3
+    rng = np.random.default_rng(shift)
+    high = rng.integers(0, 256, (n, W * H), dtype=np.uint8)
+    low = rng.integers(0, 256, (n, W * H), dtype=np.uint8)
+    flags = np.array([2, 0, 2], np.uint8)
+    with fpv.Context(W, H, shift, 1, max_batch=4) as ctx:
+        raw = ctx.decode(high, low, flags, fpv.DEC_UNEXTRACT)
+        for i in range(n):
+            exp = oracle.unextract(oracle.inverse(high[i], low[i], None, W, H, int(flags[i])), shift, 1)
+            assert np.array_equal(raw[i].view(np.uint8), exp)
+        with pytest.raises(fpv.FpvError) as e:
+            ctx.encode(np.zeros((1, W * H), np.uint16))
+        assert e.value.code == 3
+
+
 def test_use_delta_without_delta_frame_is_an_error():
     with fpv.Context(16, 16, 0, 0, max_batch=1) as ctx:
         with pytest.raises(fpv.FpvError) as e:
