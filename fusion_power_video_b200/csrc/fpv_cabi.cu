@@ -116,10 +116,11 @@ int ensure_scratch(fpv_ctx* c, int idx) {
   if (s.stats) return FPV_OK;
   uint32_t cap = c->max_batch;
   FPV_CUDA(cudaMalloc(&s.stats, sizeof(FrameStat) * (size_t)cap));
+  FPV_CUDA(cudaMemset(s.stats, 0, sizeof(FrameStat) * (size_t)cap));   // the fast path keeps them zero between calls
   FPV_CUDA(cudaMalloc(&s.lists, sizeof(uint32_t) * 3 * (size_t)cap));
-  FPV_CUDA(cudaMalloc(&s.counts, sizeof(uint32_t) * 4));
-  FPV_CUDA(cudaMalloc(&s.preview_raw, (size_t)cap * (c->g.PP ? c->g.PP : 1)));
-  uint32_t init[4] = {0, 0, 0, 3};  // first guess: USE_DELTA | USE_CG
+  FPV_CUDA(cudaMalloc(&s.counts, sizeof(uint32_t) * 5));
+  // (preview_raw: scratch of the generic path only, allocated by enqueue_encode when that path first runs)
+  uint32_t init[5] = {0, 0, 0, 3, 3};  // first guess: USE_DELTA | USE_CG
   FPV_CUDA(cudaMemcpy(s.counts, init, sizeof init, cudaMemcpyHostToDevice));
   s.cap = cap;
   return FPV_OK;

@@ -139,6 +139,20 @@ __device__ __forceinline__ uint2 pack8(uint32_t a, uint32_t b, uint32_t c, uint3
   return make_uint2(__byte_perm(a, b, 0x6420), __byte_perm(c, d, 0x6420));
 }
 
+// ClampedGradient residual of four consecutive preview pixels (one word) on the preview's flat array (.cc:575-586):
+// c = the word, cm = the word before it in flat order (only its last pixel is used), n / nm = the same one row up.
+__device__ __forceinline__ uint32_t finalize_word(uint32_t c, uint32_t cm, uint32_t n, uint32_t nm) {
+  const uint32_t wv = __funnelshift_l(cm, c, 8);    // bytes i-1 .. i+2
+  const uint32_t nwv = __funnelshift_l(nm, n, 8);
+  // lane form: pixels (0,1) and (2,3)
+  const uint32_t c01 = __byte_perm(c, 0u, 0x4140), c23 = __byte_perm(c, 0u, 0x4342);
+  const uint32_t n01 = __byte_perm(n, 0u, 0x4140), n23 = __byte_perm(n, 0u, 0x4342);
+  const uint32_t w01 = __byte_perm(wv, 0u, 0x4140), w23 = __byte_perm(wv, 0u, 0x4342);
+  const uint32_t q01 = __byte_perm(nwv, 0u, 0x4140), q23 = __byte_perm(nwv, 0u, 0x4342);
+  const uint32_t r01 = sub2(c01, cg2(n01, w01, q01)), r23 = sub2(c23, cg2(n23, w23, q23));
+  return __byte_perm(r01, r23, 0x6420);
+}
+
 // ---- q form / S form (fast encode kernel) -------------------------------------
 
 constexpr uint32_t kHiBytes = 0xff00ff00u;
@@ -211,9 +225,10 @@ struct FrameStat {
   // raw high byte has bit k set.  Enough to decide USE_DELTA in all but
   // near-constant frames (see k_decide), with no shared-memory atomics.
   uint32_t dbits[8];
-  uint32_t delta_known;  // USE_DELTA decision already taken (redo passes keep it)
+  uint32_t delta_known;  // USE_DELTA decision already taken (redo passes keep it)            (generic path)
   uint32_t delta_dec;
-  uint32_t pad_[2];
+  uint32_t tickets;      // fast path: warps that have published their part of the frame in this pass
+  uint32_t pad_;
 };
 
 // EstimateEntropy (.cc:235-244) evaluated by one 256-thread block, one bin per

@@ -233,18 +233,6 @@ __global__ void k_finalize(const FrameStat* stats, const uint8_t* preview_raw, u
 // thread-item per launch slot, all loads issued up front (two 128-bit and two 32-bit ones; the
 // 32-bit ones hit lines the neighbour threads fetch).  The 4-pixel kernel above is latency bound:
 // its threads walk ~30 dependent iterations.
-__device__ __forceinline__ uint32_t finalize_word(uint32_t c, uint32_t cm, uint32_t n, uint32_t nm) {
-  const uint32_t wv = __funnelshift_l(cm, c, 8);    // bytes i-1 .. i+2
-  const uint32_t nwv = __funnelshift_l(nm, n, 8);
-  // lane form: pixels (0,1) and (2,3)
-  const uint32_t c01 = __byte_perm(c, 0u, 0x4140), c23 = __byte_perm(c, 0u, 0x4342);
-  const uint32_t n01 = __byte_perm(n, 0u, 0x4140), n23 = __byte_perm(n, 0u, 0x4342);
-  const uint32_t w01 = __byte_perm(wv, 0u, 0x4140), w23 = __byte_perm(wv, 0u, 0x4342);
-  const uint32_t q01 = __byte_perm(nwv, 0u, 0x4140), q23 = __byte_perm(nwv, 0u, 0x4342);
-  const uint32_t r01 = sub2(c01, cg2(n01, w01, q01)), r23 = sub2(c23, cg2(n23, w23, q23));
-  return __byte_perm(r01, r23, 0x6420);
-}
-
 __global__ void __launch_bounds__(256)
 k_finalize16(const FrameStat* __restrict__ stats, const uint8_t* __restrict__ preview_raw,
              uint8_t* __restrict__ preview, uint8_t* __restrict__ flags, uint32_t* counts, uint32_t n,
@@ -478,7 +466,7 @@ int enqueue_split(const Geom& g, const uint16_t* frames, uint32_t n, uint8_t* hi
 }
 
 bool encode_fast_supported(const Geom& g, const EncodeTuning& t) {
-  if (g.W % 8 != 0 || g.W < 8) return false;
+  if (g.W % 16 != 0 || g.W < 16) return false;   // 8 pixels per lane; the in-kernel preview pass works on words of 4 preview pixels
   if (g.W > 32 * 31 * 8) return false;  // at most 31 compute warps + 1 producer
   if (g.W > 4096) return false;
   int stages = t.stages < 2 ? 2 : t.stages;
@@ -486,14 +474,14 @@ bool encode_fast_supported(const Geom& g, const EncodeTuning& t) {
 }
 
 
-template <int MODE, bool FULL, int RPS>
+template <int MODE, bool FULL, int RPS, bool PASS0>
 static cudaError_t launch_fast(const FastParams& fp, int grid, int threads, size_t smem,
                                cudaStream_t stream) {
   // per launch: the attribute is per device and is lost by cudaDeviceReset; the call costs about a microsecond
-  cudaError_t ea = cudaFuncSetAttribute(k_encode_fast<MODE, FULL, RPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  cudaError_t ea = cudaFuncSetAttribute(k_encode_fast<MODE, FULL, RPS, PASS0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         232448 - 1024);
   if (ea != cudaSuccess) return ea;
-  k_encode_fast<MODE, FULL, RPS><<<grid, threads, smem, stream>>>(fp);
+  k_encode_fast<MODE, FULL, RPS, PASS0><<<grid, threads, smem, stream>>>(fp);
   return cudaGetLastError();
 }
 
@@ -506,7 +494,7 @@ int enqueue_delta_from_raw(const Geom& g, const uint16_t* raw, uint16_t* delta_i
   return *err == cudaSuccess ? 1 : -1;
 }
 
-int enqueue_encode(const Geom& g, const EncodeTuning& t, const EncodeScratch& s,
+int enqueue_encode(const Geom& g, const EncodeTuning& t, EncodeScratch& s,
                    const uint16_t* frames, const uint16_t* delta, uint32_t n, bool force_generic,
                    uint8_t* flags, uint8_t* high, uint8_t* low, uint8_t* preview,
                    cudaStream_t stream, cudaError_t* err, const TimingHook* hook) {
@@ -521,19 +509,30 @@ int enqueue_encode(const Geom& g, const EncodeTuning& t, const EncodeScratch& s,
     if (*err != cudaSuccess) return -1;            \
   } while (0)
 
-  k_encode_init<<<n, 256, 0, stream>>>(s.stats, s.lists, s.counts, n, s.cap, has_delta, fast ? 1 : 0);
-  FPV_CHECK_LAUNCH();
-
   if (fast) {
+    // ---- fast path: one launch does everything per frame (transform, decisions, flags, preview prediction); two
+    //      more launches redo the frames whose assumed flags were wrong -- normally none, they exit at once.
+    if (s.dirty) {
+      k_encode_init<<<n, 256, 0, stream>>>(s.stats, s.lists, s.counts, n, s.cap, has_delta, 0);
+      FPV_CHECK_LAUNCH();
+      s.dirty = false;
+    }
+    *err = cudaMemsetAsync(s.counts + 1, 0, 2 * sizeof(uint32_t), stream);
+    if (*err != cudaSuccess) return -1;
     FastParams fp;
     fp.frames = frames; fp.delta = delta; fp.stats = s.stats;
-    fp.high = high; fp.low = low; fp.preview_raw = s.preview_raw;
+    fp.n = n;
+    fp.guess_in = s.counts + 3 + (s.calls & 1u);
+    fp.guess_out = s.counts + 3 + ((s.calls + 1) & 1u);
+    s.calls++;
+    fp.high = high; fp.low = low; fp.preview = preview; fp.flags = flags;
     fp.W = g.W; fp.H = g.H; fp.P = g.P; fp.PP = g.PP; fp.PW = g.PW; fp.shift = g.shift;
     const int rps = t.rows_per_stage == 2 ? 2 : 4;
     fp.stages = t.stages < 2 ? 2 : t.stages;
     fp.rows_per_stage = (uint32_t)rps;
     fp.stage_bytes = ((uint32_t)rps * g.W + kHaloPx) * 2;
     fp.compute_warps = (g.W + kStripPx - 1) / kStripPx;
+    fp.prev_pitch = (g.PW + 15) / 16 * 16;
     fp.qc = make_qconst(g.mode, g.shift);
     // Band height: whole multiples of 4 rows; shrink for small batches so that
     // there are at least ~4 tasks per SM.
@@ -554,31 +553,40 @@ int enqueue_encode(const Geom& g, const EncodeTuning& t, const EncodeScratch& s,
     uint64_t max_tasks = (uint64_t)n * fp.bands;
     int grid = t.num_sms * ctas_per_sm;
     if ((uint64_t)grid > max_tasks) grid = (int)max_tasks;
+    const bool full = g.W % kStripPx == 0;
     for (int pass = 0; pass < 3; pass++) {
-      fp.list = s.lists + (size_t)pass * s.cap;
-      fp.count = s.counts + pass;
+      fp.list = pass == 0 ? nullptr : s.lists + (size_t)pass * s.cap;
+      fp.count = pass == 0 ? nullptr : s.counts + pass;
+      fp.next_list = pass < 2 ? s.lists + (size_t)(pass + 1) * s.cap : nullptr;
+      fp.next_count = pass < 2 ? s.counts + pass + 1 : nullptr;
       // redo passes are almost always empty: a small grid is enough
       int gpass = pass == 0 ? grid : (grid < 2 * t.num_sms ? grid : 2 * t.num_sms);
       cudaError_t e = cudaSuccess;
       if (hook && pass == 0) cudaEventRecord(hook->start, stream);
-      const bool full = g.W % kStripPx == 0;
-      if (rps == 4) {
-        if (full) { FPV_DISPATCH_MODE(g.mode, (e = launch_fast<M, true, 4>(fp, gpass, threads, smem, stream))); }
-        else { FPV_DISPATCH_MODE(g.mode, (e = launch_fast<M, false, 4>(fp, gpass, threads, smem, stream))); }
-      } else {
-        if (full) { FPV_DISPATCH_MODE(g.mode, (e = launch_fast<M, true, 2>(fp, gpass, threads, smem, stream))); }
-        else { FPV_DISPATCH_MODE(g.mode, (e = launch_fast<M, false, 2>(fp, gpass, threads, smem, stream))); }
-      }
+#define FPV_LAUNCH_FAST(F, R)                                                                                       \
+  do {                                                                                                              \
+    if (pass == 0) { FPV_DISPATCH_MODE(g.mode, (e = launch_fast<M, F, R, true>(fp, gpass, threads, smem, stream))); } \
+    else { FPV_DISPATCH_MODE(g.mode, (e = launch_fast<M, F, R, false>(fp, gpass, threads, smem, stream))); }         \
+  } while (0)
+      if (rps == 4) { if (full) FPV_LAUNCH_FAST(true, 4); else FPV_LAUNCH_FAST(false, 4); }
+      else { if (full) FPV_LAUNCH_FAST(true, 2); else FPV_LAUNCH_FAST(false, 2); }
+#undef FPV_LAUNCH_FAST
       if (hook && pass == 0) cudaEventRecord(hook->stop, stream);
       launches++;
       if (e != cudaSuccess) { *err = e; return -1; }
-      if (pass < 2) {
-        k_decide<<<n, 256, 0, stream>>>(s.stats, fp.list, fp.count, s.lists + (size_t)(pass + 1) * s.cap,
-                                        s.counts + pass + 1, 0, has_delta, has_low, frames, g.P, g.mode, g.shift);
-        FPV_CHECK_LAUNCH();
-      }
     }
-  } else {
+    return launches;
+  }
+
+  // ---- generic path: statistics first, then transform (plain loads, any xsize % 4 == 0) ----------------------
+  s.dirty = true;
+  if (!s.preview_raw) {
+    *err = cudaMalloc(&s.preview_raw, (size_t)s.cap * (g.PP ? g.PP : 1));
+    if (*err != cudaSuccess) return -1;
+  }
+  k_encode_init<<<n, 256, 0, stream>>>(s.stats, s.lists, s.counts, n, s.cap, has_delta, 0);
+  FPV_CHECK_LAUNCH();
+  {
     const uint32_t chunk = 8192;
     dim3 gA((unsigned)((g.P + chunk - 1) / chunk), n);
     FPV_DISPATCH_MODE(g.mode, (k_gen_stats_delta<M><<<gA, 256, 0, stream>>>(frames, s.stats, g.P, g.shift, chunk)));

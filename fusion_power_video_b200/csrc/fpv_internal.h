@@ -23,9 +23,14 @@ struct Geom {
 struct EncodeScratch {
   FrameStat* stats = nullptr;     // [cap]
   uint32_t* lists = nullptr;      // [3][cap] frame indices for pass 0,1,2
-  uint32_t* counts = nullptr;     // [4]: list counts 0..2, [3] = flags guess for the next batch
-  uint8_t* preview_raw = nullptr; // [cap][PP]
+  uint32_t* counts = nullptr;     // [5]: [1], [2] lengths of the redo lists, [3], [4] flags guess for the next batch
+                                  // (two words used alternately, see FastParams::guess_in / guess_out)
+  uint8_t* preview_raw = nullptr; // [cap][PP]  (generic path only; allocated on its first use)
   uint32_t cap = 0;
+  uint64_t P_PP = 0;              // bytes of one frame's preview plane (for the lazy allocation above)
+  // host-side state
+  uint32_t calls = 0;             // fast-path calls so far: parity selects the guess word
+  bool dirty = false;             // the generic path left statistics behind; the fast path expects them zeroed
 };
 
 struct EncodeTuning {
@@ -51,7 +56,7 @@ bool encode_fast_supported(const Geom& g, const EncodeTuning& t);
 // Outputs: flags[n], high[n][P], low[n][P] (nullptr iff mode has no low
 // plane), preview[n][PP].  Returns the number of kernels launched, or -1 with
 // *err set.
-int enqueue_encode(const Geom& g, const EncodeTuning& t, const EncodeScratch& s,
+int enqueue_encode(const Geom& g, const EncodeTuning& t, EncodeScratch& s,
                    const uint16_t* frames, const uint16_t* delta, uint32_t n, bool force_generic,
                    uint8_t* flags, uint8_t* high, uint8_t* low, uint8_t* preview,
                    cudaStream_t stream, cudaError_t* err, const TimingHook* hook = nullptr);
