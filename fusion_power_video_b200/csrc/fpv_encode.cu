@@ -7,15 +7,17 @@
 // Two paths produce identical bytes:
 //
 //  * FAST (k_encode_fast): persistent CTAs stream contiguous 4-row stages of a
-//    frame band into a shared-memory ring with 1-D TMA bulk copies
+//    frame (or a band of one) into a shared-memory ring with 1-D TMA bulk copies
 //    (cp.async.bulk + mbarrier), one warp per 256-column strip walks down the
 //    rows keeping the previous row in registers, everything fused into one
 //    read of the raw frame and one write of each output plane.  The
 //    reference's per-frame decisions (USE_DELTA, USE_CG) depend on whole-frame
 //    histograms, so the pass runs with ASSUMED flags while accumulating the
-//    histograms; k_decide then evaluates the integer heuristics exactly and
-//    frames whose assumption was wrong are redone (at most twice) by the same
-//    kernel.  In the common case compulsory HBM traffic is 4.0625 B/pixel.
+//    histograms; the CTA that completes a frame evaluates the integer
+//    heuristics exactly inside the kernel (task_done / decide_core) and frames
+//    whose assumption was wrong are redone (at most twice) by the same kernel;
+//    k_finalize16 then predicts the preview planes.  In the common case
+//    compulsory HBM traffic is 4.0625 B/pixel.
 //
 //  * GENERIC (k_gen_*): statistics first, then transform; plain loads, any
 //    xsize % 4 == 0.  Used for geometries the bulk-copy path cannot take
@@ -179,14 +181,15 @@ k_decide(FrameStat* stats, const uint32_t* in, const uint32_t* in_count, uint32_
 
 // Writes the flags byte and the final preview (ClampedGradient applied on the
 // preview's own flat array of width W/4 iff USE_CG, .cc:575-586).
+// flags_in != nullptr (fast path): the flags byte is final already (frame_decide wrote it), only the preview is done.
 __global__ void k_finalize(const FrameStat* stats, const uint8_t* preview_raw, uint8_t* preview,
                            uint8_t* flags, uint32_t* counts, uint32_t n, uint32_t PW,
-                           uint64_t PP, int has_low) {
+                           uint64_t PP, int has_low, const uint8_t* flags_in) {
   uint32_t f = blockIdx.y;
   const FrameStat& st = stats[f];
   // NO_LOW_BYTES is only known once every pass has OR-ed its low bytes in.
-  uint32_t fin = (st.final_flags & 3u) |
-                 (has_low ? (st.low_or == 0 ? kFlagNoLow : 0) : kFlagNoLow);
+  uint32_t fin = flags_in ? flags_in[f]
+                          : (st.final_flags & 3u) | (has_low ? (st.low_or == 0 ? kFlagNoLow : 0) : kFlagNoLow);
   const uint8_t* pr = preview_raw + (uint64_t)f * PP;
   uint8_t* po = preview + (uint64_t)f * PP;
   if ((PP & 3) == 0 && (PW & 3) == 0) {
@@ -223,46 +226,64 @@ __global__ void k_finalize(const FrameStat* stats, const uint8_t* preview_raw, u
       po[i] = (uint8_t)v;
     }
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
+  if (blockIdx.x == 0 && threadIdx.x == 0 && !flags_in) {
     flags[f] = (uint8_t)fin;
     if (f == n - 1) counts[3] = fin & 3u;  // guess for the next batch
   }
 }
 
-// The same for PW % 16 == 0 (every geometry of the benchmarks): 16 preview pixels per thread, one
-// thread-item per launch slot, all loads issued up front (two 128-bit and two 32-bit ones; the
-// 32-bit ones hit lines the neighbour threads fetch).  The 4-pixel kernel above is latency bound:
-// its threads walk ~30 dependent iterations.
+// The same for PW % 16 == 0 (every geometry of the benchmarks), 16 preview pixels at a time.  The 4-pixel kernel
+// above is latency bound: its threads walk ~30 dependent iterations.
+// One 16-pixel group of a preview plane (PW % 16 == 0): ClampedGradient on the preview's own flat array.
+__device__ __forceinline__ uint4 finalize_group(const uint4 c, const uint4 nn, const uint32_t cm, const uint32_t nm,
+                                                const bool first_of_row1) {
+  uint4 o;
+  o.x = finalize_word(c.x, cm, nn.x, nm);
+  o.y = finalize_word(c.y, c.x, nn.y, nn.x);
+  o.z = finalize_word(c.z, c.y, nn.z, nn.y);
+  o.w = finalize_word(c.w, c.z, nn.w, nn.z);
+  if (first_of_row1) o.x = (o.x & 0xffffff00u) | (c.x & 0xffu);  // index PW is copied (.cc:578, :584)
+  return o;
+}
+
+// GROUPS 16-pixel groups per thread, every load issued before the first use (the one-group-per-thread form was
+// latency bound: 44 us per 1184 previews of 320x200, 3.4 TB/s of its 152 MB).
+constexpr int kFinGroups = 4;
 __global__ void __launch_bounds__(256)
 k_finalize16(const FrameStat* __restrict__ stats, const uint8_t* __restrict__ preview_raw,
              uint8_t* __restrict__ preview, uint8_t* __restrict__ flags, uint32_t* counts, uint32_t n,
-             uint32_t PW, uint64_t PP, int has_low) {
+             uint32_t PW, uint64_t PP, int has_low, const uint8_t* __restrict__ flags_in) {
   const uint32_t f = blockIdx.y;
-  const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;     // 16-pixel group of the frame's preview
   const uint32_t groups = (uint32_t)(PP / 16), pw16 = PW / 16;
   const FrameStat& st = stats[f];
-  const uint32_t fin = (st.final_flags & 3u) | (has_low ? (st.low_or == 0 ? kFlagNoLow : 0) : kFlagNoLow);
-  if (q == 0) {
+  const uint32_t fin = flags_in ? flags_in[f]
+                                : (st.final_flags & 3u) | (has_low ? (st.low_or == 0 ? kFlagNoLow : 0) : kFlagNoLow);
+  if (blockIdx.x == 0 && threadIdx.x == 0 && !flags_in) {
     flags[f] = (uint8_t)fin;
     if (f == n - 1) counts[3] = fin & 3u;  // guess for the next batch
   }
-  if (q >= groups) return;
   const uint4* pr = reinterpret_cast<const uint4*>(preview_raw + (uint64_t)f * PP);
+  const uint32_t* pr32 = reinterpret_cast<const uint32_t*>(pr);
   uint4* po = reinterpret_cast<uint4*>(preview + (uint64_t)f * PP);
-  const uint4 c = __ldg(pr + q);
-  uint4 o = c;
-  if ((fin & kFlagCG) && q >= pw16) {            // rows >= 1; pixel PW itself is patched below
-    const uint32_t* pr32 = reinterpret_cast<const uint32_t*>(pr);
-    const uint4 nn = __ldg(pr + q - pw16);
-    const uint32_t cm = __ldg(pr32 + 4 * q - 1);                          // 4 pixels to the west (flat order)
-    const uint32_t nm = q > pw16 ? __ldg(pr32 + 4 * (q - pw16) - 1) : 0u;
-    o.x = finalize_word(c.x, cm, nn.x, nm);
-    o.y = finalize_word(c.y, c.x, nn.y, nn.x);
-    o.z = finalize_word(c.z, c.y, nn.z, nn.y);
-    o.w = finalize_word(c.w, c.z, nn.w, nn.z);
-    if (q == pw16) o.x = (o.x & 0xffffff00u) | (c.x & 0xffu);  // index PW is copied (.cc:578, :584)
+  const uint32_t q0 = blockIdx.x * (blockDim.x * kFinGroups) + threadIdx.x;   // groups q0 + 256 k of this thread
+  const bool cg = (fin & kFlagCG) != 0;
+  uint4 c[kFinGroups], nn[kFinGroups];
+  uint32_t cm[kFinGroups], nm[kFinGroups];
+#pragma unroll
+  for (int k = 0; k < kFinGroups; k++) {
+    const uint32_t q = q0 + 256u * k;
+    const bool in = q < groups, pred = in && cg && q >= pw16;
+    c[k] = in ? __ldg(pr + q) : make_uint4(0, 0, 0, 0);
+    nn[k] = pred ? __ldg(pr + q - pw16) : make_uint4(0, 0, 0, 0);
+    cm[k] = pred ? __ldg(pr32 + 4 * q - 1) : 0u;                        // 4 pixels to the west (flat order)
+    nm[k] = pred && q > pw16 ? __ldg(pr32 + 4 * (q - pw16) - 1) : 0u;
   }
-  po[q] = o;
+#pragma unroll
+  for (int k = 0; k < kFinGroups; k++) {
+    const uint32_t q = q0 + 256u * k;
+    if (q >= groups) continue;
+    po[q] = (cg && q >= pw16) ? finalize_group(c[k], nn[k], cm[k], nm[k], q == pw16) : c[k];
+  }
 }
 
 // =====================================================================================
@@ -525,14 +546,17 @@ int enqueue_encode(const Geom& g, const EncodeTuning& t, EncodeScratch& s,
     fp.guess_in = s.counts + 3 + (s.calls & 1u);
     fp.guess_out = s.counts + 3 + ((s.calls + 1) & 1u);
     s.calls++;
-    fp.high = high; fp.low = low; fp.preview = preview; fp.flags = flags;
+    if (!s.preview_raw) {
+      *err = cudaMalloc(&s.preview_raw, (size_t)s.cap * (g.PP ? g.PP : 1));
+      if (*err != cudaSuccess) return -1;
+    }
+    fp.high = high; fp.low = low; fp.preview_raw = s.preview_raw; fp.flags = flags;
     fp.W = g.W; fp.H = g.H; fp.P = g.P; fp.PP = g.PP; fp.PW = g.PW; fp.shift = g.shift;
     const int rps = t.rows_per_stage == 2 ? 2 : 4;
     fp.stages = t.stages < 2 ? 2 : t.stages;
     fp.rows_per_stage = (uint32_t)rps;
     fp.stage_bytes = ((uint32_t)rps * g.W + kHaloPx) * 2;
     fp.compute_warps = (g.W + kStripPx - 1) / kStripPx;
-    fp.prev_pitch = (g.PW + 15) / 16 * 16;
     fp.qc = make_qconst(g.mode, g.shift);
     // Band height: whole multiples of 4 rows; shrink for small batches so that
     // there are at least ~4 tasks per SM.
@@ -541,8 +565,6 @@ int enqueue_encode(const Geom& g, const EncodeTuning& t, EncodeScratch& s,
     if (band > 1024) band = 1024;  // per-lane delta-decision counters are 16 bit
     while (band > 8 && (uint64_t)n * ((g.H + band - 1) / band) < (uint64_t)t.num_sms * 4) band = ((band / 2) / 4) * 4;
     if (band > g.H) band = g.H;
-    fp.band_rows = band;
-    fp.bands = (g.H + band - 1) / band;
     const int threads = (int)(fp.compute_warps + 1) * 32;
     const size_t smem = fast_smem_bytes(g.W, (int)fp.stages, rps);
     int ctas_per_sm = (int)((size_t)(t.max_smem_optin + 1024) / (smem + 1024));
@@ -550,8 +572,16 @@ int enqueue_encode(const Geom& g, const EncodeTuning& t, EncodeScratch& s,
     int by_threads = 2048 / threads; if (by_threads < 1) by_threads = 1;
     if (ctas_per_sm > by_threads) ctas_per_sm = by_threads;
     if (t.max_ctas > 0 && ctas_per_sm > t.max_ctas) ctas_per_sm = t.max_ctas;
-    uint64_t max_tasks = (uint64_t)n * fp.bands;
     int grid = t.num_sms * ctas_per_sm;
+    // A task is a WHOLE FRAME whenever that keeps the CTAs evenly loaded: the frame's statistics then never leave
+    // the CTA's shared memory (the decision is taken there, task_done), and no halo row is read twice.
+    if ((uint64_t)n >= (uint64_t)grid && g.P / 480 < 60000 && !getenv("FPV_NO_FRAME_TASKS")) {
+      const uint64_t waves = ((uint64_t)n + grid - 1) / grid;
+      if ((double)n / (double)(waves * grid) >= 0.94) band = g.H;
+    }
+    fp.band_rows = band;
+    fp.bands = (g.H + band - 1) / band;
+    uint64_t max_tasks = (uint64_t)n * fp.bands;
     if ((uint64_t)grid > max_tasks) grid = (int)max_tasks;
     const bool full = g.W % kStripPx == 0;
     for (int pass = 0; pass < 3; pass++) {
@@ -575,6 +605,16 @@ int enqueue_encode(const Geom& g, const EncodeTuning& t, EncodeScratch& s,
       launches++;
       if (e != cudaSuccess) { *err = e; return -1; }
     }
+    // the preview's own ClampedGradient pass (.cc:575-586), under the flags the passes above made final
+    if (g.PW % 16 == 0 && (reinterpret_cast<uintptr_t>(preview) & 15) == 0) {
+      dim3 g16((unsigned)((g.PP / 16 + 256 * kFinGroups - 1) / (256 * kFinGroups)), n);
+      k_finalize16<<<g16, 256, 0, stream>>>(s.stats, s.preview_raw, preview, flags, s.counts, n, g.PW, g.PP, has_low, flags);
+    } else {
+      unsigned gfx = (unsigned)((g.PP / 4 + 255) / 256); if (gfx < 1) gfx = 1;
+      { unsigned cap = n >= 1024 ? 2u : n >= 256 ? 4u : n >= 64 ? 16u : 64u; if (gfx > cap) gfx = cap; }
+      k_finalize<<<dim3(gfx, n), 256, 0, stream>>>(s.stats, s.preview_raw, preview, flags, s.counts, n, g.PW, g.PP, has_low, flags);
+    }
+    FPV_CHECK_LAUNCH();
     return launches;
   }
 
@@ -617,10 +657,10 @@ int enqueue_encode(const Geom& g, const EncodeTuning& t, EncodeScratch& s,
   { unsigned cap = n >= 1024 ? 2u : n >= 256 ? 4u : n >= 64 ? 16u : 64u; if (gfx > cap) gfx = cap; }
   dim3 gF(gfx, n);
   if (g.PW % 16 == 0 && g.PP % 16 == 0 && (reinterpret_cast<uintptr_t>(preview) & 15) == 0 && !getenv("FPV_FINALIZE4")) {
-    dim3 g16((unsigned)((g.PP / 16 + 255) / 256), n);
-    k_finalize16<<<g16, 256, 0, stream>>>(s.stats, s.preview_raw, preview, flags, s.counts, n, g.PW, g.PP, has_low);
+    dim3 g16((unsigned)((g.PP / 16 + 256 * kFinGroups - 1) / (256 * kFinGroups)), n);
+    k_finalize16<<<g16, 256, 0, stream>>>(s.stats, s.preview_raw, preview, flags, s.counts, n, g.PW, g.PP, has_low, nullptr);
   } else {
-    k_finalize<<<gF, 256, 0, stream>>>(s.stats, s.preview_raw, preview, flags, s.counts, n, g.PW, g.PP, has_low);
+    k_finalize<<<gF, 256, 0, stream>>>(s.stats, s.preview_raw, preview, flags, s.counts, n, g.PW, g.PP, has_low, nullptr);
   }
   FPV_CHECK_LAUNCH();
 #undef FPV_CHECK_LAUNCH

@@ -6,8 +6,8 @@
 // :550-562).
 //
 // Work decomposition
-//   task   = (frame, band of `band_rows` rows; 32 rows for short frame lists); persistent CTAs (at most
-//            4 per SM) take tasks round-robin.
+//   task   = a whole frame when that keeps the persistent CTAs (at most 4 per SM) evenly loaded (the normal case),
+//            else a band of `band_rows` rows (32 rows for short frame lists); CTAs take tasks round-robin.
 //   stage  = up to 4 (or 2) consecutive rows of the band = ONE contiguous flat range
 //            of the raw frame (and of the delta image), fetched with
 //            cp.async.bulk (TMA, 1-D) into a shared-memory ring and signalled
@@ -32,16 +32,14 @@
 // The delta decision needs no histogram in the common case: only 8 bit
 // counters per frame (see frame_decide).
 //
-// Everything per frame happens inside this kernel (round 2; before, k_encode_init, two k_decide launches and
-// k_finalize16 cost 9 % of a step):
-//   * decisions: every warp that finishes its part of a frame takes a ticket; the last one evaluates the
-//     reference's two integer heuristics for the frame (frame_decide), writes the flags byte when the
-//     assumption held, or puts the frame on the next pass's list, and clears the frame's statistics for the
-//     next call (no init kernel);
-//   * preview: the consumer warps write the un-predicted 4x4 box means into a small shared-memory ring, the
-//     service warp applies ClampedGradient on the preview's own flat array of width W/4 (.cc:575-586) under the
-//     same assumed flag and writes the final preview rows (no finalize kernel, no scratch plane in HBM).  A band
-//     that does not start at row 0 is therefore primed by FOUR halo rows (one preview row), not one.
+// Decisions are taken inside this kernel (round 2; before, k_encode_init and two k_decide launches sat between the
+// passes).  Every warp adds its statistics of a task into a CTA-level table in shared memory.  With whole-frame
+// tasks that table IS the frame's statistics: the last warp of the CTA to finish evaluates the reference's two
+// integer heuristics right out of shared memory (decide_core), writes the flags byte when the assumption held or
+// puts the frame on the next pass's list -- no global atomics, no fence, no init kernel.  With band tasks the
+// tables are merged in global memory behind a ticket (task_done).  What this costs and what was tried first
+// (a fence per warp: +25 %; the decision in a non-inlined function: +20 %; preview prediction in the service
+// warp: slower than the separate k_finalize16) is in profiles/r02_encode.md.
 #pragma once
 
 #include "fpv_internal.h"
@@ -54,7 +52,7 @@ constexpr int kMaxRowsPerStage = 4; // rows per stage: 4 (one preview row group)
 constexpr int kHaloPx = 8;          // pixels copied before a stage's first pixel (16 B)
 constexpr int kWarpHistWords = 512; // hist_a, hist_b: 256 u32 counters each, warp-private
 constexpr int kWarpScratchBytes = kWarpHistWords * 4;
-constexpr int kPrevRing = 8;        // preview rows kept in shared memory (consumers run at most a few rows ahead)
+constexpr int kCtaStatWords = 512 + 8 + 2;   // CTA-level statistics of one task: hist_a | hist_b | dbits | low_or | arrivals
 
 struct FastParams {
   const uint16_t* frames;
@@ -70,7 +68,7 @@ struct FastParams {
                                 // CTAs of this launch may still be reading guess_in)
   uint8_t* high;
   uint8_t* low;
-  uint8_t* preview;
+  uint8_t* preview_raw;         // un-predicted preview planes (k_finalize16 predicts them)
   uint8_t* flags;
   uint32_t W, H;
   uint64_t P, PP;
@@ -82,7 +80,6 @@ struct FastParams {
   uint32_t rows_per_stage;      // 2 or 4
   uint32_t stage_bytes;         // bytes of one plane of one stage: (rows_per_stage * W + 8) * 2
   uint32_t compute_warps;       // ceil(W / 256)
-  uint32_t prev_pitch;          // bytes per preview row in the shared-memory ring (PW rounded up to 16)
   QConst qc;                    // make_qconst(mode, shift)
 };
 
@@ -92,7 +89,7 @@ struct FastParams {
 // running stage number.
 struct StageCursor {
   uint32_t t, f, y0, y1, ys, rps;
-  uint32_t pseq = 0;            // preview rows this CTA has completed before the current stage: ring slot = pseq % kPrevRing
+  uint32_t tseq = 0;            // tasks this CTA has started before the current one (parity selects the CTA-level table)
   uint32_t band_rows, bands;    // of this launch (short frame lists use shorter bands, see the kernel)
   __device__ __forceinline__ bool load_task(const FastParams& p, uint32_t total) {
     if (t >= total) return false;
@@ -100,7 +97,7 @@ struct StageCursor {
     const uint32_t b = t % bands;
     y0 = b * band_rows;
     y1 = min(p.H, y0 + band_rows);
-    ys = y0 > 0 ? y0 - 4 : 0;   // four halo rows = one preview row (bands start on multiples of 4)
+    ys = y0 > 0 ? y0 - 1 : 0;   // one halo row: the north neighbours of the band's first row
     return true;
   }
   __device__ __forceinline__ bool halo() const { return ys < y0; }
@@ -110,9 +107,9 @@ struct StageCursor {
   __device__ __forceinline__ bool last_of_task() const { return ys >= y0 && ys + nrows() >= y1; }
   __device__ __forceinline__ bool advance(const FastParams& p, uint32_t total) {
     ys += nrows();
-    if ((ys & 3u) == 0) pseq++;   // the stage completed a group of four rows = one preview row
     if (ys < y1) return true;
     t += gridDim.x;
+    tseq++;
     return load_task(p, total);
   }
 };
@@ -173,8 +170,7 @@ __device__ __forceinline__ void fast_row(
     StripState& st, const uint32_t raw_a /* shared addr of this lane's 8 px */, const uint32_t del_a,
     const QConst qc, const bool use_delta_rt, const bool use_cg_rt, const bool active, const bool own,
     const uint32_t y, const bool emit_preview, const uint32_t c0, const uint32_t w31,
-    uint8_t* __restrict__ out_high, uint8_t* __restrict__ out_low, const uint32_t prev_sm /* shared address of this
-    lane's two preview pixels in the preview ring */,
+    uint8_t* __restrict__ out_high, uint8_t* __restrict__ out_low, uint8_t* __restrict__ out_prev,
     const uint32_t hist_a) {
   const bool use_delta = DC || use_delta_rt, use_cg = DC || use_cg_rt;
   uint32_t hr[4], hs[4], lo[4], w[4];
@@ -194,10 +190,11 @@ __device__ __forceinline__ void fast_row(
   // statistics of the RAW planes: OR of the low bytes (bytes 0 / 2 of lof), 4x4 box sums of the
   // high bytes (bytes 1 / 3 of hs1)
   const bool counted = !FIRSTROWS || own;
-  if (counted) st.orl |= (lo[0] | lo[1]) | (lo[2] | lo[3]);
-  // (halo rows too: their preview row is the north neighbour of the band's first one)
-  st.accA = __dp4a(hr[0], 0x01000100u, __dp4a(hr[1], 0x01000100u, st.accA));
-  st.accB = __dp4a(hr[2], 0x01000100u, __dp4a(hr[3], 0x01000100u, st.accB));
+  if (counted) {
+    st.orl |= (lo[0] | lo[1]) | (lo[2] | lo[3]);
+    st.accA = __dp4a(hr[0], 0x01000100u, __dp4a(hr[1], 0x01000100u, st.accA));
+    st.accB = __dp4a(hr[2], 0x01000100u, __dp4a(hr[3], 0x01000100u, st.accB));
+  }
   if (use_delta) {
     // Bytes wrap independently (.cc:534-537).  High: bits 8-15 / 24-31 of
     // (q & HI) + 2^16 - (d & HI); bit 16 is junk.  Low: bytes 0 / 2 of
@@ -249,15 +246,15 @@ __device__ __forceinline__ void fast_row(
       red_shared_inc(hist_a + 4 * a);
       red_shared_inc(hist_a + 1024 + 4 * b);
     }
-  }
-  if (emit_preview) {
-    // the un-predicted preview pixels (.cc:500-512) go to the shared-memory ring; the service warp predicts them
-    if (FULL || active) {
-      const uint32_t pv = ((st.accA >> 4) & 0xfeu) | (((st.accB >> 4) & 0xfeu) << 8);
-      sts16(prev_sm, pv);
+    if (emit_preview) {
+      // the un-predicted preview pixels (.cc:500-512); k_finalize16 applies ClampedGradient to the preview plane
+      if (FULL || active) {
+        const uint32_t pv = ((st.accA >> 4) & 0xfeu) | (((st.accB >> 4) & 0xfeu) << 8);
+        *reinterpret_cast<uint16_t*>(out_prev) = (uint16_t)pv;
+      }
+      st.accA = 0;
+      st.accB = 0;
     }
-    st.accA = 0;
-    st.accB = 0;
   }
   st.kc = min(st.kc - w31, st.kc - w31 + 31u);   // (kc - W) mod 31; one of the two wrapped around
 #pragma unroll
@@ -283,20 +280,21 @@ __device__ __forceinline__ uint64_t warp_entropy256(const uint32_t (&v)[8]) {
   return (1024ull * sum_of_logs) / (uint64_t)sum;
 }
 
-// Runs in the warp that finished the LAST part of frame f in this pass (ticket): the frame's statistics are complete.
-// Evaluates the reference's two decisions exactly (see the comment on k_decide in fpv_encode.cu for the delta one:
-// USE_DELTA <=> EstimateEntropy(hist of every 15th raw high byte) > 0, provable from 8 bit counters except for
-// near-constant frames, where the exact histogram is rebuilt here).  If the pass's assumption held, the frame is
-// final: its flags byte is written.  Otherwise it goes onto the next pass's list with the corrected assumption.
-// Either way the statistics are cleared, so the next pass / the next call starts from zero without an init kernel.
+// The reference's two decisions for frame f from its complete statistics (held by the calling warp: lane l has bins
+// 8 l .. 8 l + 7 of both ClampedGradient histograms, lanes 0..7 the eight bit counters of the delta decision).
+// USE_DELTA <=> EstimateEntropy(hist of every 15th raw high byte) > 0 (see the comment on k_decide in fpv_encode.cu),
+// provable from the bit counters except for near-constant frames, where the exact histogram is rebuilt here.
+// If the pass's assumption held, the frame is final: its flags byte is written.  Otherwise it goes onto the next
+// pass's list with the corrected assumption.
 template <int MODE>
-__device__ __noinline__ void frame_decide(const FastParams& p, const uint32_t f, const uint32_t assumed, const int lane) {
+__device__ __forceinline__ void decide_core(const FastParams& p, const uint32_t f, const uint32_t assumed, const int lane,
+                                            const uint32_t dbit, const uint32_t (&va)[8], const uint32_t (&vb)[8],
+                                            const uint32_t low_or) {
   FrameStat& st = p.stats[f];
-  __threadfence();
   uint32_t dec_delta = 0;
   if (p.delta != nullptr) {
     const uint64_t N = (p.P + 14) / 15;
-    const uint64_t c = lane < 8 ? (uint64_t)__ldcg(&st.dbits[lane]) : 0;
+    const uint64_t c = lane < 8 ? (uint64_t)dbit : 0;
     const uint64_t m = c < N - c ? c : N - c;
     const bool proven = __any_sync(0xffffffffu, lane < 8 && 1024 * m >= N);
     const bool constant = __all_sync(0xffffffffu, lane >= 8 || m == 0);
@@ -321,26 +319,13 @@ __device__ __noinline__ void frame_decide(const FastParams& p, const uint32_t f,
       dec_delta = warp_entropy256(v) > 0 ? 1u : 0u;
     }
   }
-  uint32_t va[8], vb[8];
-#pragma unroll
-  for (int j = 0; j < 8; j++) {
-    va[j] = __ldcg(&st.hist_a[8 * lane + j]);
-    vb[j] = __ldcg(&st.hist_b[8 * lane + j]);
-    st.hist_a[8 * lane + j] = 0;
-    st.hist_b[8 * lane + j] = 0;
-  }
-  const uint32_t low_or = __ldcg(&st.low_or);
   uint32_t want = dec_delta | (assumed & 2u);
   if (dec_delta == (assumed & 1u)) {
     // the ClampedGradient histograms were taken on the right (post-delta) plane: .cc:564
     const uint64_t e_a = warp_entropy256(va), e_b = warp_entropy256(vb);
     want = dec_delta | ((e_b < e_a) ? 2u : 0u);
   }
-  __syncwarp();
-  if (lane < 8) st.dbits[lane] = 0;
   if (lane == 0) {
-    st.low_or = 0;
-    st.tickets = 0;
     if (want != assumed && p.next_list != nullptr) {
       st.assumed = want;
       p.next_list[atomicAdd(p.next_count, 1u)] = f;
@@ -353,20 +338,98 @@ __device__ __noinline__ void frame_decide(const FastParams& p, const uint32_t f,
   __syncwarp();
 }
 
-// Takes this warp's ticket for frame f after it has published its statistics; the last of `parts` runs the decision.
+// End of a task for one warp.  The warp's statistics are already in the CTA-level table of the task (shared memory);
+// the LAST of the CTA's warps to get here (roll call: shared atomic, CTA-scope fence) closes the task.
+//   * bands == 1 (the normal case: a task is a whole frame): the table IS the frame's statistics.  The decision is
+//     taken right here, out of shared memory -- no global atomics, no fence, nothing to wait for.
+//   * bands > 1 (few frames, or the redo passes): the table is added to the frame's global statistics with
+//     value-returning atomics; once their results are back the additions have been performed at L2, and only then
+//     the frame's ticket is taken; the CTA that takes the last of the `bands` tickets decides from the global record
+//     and clears it.  (A memory fence per warp and task instead cost a quarter of the kernel's time, and any wait
+//     of a pipeline warp stalls its whole CTA within one stage: see profiles/r02_encode.md.)
+//   ctab: shared address of the task's table (hist_a[256] | hist_b[256] | dbits[8] | low_or | arrivals)
 template <int MODE>
-__device__ __forceinline__ void frame_ticket(const FastParams& p, const uint32_t f, const uint32_t assumed,
-                                             const uint32_t parts, const int lane) {
-  __threadfence();
+__device__ __forceinline__ void task_done(const FastParams& p, const uint32_t f, const uint32_t assumed, const uint32_t bands,
+                                          const uint32_t ctab, const uint32_t warps, const int lane) {
+#ifdef FPV_ABL_NO_TICKET
+  return;                                              // timing experiment only
+#endif
+  __threadfence_block();
   __syncwarp();
+  uint32_t arrived = 0;
+  if (lane == 0) arrived = atoms_add(ctab + 4 * (512 + 8 + 1), 1u);
+  arrived = __shfl_sync(0xffffffffu, arrived, 0);
+  if (arrived + 1 != warps) return;
+  // ---- last warp of the CTA on this task ----
+  __threadfence_block();
+  FrameStat& st = p.stats[f];
+  uint32_t va[8], vb[8];
+  if (bands == 1) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      va[j] = lds32(ctab + 4 * (8 * lane + j));
+      vb[j] = lds32(ctab + 4 * (256 + 8 * lane + j));
+      sts32(ctab + 4 * (8 * lane + j), 0);
+      sts32(ctab + 4 * (256 + 8 * lane + j), 0);
+    }
+    const uint32_t dbit = lane < 8 ? lds32(ctab + 4 * (512 + lane)) : 0u;
+    const uint32_t low_or = lds32(ctab + 4 * (512 + 8));
+    __syncwarp();
+    if (lane < 10) sts32(ctab + 4 * (512 + lane), 0);   // bit counters, low_or, arrivals
+    decide_core<MODE>(p, f, assumed, lane, dbit, va, vb, low_or);
+    return;
+  }
+  uint32_t dep = 0;
+#pragma unroll 4
+  for (uint32_t i = (uint32_t)lane; i < 512; i += 32) {
+    const uint32_t v = lds32(ctab + 4 * i);
+    if (v) {
+      sts32(ctab + 4 * i, 0);
+      dep |= atomicAdd(&st.hist_a[i], v);    // hist_a, hist_b are contiguous: 512 bins
+    }
+  }
+  if (lane < 8) {
+    const uint32_t v = lds32(ctab + 4 * (512 + lane));
+    if (v) {
+      sts32(ctab + 4 * (512 + lane), 0);
+      dep |= atomicAdd(&st.dbits[lane], v);
+    }
+  }
+  if (lane == 8) {
+    const uint32_t v = lds32(ctab + 4 * (512 + 8));
+    sts32(ctab + 4 * (512 + 8), 0);
+    sts32(ctab + 4 * (512 + 8 + 1), 0);
+    if (v) dep |= atomicOr(&st.low_or, v);
+  }
+  // the ticket is issued after every atomic above has returned (data dependency through `dep`)
+  dep = __reduce_or_sync(0xffffffffu, dep);   // cannot issue before every lane's atomics have written their result
   uint32_t t = 0;
-  if (lane == 0) t = atomicAdd(&p.stats[f].tickets, 1u);
+  if (lane == 0)
+    asm volatile("atom.global.add.u32 %0, [%1], 1;   // after %2" : "=r"(t) : "l"(&st.tickets), "r"(dep) : "memory");
   t = __shfl_sync(0xffffffffu, t, 0);
-  if (t + 1 == parts) frame_decide<MODE>(p, f, assumed, lane);
+  if (t + 1 != bands) return;
+  // ---- last ticket of the frame: decide from the global record, and clear it for the next pass / call ----
+  __threadfence();
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    va[j] = __ldcg(&st.hist_a[8 * lane + j]);
+    vb[j] = __ldcg(&st.hist_b[8 * lane + j]);
+    st.hist_a[8 * lane + j] = 0;
+    st.hist_b[8 * lane + j] = 0;
+  }
+  const uint32_t dbit = lane < 8 ? __ldcg(&st.dbits[lane]) : 0u;
+  const uint32_t low_or = __ldcg(&st.low_or);
+  __syncwarp();
+  if (lane < 8) st.dbits[lane] = 0;
+  if (lane == 0) {
+    st.low_or = 0;
+    st.tickets = 0;
+  }
+  decide_core<MODE>(p, f, assumed, lane, dbit, va, vb, low_or);
 }
 
-// Shared memory: [ring: stages x {raw stage, delta stage}] [per consumer warp:
-// hist_a | hist_b] [preview ring: kPrevRing rows] [full barriers] [empty barriers]
+// Shared memory: [ring: stages x {raw stage, delta stage}] [per consumer warp: hist_a | hist_b]
+// [two CTA-level task tables] [full barriers] [empty barriers]
 // FULL: xsize is a multiple of 256, every lane of every consumer warp owns pixels.
 // PASS0: all n frames of the batch under the guessed flags; otherwise the frames of p.list under their own.
 #ifndef FPV_FAST_MAXNREG
@@ -375,21 +438,22 @@ __device__ __forceinline__ void frame_ticket(const FastParams& p, const uint32_t
 template <int MODE, bool FULL, int RPS, bool PASS0>
 __global__ void __maxnreg__(FPV_FAST_MAXNREG) k_encode_fast(const FastParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
+  if (!PASS0 && *p.count == 0) return;   // a redo pass with nothing to redo (the normal case): gone in a microsecond
   const uint32_t S = p.stages;
   const uint32_t slot_bytes = 2 * p.stage_bytes;
   const int NW = (int)p.compute_warps;
   uint8_t* scratch = smem + (size_t)S * slot_bytes;
-  uint8_t* prevring = scratch + (size_t)NW * kWarpScratchBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(prevring + (size_t)kPrevRing * p.prev_pitch);
+  uint8_t* ctabs = scratch + (size_t)NW * kWarpScratchBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ctabs + 2 * kCtaStatWords * 4);
   const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + S);
   const uint32_t ring0 = smem_u32(smem);
-  const uint32_t prev0 = smem_u32(prevring);
+  const uint32_t ctab0 = smem_u32(ctabs);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t W = p.W;
   const QConst qc = p.qc;   // from the host: each mask is a constant-bank operand of its LOP3, not a derived register
 
-  for (uint32_t i = threadIdx.x; i < (uint32_t)NW * kWarpScratchBytes / 4; i += blockDim.x)
+  for (uint32_t i = threadIdx.x; i < ((uint32_t)NW * kWarpScratchBytes + 2 * kCtaStatWords * 4) / 4; i += blockDim.x)
     reinterpret_cast<uint32_t*>(scratch)[i] = 0;
   if (threadIdx.x == 0) {
     for (uint32_t i = 0; i < S; i++) {
@@ -408,7 +472,6 @@ __global__ void __maxnreg__(FPV_FAST_MAXNREG) k_encode_fast(const FastParams p) 
   cur.band_rows = short_list ? 32u : p.band_rows;
   cur.bands = short_list ? (p.H + 31u) / 32u : p.bands;
   const uint32_t total_tasks = nframes * cur.bands;
-  const uint32_t parts = cur.bands * (uint32_t)(NW + 1);   // tickets per frame: every warp of every band
   const uint32_t guess = PASS0 ? (*p.guess_in & (p.delta != nullptr ? 3u : 2u)) : 0u;
   cur.t = blockIdx.x;
   cur.rps = RPS;
@@ -416,7 +479,7 @@ __global__ void __maxnreg__(FPV_FAST_MAXNREG) k_encode_fast(const FastParams p) 
   RingPos rp;        // ring position of the stage this warp works on
 
   if (warp == NW) {
-    // ---------- service warp: TMA producer, delta-decision sampler, preview ClampedGradient ----------
+    // ------------------- service warp: TMA producer + delta-decision sampler -------------------
     StageCursor ic = cur;  // issue cursor, runs S-1 stages ahead
     bool imore = more;
     RingPos ip;
@@ -440,63 +503,11 @@ __global__ void __maxnreg__(FPV_FAST_MAXNREG) k_encode_fast(const FastParams p) 
       ip.next(S);
       imore = ic.advance(p, total_tasks);
     };
-    for (uint32_t i = 0; i < S && imore; i++) issue();    // the first S stages; stage k + S is issued at the end of iteration k
-
-    // ---- preview: one row per group of four image rows; the stage that was consumed one iteration ago -------
-    const uint32_t PW = p.PW, pww = PW / 4;            // (PW % 4 == 0 on this path)
-    uint32_t last1 = 0, last2 = 0;                     // last pixel of the two preview rows above the current one
-    StageCursor pc = cur;
-    RingPos pr;
-    bool have_prev = false;
-    auto preview_stage = [&]() {
-      // every consumer warp has released the stage (its preview pixels are in the ring)
-      mbar_wait(empty0 + 8 * pr.slot, pr.phase);
-      const uint32_t yend = pc.ys + pc.nrows();
-      if (yend & 3u) return;                           // (2-row stages: the row group is not complete yet)
-      const uint32_t q = (yend >> 2) - 1;              // preview row just completed
-      const uint32_t row_q = prev0 + (pc.pseq & (kPrevRing - 1)) * p.prev_pitch;
-      if (pc.halo()) {
-        // rows above a band: only their last pixels matter (west / north-west of the band's first preview pixel)
-        last1 = lds8(row_q + PW - 1);
-        last2 = 0;
-        if (q >= 1) {
-          // last pixel of preview row q - 1: 4x4 box of the raw frame, straight from global memory
-          uint32_t sum = 0;
-          if (lane < 4) {
-            const uint2 x = *reinterpret_cast<const uint2*>(p.frames + (uint64_t)pc.f * p.P +
-                                                            (uint64_t)(4 * (q - 1) + (uint32_t)lane) * W + W - 4);
-            sum = ((make_q2<MODE>(x.x, qc) >> 8) & 0xffu) + (make_q2<MODE>(x.x, qc) >> 24) +
-                  ((make_q2<MODE>(x.y, qc) >> 8) & 0xffu) + (make_q2<MODE>(x.y, qc) >> 24);
-          }
-          sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-          sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-          last2 = __shfl_sync(0xffffffffu, (sum >> 4) & 0xfeu, 0);
-        }
-        return;
-      }
-      const uint32_t fl = PASS0 ? guess : p.stats[pc.f].assumed;
-      const bool use_cg = (fl & 2u) != 0 && q >= 1;
-      const uint32_t row_n = prev0 + ((pc.pseq - 1) & (kPrevRing - 1)) * p.prev_pitch;   // the row completed just before
-      uint32_t* out = reinterpret_cast<uint32_t*>(p.preview + (uint64_t)pc.f * p.PP + (uint64_t)q * PW);
-      for (uint32_t w = (uint32_t)lane; w < pww; w += 32) {
-        const uint32_t c = lds32(row_q + 4 * w);
-        uint32_t o = c;
-        if (use_cg) {
-          const uint32_t n = lds32(row_n + 4 * w);
-          // the four pixels to the west in flat order: column 0's are the ends of the rows above (.cc:580-582)
-          const uint32_t cm = w > 0 ? lds32(row_q + 4 * w - 4) : last1 << 24;
-          const uint32_t nm = w > 0 ? lds32(row_n + 4 * w - 4) : last2 << 24;
-          o = finalize_word(c, cm, n, nm);
-          if (q == 1 && w == 0) o = (o & 0xffffff00u) | (c & 0xffu);   // flat index PW is copied (.cc:578, :584)
-        }
-        out[w] = o;
-      }
-      last2 = last1;
-      last1 = lds8(row_q + PW - 1);
-    };
+    for (uint32_t i = 0; i + 1 < S && imore; i++) issue();
 
     uint32_t acc[4] = {0, 0, 0, 0};  // per-lane counts of set bits {0,2},{1,3},{4,6},{5,7}, two u16 each
     while (more) {
+      if (imore) issue();
       const uint32_t slot = rp.slot;
       mbar_wait(full0 + 8 * slot, rp.phase);
       if (!cur.halo()) {
@@ -517,10 +528,8 @@ __global__ void __maxnreg__(FPV_FAST_MAXNREG) k_encode_fast(const FastParams p) 
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(empty0 + 8 * slot);
-      const bool task_end = cur.last_of_task();
-      const uint32_t task_f = cur.f;
-      if (task_end) {
-        uint32_t* gb = p.stats[cur.f].dbits;
+      if (cur.last_of_task()) {
+        const uint32_t ctab = ctab0 + (cur.tseq & 1u) * (kCtaStatWords * 4);
 #pragma unroll
         for (int k = 0; k < 4; k++) {
           const uint32_t s0 = __reduce_add_sync(0xffffffffu, acc[k] & 0xffffu);
@@ -528,26 +537,16 @@ __global__ void __maxnreg__(FPV_FAST_MAXNREG) k_encode_fast(const FastParams p) 
           // acc[0]: bits 0,2  acc[1]: bits 1,3  acc[2]: bits 4,6  acc[3]: bits 5,7
           const int b0 = (k & 1) + 4 * (k >> 1);
           if (lane == 0) {
-            if (s0) atomicAdd(&gb[b0], s0);
-            if (s1) atomicAdd(&gb[b0 + 2], s1);
+            if (s0) atoms_add(ctab + 4 * (512 + b0), s0);
+            if (s1) atoms_add(ctab + 4 * (512 + b0 + 2), s1);
           }
           acc[k] = 0;
         }
+        task_done<MODE>(p, cur.f, PASS0 ? guess : p.stats[cur.f].assumed, cur.bands, ctab, (uint32_t)NW + 1, lane);
       }
-      // The previous stage's preview row: every consumer released that stage before the stage sampled above could
-      // be issued (ring depth), so this never waits, and it runs while the consumers are busy with the current stage.
-      if (have_prev) preview_stage();
-      pc = cur;
-      pr = rp;
-      have_prev = true;
       more = cur.advance(p, total_tasks);
       rp.next(S);
-      // Next TMA issue LAST: lane 0 sleeps on the slot's empty barrier and fires the copy the moment the last
-      // consumer lets go -- nothing may sit between that release and the issue (the kernel waits on stage data).
-      if (imore) issue();
-      if (task_end) frame_ticket<MODE>(p, task_f, PASS0 ? guess : p.stats[task_f].assumed, parts, lane);
     }
-    if (have_prev) preview_stage();
     return;
   }
 
@@ -559,7 +558,6 @@ __global__ void __maxnreg__(FPV_FAST_MAXNREG) k_encode_fast(const FastParams p) 
   const uint32_t rowb = W * 2;                            // bytes per row in a stage
   uint32_t hist_a = smem_u32(scratch + (size_t)warp * kWarpScratchBytes);
   asm volatile("" : "+r"(hist_a));  // keep it in a register instead of recomputing it per row
-  const uint32_t prev_lane = prev0 + (c0 >> 2);           // this lane's two pixels within a preview row of the ring
 
   while (more) {
     // ---- start of a task ---------------------------------------------------------
@@ -567,6 +565,8 @@ __global__ void __maxnreg__(FPV_FAST_MAXNREG) k_encode_fast(const FastParams p) 
     const uint32_t assumed = PASS0 ? guess : p.stats[f].assumed;
     const bool use_delta = p.delta != nullptr && (assumed & 1u);
     const bool use_cg = (assumed & 2u) != 0;
+    const uint32_t ctab = ctab0 + (cur.tseq & 1u) * (kCtaStatWords * 4);
+    const uint32_t bands = cur.bands;
     StripState st;
 #pragma unroll
     for (int j = 0; j < 4; j++) { st.ph[j] = 0; st.pw[j] = 0; }
@@ -580,6 +580,7 @@ __global__ void __maxnreg__(FPV_FAST_MAXNREG) k_encode_fast(const FastParams p) 
     }
     uint8_t* oh = p.high + (uint64_t)f * p.P + (uint64_t)y * W + c0;
     uint8_t* ol = mode_has_low(MODE) ? p.low + (uint64_t)f * p.P + (uint64_t)y * W + c0 : nullptr;
+    uint8_t* op = p.preview_raw + (uint64_t)f * p.PP + (uint64_t)(y >> 2) * p.PW + (c0 >> 2);
 
     for (;;) {
       const uint32_t nrows = cur.nrows();
@@ -589,17 +590,16 @@ __global__ void __maxnreg__(FPV_FAST_MAXNREG) k_encode_fast(const FastParams p) 
       mbar_wait(full0 + 8 * slot, rp.phase);
       const uint32_t raw_lane = ring0 + slot * slot_bytes + kHaloPx * 2 + c0 * 2;  // pixel (y, c0)
 
-      if (own && y >= 4 && nrows == RPS) {
+      if (y >= 4 && nrows == RPS) {
         // steady state: RPS owned rows, none of them row 0 / row 1; stages start on even rows
         // (bands on multiples of 4), so a preview row group ends with the last row of a stage
         const bool group_end = RPS == 4 || (y & 2u);
-        const uint32_t prev_sm = prev_lane + (cur.pseq & (kPrevRing - 1)) * p.prev_pitch;
         if (use_delta && use_cg) {
 #pragma unroll
           for (int r = 0; r < RPS; r++) {
             fast_row<MODE, false, FULL, true>(st, raw_lane + r * rowb, raw_lane + r * rowb + p.stage_bytes, qc, true,
                                               true, active, true, y + r, r == RPS - 1 && group_end, c0, w31, oh, ol,
-                                              prev_sm, hist_a);
+                                              op, hist_a);
             oh += W;
             if (mode_has_low(MODE)) ol += W;
           }
@@ -608,19 +608,21 @@ __global__ void __maxnreg__(FPV_FAST_MAXNREG) k_encode_fast(const FastParams p) 
           for (int r = 0; r < RPS; r++) {
             fast_row<MODE, false, FULL, false>(st, raw_lane + r * rowb, raw_lane + r * rowb + p.stage_bytes, qc,
                                                use_delta, use_cg, active, true, y + r, r == RPS - 1 && group_end, c0,
-                                               w31, oh, ol, prev_sm, hist_a);
+                                               w31, oh, ol, op, hist_a);
             oh += W;
             if (mode_has_low(MODE)) ol += W;
           }
         }
+        if (group_end) op += p.PW;
         y += RPS;
       } else {
         for (uint32_t r = 0; r < nrows; r++) {
           fast_row<MODE, true, FULL, false>(st, raw_lane + r * rowb, raw_lane + r * rowb + p.stage_bytes, qc,
-                                            use_delta, use_cg, active, own, y, (y & 3u) == 3u, c0, w31, oh, ol,
-                                            prev_lane + (cur.pseq & (kPrevRing - 1)) * p.prev_pitch, hist_a);
+                                            use_delta, use_cg, active, own, y, (y & 3u) == 3u, c0, w31, oh, ol, op,
+                                            hist_a);
           oh += W;
           if (mode_has_low(MODE)) ol += W;
+          if ((y & 3u) == 3u) op += p.PW;
           y++;
         }
       }
@@ -631,29 +633,27 @@ __global__ void __maxnreg__(FPV_FAST_MAXNREG) k_encode_fast(const FastParams p) 
       if (last) break;
     }
 
-    // ---- end of task: publish low-OR and this warp's histograms, take the frame's ticket ----------
+    // ---- end of task: this warp's low-OR and histograms into the CTA-level table, then the task's roll call ----
     if (mode_has_low(MODE)) {
       // lanes past the end of the row accumulated garbage (see fast_row)
       const uint32_t orl = __reduce_or_sync(0xffffffffu, (FULL || active) ? (st.orl & kLoBytes) : 0u);
-      if (lane == 0 && orl) atomicOr(&p.stats[f].low_or, orl);
+      if (lane == 0 && orl) atoms_or(ctab + 4 * (512 + 8), orl);
     }
-    uint32_t* gh = p.stats[f].hist_a;  // hist_a, hist_b are contiguous: 512 bins
     for (uint32_t i = lane; i < kWarpHistWords; i += 32) {
       const uint32_t v = lds32(hist_a + 4 * i);
       if (v) {
         sts32(hist_a + 4 * i, 0);
-        atomicAdd(&gh[i], v);
+        atoms_add(ctab + 4 * i, v);
       }
     }
-    frame_ticket<MODE>(p, f, assumed, parts, lane);
+    task_done<MODE>(p, f, assumed, bands, ctab, (uint32_t)NW + 1, lane);
   }
 }
 
 static inline size_t fast_smem_bytes(uint32_t W, int stages, int rows_per_stage) {
   const size_t stage_bytes = ((size_t)rows_per_stage * W + kHaloPx) * 2;
   const size_t warps = (W + kStripPx - 1) / kStripPx;
-  const size_t prev_pitch = ((W / 4) + 15) / 16 * 16;
-  return (size_t)stages * 2 * stage_bytes + warps * kWarpScratchBytes + kPrevRing * prev_pitch + 2 * (size_t)stages * 8;
+  return (size_t)stages * 2 * stage_bytes + warps * kWarpScratchBytes + 2 * kCtaStatWords * 4 + 2 * (size_t)stages * 8;
 }
 
 }  // namespace fpv

@@ -75,6 +75,15 @@ __device__ __forceinline__ void sts16(uint32_t a, uint32_t v) {
 __device__ __forceinline__ void sts32(uint32_t a, uint32_t v) {
   asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
 }
+// shared-memory atomics on a shared-space address
+__device__ __forceinline__ uint32_t atoms_add(uint32_t a, uint32_t v) {
+  uint32_t old;
+  asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(a), "r"(v) : "memory");
+  return old;
+}
+__device__ __forceinline__ void atoms_or(uint32_t a, uint32_t v) {
+  asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
 __device__ __forceinline__ void red_shared_inc(uint32_t a) {
   asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a) : "memory");
 }
