@@ -50,6 +50,8 @@
 // frames) is L2-resident.
 #pragma once
 
+#include <type_traits>
+
 #include "fpv_internal.h"
 #include "fpv_ptx.cuh"
 
@@ -132,11 +134,23 @@ __device__ __forceinline__ uint32_t bitselect(uint32_t a, uint32_t b, uint32_t m
   return r;
 }
 
-// One step of the chain for two pixels: x = (c + min3(n,w,nw) + max3(n,w,nw)) & 0x00ff00ff.  (Doing the two
-// additions as IMADs on the FMA pipe instead of one IADD3 measured no different: the chain is bound by the
-// dependent latency max3 -> add -> and, not by the ALU pipe's issue rate.)
+// One step of the chain for two pixels in S FORM: each 16-bit lane holds (byte << 8) | guard.
+//     x = c + min3(n,w,nw) + max3(n,w,nw),   c = r - nw   (plain 32-bit arithmetic)
+// because CG = n + w - median(n,w,nw) = min3 + max3 - nw (.cc:247-252).  With the byte in the TOP half of its
+// lane the mod-256 wrap of the reference's uint8 arithmetic (.cc:330) happens by itself: what overflows
+// the high lane leaves the register, what overflows the low lane (0..2 per step: the lane sum r - nw + min3 +
+// max3 = r + n + w - median lies in [0, 765]) lands in the GUARD byte of the high lane.  The low lane's guard
+// stays 0 (nothing carries into bit 0).  The high lane's guard only ever grows by that carry: n and nw are
+// clean (guard 0), so if the 16-bit compare picks w it propagates w's guard once (w cannot be both the
+// strict minimum and the strict maximum; if all three tie w equals the clean n), hence
+//     guard(x) <= guard(w) + 2   and   guard <= 2 L <= 80 < 256 within a segment of L <= 40 pixels,
+// starting from a clean incoming value.  A non-zero guard never changes a byte: it can only break ties
+// between equal bytes, and either choice has the same top byte.  The finished row is cleaned once
+// (& 0xff00ff00) before it becomes the next row's n / nw and the IO warp's input.  Against the masked
+// lane-form step (min3, max3, add, and) this is one ALU-pipe instruction less per step and a dependent
+// depth of 2 instead of 3; two chain warps share a sub-partition's ALU pipe, so both count.
 __device__ __forceinline__ uint32_t chain_step(uint32_t c, uint32_t n, uint32_t w, uint32_t nw) {
-  return (c + __vimin3_u16x2(n, w, nw) + __vimax3_u16x2(n, w, nw)) & kLaneMask;
+  return c + __vimin3_u16x2(n, w, nw) + __vimax3_u16x2(n, w, nw);
 }
 
 // One row of the chain warp: residual row (pair form, in PRE) -> finished row in x[] and in POST.
@@ -162,7 +176,7 @@ __device__ __forceinline__ void pair_chain_row(const uint32_t (&n)[8 * LW2], uin
     const uint4 v = lds128(pre + k * 512 + (k < LW2 ? a_lo : a_hi));
     x[4 * k + 0] = v.x; x[4 * k + 1] = v.y; x[4 * k + 2] = v.z; x[4 * k + 3] = v.w;
   }
-  // PRE holds r + 256 per lane (see the helper's pre_row)
+  // PRE holds the residual row in S form (see the helper's pre_row)
   if (cgmask != 0 && y > 0) {
     uint32_t c[L];
     uint32_t nw_in = __shfl_up_sync(0xffffffffu, n[L - 1], 1);
@@ -173,7 +187,7 @@ __device__ __forceinline__ void pair_chain_row(const uint32_t (&n)[8 * LW2], uin
     // flat index W (row 1, column 0) is not predicted (.cc:327 starts at W+1)
     const bool copy_first = (y == 1) && (lane == 0);
     const uint32_t copy_mask = SPLIT ? 0x0000ffffu : 0xffffffffu;   // split: only the left half has a column 0
-    const uint32_t r_first = x[0] - kLaneBias;
+    const uint32_t r_first = x[0];
 #pragma unroll
     for (int t = 0; t < L; t++) c[t] = x[t] - (t == 0 ? nw_in : n[t - 1]);
     PROF_MARK(0);
@@ -193,6 +207,7 @@ __device__ __forceinline__ void pair_chain_row(const uint32_t (&n)[8 * LW2], uin
         w = chain_step(c[t], nn, w, nw);
         nw = nn;
       }
+      w &= kHiBytes;                                // drop the guard byte before handing the value on
       w_in = __shfl_up_sync(0xffffffffu, w, 1);
       if (SPLIT) {
         // the left half's last segment feeds the right half's first (a guess, repaired below)
@@ -222,7 +237,7 @@ __device__ __forceinline__ void pair_chain_row(const uint32_t (&n)[8 * LW2], uin
     if (false)
 #endif
     for (;;) {
-      uint32_t w_new = __shfl_up_sync(0xffffffffu, x[L - 1], 1);
+      uint32_t w_new = __shfl_up_sync(0xffffffffu, x[L - 1] & kHiBytes, 1);
       if (SPLIT) {
         uint32_t xl = x[L - 1];
         if (!FULL) {
@@ -230,7 +245,7 @@ __device__ __forceinline__ void pair_chain_row(const uint32_t (&n)[8 * LW2], uin
           for (int k = 0; k < 2 * LW2; k++)
             if ((uint32_t)(4 * k + 3) == last_t) xl = x[4 * k + 3];
         }
-        xl = __shfl_sync(0xffffffffu, xl, (int)last_lane);
+        xl = __shfl_sync(0xffffffffu, xl, (int)last_lane);   // only its (guard-free) low lane is used
         if (lane == 0) w_new = (last_prev >> 16) | (xl << 16);
       } else if (lane == 0) {
         w_new = last_prev;
@@ -264,20 +279,22 @@ __device__ __forceinline__ void pair_chain_row(const uint32_t (&n)[8 * LW2], uin
       if (settled && !(SPLIT && !FULL)) break;
     }
     PROF_MARK(3);
-    if (cgmask != 0xffffffffu) {
+    if (cgmask == 0xffffffffu) {
+      // clean the guard bytes: this row is the next row's n / nw and the IO warp's input
+#pragma unroll
+      for (int t = 0; t < L; t++) x[t] &= kHiBytes;
+    } else {
       // one of the two frames is not ClampedGradient-predicted: its row is the residual row
+      const uint32_t keep = cgmask & kHiBytes;
 #pragma unroll
       for (int k = 0; k < 2 * LW2; k++) {
         const uint4 v = lds128(pre + k * 512 + (k < LW2 ? a_lo : a_hi));
-        x[4 * k + 0] = (x[4 * k + 0] & cgmask) | ((v.x - kLaneBias) & ~cgmask);
-        x[4 * k + 1] = (x[4 * k + 1] & cgmask) | ((v.y - kLaneBias) & ~cgmask);
-        x[4 * k + 2] = (x[4 * k + 2] & cgmask) | ((v.z - kLaneBias) & ~cgmask);
-        x[4 * k + 3] = (x[4 * k + 3] & cgmask) | ((v.w - kLaneBias) & ~cgmask);
+        x[4 * k + 0] = (x[4 * k + 0] & keep) | (v.x & ~cgmask);
+        x[4 * k + 1] = (x[4 * k + 1] & keep) | (v.y & ~cgmask);
+        x[4 * k + 2] = (x[4 * k + 2] & keep) | (v.z & ~cgmask);
+        x[4 * k + 3] = (x[4 * k + 3] & keep) | (v.w & ~cgmask);
       }
     }
-  } else {
-#pragma unroll
-    for (int t = 0; t < L; t++) x[t] -= kLaneBias;
   }
 #pragma unroll
   for (int k = 0; k < 2 * LW2; k++)
@@ -365,7 +382,7 @@ __global__ void __launch_bounds__(kPairThreads, 2) k_decode_pair(const PairParam
   if (is_chain) {
     // =============================== chain warp ===================================
     const bool lane_valid = FULL || col0 < W;
-    const uint32_t vmask = lane_valid ? cgmask : 0u;
+    const uint32_t vmask = lane_valid ? (cgmask & kHiBytes) : 0u;   // compares look at the bytes, not the guards
     const uint32_t last_lane = FULL ? 31u : (W - 1) / L, last_t = FULL ? (uint32_t)(L - 1) : (W - 1) % L;
     uint32_t ra[L], rb[L];                    // finished rows, alternating roles
 #pragma unroll
@@ -403,7 +420,6 @@ __global__ void __launch_bounds__(kPairThreads, 2) k_decode_pair(const PairParam
   // UnextractFrame byte swap (.cc:857-860) is folded into the selector
   const uint32_t selA = do_swap ? 0x4501u : 0x5410u, selB = do_swap ? 0x6723u : 0x7632u;
   const uint32_t dmask = (delA ? 0x0000ffffu : 0u) | (delB ? 0xffff0000u : 0u);
-  const uint32_t mh = kHiBytes & dmask, ml = kLoBytes & dmask;
   const uint32_t r2_bytes = (lowA ? W : 0u) + (lowB ? W : 0u) + (dmask ? 4 * RB : 0u);
 
   if (is_helper && elected) {
@@ -480,20 +496,22 @@ __global__ void __launch_bounds__(kPairThreads, 2) k_decode_pair(const PairParam
     uint2 A[LW2], B[LW2];
 #pragma unroll
     for (int k = 0; k < LW2; k++) { A[k] = lds64(ra + 8 * chunk(k)); B[k] = lds64(ra + RB + 8 * chunk(k)); }
-    // PRE holds r + 256 per 16-bit lane (the chain's c = r + 256 - nw then is one subtraction): the
-    // 0x01 bytes come out of the shifts' addends, t = [0, 1, b0, b1] and u = [b2, b3, 0, 1]
+    // PRE holds the residuals in S form, bytes [0, a_j, 0, b_j]; the zero bytes come out of the shifted
+    // B words t = [0, 0, b0, b1] and u = [b2, b3, 0, 0] (the shifts are FMA-pipe multiplies)
 #pragma unroll
     for (int k = 0; k < LW2; k++) {
-      uint32_t t = B[k].x * 65536u + 0x0100u, u = __umulhi(B[k].x, 65536u) + 0x01000000u;
-      sts128(dst + (2 * chunk(k)) * 512, __byte_perm(A[k].x, t, 0x5650), __byte_perm(A[k].x, t, 0x5751),
-             __byte_perm(A[k].x, u, 0x7472), __byte_perm(A[k].x, u, 0x7573));
-      t = B[k].y * 65536u + 0x0100u; u = __umulhi(B[k].y, 65536u) + 0x01000000u;
-      sts128(dst + (2 * chunk(k) + 1) * 512, __byte_perm(A[k].y, t, 0x5650), __byte_perm(A[k].y, t, 0x5751),
-             __byte_perm(A[k].y, u, 0x7472), __byte_perm(A[k].y, u, 0x7573));
+      uint32_t t = B[k].x * 65536u, u = __umulhi(B[k].x, 65536u);
+      sts128(dst + (2 * chunk(k)) * 512, __byte_perm(A[k].x, t, 0x6404), __byte_perm(A[k].x, t, 0x7414),
+             __byte_perm(A[k].x, u, 0x4626), __byte_perm(A[k].x, u, 0x5636));
+      t = B[k].y * 65536u; u = __umulhi(B[k].y, 65536u);
+      sts128(dst + (2 * chunk(k) + 1) * 512, __byte_perm(A[k].y, t, 0x6404), __byte_perm(A[k].y, t, 0x7414),
+             __byte_perm(A[k].y, u, 0x4626), __byte_perm(A[k].y, u, 0x5636));
     }
   };
-  // finished row in POST[buf] -> output pixels (.cc:335-344 and .cc:850-862), then one bulk store per frame
-  auto post_row = [&](uint32_t buf) {
+  // finished row in POST[buf] (S form) -> output pixels (.cc:335-344 and .cc:850-862), then one bulk store per
+  // frame.  DALL: both frames of the pair add the delta image (the common case, no per-lane delta mask).
+  auto post_row = [&](uint32_t buf, auto dall_tag) {
+    constexpr bool DALL = decltype(dall_tag)::value;
     if (r2_bytes) mbar_wait(full2 + 8 * c2_slot, c2_par);
     const uint32_t src = sm0 + kPost + buf * kBuf + slot0;
     const uint32_t la = sm0 + kR2 + c2_slot * kR2Slot + col0, da = sm0 + kR2 + c2_slot * kR2Slot + 2 * RB + slot0;
@@ -516,10 +534,11 @@ __global__ void __launch_bounds__(kPairThreads, 2) k_decode_pair(const PairParam
 #pragma unroll
     for (int k = 0; k < LW2; k++) {     // 8 columns per step
       uint32_t Z[8], V[8];
-      uint32_t t = B[k].x << 16, u = B[k].x >> 16;
+      // low bytes of both frames in lane form [lA, 0, lB, 0]; the shifts are FMA-pipe multiplies
+      uint32_t t = B[k].x * 65536u, u = __umulhi(B[k].x, 65536u);
       Z[0] = __byte_perm(A[k].x, t, 0x4640); Z[1] = __byte_perm(A[k].x, t, 0x4741);
       Z[2] = __byte_perm(A[k].x, u, 0x6462); Z[3] = __byte_perm(A[k].x, u, 0x6563);
-      t = B[k].y << 16; u = B[k].y >> 16;
+      t = B[k].y * 65536u; u = __umulhi(B[k].y, 65536u);
       Z[4] = __byte_perm(A[k].y, t, 0x4640); Z[5] = __byte_perm(A[k].y, t, 0x4741);
       Z[6] = __byte_perm(A[k].y, u, 0x6462); Z[7] = __byte_perm(A[k].y, u, 0x6563);
       const uint32_t Xs[8] = {X[2 * k].x, X[2 * k].y, X[2 * k].z, X[2 * k].w,
@@ -528,15 +547,16 @@ __global__ void __launch_bounds__(kPairThreads, 2) k_decode_pair(const PairParam
                               D[2 * k + 1].x, D[2 * k + 1].y, D[2 * k + 1].z, D[2 * k + 1].w};
 #pragma unroll
       for (int j = 0; j < 8; j++) {
-        // per 16-bit lane: ((x + dh) & 0xff) << 8 | ((l + dl) & 0xff).  The delta's high and low
-        // bytes are added separately so that a carry out of one byte only ever lands in a bit the
-        // final select drops (.cc:337-338: the bytes wrap independently); mh / ml also switch the
-        // delta off for a frame of the pair that does not use it.
+        // per 16-bit lane: ((x + dh) & 0xff) << 8 | ((l + dl) & 0xff) with packed 16-bit adds (VIADD.16x2:
+        // no carry between the lanes).  x arrives as x << 8, so the first sum has the high byte in place
+        // (its low byte is dl: dropped by the select); the second has the low byte in place (its carry
+        // lands in the high byte: dropped) -- the bytes wrap independently, .cc:337-338.  dmask switches
+        // the delta off for a frame of the pair that does not use it.
 #ifdef FPV_ABL_IO_LIGHT
         V[j] = Xs[j] ^ Ds[j] ^ Z[j];
 #else
-        const uint32_t hi = Xs[j] * 256u + (Ds[j] & mh), lo = Z[j] + (Ds[j] & ml);
-        V[j] = bitselect(hi, lo, kHiBytes);
+        const uint32_t d = DALL ? Ds[j] : (Ds[j] & dmask);
+        V[j] = bitselect(__vadd2(Xs[j], d), __vadd2(Z[j], d), kHiBytes);
         if (SHIFT) V[j] = __umulhi(V[j], shmul) & um;     // per lane: (pixel >> shift), .cc:855
 #endif
       }
@@ -575,8 +595,12 @@ __global__ void __launch_bounds__(kPairThreads, 2) k_decode_pair(const PairParam
   }
   pair_bar_sync(bar_id);
   PROF_DECL(3);
+  const bool dall = dmask == 0xffffffffu;
   for (uint32_t y = 0; y < H; y++) {
-    if (y >= 1) post_row((y - 1) & 1u);
+    if (y >= 1) {
+      if (dall) post_row((y - 1) & 1u, std::true_type{});
+      else post_row((y - 1) & 1u, std::false_type{});
+    }
     PROF_MARK(0);
     if (elected) bulk_wait_read0();   // the output row buffer may be rewritten after the barrier
     PROF_MARK(1);
@@ -584,7 +608,8 @@ __global__ void __launch_bounds__(kPairThreads, 2) k_decode_pair(const PairParam
     PROF_MARK(2);
   }
   PROF_FLUSH(8, 3);
-  post_row((H - 1) & 1u);
+  if (dall) post_row((H - 1) & 1u, std::true_type{});
+  else post_row((H - 1) & 1u, std::false_type{});
   if (elected) bulk_wait0();
 }
 
