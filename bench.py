@@ -322,6 +322,7 @@ def main():
     ap.add_argument("--ingest-seconds", type=float, default=1.5)
     ap.add_argument("--frames", type=int, default=1184,
                     help="frames per GPU per step (device-resident); 1184 = 148 SMs x 2 resident decode CTAs x 4 frames")
+    ap.add_argument("--decode-frames", type=int, default=0, help="frames of the device-resident decode leg (0: one wave)")
     ap.add_argument("--e2e-frames", type=int, default=512, help="frames per step of the host-buffer (e2e) legs")
     ap.add_argument("--e2e-batch", type=int, default=64)
     ap.add_argument("--e2e-slots", type=int, default=3, help="overlapped submit slots of the host-buffer legs (<= 4)")
@@ -490,7 +491,7 @@ def main():
 
     # ---- decode (inverse transform) on the planes just produced: extra, device-resident -------------
     decode = None
-    Fd = min(F, 1184 if P < 4000000 else 592)     # decode legs: one full wave of the decode kernel
+    Fd = min(F, args.decode_frames or (1184 if P < 4000000 else 592))     # decode legs: one full wave of the decode kernel
     if not args.no_decode:
         d_out = torch.empty((Fd, P), dtype=torch.int16, device=dev)
         dsteps = max(3, min(args.steps, 20))

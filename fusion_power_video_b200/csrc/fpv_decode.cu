@@ -25,6 +25,7 @@
 
 #include "fpv_internal.h"
 #include "fpv_decode_pair.cuh"
+#include "fpv_decode_fused.cuh"
 
 namespace fpv {
 
@@ -69,6 +70,8 @@ struct DecodeParams {
   const uint8_t* flags;
   const uint16_t* delta;   // image form, may be nullptr
   uint16_t* out;
+  uint8_t* plane_out;      // planes mode (fpv_unpredict_planes): the reconstructed byte plane goes here (must be
+                           // `high`: in place) and nothing else is done -- no low plane, no delta, no `out`
   uint32_t W, H;
   uint64_t P;
   int shift, big_endian, unextract;
@@ -237,6 +240,26 @@ __global__ void __launch_bounds__(128) k_decode_spec(const DecodeParams p) {
       const uint32_t* lb = st + slot_words;
       const uint32_t* db = st + slot_words + Wp / 4;
       uint16_t* orow = fout + (uint64_t)y * W;
+      if (p.plane_out != nullptr) {
+        // planes mode: the row of reconstructed bytes, in place (row y was staged before it is overwritten;
+        // rows further down are only read)
+        uint8_t* prow = p.plane_out + (uint64_t)f * p.P + (uint64_t)y * W;
+        if (use_cg && y > 0)
+          for (uint32_t q = lane; q < (W + 3) / 4; q += 32) {
+            uint32_t col = 4 * q;
+            uint32_t sg = __umulhi(col, p.div_magic);
+            if ((sg + 1) * L <= col) sg++;
+            else if (sg * L > col) sg--;
+            const uint32_t hw = hcur[sg * SW + ((col - sg * L) >> 2)];
+            if (ALIGN >= 4) {
+              *reinterpret_cast<uint32_t*>(prow + col) = hw;
+            } else {
+#pragma unroll
+              for (uint32_t b = 0; b < 4; b++)
+                if (col + b < W) prow[col + b] = (uint8_t)(hw >> (8 * b));
+            }
+          }
+      } else
       for (uint32_t q = lane; q < (W + 3) / 4; q += 32) {
         uint32_t col = 4 * q;
         uint32_t sg = __umulhi(col, p.div_magic);
@@ -642,28 +665,74 @@ int enqueue_delta_dup(const Geom& g, const uint16_t* delta_image, uint32_t* ddup
 
 // Which decode kernel handles a geometry; FPV_DECODE_KERNEL=pair|simd|spec forces one
 // (tests run every kernel on every case it supports).
-enum DecodeKernel { kDecPair, kDecSimd, kDecSpec };
+enum DecodeKernel { kDecFused, kDecPair, kDecSimd, kDecSpec };
 
 static DecodeKernel pick_decode_kernel(const Geom& g, const uint16_t* delta, const uint32_t* ddup) {
   const bool pair_ok = (pair_width_ok(g.W) || split_width_ok(g.W)) && (delta == nullptr || ddup != nullptr);
   const bool simd_ok = g.W % 4 == 0 && g.W <= 64 * 32 && g.W >= 64;
   if (const char* v = getenv("FPV_DECODE_KERNEL")) {
+    if (!strcmp(v, "fused") && pair_ok) return kDecFused;
     if (!strcmp(v, "pair") && pair_ok) return kDecPair;
     if (!strcmp(v, "simd") && simd_ok) return kDecSimd;
     if (!strcmp(v, "spec")) return kDecSpec;
   }
   if (getenv("FPV_DECODE_SEGMENTED")) return kDecSpec;
-  if (pair_ok) return kDecPair;
+  if (pair_ok) return kDecFused;
   if (simd_ok) return kDecSimd;
   return kDecSpec;
 }
+
+// k_decode_spec for the geometry in p (W, H, P, n and the pointers set by the caller).
+static int launch_spec(DecodeParams p, int num_sms, cudaStream_t stream, cudaError_t* err, const TimingHook* hook) {
+  uint32_t L = (p.W + 31) / 32;
+  L = (L + 3) / 4 * 4;
+  p.L = L; p.Lw = L / 4; p.SW = p.Lw | 1u;
+  p.Wp = (p.W + 15) / 16 * 16;
+  p.div_magic = (uint32_t)((0x100000000ull + L - 1) / L);
+  const uint32_t slot_words = 32 * p.SW;
+  const uint32_t stage_words = slot_words + p.Wp / 4 + p.Wp / 2;
+  const int warps_per_block = 4;
+  const size_t limit = 200 * 1024;
+  int nst = 3;
+  while (nst > 1 && (size_t)(2 * slot_words + nst * stage_words) * 4 * warps_per_block > limit) nst--;
+  int wpb = warps_per_block;
+  while (wpb > 1 && (size_t)(2 * slot_words + nst * stage_words) * 4 * wpb > limit) wpb--;
+  p.nst = nst;
+  p.warp_smem_words = 2 * slot_words + nst * stage_words;
+  size_t smem = (size_t)p.warp_smem_words * 4 * wpb;
+  if (smem > limit) {
+    *err = cudaErrorInvalidConfiguration;  // geometry not supported: the caller falls back to enqueue_decode_serial
+    return -2;
+  }
+  int blocks = (int)((p.n + wpb - 1) / wpb);
+  int max_blocks = num_sms * 16;
+  if (blocks > max_blocks) blocks = max_blocks;
+  int align = (p.W % 16 == 0) ? 16 : (p.W % 4 == 0 ? 4 : 1);
+  cudaError_t e = cudaSuccess;
+  if (hook) cudaEventRecord(hook->start, stream);
+  if (align == 16) {
+    e = cudaFuncSetAttribute(k_decode_spec<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit);
+    if (e == cudaSuccess) k_decode_spec<16><<<blocks, wpb * 32, smem, stream>>>(p);
+  } else if (align == 4) {
+    e = cudaFuncSetAttribute(k_decode_spec<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit);
+    if (e == cudaSuccess) k_decode_spec<4><<<blocks, wpb * 32, smem, stream>>>(p);
+  } else {
+    e = cudaFuncSetAttribute(k_decode_spec<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit);
+    if (e == cudaSuccess) k_decode_spec<1><<<blocks, wpb * 32, smem, stream>>>(p);
+  }
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (hook) cudaEventRecord(hook->stop, stream);
+  *err = e;
+  return e == cudaSuccess ? 1 : -1;
+}
+
 
 int enqueue_decode(const Geom& g, int num_sms, const uint8_t* high, const uint8_t* low,
                    const uint8_t* flags, const uint16_t* delta, const uint32_t* ddup, uint32_t n,
                    bool unextract, uint16_t* out, cudaStream_t stream, cudaError_t* err,
                    const TimingHook* hook) {
   const DecodeKernel which = pick_decode_kernel(g, delta, ddup);
-  if (which == kDecPair) {
+  if (which == kDecPair || which == kDecFused) {
     PairParams pp;
     pp.high = high; pp.low = low; pp.flags = flags; pp.ddup = delta ? ddup : nullptr; pp.out = out;
     const bool split = split_width_ok(g.W);
@@ -677,7 +746,21 @@ int enqueue_decode(const Geom& g, int num_sms, const uint8_t* high, const uint8_
     const int blocks = split ? (int)((n + 1) / 2) : (int)((n + 3) / 4);
     cudaError_t e = cudaSuccess;
     if (hook) cudaEventRecord(hook->start, stream);
-    if (split) {
+    if (which == kDecFused) {
+      // one warp per pair of frames (split mode: per frame)
+      if (split) {
+        if (LW2 == 3) e = launch_fused<3, true>(pp, full, stream);
+        else if (LW2 == 4) e = launch_fused<4, true>(pp, full, stream);
+        else e = launch_fused<5, true>(pp, full, stream);
+      } else
+      switch (LW2) {
+        case 1: e = launch_fused<1>(pp, full, stream); break;
+        case 2: e = launch_fused<2>(pp, full, stream); break;
+        case 3: e = launch_fused<3>(pp, full, stream); break;
+        case 4: e = launch_fused<4>(pp, full, stream); break;
+        default: e = launch_fused<5>(pp, full, stream); break;
+      }
+    } else if (split) {
       // half widths of 641..1280 columns
       if (LW2 == 3) e = launch_pair<3, true>(pp, full, blocks, stream);
       else if (LW2 == 4) e = launch_pair<4, true>(pp, full, blocks, stream);
@@ -728,49 +811,10 @@ int enqueue_decode(const Geom& g, int num_sms, const uint8_t* high, const uint8_
     return e == cudaSuccess ? 1 : -1;
   }
   DecodeParams p;
-  p.high = high; p.low = low; p.flags = flags; p.delta = delta; p.out = out;
+  p.high = high; p.low = low; p.flags = flags; p.delta = delta; p.out = out; p.plane_out = nullptr;
   p.W = g.W; p.H = g.H; p.P = g.P; p.shift = g.shift; p.big_endian = g.big_endian;
   p.unextract = unextract ? 1 : 0; p.n = n;
-  uint32_t L = (g.W + 31) / 32;
-  L = (L + 3) / 4 * 4;
-  p.L = L; p.Lw = L / 4; p.SW = p.Lw | 1u;
-  p.Wp = (g.W + 15) / 16 * 16;
-  p.div_magic = (uint32_t)((0x100000000ull + L - 1) / L);
-  const uint32_t slot_words = 32 * p.SW;
-  const uint32_t stage_words = slot_words + p.Wp / 4 + p.Wp / 2;
-  const int warps_per_block = 4;
-  const size_t limit = 200 * 1024;
-  int nst = 3;
-  while (nst > 1 && (size_t)(2 * slot_words + nst * stage_words) * 4 * warps_per_block > limit) nst--;
-  int wpb = warps_per_block;
-  while (wpb > 1 && (size_t)(2 * slot_words + nst * stage_words) * 4 * wpb > limit) wpb--;
-  p.nst = nst;
-  p.warp_smem_words = 2 * slot_words + nst * stage_words;
-  size_t smem = (size_t)p.warp_smem_words * 4 * wpb;
-  if (smem > limit) {
-    *err = cudaErrorInvalidConfiguration;  // geometry not supported: the caller falls back to enqueue_decode_serial
-    return -2;
-  }
-  int blocks = (int)((n + wpb - 1) / wpb);
-  int max_blocks = num_sms * 16;
-  if (blocks > max_blocks) blocks = max_blocks;
-  int align = (g.W % 16 == 0) ? 16 : (g.W % 4 == 0 ? 4 : 1);
-  cudaError_t e = cudaSuccess;
-  if (hook) cudaEventRecord(hook->start, stream);
-  if (align == 16) {
-    e = cudaFuncSetAttribute(k_decode_spec<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit);
-    if (e == cudaSuccess) k_decode_spec<16><<<blocks, wpb * 32, smem, stream>>>(p);
-  } else if (align == 4) {
-    e = cudaFuncSetAttribute(k_decode_spec<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit);
-    if (e == cudaSuccess) k_decode_spec<4><<<blocks, wpb * 32, smem, stream>>>(p);
-  } else {
-    e = cudaFuncSetAttribute(k_decode_spec<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit);
-    if (e == cudaSuccess) k_decode_spec<1><<<blocks, wpb * 32, smem, stream>>>(p);
-  }
-  if (e == cudaSuccess) e = cudaGetLastError();
-  if (hook) cudaEventRecord(hook->stop, stream);
-  *err = e;
-  return e == cudaSuccess ? 1 : -1;
+  return launch_spec(p, num_sms, stream, err, hook);
 }
 
 // Serial fallback: `scratch_high` must hold a writable copy of the high planes.
@@ -787,15 +831,22 @@ int enqueue_decode_serial(const Geom& g, uint8_t* scratch_high, const uint8_t* l
   return *err == cudaSuccess ? 2 : -1;
 }
 
+// Frame::Uncompress's undo of Predict on byte planes, in place (.cc:595-641): inverse ClampedGradient of the high
+// plane (width W) and of the preview (width W / 4) with the segmented speculative row kernel in planes mode, then
+// the delta planes are added back.
 int enqueue_unpredict_planes(const Geom& g, int num_sms, uint8_t* high, uint8_t* low,
                              uint8_t* preview, const uint8_t* flags, const uint16_t* delta,
                              uint32_t n, cudaStream_t stream, cudaError_t* err) {
-  (void)num_sms;
   int launches = 0;
-  k_cg_inverse_serial<<<(n + 31) / 32, 32, 0, stream>>>(high, flags, g.W, g.P, n);
+  DecodeParams p;
+  p.low = nullptr; p.flags = flags; p.delta = nullptr; p.out = nullptr;
+  p.shift = 0; p.big_endian = 0; p.unextract = 0; p.n = n;
+  p.high = high; p.plane_out = high; p.W = g.W; p.H = g.H; p.P = g.P;
+  if (launch_spec(p, num_sms, stream, err, nullptr) < 0) return -1;
   launches++;
   if (preview) {
-    k_cg_inverse_serial<<<(n + 31) / 32, 32, 0, stream>>>(preview, flags, g.PW, g.PP, n);
+    p.high = preview; p.plane_out = preview; p.W = g.PW; p.H = g.H / 4; p.P = g.PP;
+    if (launch_spec(p, num_sms, stream, err, nullptr) < 0) return -1;
     launches++;
   }
   if (delta) {

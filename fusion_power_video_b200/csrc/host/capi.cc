@@ -12,6 +12,7 @@
 
 #include "columnar_batch.h"
 #include "fusion_power_video.h"
+#include "host_internal.h"
 
 namespace {
 
@@ -205,6 +206,44 @@ long fpvh_columnar_roundtrip(size_t xsize, size_t ysize, int shift, int big_endi
   if (batches) *batches = st.batches;
   if (compressed_bytes) *compressed_bytes = st.compressed;
   return (st.failed || !enc->ok()) ? -1 : (long)st.count;
+}
+
+// Parity probe for the columnar path: pushes `n` frames through a ColumnarBatchEncoder and brotli-DECODES the plane
+// columns of every Batch it emits, frame by frame: flags[i], high[i][P], low[i][P] (zeros if the frame has no low
+// plane) and preview[i][P/16] are what Frame::Predict left in the planes (reference columnar_batch.cc:65-90 compresses
+// exactly those).  Returns the number of frames, -1 on failure.
+long fpvh_columnar_planes(size_t xsize, size_t ysize, int shift, int big_endian, int frames_per_batch,
+                          const uint16_t* frames, const int64_t* timestamps, size_t n, uint8_t* flags, uint8_t* high,
+                          uint8_t* low, uint8_t* preview) {
+  namespace cb = fpvc::columnarbatch;
+  const size_t P = xsize * ysize, PP = (xsize / 4) * (ysize / 4);
+  size_t count = 0;
+  bool failed = false;
+  std::unique_ptr<cb::ColumnarBatchEncoder> enc;
+  enc.reset(new cb::ColumnarBatchEncoder(xsize, ysize, shift, big_endian != 0, [&](cb::BatchPtr batch) {
+    if (!batch) return;
+    for (size_t i = 0; i < batch->length() && count < n; i++, count++) {
+      const uint8_t fl = batch->flags()[i];
+      flags[count] = fl;
+      size_t pos = batch->high_plane_offsets()[i];
+      if (!fpvc::internal::BrotliUnplane(batch->high_plane_column().data(), batch->high_plane_offsets()[i + 1], &pos, high + count * P, P))
+        failed = true;
+      pos = batch->preview_offsets()[i];
+      if (!fpvc::internal::BrotliUnplane(batch->preview_column().data(), batch->preview_offsets()[i + 1], &pos, preview + count * PP, PP))
+        failed = true;
+      memset(low + count * P, 0, P);
+      if (!(fl & 4)) {
+        pos = batch->low_plane_offsets()[i];
+        if (!fpvc::internal::BrotliUnplane(batch->low_plane_column().data(), batch->low_plane_offsets()[i + 1], &pos, low + count * P, P))
+          failed = true;
+      }
+    }
+    enc->ReturnProcessedBatch(batch);
+  }, frames_per_batch));
+  for (size_t i = 0; i < n; i++)
+    enc->PushFrame((uint64_t)timestamps[i], const_cast<uint16_t*>(frames + i * P), nullptr).wait();
+  enc->Close().get();
+  return (failed || !enc->ok()) ? -1 : (long)count;
 }
 
 // Real-time ingest (BASELINE configs[4]; the loop of reference encode.cc:63-96 driven by a camera clock instead of

@@ -40,6 +40,8 @@ def lib() -> C.CDLL:
     L.fpvh_columnar_roundtrip.argtypes = [sz, sz, i32, i32, i32, i32, i32, vp, vp, sz, vp, vp, sz, C.POINTER(sz),
                                           C.POINTER(C.c_long), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(sz)]
     L.fpvh_columnar_roundtrip.restype = C.c_long
+    L.fpvh_columnar_planes.argtypes = [sz, sz, i32, i32, i32, vp, vp, sz, vp, vp, vp, vp]
+    L.fpvh_columnar_planes.restype = C.c_long
     L.fpvh_encode_stream_multi.argtypes = [sz, sz, i32, i32, sz, u32, vp, i32, i32, vp, vp, sz, vp, sz, C.POINTER(C.c_double)]
     L.fpvh_encode_stream_multi.restype = sz
     L.fpvh_ingest.argtypes = [sz, sz, i32, i32, sz, u32, i32, i32, vp, sz, C.c_double, C.c_double, sz, C.POINTER(C.c_double)]
@@ -227,3 +229,19 @@ def columnar_roundtrip(frames, timestamps, xsize, ysize, shift=0, big_endian=Fal
         images = images.view(np.uint16)
     return images, out_ts[:cnt], {"batches": batches.value, "encoder_close": ec.value, "decoder_close": dc.value,
                                   "compressed_bytes": comp.value, "bytes_per_image": bpi.value}
+
+
+def columnar_planes(frames, timestamps, xsize, ysize, shift=0, big_endian=False, frames_per_batch=10):
+    """frames -> ColumnarBatchEncoder -> Batches; the plane columns of every batch brotli-decoded again.
+    Returns (flags[n], high[n][P], low[n][P] (zeros where a frame has no low plane), preview[n][P/16])."""
+    L = lib()
+    frames = np.ascontiguousarray(frames, dtype=np.uint16).reshape(-1, xsize * ysize)
+    ts = np.ascontiguousarray(timestamps, dtype=np.int64)
+    n, P, PP = frames.shape[0], xsize * ysize, (xsize // 4) * (ysize // 4)
+    flags = np.zeros(n, np.uint8)
+    high, low, preview = np.zeros((n, P), np.uint8), np.zeros((n, P), np.uint8), np.zeros((n, PP), np.uint8)
+    cnt = L.fpvh_columnar_planes(xsize, ysize, shift, int(big_endian), frames_per_batch, _p(frames), _p(ts), n, _p(flags),
+                                 _p(high), _p(low), _p(preview))
+    if cnt != n:
+        raise HostError(f"columnar planes probe failed ({cnt} of {n} frames): {last_error()}")
+    return flags, high, low, preview

@@ -5,8 +5,14 @@ import numpy as np
 import pytest
 
 from fusion_power_video_b200 import host, synth
+from oracle_binding import Oracle
 
 pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    return Oracle()
 
 
 def left_aligned(frames, shift, be):
@@ -60,3 +66,31 @@ def test_reference_smoke_sequence():
     ts = np.array([123456, 234567, 345678], np.int64)
     img, t, info = host.columnar_roundtrip(frames, ts, W, H, 0, False, 2, host.IMAGE_FULL)
     assert np.array_equal(img, frames) and np.array_equal(t, ts) and info["batches"] == 2
+
+
+@pytest.mark.parametrize("W,H,bits,shift,be,n,fpb", [
+    (100, 100, 16, 0, False, 5, 2),
+    (1280, 160, 12, 4, False, 12, 5),
+    (256, 64, 16, 0, True, 7, 7),
+    (320, 48, 8, 8, False, 5, 2),
+])
+def test_batch_planes_match_oracle_predict(oracle, W, H, bits, shift, be, n, fpb):
+    """The plane columns of a Batch, brotli-decoded, are exactly what the reference's Frame ctor + Predict leave in
+    high() / low() / preview() with the first frame as the delta frame (columnar_batch_encoder.cc:37-46,
+    columnar_batch.cc:65-90) -- checked against the oracle, not against a round trip."""
+    frames = synth.plasma_frames(n, W, H, bits=bits, seed=21).reshape(n, -1)
+    frames[n - 1] = frames[0]                 # a frame equal to the delta frame: planes of zeros
+    if be:
+        frames = frames.byteswap()
+    ts = np.arange(n, dtype=np.int64) + 5
+    flags, high, low, preview = host.columnar_planes(frames, ts, W, H, shift, be, fpb)
+    seen = set()
+    for i in range(n):
+        f, h, l, p = oracle.predict(frames[i], W, H, shift, be, frames[0])
+        seen.add(f)
+        assert flags[i] == f, f"frame {i}: flags {flags[i]} != {f}"
+        assert np.array_equal(high[i], h), f"frame {i}: high plane"
+        assert np.array_equal(preview[i], p), f"frame {i}: preview"
+        if not (f & 4):
+            assert np.array_equal(low[i], l), f"frame {i}: low plane"
+    assert len(seen) >= 1

@@ -64,7 +64,7 @@ def test_arbitrary_geometry_random_planes(oracle, W, H):
             assert np.array_equal(raw[i].view(np.uint8), oracle.unextract(exp, 3, 0))
 
 
-@pytest.mark.parametrize("kernel", ["default", "simd"])
+@pytest.mark.parametrize("kernel", ["default", "pair", "simd"])
 @pytest.mark.parametrize("kind", ["random", "smooth", "sparse", "sawtooth"])
 @pytest.mark.parametrize("W,H", [(1280, 40), (1024, 64), (2048, 16), (4096, 8)])
 def test_speculation_adversarial(oracle, W, H, kind, kernel, monkeypatch):
@@ -97,10 +97,10 @@ PAIR_GEOMS = [(64, 5), (80, 7), (128, 3), (256, 9), (320, 6), (512, 4), (768, 5)
               (1312, 5), (1536, 4), (1920, 7), (2016, 2), (2048, 1), (2048, 6), (2560, 3)]
 
 
-@pytest.mark.parametrize("kernel", ["pair", "simd", "spec"])
+@pytest.mark.parametrize("kernel", ["fused", "pair", "simd", "spec"])
 @pytest.mark.parametrize("W,H", PAIR_GEOMS)
 def test_every_kernel_mixed_flags(oracle, W, H, kernel, monkeypatch):
-    """All three row kernels on the same planes; neighbouring frames differ in every flag, so the
+    """All four row kernels on the same planes; neighbouring frames differ in every flag, so the
     pair kernel sees frame pairs that mix delta / ClampedGradient / low-plane use, and an odd tail."""
     monkeypatch.setenv("FPV_DECODE_KERNEL", kernel)
     rng = np.random.default_rng(W * 31 + H)
@@ -124,8 +124,9 @@ def test_every_kernel_mixed_flags(oracle, W, H, kernel, monkeypatch):
                 assert np.array_equal(raw[i].view(np.uint8), oracle.unextract(exp, shift, be)), f"unextract, frame {i}"
 
 
-def test_pair_kernel_without_delta_and_low(oracle, monkeypatch):
-    monkeypatch.setenv("FPV_DECODE_KERNEL", "pair")
+@pytest.mark.parametrize("kernel", ["fused", "pair"])
+def test_pair_kernel_without_delta_and_low(oracle, kernel, monkeypatch):
+    monkeypatch.setenv("FPV_DECODE_KERNEL", kernel)
     W, H, n = 1280, 24, 5
     img = synth.plasma_frames(n, W, H, bits=8, seed=77).reshape(n, -1)
     high = np.stack([oracle.cg_forward(f.astype(np.uint8), W) for f in img])
@@ -174,8 +175,10 @@ def test_use_delta_without_delta_frame_is_an_error():
         assert e.value.code == 4  # "delta frame not given", .cc:310
 
 
-def test_unpredict_planes_vs_oracle(oracle):
-    W, H, n = 128, 32, 4
+@pytest.mark.parametrize("W,H,n", [(128, 32, 4), (100, 100, 3), (36, 8, 5), (1280, 64, 3), (2052, 16, 3)])
+def test_unpredict_planes_vs_oracle(oracle, W, H, n):
+    """Frame::Uncompress's undo on byte planes (k_decode_spec in planes mode, in place): high planes of every
+    alignment class and previews whose width W / 4 is odd."""
     frames = synth.plasma_frames(n, W, H, bits=16, seed=31).reshape(n, -1)
     yy, xx = np.meshgrid(np.arange(H), np.arange(W), indexing="ij")
     frames[2] = ((xx * 300 + yy * 500) & 0xFFFF).astype(np.uint16).reshape(-1)

@@ -131,7 +131,11 @@ def check_columnar(prefix):
         assert ours.returncode == 0, (t, ours.returncode)
         if t == "columnar_batch_decoder_test":
             pick = lambda s: [ln for ln in s.decode().splitlines() if ln.startswith(("Got the Image", "Bad Pixel"))]
-            assert pick(ref.stdout) == pick(ours.stdout)
+            assert not any(ln.startswith("Bad Pixel") for ln in pick(ours.stdout)), "facade build decoded a wrong pixel"
+            # the reference build's undefined behaviour sometimes survives with corrupted images ("Bad Pixel" lines,
+            # seen on one run in ~10): only a clean reference run is a meaningful expectation
+            if not any(ln.startswith("Bad Pixel") for ln in pick(ref.stdout)):
+                assert pick(ref.stdout) == pick(ours.stdout)
 
 
 # ---- CPU: the host layer on the stand-in C ABI ----------------------------------------------------------------------
