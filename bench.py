@@ -236,7 +236,7 @@ def geometry_leg(fpv, synth, torch, dev, local, name, peak, steps=10):
     the dominant kernel, inputs far larger than L2): roofline fractions for the `configs` entry of the N = 1 line."""
     W, H, bits, shift, desc = WORKLOADS[name]
     P = W * H
-    F = 1184 if P < 4000000 else 592
+    F = 2368 if P < 4000000 else 1184      # one full wave of the decode kernel (16 / 8 frames per SM)
     frames = torch.empty((F, P), dtype=torch.uint16, device=dev)
     for c in range(0, F, 64):
         m = min(64, F - c)
@@ -320,8 +320,8 @@ def main():
     ap.add_argument("--no-ingest", action="store_true", help="skip the paced real-time ingest leg")
     ap.add_argument("--no-configs", action="store_true", help="skip the configs[0] / configs[2] geometry legs (N = 1)")
     ap.add_argument("--ingest-seconds", type=float, default=1.5)
-    ap.add_argument("--frames", type=int, default=1184,
-                    help="frames per GPU per step (device-resident); 1184 = 148 SMs x 2 resident decode CTAs x 4 frames")
+    ap.add_argument("--frames", type=int, default=2368,
+                    help="frames per GPU per step (device-resident); 2368 = 148 SMs x 8 decode warps x 2 frames")
     ap.add_argument("--decode-frames", type=int, default=0, help="frames of the device-resident decode leg (0: one wave)")
     ap.add_argument("--e2e-frames", type=int, default=512, help="frames per step of the host-buffer (e2e) legs")
     ap.add_argument("--e2e-batch", type=int, default=64)
@@ -491,7 +491,7 @@ def main():
 
     # ---- decode (inverse transform) on the planes just produced: extra, device-resident -------------
     decode = None
-    Fd = min(F, args.decode_frames or (1184 if P < 4000000 else 592))     # decode legs: one full wave of the decode kernel
+    Fd = min(F, args.decode_frames or (2368 if P < 4000000 else 1184))     # decode legs: one full wave of the decode kernel
     if not args.no_decode:
         d_out = torch.empty((Fd, P), dtype=torch.int16, device=dev)
         dsteps = max(3, min(args.steps, 20))
@@ -521,8 +521,8 @@ def main():
                   "unit": "GB/s", "frames_per_s": world * Fd / (dms * 1e-3), "frames_per_gpu": Fd, "ms_per_step": dms, "steps": dsteps,
                   "round_trip_exact": ok,
                   "roofline": {"bound": "hbm (chain-latency limited, see DESIGN.md)",
-                               "kernel": ("k_decode_pair" if (W % 16 == 0 and 64 <= W <= 1280) else
-                                          "k_decode_pair (split mode)" if (W % 32 == 0 and W <= 2560) else "k_decode_simd"),
+                               "kernel": ("k_decode_fused" if (W % 16 == 0 and 64 <= W <= 1280) else
+                                          "k_decode_fused (split mode)" if (W % 32 == 0 and W <= 2560) else "k_decode_simd"),
                                "achieved": dach, "peak": peak, "unit": "GB/s", "frac": dach / peak,
                                "traffic": ncu_traffic("decode", DEC_BYTES_PER_PX * Fd * P)}}
         del d_out

@@ -275,9 +275,12 @@ __device__ __forceinline__ void fused_chain_row(FusedCtx<LW2>& cx, const uint32_
     }
     w &= kHiBytes;                                // drop the guard byte before handing the value on
     w_in = __shfl_up_sync(0xffffffffu, w, 1);
+    uint32_t wl = 0;
+    if (SPLIT) wl = __shfl_sync(0xffffffffu, w, (int)last_lane);
+    // the first chunk of the write-out of row y-1 goes here: something to issue while the shuffles are in flight
+    fused_out_chunk<LW2, SHIFT, DALL>(cx, o, n, 0);
     if (SPLIT) {
       // the left half's last segment feeds the right half's first (a guess, repaired below)
-      const uint32_t wl = __shfl_sync(0xffffffffu, w, (int)last_lane);
       if (lane == 0) w_in = (last_prev >> 16) | (wl << 16);
     } else if (lane == 0) {
       w_in = last_prev;                           // exact for segment 0
@@ -298,10 +301,9 @@ __device__ __forceinline__ void fused_chain_row(FusedCtx<LW2>& cx, const uint32_
         w = v;
         nw = nn;
       }
-      fused_out_chunk<LW2, SHIFT, DALL>(cx, o, n, k);
+      if (k + 1 < LW2) fused_out_chunk<LW2, SHIFT, DALL>(cx, o, n, k + 1);
     }
   }
-  fused_out_store<LW2>(cx);
   // repair: re-run segments whose incoming value was wrong until nothing changes
   for (;;) {
     uint32_t w_new = __shfl_up_sync(0xffffffffu, x[L - 1] & kHiBytes, 1);
@@ -364,6 +366,9 @@ __device__ __forceinline__ void fused_chain_row(FusedCtx<LW2>& cx, const uint32_
     last_prev2 = last_prev;
     last_prev = __shfl_sync(0xffffffffu, v, (int)last_lane);
   }
+  // The bulk stores of row y-1 go last: fence.proxy.async waits for every shared-memory write of the warp, and by
+  // now the OUT row's stores have long completed (right after pass 1 the fence took 8 % of all stall samples).
+  fused_out_store<LW2>(cx);
 }
 
 // LW2:   a lane's segment is L = 8 LW2 px (LW2 = ceil(W / 256)).
