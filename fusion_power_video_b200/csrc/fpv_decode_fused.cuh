@@ -46,7 +46,11 @@ static inline size_t fused_warp_bytes(int LW2) {
 static inline size_t fused_smem_bytes(int LW2) { return kFusedWarps * fused_warp_bytes(LW2); }
 
 // Per-warp state of the TMA rings and the write-out.  Everything is warp-uniform.
-template <int LW2>
+// DIRECT: the output row does not go through shared memory: every lane stores its own 2 L bytes per frame with
+// 256-bit global stores (full 32-byte sectors; needs L % 16 == 0 and a 32-byte aligned output).  With L = 32 the
+// lanes' pieces of the OUT row lie 64 bytes apart, a 4-way bank conflict on every 128-bit shared store, and the
+// proxy fence in front of the bulk stores has to wait for them.
+template <int LW2, bool DIRECT = false>
 struct FusedCtx {
   static constexpr uint32_t L = 8 * LW2, RB = 32 * L;
   static constexpr uint32_t kR1 = 0, kLow = kR1 + kFusedR1 * 2 * RB, kDel = kLow + kFusedLow * 2 * RB;
@@ -62,6 +66,7 @@ struct FusedCtx {
   bool lowA, lowB, store_b;
   uint32_t dmask, cgmask;
   uint32_t shmul, um, selA, selB;
+  uint32_t col0;                      // first column of this lane
   int lane;
 
   __device__ __forceinline__ uint32_t bar_r1(uint32_t s) const { return sm0 + kBars + 8 * s; }
@@ -141,12 +146,13 @@ template <int LW2>
 struct FusedOutRegs {
   uint2 A[LW2], B[LW2];
   uint4 D[2 * LW2];
+  uint32_t pa[4], pb[4];       // DIRECT: output words of the even chunk, waiting for the odd one (one 256-bit store)
 };
 
-template <int LW2>
-__device__ __forceinline__ void fused_out_load(FusedCtx<LW2>& cx, FusedOutRegs<LW2>& o) {
+template <int LW2, bool DIRECT>
+__device__ __forceinline__ void fused_out_load(FusedCtx<LW2, DIRECT>& cx, FusedOutRegs<LW2>& o) {
   constexpr uint32_t L = 8 * LW2, RB = 32 * L;
-  using C = FusedCtx<LW2>;
+  using C = FusedCtx<LW2, DIRECT>;
   if (cx.lowA || cx.lowB) mbar_wait(cx.bar_low(cx.cl_slot), cx.cl_par);
   if (cx.dmask) mbar_wait(cx.bar_del(cx.cd_slot), cx.cd_par);
   const uint32_t la = cx.sm0 + C::kLow + cx.cl_slot * 2 * RB + (uint32_t)cx.lane * L;
@@ -166,9 +172,11 @@ __device__ __forceinline__ void fused_out_load(FusedCtx<LW2>& cx, FusedOutRegs<L
   }
 #pragma unroll
   for (int k = 0; k < 2 * LW2; k++) o.D[k] = lds128(da + k * 512);   // pair_ddup_word: slot (2 chunk + half) 32 + lane
-  // the previous row's bulk stores must have read the OUT row before it is rewritten
-  if (cx.lane == 0) bulk_wait_read0();
-  __syncwarp();
+  if constexpr (!DIRECT) {
+    // the previous row's bulk stores must have read the OUT row before it is rewritten
+    if (cx.lane == 0) bulk_wait_read0();
+    __syncwarp();
+  }
 }
 
 // Columns [8k, 8k + 8) of this lane: finished row (S form, in xs) -> output pixels in the OUT row.
@@ -176,11 +184,11 @@ __device__ __forceinline__ void fused_out_load(FusedCtx<LW2>& cx, FusedOutRegs<L
 // between the lanes).  x arrives as x << 8, so the first sum has the high byte in place (its low byte is dl:
 // dropped by the select); the second has the low byte in place (its carry lands in the high byte: dropped) --
 // the bytes wrap independently, .cc:337-338.  dmask switches the delta off for a frame that does not use it.
-template <int LW2, bool SHIFT, bool DALL>
-__device__ __forceinline__ void fused_out_chunk(const FusedCtx<LW2>& cx, const FusedOutRegs<LW2>& o,
+template <int LW2, bool SHIFT, bool DALL, bool DIRECT>
+__device__ __forceinline__ void fused_out_chunk(const FusedCtx<LW2, DIRECT>& cx, FusedOutRegs<LW2>& o,
                                                 const uint32_t (&xs)[8 * LW2], const int k) {
   constexpr uint32_t L = 8 * LW2, RB = 32 * L;
-  using C = FusedCtx<LW2>;
+  using C = FusedCtx<LW2, DIRECT>;
   uint32_t Z[8], V[8];
   // low bytes of both frames in lane form [lA, 0, lB, 0]
   uint32_t t = o.B[k].x * 65536u, u = __umulhi(o.B[k].x, 65536u);
@@ -197,24 +205,41 @@ __device__ __forceinline__ void fused_out_chunk(const FusedCtx<LW2>& cx, const F
     V[j] = bitselect(__vadd2(xs[8 * k + j], d), __vadd2(Z[j], d), kHiBytes);
     if (SHIFT) V[j] = __umulhi(V[j], cx.shmul) & cx.um;     // per lane: (pixel >> shift), .cc:855
   }
-  const uint32_t oa = cx.sm0 + C::kOut + (uint32_t)cx.lane * 2 * L + 16 * k;
-  sts128(oa, __byte_perm(V[0], V[1], cx.selA), __byte_perm(V[2], V[3], cx.selA),
-         __byte_perm(V[4], V[5], cx.selA), __byte_perm(V[6], V[7], cx.selA));               // frame A: 8 pixels
-  sts128(oa + 2 * RB, __byte_perm(V[0], V[1], cx.selB), __byte_perm(V[2], V[3], cx.selB),
-         __byte_perm(V[4], V[5], cx.selB), __byte_perm(V[6], V[7], cx.selB));               // frame B
+  const uint32_t a0 = __byte_perm(V[0], V[1], cx.selA), a1 = __byte_perm(V[2], V[3], cx.selA),
+                 a2 = __byte_perm(V[4], V[5], cx.selA), a3 = __byte_perm(V[6], V[7], cx.selA);   // frame A: 8 pixels
+  const uint32_t b0 = __byte_perm(V[0], V[1], cx.selB), b1 = __byte_perm(V[2], V[3], cx.selB),
+                 b2 = __byte_perm(V[4], V[5], cx.selB), b3 = __byte_perm(V[6], V[7], cx.selB);   // frame B
+  if constexpr (DIRECT) {
+    if ((k & 1) == 0) {
+      o.pa[0] = a0; o.pa[1] = a1; o.pa[2] = a2; o.pa[3] = a3;
+      o.pb[0] = b0; o.pb[1] = b1; o.pb[2] = b2; o.pb[3] = b3;
+    } else if (cx.col0 + 8u * (uint32_t)(k + 1) <= cx.W) {    // W % 16 == 0: the 16 columns are inside the row or not
+      // cx.oA / cx.oB point at this lane's first pixel of the row being written
+      stg256(cx.oA + 8 * (k - 1), o.pa[0], o.pa[1], o.pa[2], o.pa[3], a0, a1, a2, a3);
+      if (cx.store_b) stg256(cx.oB + 8 * (k - 1), o.pb[0], o.pb[1], o.pb[2], o.pb[3], b0, b1, b2, b3);
+    }
+  } else {
+    const uint32_t oa = cx.sm0 + C::kOut + (uint32_t)cx.lane * 2 * L + 16 * k;
+    sts128(oa, a0, a1, a2, a3);
+    sts128(oa + 2 * RB, b0, b1, b2, b3);
+  }
 }
 
 // OUT row -> global memory (one bulk store per frame), then refill the rings this row's write-out freed.
-template <int LW2>
-__device__ __forceinline__ void fused_out_store(FusedCtx<LW2>& cx) {
+template <int LW2, bool DIRECT>
+__device__ __forceinline__ void fused_out_store(FusedCtx<LW2, DIRECT>& cx) {
   constexpr uint32_t L = 8 * LW2, RB = 32 * L;
-  using C = FusedCtx<LW2>;
-  fence_proxy_async();
-  __syncwarp();
-  if (cx.lane == 0) {
-    bulk_s2g(cx.oA, cx.sm0 + C::kOut, 2 * cx.W);
-    if (cx.store_b) bulk_s2g(cx.oB, cx.sm0 + C::kOut + 2 * RB, 2 * cx.W);
-    bulk_commit();
+  using C = FusedCtx<LW2, DIRECT>;
+  if constexpr (!DIRECT) {
+    fence_proxy_async();
+    __syncwarp();
+    if (cx.lane == 0) {
+      bulk_s2g(cx.oA, cx.sm0 + C::kOut, 2 * cx.W);
+      if (cx.store_b) bulk_s2g(cx.oB, cx.sm0 + C::kOut + 2 * RB, 2 * cx.W);
+      bulk_commit();
+    }
+  } else {
+    __syncwarp();          // every lane has read its LOW / DEL slots: they may be refilled
   }
   cx.oA += cx.stride; cx.oB += cx.stride;
   cx.issue_low();
@@ -222,24 +247,24 @@ __device__ __forceinline__ void fused_out_store(FusedCtx<LW2>& cx) {
 }
 
 // The write-out of a whole row at once (first / last rows and frames without ClampedGradient).
-template <int LW2, bool SHIFT>
-__device__ __forceinline__ void fused_out_row(FusedCtx<LW2>& cx, const uint32_t (&xs)[8 * LW2]) {
+template <int LW2, bool SHIFT, bool DIRECT>
+__device__ __forceinline__ void fused_out_row(FusedCtx<LW2, DIRECT>& cx, const uint32_t (&xs)[8 * LW2]) {
   FusedOutRegs<LW2> o;
-  fused_out_load<LW2>(cx, o);
+  fused_out_load<LW2, DIRECT>(cx, o);
   if (cx.dmask == 0xffffffffu) {
 #pragma unroll
-    for (int k = 0; k < LW2; k++) fused_out_chunk<LW2, SHIFT, true>(cx, o, xs, k);
+    for (int k = 0; k < LW2; k++) fused_out_chunk<LW2, SHIFT, true, DIRECT>(cx, o, xs, k);
   } else {
 #pragma unroll
-    for (int k = 0; k < LW2; k++) fused_out_chunk<LW2, SHIFT, false>(cx, o, xs, k);
+    for (int k = 0; k < LW2; k++) fused_out_chunk<LW2, SHIFT, false, DIRECT>(cx, o, xs, k);
   }
-  fused_out_store<LW2>(cx);
+  fused_out_store<LW2, DIRECT>(cx);
 }
 
 // One row y >= 1 of a pair with at least one ClampedGradient frame: chain of row y (into x, north row n)
 // interleaved with the write-out of row y - 1 (= n).  See pair_chain_row for the chain itself.
-template <int LW2, bool FULL, bool SHIFT, bool SPLIT, int K0T, int G, bool DALL>
-__device__ __forceinline__ void fused_chain_row(FusedCtx<LW2>& cx, const uint32_t (&n)[8 * LW2], uint32_t (&x)[8 * LW2],
+template <int LW2, bool FULL, bool SHIFT, bool SPLIT, int K0T, int G, bool DALL, bool DIRECT>
+__device__ __forceinline__ void fused_chain_row(FusedCtx<LW2, DIRECT>& cx, const uint32_t (&n)[8 * LW2], uint32_t (&x)[8 * LW2],
                                                 const uint32_t y, const uint32_t vmask, const uint32_t last_lane,
                                                 const uint32_t last_t, uint32_t& last_prev, uint32_t& last_prev2) {
   constexpr int L = 8 * LW2;
@@ -249,7 +274,7 @@ __device__ __forceinline__ void fused_chain_row(FusedCtx<LW2>& cx, const uint32_
   uint32_t c[L];
   cx.load_residuals(c);                        // c holds r for now
   FusedOutRegs<LW2> o;
-  fused_out_load<LW2>(cx, o);                  // staged early: the loads fly while pass 0 runs
+  fused_out_load<LW2, DIRECT>(cx, o);                  // staged early: the loads fly while pass 0 runs
 
   uint32_t nw_in = __shfl_up_sync(0xffffffffu, n[L - 1], 1);
   // lane 0: the pixel before column 0 in flat order.  Pair mode: the last pixel of row y-2 of each
@@ -278,7 +303,7 @@ __device__ __forceinline__ void fused_chain_row(FusedCtx<LW2>& cx, const uint32_
     uint32_t wl = 0;
     if (SPLIT) wl = __shfl_sync(0xffffffffu, w, (int)last_lane);
     // the first chunk of the write-out of row y-1 goes here: something to issue while the shuffles are in flight
-    fused_out_chunk<LW2, SHIFT, DALL>(cx, o, n, 0);
+    fused_out_chunk<LW2, SHIFT, DALL, DIRECT>(cx, o, n, 0);
     if (SPLIT) {
       // the left half's last segment feeds the right half's first (a guess, repaired below)
       if (lane == 0) w_in = (last_prev >> 16) | (wl << 16);
@@ -301,7 +326,7 @@ __device__ __forceinline__ void fused_chain_row(FusedCtx<LW2>& cx, const uint32_
         w = v;
         nw = nn;
       }
-      if (k + 1 < LW2) fused_out_chunk<LW2, SHIFT, DALL>(cx, o, n, k + 1);
+      if (k + 1 < LW2) fused_out_chunk<LW2, SHIFT, DALL, DIRECT>(cx, o, n, k + 1);
     }
   }
   // repair: re-run segments whose incoming value was wrong until nothing changes
@@ -368,20 +393,21 @@ __device__ __forceinline__ void fused_chain_row(FusedCtx<LW2>& cx, const uint32_
   }
   // The bulk stores of row y-1 go last: fence.proxy.async waits for every shared-memory write of the warp, and by
   // now the OUT row's stores have long completed (right after pass 1 the fence took 8 % of all stall samples).
-  fused_out_store<LW2>(cx);
+  fused_out_store<LW2, DIRECT>(cx);
 }
 
 // LW2:   a lane's segment is L = 8 LW2 px (LW2 = ceil(W / 256)).
 // FULL:  W == 32 L (every lane owns a complete segment).
 // SHIFT: UnextractFrame with a non-zero shift is fused into the write-out.
 // SPLIT: the two 16-bit lanes are the left and the right half of ONE frame (widths 1281..2560).
-template <int LW2, bool FULL, bool SHIFT, bool SPLIT = false, int K0T = FPV_PAIR_K0,
+template <int LW2, bool FULL, bool SHIFT, bool SPLIT = false, bool DIRECT = false, int K0T = FPV_PAIR_K0,
           int G = (FPV_PAIR_G ? FPV_PAIR_G : (LW2 == 4 ? 16 : 8))>
 __global__ void __launch_bounds__(32 * kFusedWarps, 2) k_decode_fused(const PairParams p) {
   extern __shared__ __align__(128) uint8_t fsm[];
   constexpr int L = 8 * LW2;
   constexpr uint32_t RB = 32 * L;
-  using C = FusedCtx<LW2>;
+  using C = FusedCtx<LW2, DIRECT>;
+  static_assert(!DIRECT || LW2 % 2 == 0, "256-bit stores need 16 columns per lane and store");
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t unit = blockIdx.x * kFusedWarps + warp;
   // pair mode: frames (fA, fA + 1); split mode: the two halves of frame fA
@@ -406,8 +432,9 @@ __global__ void __launch_bounds__(32 * kFusedWarps, 2) k_decode_fused(const Pair
   cx.s2A = p.low + (uint64_t)fA * p.P;                // dereferenced only if lowA / lowB
   cx.s2B = p.low + (uint64_t)fB * p.P + offB;
   cx.s2D = p.ddup;
-  cx.oA = p.out + (uint64_t)fA * p.P;
-  cx.oB = p.out + (uint64_t)fB * p.P + offB;
+  cx.col0 = (uint32_t)lane * L;
+  cx.oA = p.out + (uint64_t)fA * p.P + (DIRECT ? cx.col0 : 0u);
+  cx.oB = p.out + (uint64_t)fB * p.P + offB + (DIRECT ? cx.col0 : 0u);
   cx.i1_row = cx.i1_slot = cx.il_row = cx.il_slot = cx.id_row = cx.id_slot = 0;
   cx.c1_slot = cx.c1_par = cx.cl_slot = cx.cl_par = cx.cd_slot = cx.cd_par = 0;
   const bool do_swap = p.unextract && p.big_endian;
@@ -465,30 +492,30 @@ __global__ void __launch_bounds__(32 * kFusedWarps, 2) k_decode_fused(const Pair
     // neither frame is ClampedGradient-predicted: rows are the residual rows
     for (uint32_t y = 1; y < H; y += 2) {
       cx.load_residuals(rb);
-      fused_out_row<LW2, SHIFT>(cx, ra);
+      fused_out_row<LW2, SHIFT, DIRECT>(cx, ra);
       if (y + 1 < H) {
         cx.load_residuals(ra);
-        fused_out_row<LW2, SHIFT>(cx, rb);
+        fused_out_row<LW2, SHIFT, DIRECT>(cx, rb);
       }
     }
   } else if (cx.dmask == 0xffffffffu) {
     for (uint32_t y = 1; y < H; y += 2) {
-      fused_chain_row<LW2, FULL, SHIFT, SPLIT, K0T, G, true>(cx, ra, rb, y, vmask, last_lane, last_t, last_prev, last_prev2);
+      fused_chain_row<LW2, FULL, SHIFT, SPLIT, K0T, G, true, DIRECT>(cx, ra, rb, y, vmask, last_lane, last_t, last_prev, last_prev2);
       if (y + 1 < H)
-        fused_chain_row<LW2, FULL, SHIFT, SPLIT, K0T, G, true>(cx, rb, ra, y + 1, vmask, last_lane, last_t, last_prev,
+        fused_chain_row<LW2, FULL, SHIFT, SPLIT, K0T, G, true, DIRECT>(cx, rb, ra, y + 1, vmask, last_lane, last_t, last_prev,
                                                                last_prev2);
     }
   } else {
     for (uint32_t y = 1; y < H; y += 2) {
-      fused_chain_row<LW2, FULL, SHIFT, SPLIT, K0T, G, false>(cx, ra, rb, y, vmask, last_lane, last_t, last_prev, last_prev2);
+      fused_chain_row<LW2, FULL, SHIFT, SPLIT, K0T, G, false, DIRECT>(cx, ra, rb, y, vmask, last_lane, last_t, last_prev, last_prev2);
       if (y + 1 < H)
-        fused_chain_row<LW2, FULL, SHIFT, SPLIT, K0T, G, false>(cx, rb, ra, y + 1, vmask, last_lane, last_t, last_prev,
+        fused_chain_row<LW2, FULL, SHIFT, SPLIT, K0T, G, false, DIRECT>(cx, rb, ra, y + 1, vmask, last_lane, last_t, last_prev,
                                                                 last_prev2);
     }
   }
   // the last row's write-out: row H - 1 is in ra if H - 1 is even
-  if ((H - 1) & 1u) fused_out_row<LW2, SHIFT>(cx, rb);
-  else fused_out_row<LW2, SHIFT>(cx, ra);
+  if ((H - 1) & 1u) fused_out_row<LW2, SHIFT, DIRECT>(cx, rb);
+  else fused_out_row<LW2, SHIFT, DIRECT>(cx, ra);
   if (lane == 0) bulk_wait0();
 }
 
@@ -498,16 +525,29 @@ static cudaError_t launch_fused(const PairParams& p, bool full, cudaStream_t str
   const bool shift = p.unextract && p.shift != 0;
   const uint32_t units = SPLIT ? p.n : (p.n + 1) / 2;
   const int blocks = (int)((units + kFusedWarps - 1) / kFusedWarps);
+  // 256-bit stores straight from registers where a lane's piece of the row is a whole number of 32-byte sectors
+  const bool direct = LW2 % 2 == 0 && reinterpret_cast<uintptr_t>(p.out) % 32 == 0 && getenv("FPV_FUSED_NO_DIRECT") == nullptr;
   cudaError_t e = cudaSuccess;
-#define FPV_LAUNCH_FUSED(F, S)                                                                                            \
-  do {                                                                                                                    \
-    e = cudaFuncSetAttribute(k_decode_fused<LW2, F, S, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
-    if (e == cudaSuccess) k_decode_fused<LW2, F, S, SPLIT><<<blocks, 32 * kFusedWarps, smem, stream>>>(p);                \
+#define FPV_LAUNCH_FUSED(F, S, D)                                                                                            \
+  do {                                                                                                                       \
+    e = cudaFuncSetAttribute(k_decode_fused<LW2, F, S, SPLIT, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
+    if (e == cudaSuccess) k_decode_fused<LW2, F, S, SPLIT, D><<<blocks, 32 * kFusedWarps, smem, stream>>>(p);                \
   } while (0)
-  if (full && shift) FPV_LAUNCH_FUSED(true, true);
-  else if (full) FPV_LAUNCH_FUSED(true, false);
-  else if (shift) FPV_LAUNCH_FUSED(false, true);
-  else FPV_LAUNCH_FUSED(false, false);
+#define FPV_LAUNCH_FUSED_D(D)                       \
+  do {                                              \
+    if (full && shift) FPV_LAUNCH_FUSED(true, true, D);   \
+    else if (full) FPV_LAUNCH_FUSED(true, false, D);      \
+    else if (shift) FPV_LAUNCH_FUSED(false, true, D);     \
+    else FPV_LAUNCH_FUSED(false, false, D);               \
+  } while (0)
+  if constexpr (LW2 % 2 == 0) {
+    if (direct) FPV_LAUNCH_FUSED_D(true);
+    else FPV_LAUNCH_FUSED_D(false);
+  } else {
+    (void)direct;
+    FPV_LAUNCH_FUSED_D(false);
+  }
+#undef FPV_LAUNCH_FUSED_D
 #undef FPV_LAUNCH_FUSED
   return e == cudaSuccess ? cudaGetLastError() : e;
 }

@@ -194,10 +194,13 @@ def test_unpredict_planes_vs_oracle(oracle, W, H, n):
             assert np.array_equal((h2[i].astype(np.uint16) << 8) | l2[i], frames[i])
 
 
-def test_device_pointer_decode(oracle):
+@pytest.mark.parametrize("W,H,n,skew", [(1024, 256, 6, 0), (1024, 64, 5, 8), (2048, 32, 3, 8), (512, 32, 7, 8), (1008, 24, 5, 0)])
+def test_device_pointer_decode(oracle, W, H, n, skew):
+    """Device pointers on a caller's stream.  skew: the output starts 16 bytes into its allocation, so it is not
+    32-byte aligned and the fused kernel must leave its 256-bit-store path for the bulk-store one; 1008 columns:
+    the last lane with columns stores half of its 32 (one 256-bit store)."""
     import torch
 
-    W, H, n = 1024, 256, 6
     frames = synth.plasma_frames(n, W, H, bits=16, seed=13).reshape(n, -1)
     dev = torch.device("cuda:0")
     with fpv.Context(W, H, 0, 0, max_batch=8) as ctx:
@@ -206,12 +209,14 @@ def test_device_pointer_decode(oracle):
         d_high = torch.from_numpy(high).to(dev)
         d_low = torch.from_numpy(low).to(dev)
         d_flags = torch.from_numpy(flags).to(dev)
-        d_out = torch.zeros((n, W * H), dtype=torch.int16, device=dev)
+        d_buf = torch.zeros(n * W * H + 64, dtype=torch.int16, device=dev)
+        d_out = d_buf[skew:skew + n * W * H]
         s = torch.cuda.Stream()
         with torch.cuda.stream(s):
             ctx.decode_device(d_high.data_ptr(), d_low.data_ptr(), d_flags.data_ptr(), n, d_out.data_ptr(), stream=s.cuda_stream)
         s.synchronize()
-        assert np.array_equal(d_out.cpu().numpy().view(np.uint16), frames)
+        assert np.array_equal(d_out.cpu().numpy().view(np.uint16).reshape(n, -1), frames)
+        assert not d_buf[:skew].any() and not d_buf[skew + n * W * H:].any(), "wrote outside the output"
 
 
 @pytest.mark.parametrize("W,H,bits,shift,n", [(1280, 800, 12, 4, 5), (1024, 1024, 16, 0, 5), (2048, 2048, 16, 0, 3)])
