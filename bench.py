@@ -231,6 +231,55 @@ def run_reference_arm(args, W, H, bits, shift, desc):
     print(json.dumps(line), flush=True)
 
 
+def pcie_probe(torch, dist, world, dev, seconds=0.5, mb=64):
+    """Host <-> device copy ceilings of THIS box with all `world` ranks copying at once (pinned memory, 64 MiB pieces):
+    H2D alone, D2H alone, both directions at the same time.  The host-buffer legs (`e2e`, `decode_e2e`) move about
+    2 B/px each way concurrently, so their ceiling in raw-pixel GB/s is the `bidir_each` figure."""
+    n = mb << 20
+    h_in = torch.empty(n, dtype=torch.uint8).pin_memory()
+    h_out = torch.empty(n, dtype=torch.uint8).pin_memory()
+    d_in = torch.empty(n, dtype=torch.uint8, device=dev)
+    d_out = torch.empty(n, dtype=torch.uint8, device=dev)
+    s1, s2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+
+    def h2d():
+        with torch.cuda.stream(s1):
+            d_in.copy_(h_in, non_blocking=True)
+
+    def d2h():
+        with torch.cuda.stream(s2):
+            h_out.copy_(d_out, non_blocking=True)
+
+    def both():
+        h2d()
+        d2h()
+
+    out = {"piece_mb": mb, "seconds_per_mode": seconds}
+    for name, fn in (("h2d", h2d), ("d2h", d2h), ("bidir_each", both)):
+        fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        reps = 0
+        while time.perf_counter() - t0 < seconds:
+            for _ in range(4):
+                fn()
+            torch.cuda.synchronize()
+            reps += 4
+        rate = n * reps / (time.perf_counter() - t0) / 1e9
+        t = torch.tensor([rate, -rate], dtype=torch.float64, device=dev)
+        if world > 1:
+            tsum = t.clone()
+            dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            out[name + "_sum_gbs"], out[name + "_min_gbs"] = float(tsum[0].item()), -float(t[1].item())
+        else:
+            out[name + "_sum_gbs"] = out[name + "_min_gbs"] = rate
+    del h_in, h_out, d_in, d_out
+    return out
+
+
 def geometry_leg(fpv, synth, torch, dev, local, name, peak, steps=10):
     """Device-resident encode + decode of another BASELINE geometry, measured like the headline (CUDA events around
     the dominant kernel, inputs far larger than L2): roofline fractions for the `configs` entry of the N = 1 line."""
@@ -611,6 +660,10 @@ def main():
                "frames_per_s": world * Fe / e2e_s, "matches_device_path": e2e_ok,
                "slots": NS,
                "what": "fpv_encode_submit/fpv_wait on pinned host buffers, slots overlapped (no brotli)"}
+        # the box's own copy ceiling with every rank copying at once, measured in the same run
+        pc = pcie_probe(torch, dist, world, dev)
+        e2e["pcie_ceiling"] = pc
+        e2e["frac_of_pcie_ceiling"] = e2e["value"] / pc["bidir_each_sum_gbs"]
 
     # ---- e2e with the entropy stage on the GPU: raw frames in, container chunks (coded streams) out ----------------
     e2e_stream = None
