@@ -148,7 +148,7 @@ uint32_t chunks_of(uint64_t bytes) { return (uint32_t)((bytes + kEntropyChunk - 
 // plane stream the WBITS bit and the final 0x03.
 size_t stream_bound(const fpv_ctx* c, uint32_t n) {
   const uint64_t cpf = chunks_of(c->g.PP) + 2ull * chunks_of(c->g.P);
-  return (size_t)n * (size_t)(11 + c->g.PP + 2 * c->g.P + 8 * cpf + 16);
+  return (size_t)n * (size_t)(11 + c->g.PP + 2 * c->g.P + (8 + kDirBlock) * cpf + 16);
 }
 
 int ensure_entropy(fpv_ctx* c, int idx, bool with_out) {

@@ -8,6 +8,8 @@
 //
 //   plane stream := chunk* 0x03                       (0x03 = ISLAST, ISLASTEMPTY)
 //   chunk        := [WBITS bit, first chunk only]
+//                   metadata meta-block of kDirBytes bytes: the DIRECTORY for k_entropy_decode (below); brotli
+//                     decoders skip it
 //                   compressed meta-block: MLEN = chunk size (<= 65536), one block type per
 //                     category, NTREES = 1, one literal prefix code (canonical Huffman from the
 //                     chunk's own histogram, max depth 15, stored as a "complex" code without
@@ -62,6 +64,14 @@ __device__ __forceinline__ void put_bits(Shared& s, uint32_t& pos, uint32_t valu
   atomicOr(&s.out[w], value << sh);
   if (sh + nbits > 32) atomicOr(&s.out[w + 1], value >> (32 - sh));
   pos += nbits;
+}
+
+// `nbytes` little-endian bytes of `value` at byte `idx` of the directory payload (each byte is written once)
+__device__ __forceinline__ void dir_put(Shared& s, uint32_t idx, uint32_t value, uint32_t nbytes) {
+  for (uint32_t i = 0; i < nbytes; i++) {
+    const uint32_t b = 2 + idx + i;
+    atomicOr(&s.out[b >> 2], ((value >> (8 * i)) & 255u) << (8 * (b & 3u)));
+  }
 }
 
 // exclusive scan of one value per thread over the CTA; returns the prefix, *total = sum
@@ -265,6 +275,13 @@ __global__ void __launch_bounds__(kET) k_entropy_chunk(const EntropyParams p) {
   if (tid == 0) {
     uint32_t pos = 0;
     if (first) put_bits(s, pos, 0, 1);                 // WBITS = 16
+    // the directory: metadata meta-block (ISLAST 0, MNIBBLES coded 3, reserved 0, MSKIPBYTES 1, MSKIPLEN - 1), padded
+    // to two bytes; its payload is filled in as the numbers become known
+    put_bits(s, pos, 0, 1); put_bits(s, pos, 3, 2); put_bits(s, pos, 0, 1); put_bits(s, pos, 1, 2);
+    put_bits(s, pos, kDirBytes - 1, 8);
+    dir_put(s, 0, 0x46u | (0x44u << 8) | (1u << 16), 3);                 // 'F' 'D' version 1
+    dir_put(s, 7, n - 1, 2);
+    pos = kDirBits;                                    // the compressed meta-block starts on the next byte
     put_bits(s, pos, 0, 1);                            // ISLAST = 0
     const uint32_t nib = (n - 1) < (1u << 16) ? 4 : (n - 1) < (1u << 20) ? 5 : 6;
     put_bits(s, pos, nib - 4, 2);
@@ -333,14 +350,19 @@ __global__ void __launch_bounds__(kET) k_entropy_chunk(const EntropyParams p) {
     __syncthreads();
   }
   const uint32_t lit_start = s.lit_start;
-  const uint32_t comp_bytes = (lit_start + lit_bits + 6 + 7) / 8;
+  const uint32_t comp_bytes = (lit_start - kDirBits + lit_bits + 6 + 7) / 8;
   const bool raw = comp_bytes > n + 4;       // Huffman coding does not pay: uncompressed meta-block
 
   uint32_t bytes;
   uint8_t* dst = p.scratch + (uint64_t)c * kEntropyChunkCap;
   if (!raw) {
-    // ---- literals: thread t codes the bytes [t S, (t+1) S) ------------------------------------
-    const uint32_t S = (((n + kET - 1) / kET) + 15u) & ~15u;
+    // directory: the code lengths as nibbles, the kind
+    if (tid < 128) dir_put(s, kDirLengths + tid, (uint32_t)s.len[2 * tid] | ((uint32_t)s.len[2 * tid + 1] << 4), 1);
+    if (tid == 0 && nz < 2) { dir_put(s, 3, kKindConstant, 1); dir_put(s, 9, last_sym, 1); }
+    // ---- literals: thread t codes the bytes [t S, (t+1) S); S is a power of two so that the decoder's spans of
+    //      kEntropySpan bytes start where a thread starts ------------------------------------------
+    uint32_t S = 16;
+    while (S * kET < n) S <<= 1;
     const uint32_t b0 = tid * S < n ? tid * S : n, b1 = b0 + S < n ? b0 + S : n;
     uint32_t mybits = 0;
     if (aligned) {
@@ -360,6 +382,7 @@ __global__ void __launch_bounds__(kET) k_entropy_chunk(const EntropyParams p) {
     const uint32_t o = block_excl_scan(s, mybits, &total);
     {
       const uint32_t bitpos = lit_start + o;
+      if (b0 < n && b0 % kEntropySpan == 0) dir_put(s, kDirSpans + 3 * (b0 / kEntropySpan), bitpos, 3);
       uint32_t wi = bitpos >> 5, nb = bitpos & 31u;
       unsigned long long acc = 0;
       auto emit = [&](uint32_t byte) {
@@ -395,6 +418,7 @@ __global__ void __launch_bounds__(kET) k_entropy_chunk(const EntropyParams p) {
       // empty metadata meta-block: ISLAST = 0, MNIBBLES = 0 (coded 3), reserved 0, MSKIPBYTES = 0; pads to a byte
       put_bits(s, pos, 0, 1); put_bits(s, pos, 3, 2); put_bits(s, pos, 0, 1); put_bits(s, pos, 0, 2);
       uint32_t nbytes = (pos + 7) / 8;
+      dir_put(s, 4, nbytes, 3);                          // chunk bytes (without the stream's final 0x03)
       if (last) {
         reinterpret_cast<uint8_t*>(s.out)[nbytes] = 0x03;    // ISLAST, ISLASTEMPTY
         nbytes++;
@@ -406,19 +430,26 @@ __global__ void __launch_bounds__(kET) k_entropy_chunk(const EntropyParams p) {
     for (uint32_t i = tid; i < (bytes + 3) / 4; i += kET) reinterpret_cast<uint32_t*>(dst)[i] = s.out[i];
   } else {
     // ---- uncompressed meta-block: header up to ISUNCOMPRESSED = 1, pad, raw bytes -------------
-    const uint32_t hdr_bits = s.misc + 1;
+    const uint32_t hdr_bits = s.misc + 1 - kDirBits;   // bits of the meta-block header up to ISUNCOMPRESSED
     const uint32_t hb = (hdr_bits + 7) / 8;
     __syncthreads();
     if (tid == 0) {
-      uint32_t pos = s.misc;
-      // everything after the ISUNCOMPRESSED bit is dropped: rebuild the first bytes
-      uint32_t w0 = s.out[0] & ((pos >= 32) ? 0xffffffffu : ((1u << pos) - 1u));
-      w0 |= 1u << pos;                                    // hdr_bits <= 1 + 1 + 2 + 24 + 1 = 29
-      for (uint32_t i = 0; i < hb; i++) dst[i] = (uint8_t)(w0 >> (8 * i));
-      if (last) dst[hb + n] = 0x03;
+      dir_put(s, 3, kKindRaw, 1);
+      dir_put(s, 4, kDirBlock + hb + n, 3);
+      dir_put(s, kDirSpans, 8 * (kDirBlock + hb), 3);     // where the raw bytes start
     }
-    for (uint32_t i = tid; i < n; i += kET) dst[hb + i] = src[i];
-    bytes = hb + n + (last ? 1u : 0u);
+    __syncthreads();
+    // the directory block as it is; of the compressed header everything after the ISUNCOMPRESSED bit is dropped
+    for (uint32_t i = tid; i < kDirBlock; i += kET) dst[i] = reinterpret_cast<const uint8_t*>(s.out)[i];
+    if (tid == 0) {
+      const uint32_t pos = s.misc - kDirBits;             // kDirBits is a multiple of 32: the header is in one word
+      uint32_t w0 = s.out[kDirBits / 32] & ((1u << pos) - 1u);
+      w0 |= 1u << pos;                                    // hdr_bits <= 1 + 2 + 24 + 1 = 28
+      for (uint32_t i = 0; i < hb; i++) dst[kDirBlock + i] = (uint8_t)(w0 >> (8 * i));
+      if (last) dst[kDirBlock + hb + n] = 0x03;
+    }
+    for (uint32_t i = tid; i < n; i += kET) dst[kDirBlock + hb + i] = src[i];
+    bytes = kDirBlock + hb + n + (last ? 1u : 0u);
   }
   if (tid == 0) p.chunk_bytes[c] = bytes;
 }

@@ -63,7 +63,14 @@ int enqueue_encode(const Geom& g, const EncodeTuning& t, EncodeScratch& s,
 
 // ---- GPU entropy coder (fpv_entropy.cu) -----------------------------------------------------
 constexpr uint32_t kEntropyChunk = 65536;                 // plane bytes per independently coded chunk
-constexpr uint32_t kEntropyChunkCap = kEntropyChunk + 128;  // scratch bytes per chunk (a coded chunk is <= n + 5 bytes)
+// Every coded chunk starts with a metadata meta-block (skipped by brotli decoders) that carries a directory for
+// k_entropy_decode: 2 header bytes, then 'F' 'D' | version | kind | chunk bytes u24 | n - 1 u16 | constant symbol |
+// 256 code lengths as nibbles | 32 span bit positions u24 (tests/huffcoder_ref.py states the same layout).
+constexpr uint32_t kDirBytes = 234, kDirBlock = 2 + kDirBytes, kDirBits = 8 * kDirBlock;
+constexpr uint32_t kDirLengths = 10, kDirSpans = 138;       // payload offsets
+constexpr uint32_t kEntropySpan = 2048;                      // plane bytes one decoder lane reconstructs
+constexpr uint32_t kKindHuffman = 0, kKindRaw = 1, kKindConstant = 2;
+constexpr uint32_t kEntropyChunkCap = kEntropyChunk + kDirBlock + 128;  // scratch bytes per chunk (directory + <= n + 5 bytes)
 
 struct EntropyParams {
   const uint8_t* high;      // [n][P]

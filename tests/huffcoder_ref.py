@@ -4,7 +4,10 @@ The GPU coder emits, per plane, a valid RFC 7932 (brotli) stream made of indepen
 chunks: one compressed meta-block per chunk with a single literal prefix code (canonical Huffman,
 max length 15, built from the chunk's histogram), one insert-and-copy command that inserts the whole
 chunk, no backward references, followed by an empty metadata meta-block that pads to a byte boundary.
-Any brotli decoder (the reference's decode.cc uses libbrotlidec) decodes it.
+Every chunk starts with a metadata meta-block -- skipped by every brotli decoder -- that carries a DIRECTORY for
+the GPU entropy decoder (k_entropy_decode): the chunk's size, its code lengths and the bit positions of its 2048-byte
+spans, so that a warp decodes a chunk without parsing a prefix-code header and with every lane busy.
+Any brotli decoder (the reference's decode.cc uses libbrotlidec) decodes the stream.
 
 This module states the same bitstream in plain Python / numpy so that tests can (a) check the format
 against libbrotlidec without a GPU and (b) compare the GPU output byte for byte.
@@ -18,6 +21,10 @@ import numpy as np
 
 CHUNK = 65536
 MAX_BITS = 15
+SPAN = 2048            # bytes of a chunk one decoder lane reconstructs
+DIR_BYTES = 234        # payload of the directory meta-block
+DIR_BLOCK = 2 + DIR_BYTES   # its header is 14 (first chunk of a stream: 15) bits, padded to two bytes
+KIND_HUFFMAN, KIND_RAW, KIND_CONSTANT = 0, 1, 2
 # RFC 7932 section 5: insert length code -> (base, extra bits)
 INSERT_BASE = [0, 1, 2, 3, 4, 5, 6, 8, 10, 14, 18, 26, 34, 50, 66, 98, 130, 194, 322, 578, 1090, 2114, 6210, 22594]
 INSERT_EXTRA = [0, 0, 0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 7, 8, 9, 10, 12, 14, 24]
@@ -130,12 +137,32 @@ def write_complex_code(bw, lengths):
         bw.put(cl_code[l], cl_eff[l])
 
 
+def directory(kind, chunk_bytes, n, constant, lengths, spans):
+    """The directory payload: 'F' 'D' | version 1 | kind | chunk bytes u24 | n - 1 u16 | constant symbol |
+    256 code lengths as nibbles | 32 span bit positions u24 (relative to the start of the chunk)."""
+    d = bytearray(DIR_BYTES)
+    d[0], d[1], d[2], d[3] = 0x46, 0x44, 1, kind
+    d[4:7] = chunk_bytes.to_bytes(3, "little")
+    d[7:9] = (n - 1).to_bytes(2, "little")
+    d[9] = constant
+    for i in range(128):
+        d[10 + i] = lengths[2 * i] | (lengths[2 * i + 1] << 4)
+    for k, v in enumerate(spans):
+        d[138 + 3 * k:141 + 3 * k] = v.to_bytes(3, "little")
+    return bytes(d)
+
+
 def encode_chunk(data: np.ndarray, first: bool) -> bytes:
     n = int(data.size)
-    assert 1 <= n <= (1 << 24)
-    bw = BitWriter()
+    assert 1 <= n <= CHUNK
+    head = BitWriter()
     if first:
-        bw.put(0, 1)                       # WBITS = 16
+        head.put(0, 1)                     # WBITS = 16
+    # the directory: a metadata meta-block (ISLAST 0, MNIBBLES coded 3, reserved 0, MSKIPBYTES 1, MSKIPLEN - 1)
+    head.put(0, 1); head.put(3, 2); head.put(0, 1); head.put(1, 2); head.put(DIR_BYTES - 1, 8)
+    head.align()
+    assert len(head.out) == 2
+    bw = BitWriter()                       # the compressed meta-block starts on the byte after the directory
     hist = np.bincount(data, minlength=256)
     used = np.flatnonzero(hist)
     bw.put(0, 1)                           # ISLAST = 0
@@ -168,17 +195,22 @@ def encode_chunk(data: np.ndarray, first: bool) -> bytes:
     if (lit_start + lit_bits + 6 + 7) // 8 > n + 4:
         # Huffman coding does not pay: uncompressed meta-block (header up to ISUNCOMPRESSED = 1, pad, raw bytes)
         bw = BitWriter()
-        if first:
-            bw.put(0, 1)
         bw.put(0, 1); bw.put(nib - 4, 2); bw.put(n - 1, 4 * nib); bw.put(1, 1)
         bw.align()
-        return bytes(bw.out) + data.tobytes()
-    for b in data.tolist():
+        body = bytes(bw.out) + data.tobytes()
+        spans = [8 * (DIR_BLOCK + len(bw.out))] + [0] * 31
+        return bytes(head.out) + directory(KIND_RAW, DIR_BLOCK + len(body), n, 0, [0] * 256, spans) + body
+    spans = [0] * 32
+    for i, b in enumerate(data.tolist()):
+        if i % SPAN == 0:
+            spans[i // SPAN] = 8 * DIR_BLOCK + 8 * len(bw.out) + bw.n
         bw.put(codes[b], lengths[b])
     # empty metadata meta-block: pads to the byte boundary
     bw.put(0, 1); bw.put(3, 2); bw.put(0, 1); bw.put(0, 2)
     bw.align()
-    return bytes(bw.out)
+    kind = KIND_CONSTANT if used.size == 1 else KIND_HUFFMAN
+    return (bytes(head.out) + directory(kind, DIR_BLOCK + len(bw.out), n, int(used[0]) if used.size == 1 else 0, lengths, spans)
+            + bytes(bw.out))
 
 
 def encode_plane(data, chunk=CHUNK) -> bytes:
@@ -189,6 +221,50 @@ def encode_plane(data, chunk=CHUNK) -> bytes:
     for ci, off in enumerate(range(0, data.size, chunk)):
         out += encode_chunk(data[off:off + chunk], ci == 0)
     out.append(0x03)                       # ISLAST = 1, ISLASTEMPTY = 1
+    return bytes(out)
+
+
+def scan_plane(stream: bytes, plane_bytes: int):
+    """Walks the directories of a plane stream: returns (chunk offsets, stream length) or None if the stream does not
+    carry them (a libbrotli stream)."""
+    offs, pos = [], 0
+    for _ in range((plane_bytes + CHUNK - 1) // CHUNK):
+        if pos + DIR_BLOCK > len(stream) or stream[pos + 2:pos + 5] != b"FD\x01":
+            return None
+        offs.append(pos)
+        pos += int.from_bytes(stream[pos + 6:pos + 9], "little")
+    if pos >= len(stream) or stream[pos] != 0x03:
+        return None
+    return offs, pos + 1
+
+
+def decode_chunk(chunk: bytes) -> bytes:
+    """What k_entropy_decode does with one chunk: only the directory and the literal bits are read."""
+    d = chunk[2:2 + DIR_BYTES]
+    assert d[0:3] == b"FD\x01"
+    kind, n, constant = d[3], int.from_bytes(d[7:9], "little") + 1, d[9]
+    spans = [int.from_bytes(d[138 + 3 * k:141 + 3 * k], "little") for k in range(32)]
+    if kind == KIND_RAW:
+        o = spans[0] // 8
+        return chunk[o:o + n]
+    if kind == KIND_CONSTANT:
+        return bytes([constant]) * n
+    lengths = [(d[10 + i // 2] >> (4 * (i & 1))) & 15 for i in range(256)]
+    codes = canonical_codes(lengths)
+    table = {(codes[s], lengths[s]): s for s in range(256) if lengths[s]}
+    bits = int.from_bytes(chunk, "little")
+    out = bytearray()
+    for k in range((n + SPAN - 1) // SPAN):
+        pos = spans[k]
+        for _ in range(min(SPAN, n - k * SPAN)):
+            for l in range(1, MAX_BITS + 1):
+                sym = table.get(((bits >> pos) & ((1 << l) - 1), l))
+                if sym is not None:
+                    out.append(sym)
+                    pos += l
+                    break
+            else:
+                raise ValueError("no code matches")
     return bytes(out)
 
 

@@ -40,6 +40,26 @@ def test_stream_decodes_with_libbrotlidec(name):
     assert out == data.tobytes() and used == len(stream)
 
 
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_directories_alone_reconstruct_the_plane(name):
+    """What the GPU entropy decoder reads: chunk sizes, code lengths and span bit positions from the directory
+    meta-blocks, then only the literal bits -- restated in huffcoder_ref.decode_chunk."""
+    data = CASES[name]
+    stream = href.encode_plane(data)
+    scan = href.scan_plane(stream + b"\x55\xaa", data.size)
+    assert scan is not None
+    offs, length = scan
+    assert length == len(stream) and len(offs) == (data.size + href.CHUNK - 1) // href.CHUNK
+    ends = offs[1:] + [length - 1]
+    back = b"".join(href.decode_chunk(stream[a:b]) for a, b in zip(offs, ends))
+    assert back == data.tobytes()
+
+
+def test_libbrotli_streams_carry_no_directory():
+    # a stream that starts like brotli quality 1 output is not mistaken for a directory-carrying one
+    assert href.scan_plane(bytes([0x1b, 0x03, 0x00, 0xf8, 0x25, 0x00, 0xa2, 0x90, 0xa8, 0x00]), 4) is None
+
+
 def test_depth_limit_is_enforced():
     fib = [1, 1, 2, 3, 5, 8, 13, 21, 34, 55, 89, 144, 233, 377, 610, 987, 1597, 2584, 4181, 6765, 10946, 17711, 28657]
     assert max(href.huffman_lengths(fib, 15)) <= 15
@@ -53,4 +73,4 @@ def test_compressible_planes_shrink_and_noise_does_not_grow():
     skew = np.minimum(rng.geometric(0.4, 1 << 18) - 1, 255).astype(np.uint8)
     assert len(href.encode_plane(skew)) < 0.4 * skew.size
     noise = rng.integers(0, 256, 1 << 18).astype(np.uint8)
-    assert len(href.encode_plane(noise)) <= noise.size + 6 * 4 + 2
+    assert len(href.encode_plane(noise)) <= noise.size + (6 + href.DIR_BLOCK) * 4 + 2
