@@ -106,6 +106,8 @@ def lib() -> C.CDLL:
     L.fpv_decode_device.restype = i32
     L.fpv_decode_submit.argtypes = [vp, u32, vp, vp, vp, u32, u32, vp]
     L.fpv_decode_submit.restype = i32
+    L.fpv_decode_coded.argtypes = [vp, vp, sz, vp, u32, vp, u32, u32, vp]
+    L.fpv_decode_coded.restype = i32
     L.fpv_unpredict_planes.argtypes = [vp, vp, vp, vp, vp, u32]
     L.fpv_unpredict_planes.restype = i32
     _lib = L
@@ -303,6 +305,19 @@ class Context:
         assert flags.size == n
         out = np.zeros((n, self.P), np.uint16)
         self._check(self._L.fpv_decode(self._h, _ptr(high), _ptr(low), _ptr(flags), n, options, _ptr(out)))
+        return out
+
+    def decode_coded(self, blob, chunks, flags, options=DEC_DEFAULT):
+        """fpv_decode_coded: `blob` = coded bytes, `chunks` = list of (offset, frame, plane, index)."""
+        blob = np.ascontiguousarray(np.frombuffer(bytes(blob), dtype=np.uint8))
+        flags = np.ascontiguousarray(flags, dtype=np.uint8)
+        n = flags.size
+        tab = np.zeros((len(chunks), 6), np.uint32)
+        for i, (off, f, pl, ix) in enumerate(chunks):
+            tab[i] = (off & 0xFFFFFFFF, off >> 32, f, pl, ix, 0)
+        out = np.zeros((n, self.P), np.uint16)
+        self._check(self._L.fpv_decode_coded(self._h, _ptr(blob), blob.size, _ptr(tab), len(chunks), _ptr(flags), n, options,
+                                             _ptr(out)))
         return out
 
     def decode_device(self, high_ptr, low_ptr, flags_ptr, n, out_ptr, options=DEC_DEFAULT, stream=0):

@@ -10,6 +10,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <mutex>
 #include <new>
 #include <string>
@@ -37,6 +38,12 @@ struct Slot {
   uint8_t* d_low = nullptr;
   uint8_t* d_preview = nullptr;
   uint8_t* d_flags = nullptr;
+  // fpv_decode_coded: the coded bytes, their chunk table and the decoder's error word (allocated on first use)
+  uint8_t* d_coded = nullptr;
+  size_t coded_cap = 0;
+  CodedChunk* d_chunks = nullptr;
+  size_t chunks_cap = 0;
+  uint32_t* d_dec_err = nullptr;
   bool allocated = false;
   // a pending fpv_encode_stream_submit: fpv_wait fetches the coded bytes once their number is known
   uint8_t* stream_out_host = nullptr;
@@ -329,6 +336,9 @@ void fpv_destroy(fpv_ctx* c) {
     if (s.d_low) cudaFree(s.d_low);
     if (s.d_preview) cudaFree(s.d_preview);
     if (s.d_flags) cudaFree(s.d_flags);
+    if (s.d_coded) cudaFree(s.d_coded);
+    if (s.d_chunks) cudaFree(s.d_chunks);
+    if (s.d_dec_err) cudaFree(s.d_dec_err);
     if (s.done) cudaEventDestroy(s.done);
     if (s.stream) cudaStreamDestroy(s.stream);
   }
@@ -783,6 +793,74 @@ int fpv_decode(fpv_ctx* c, const uint8_t* high_host, const uint8_t* low_host, co
     rc = fpv_wait(c, 0);
     if (rc != FPV_OK) return rc;
   }
+  return FPV_OK;
+}
+
+int fpv_decode_coded(fpv_ctx* c, const uint8_t* blob_host, size_t blob_bytes, const fpv_coded_chunk* chunks_host,
+                     uint32_t n_chunks, const uint8_t* flags_host, uint32_t n, uint32_t options, void* out_host) {
+  if (!c) return FPV_ERR_INVALID_ARG;
+  FPV_LOCK(c);
+  if (n == 0) return FPV_OK;
+  if (n > c->max_batch) return fail(c, FPV_ERR_INVALID_ARG, "n exceeds max_batch");
+  if (!blob_host || !chunks_host || !flags_host || !out_host) return fail(c, FPV_ERR_INVALID_ARG, "NULL host buffer");
+  static_assert(sizeof(fpv_coded_chunk) == sizeof(CodedChunk), "fpv_coded_chunk layout");
+  const size_t P = c->g.P;
+  const uint32_t cpl = chunks_of(P);
+  // every plane a frame needs must be covered by exactly its chunks (a missing chunk would leave stale bytes)
+  std::vector<uint32_t> seen((size_t)n * 2, 0);
+  bool any_delta = false;
+  for (uint32_t i = 0; i < n_chunks; i++) {
+    const fpv_coded_chunk& k = chunks_host[i];
+    if (k.frame >= n || k.plane > 1 || k.index >= cpl || k.offset >= blob_bytes)
+      return fail(c, FPV_ERR_INVALID_ARG, "chunk table entry out of range");
+    seen[(size_t)k.frame * 2 + k.plane]++;
+  }
+  for (uint32_t f = 0; f < n; f++) {
+    if (flags_host[f] & FPV_FLAG_USE_DELTA) any_delta = true;
+    const bool has_low = !(flags_host[f] & FPV_FLAG_NO_LOW_BYTES);
+    if (seen[(size_t)f * 2] != cpl || seen[(size_t)f * 2 + 1] != (has_low ? cpl : 0u))
+      return fail(c, FPV_ERR_INVALID_ARG, "chunk table does not cover the planes of every frame exactly once");
+  }
+  if (any_delta && !c->has_delta) return fail(c, FPV_ERR_NO_DELTA, "delta frame not given");  // .cc:310
+  FPV_CUDA(cudaSetDevice(c->device));
+  int rc = ensure_slot(c, 0);
+  if (rc != FPV_OK) return rc;
+  Slot& s = c->slots[0];
+  if (s.coded_cap < blob_bytes + 16) {
+    if (s.d_coded) cudaFree(s.d_coded);
+    s.d_coded = nullptr;
+    s.coded_cap = 0;
+    const size_t want = std::max(blob_bytes + 16, stream_bound(c, c->max_batch));
+    FPV_CUDA(cudaMalloc(&s.d_coded, want));
+    s.coded_cap = want;
+  }
+  if (s.chunks_cap < n_chunks) {
+    if (s.d_chunks) cudaFree(s.d_chunks);
+    s.d_chunks = nullptr;
+    s.chunks_cap = 0;
+    const size_t want = std::max<size_t>(n_chunks, (size_t)c->max_batch * 2 * cpl);
+    FPV_CUDA(cudaMalloc(&s.d_chunks, want * sizeof(CodedChunk)));
+    s.chunks_cap = want;
+  }
+  if (!s.d_dec_err) FPV_CUDA(cudaMalloc(&s.d_dec_err, sizeof(uint32_t)));
+  FPV_CUDA(cudaMemcpyAsync(s.d_coded, blob_host, blob_bytes, cudaMemcpyHostToDevice, s.stream));
+  FPV_CUDA(cudaMemcpyAsync(s.d_chunks, chunks_host, (size_t)n_chunks * sizeof(CodedChunk), cudaMemcpyHostToDevice, s.stream));
+  FPV_CUDA(cudaMemcpyAsync(s.d_flags, flags_host, (size_t)n, cudaMemcpyHostToDevice, s.stream));
+  FPV_CUDA(cudaMemsetAsync(s.d_dec_err, 0, sizeof(uint32_t), s.stream));
+  EntropyDecodeParams p;
+  p.blob = s.d_coded; p.blob_bytes = blob_bytes; p.chunks = s.d_chunks; p.n_chunks = n_chunks; p.n_frames = n;
+  p.high = s.d_high; p.low = s.d_low; p.P = P; p.err = s.d_dec_err;
+  cudaError_t e = cudaSuccess;
+  const int l = enqueue_entropy_decode(p, s.stream, &e);
+  if (l < 0) return cuda_fail(c, e, "entropy decode kernel launch");
+  c->launches += (uint64_t)l;
+  rc = decode_device_impl(c, s.d_high, s.d_low, s.d_flags, n, options, s.d_frames, s.stream, true);
+  if (rc != FPV_OK) return rc;
+  uint32_t dec_err = 0;
+  FPV_CUDA(cudaMemcpyAsync(&dec_err, s.d_dec_err, sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream));
+  FPV_CUDA(cudaMemcpyAsync(out_host, s.d_frames, (size_t)n * P * 2, cudaMemcpyDeviceToHost, s.stream));
+  FPV_CUDA(cudaStreamSynchronize(s.stream));
+  if (dec_err) return fail(c, FPV_ERR_INVALID_ARG, "malformed coded chunk (entropy decoder reason " + std::to_string(dec_err) + ")");
   return FPV_OK;
 }
 

@@ -539,6 +539,189 @@ __global__ void __launch_bounds__(kET) k_entropy_gather(const EntropyParams p, c
   for (uint32_t i = head + words * 4 + threadIdx.x; i < nb; i += kET) dst[i] = src[i];
 }
 
+// =====================================================================================
+// k_entropy_decode -- the inverse of k_entropy_chunk for streams that carry directories.
+//
+// One warp per chunk.  Only the directory meta-block and the literal bits are read: the code lengths come from
+// the directory's nibbles (canonical code as in RFC 7932 3.2, the same construction k_entropy_chunk uses), a
+// 10-bit lookup table per warp in shared memory resolves most symbols in one step (longer codes: canonical
+// search over the lengths 11..15), and lane k starts at the directory's bit position of span k (2048 plane
+// bytes), so all 32 lanes decode at once.  Raw and constant chunks are copied / filled.  Every read is bounded
+// by the blob size and every write by the plane: a malformed chunk sets *err and is abandoned.
+// =====================================================================================
+namespace {
+
+constexpr int kDecWarps = 4;
+constexpr uint32_t kLutBits = 10;
+
+struct DecWarp {
+  uint16_t lut[1u << kLutBits];    // symbol | length << 8; 0: a code longer than kLutBits
+  uint8_t len[256];
+  uint8_t sorted[256];             // symbols ordered by (length, symbol)
+  uint16_t first[16];              // canonical code of the first symbol of each length (MSB-first)
+  uint16_t count[16];
+  uint16_t offset[16];             // index of that symbol in sorted[]
+};
+
+__device__ __forceinline__ uint32_t load_u24(const uint8_t* p) {
+  return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16);
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(32 * kDecWarps) k_entropy_decode(const EntropyDecodeParams p) {
+  __shared__ DecWarp dsm[kDecWarps];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t ci = blockIdx.x * kDecWarps + warp;
+  if (ci >= p.n_chunks) return;
+  DecWarp& d = dsm[warp];
+  const CodedChunk ch = p.chunks[ci];
+  auto bad = [&](uint32_t why) { if (lane == 0) atomicMax(p.err, why); };
+  if (ch.offset > p.blob_bytes || p.blob_bytes - ch.offset < kDirBlock + 1) { bad(1); return; }
+  const uint8_t* base = p.blob + ch.offset;
+  const uint8_t* dir = base + 2;
+  if (dir[0] != 0x46 || dir[1] != 0x44 || dir[2] != 1) { bad(2); return; }
+  const uint32_t kind = dir[3], cb = load_u24(dir + 4), n = ((uint32_t)dir[7] | ((uint32_t)dir[8] << 8)) + 1u;
+  const uint64_t plane_off = (uint64_t)ch.index * kEntropyChunk;
+  if (cb < kDirBlock || cb > p.blob_bytes - ch.offset || ch.frame >= p.n_frames || ch.plane > 1 ||
+      plane_off + n > p.P || (plane_off + n != p.P && n != kEntropyChunk)) { bad(3); return; }
+  uint8_t* plane = ch.plane ? p.low : p.high;
+  if (plane == nullptr) { bad(4); return; }
+  uint8_t* dst = plane + (uint64_t)ch.frame * p.P + plane_off;
+  const bool dst4 = (reinterpret_cast<uintptr_t>(dst) & 3u) == 0;
+
+  if (kind == kKindConstant) {
+    const uint32_t v = dir[9];
+    for (uint32_t i = lane; i < n; i += 32) dst[i] = (uint8_t)v;
+    return;
+  }
+  if (kind == kKindRaw) {
+    const uint32_t o = load_u24(dir + kDirSpans) >> 3;
+    if (o > cb || cb - o < n) { bad(5); return; }
+    const uint8_t* src = base + o;
+    if (dst4) {
+      for (uint32_t i = 4 * lane; i + 4 <= n; i += 128)
+        *reinterpret_cast<uint32_t*>(dst + i) = (uint32_t)src[i] | ((uint32_t)src[i + 1] << 8) | ((uint32_t)src[i + 2] << 16) |
+                                                ((uint32_t)src[i + 3] << 24);
+      for (uint32_t i = (n & ~3u) + lane; i < n; i += 32) dst[i] = src[i];
+    } else {
+      for (uint32_t i = lane; i < n; i += 32) dst[i] = src[i];
+    }
+    return;
+  }
+  if (kind != kKindHuffman) { bad(6); return; }
+
+  // ---- the canonical code from the directory's code lengths ------------------------------------------
+  {
+    const uint32_t w = (uint32_t)dir[kDirLengths + 4 * lane] | ((uint32_t)dir[kDirLengths + 4 * lane + 1] << 8) |
+                       ((uint32_t)dir[kDirLengths + 4 * lane + 2] << 16) | ((uint32_t)dir[kDirLengths + 4 * lane + 3] << 24);
+#pragma unroll
+    for (int j = 0; j < 8; j++) d.len[8 * lane + j] = (uint8_t)((w >> (4 * j)) & 15u);
+  }
+  __syncwarp();
+  if (lane == 0) {
+    uint32_t cnt[16];
+    for (int i = 0; i < 16; i++) cnt[i] = 0;
+    for (int i = 0; i < 256; i++) cnt[d.len[i]]++;
+    cnt[0] = 0;
+    uint32_t code = 0, off = 0, kraft = 0;
+    for (int b = 1; b <= 15; b++) {
+      code = (code + cnt[b - 1]) << 1;
+      d.first[b] = (uint16_t)code;
+      d.count[b] = (uint16_t)cnt[b];
+      d.offset[b] = (uint16_t)off;
+      off += cnt[b];
+      kraft += cnt[b] << (15 - b);
+    }
+    d.first[0] = d.count[0] = d.offset[0] = 0;
+    uint32_t next[16];
+    for (int b = 0; b < 16; b++) next[b] = d.offset[b];
+    for (int i = 0; i < 256; i++) {
+      const uint32_t l = d.len[i];
+      if (l) d.sorted[next[l]++] = (uint8_t)i;
+    }
+    if (kraft != (1u << 15)) d.count[0] = 1;       // not a complete prefix code
+  }
+  __syncwarp();
+  if (d.count[0]) { bad(7); return; }
+  // canonical decode of the low bits of `v` (stream order: the code's first bit is bit 0), lengths lo..hi
+  auto search = [&](uint32_t v, int lo, int hi, uint32_t& sym, uint32_t& len) -> bool {
+    const uint32_t r = __brev(v);
+    for (int L = lo; L <= hi; L++) {
+      const uint32_t c = (r >> (32 - L)) - d.first[L];
+      if (c < d.count[L]) { sym = d.sorted[d.offset[L] + c]; len = (uint32_t)L; return true; }
+    }
+    return false;
+  };
+  for (uint32_t idx = lane; idx < (1u << kLutBits); idx += 32) {
+    uint32_t sym = 0, len = 0;
+    d.lut[idx] = search(idx, 1, (int)kLutBits, sym, len) ? (uint16_t)(sym | (len << 8)) : (uint16_t)0;
+  }
+  __syncwarp();
+
+  // ---- lane k decodes span k -------------------------------------------------------------------------
+  const uint32_t k = (uint32_t)lane;
+  if ((uint64_t)k * kEntropySpan >= n) return;
+  uint32_t count = n - k * kEntropySpan < kEntropySpan ? n - k * kEntropySpan : kEntropySpan;
+  const uint32_t pos = load_u24(dir + kDirSpans + 3 * k);
+  if (pos < kDirBits || pos > 8 * cb) { bad(8); return; }
+  // aligned 32-bit reads of the blob; nothing past its last word is touched
+  const uintptr_t b0 = reinterpret_cast<uintptr_t>(base);
+  const uint32_t* words = reinterpret_cast<const uint32_t*>(b0 & ~(uintptr_t)3);
+  const uint64_t abs_bit = (uint64_t)(b0 & 3u) * 8 + pos;
+  uint64_t wi = abs_bit >> 5;
+  const uint64_t last_word = (uint64_t)((reinterpret_cast<uintptr_t>(p.blob) + p.blob_bytes - 1 - (b0 & ~(uintptr_t)3)) >> 2);
+  auto next_word = [&]() -> uint32_t {
+    const uint32_t v = wi <= last_word ? __ldg(words + wi) : 0u;
+    wi++;
+    return v;
+  };
+  unsigned long long buf = (unsigned long long)next_word() >> (abs_bit & 31u);
+  uint32_t nbits = 32 - (uint32_t)(abs_bit & 31u);
+  uint8_t* o = dst + (uint64_t)k * kEntropySpan;
+  uint32_t acc = 0, na = 0;
+  const bool vec = (reinterpret_cast<uintptr_t>(o) & 15u) == 0;
+  uint32_t q[4];
+  uint32_t nq = 0;
+  while (count) {
+    if (nbits < 32) { buf |= (unsigned long long)next_word() << nbits; nbits += 32; }
+    uint32_t sym, len;
+    const uint32_t e = d.lut[(uint32_t)buf & ((1u << kLutBits) - 1u)];
+    if (e) { sym = e & 255u; len = e >> 8; }
+    else if (!search((uint32_t)buf, (int)kLutBits + 1, 15, sym, len)) { atomicMax(p.err, 9u); return; }
+    buf >>= len;
+    nbits -= len;
+    count--;
+    acc |= sym << (8 * na);
+    if (++na == 4) {
+      if (vec) {
+        q[nq++] = acc;
+        if (nq == 4) { *reinterpret_cast<uint4*>(o) = make_uint4(q[0], q[1], q[2], q[3]); o += 16; nq = 0; }
+      } else if (dst4) {
+        *reinterpret_cast<uint32_t*>(o) = acc; o += 4;
+      } else {
+        o[0] = (uint8_t)acc; o[1] = (uint8_t)(acc >> 8); o[2] = (uint8_t)(acc >> 16); o[3] = (uint8_t)(acc >> 24); o += 4;
+      }
+      acc = 0; na = 0;
+    }
+  }
+  // tails: whole words still queued, then single bytes
+  for (uint32_t i = 0; i < nq; i++) { *reinterpret_cast<uint32_t*>(o) = q[i]; o += 4; }
+  for (uint32_t i = 0; i < na; i++) o[i] = (uint8_t)(acc >> (8 * i));
+  // the directory is redundant with the bit stream: a span must end where the next one starts (a damaged
+  // directory would otherwise decode to garbage without anyone noticing), the last one inside the chunk
+  const uint64_t end_pos = wi * 32 - nbits - (uint64_t)(b0 & 3u) * 8;
+  const bool last_span = (uint64_t)(k + 1) * kEntropySpan >= n;
+  if (last_span ? end_pos > 8ull * cb : end_pos != load_u24(dir + kDirSpans + 3 * (k + 1))) atomicMax(p.err, 10u);
+}
+
+int enqueue_entropy_decode(const EntropyDecodeParams& p, cudaStream_t stream, cudaError_t* err) {
+  if (p.n_chunks == 0) { *err = cudaSuccess; return 0; }
+  k_entropy_decode<<<(p.n_chunks + kDecWarps - 1) / kDecWarps, 32 * kDecWarps, 0, stream>>>(p);
+  *err = cudaGetLastError();
+  return *err == cudaSuccess ? 1 : -1;
+}
+
 size_t entropy_smem_bytes() { return sizeof(Shared); }
 
 int enqueue_entropy(const EntropyParams& p, uint64_t* frame_off, uint8_t* out, uint64_t capacity, uint32_t* overflow,

@@ -86,6 +86,25 @@ struct EntropyParams {
 
 // Enqueues chunk coding, layout and gather for n frames; frame_off: uint64[n + 1] (device), out: the
 // container chunks of the n frames back to back (device).  Returns kernels launched or -1.
+// One chunk of a directory-carrying plane stream (the device-side twin of fpv_coded_chunk).
+struct CodedChunk {
+  uint64_t offset;   // of the chunk's first byte inside the blob
+  uint32_t frame;    // frame index in the batch
+  uint32_t plane;    // 0 = high, 1 = low
+  uint32_t index;    // chunk index inside the plane: plane bytes [index * kEntropyChunk, ...)
+  uint32_t reserved;
+};
+struct EntropyDecodeParams {
+  const uint8_t* blob;
+  uint64_t blob_bytes;
+  const CodedChunk* chunks;
+  uint32_t n_chunks, n_frames;
+  uint8_t* high;     // [n_frames][P]
+  uint8_t* low;      // [n_frames][P] or nullptr
+  uint64_t P;
+  uint32_t* err;     // set to a non-zero reason by a malformed chunk
+};
+int enqueue_entropy_decode(const EntropyDecodeParams& p, cudaStream_t stream, cudaError_t* err);
 int enqueue_entropy(const EntropyParams& p, uint64_t* frame_off, uint8_t* out, uint64_t capacity, uint32_t* overflow,
                     cudaStream_t stream, cudaError_t* err);
 

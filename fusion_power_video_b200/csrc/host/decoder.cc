@@ -32,7 +32,15 @@ struct GpuDecoder {
     size_t n = 0, left = 0;
     std::mutex m;
     std::condition_variable cv;
+    // batches whose plane streams all carry the GPU coder's directories skip libbrotlidec: the coded bytes go
+    // to the GPU as they are (fpv_decode_coded)
+    bool coded = false;
+    Pinned blob;
+    size_t blob_bytes = 0;
+    std::vector<fpv_coded_chunk> chunks;
+    std::vector<size_t> core_at, core_size;    // where each frame's core sits in the blob (for the fallback)
   } sets[2];
+  bool coded_ok = true;        // false once the C ABI said it cannot decode coded chunks (CPU stand-in)
   Pinned out;
   std::unique_ptr<Pool> pool;
 
@@ -47,6 +55,7 @@ struct GpuDecoder {
       st.high.reset();
       st.low.reset();
       st.flags.reset();
+      st.blob.reset();
     }
     out.reset();
   }
@@ -74,9 +83,57 @@ struct GpuDecoder {
 
   // Starts the brotli decoding of n <= B core chunks into buffer set `which` (returns at once when there is
   // a pool).  cores / sizes must stay valid until finish().
+  // Directory-carrying streams only: lays the cores of the batch out in the pinned blob and lists their chunks.
+  bool scan_coded(Set& st, const uint8_t* const* cores, const size_t* sizes, size_t n, bool allow_delta) {
+    if (!coded_ok || n == 0 || getenv("FPV_HOST_BROTLI_DECODE")) return false;
+    st.chunks.clear();
+    std::vector<uint64_t> offs;
+    size_t total = 0;
+    std::vector<size_t> base(n);
+    for (size_t i = 0; i < n; i++) {
+      if (sizes[i] < 2) return false;
+      const uint8_t f = cores[i][0];
+      if ((f & FPV_FLAG_USE_DELTA) && !allow_delta) return false;     // the brotli path reports it per frame
+      size_t pos = 1;
+      base[i] = total;
+      for (int plane = (f & FPV_FLAG_NO_LOW_BYTES) ? 0 : 1; plane >= 0; plane--) {   // low comes first (.cc:658-662)
+        offs.clear();
+        size_t len = 0;
+        if (!ScanCodedPlane(cores[i] + pos, sizes[i] - pos, P, &offs, &len)) return false;
+        for (size_t k = 0; k < offs.size(); k++)
+          st.chunks.push_back(fpv_coded_chunk{total + pos + offs[k], (uint32_t)i, (uint32_t)plane, (uint32_t)k, 0});
+        pos += len;
+      }
+      if (pos != sizes[i]) return false;
+      total += (sizes[i] + 15) & ~(size_t)15;
+    }
+    if (st.blob.bytes() < total && !st.blob.alloc(std::max(total, (size_t)B * (2 * P + 4096)))) return false;
+    st.blob_bytes = total;
+    st.core_at = base;
+    st.core_size.assign(sizes, sizes + n);
+    st.good.assign(n, 1);
+    st.n = n;
+    st.left = n;
+    for (size_t i = 0; i < n; i++) {
+      const uint8_t* core = cores[i];
+      const size_t size = sizes[i], at = base[i];
+      auto task = [this, &st, core, size, at, i] {
+        memcpy(st.blob.as<uint8_t>() + at, core, size);
+        st.flags.as<uint8_t>()[i] = core[0];
+        std::lock_guard<std::mutex> l(st.m);
+        if (--st.left == 0) st.cv.notify_all();
+      };
+      if (pool) pool->run(task);
+      else task();
+    }
+    return true;
+  }
+
   bool start(int which, const uint8_t* const* cores, const size_t* sizes, size_t n, bool allow_delta) {
     Set& st = sets[which];
     if (!alloc_set(st)) return false;
+    st.coded = scan_coded(st, cores, sizes, n, allow_delta);
+    if (st.coded) return true;
     st.good.assign(n, 0);
     st.n = n;
     st.left = n;
@@ -109,6 +166,24 @@ struct GpuDecoder {
     size_t k = 0;
     while (k < st.n && st.good[k]) k++;
     if (k == 0) return 0;
+    if (st.coded) {
+      const int rc = fpv_decode_coded(ctx, st.blob.as<uint8_t>(), st.blob_bytes, st.chunks.data(), (uint32_t)st.chunks.size(),
+                                      st.flags.as<uint8_t>(), (uint32_t)k, options, out.as<uint8_t>());
+      if (rc == FPV_OK) return k;
+      // A chunk the GPU decoder refused (or a C ABI without one): the same bytes through libbrotlidec, frame by
+      // frame, so that malformed streams fail exactly like libbrotli-coded ones
+      if (rc == FPV_ERR_UNSUPPORTED) coded_ok = false;
+      st.coded = false;
+      for (size_t i = 0; i < st.n; i++) {
+        uint8_t f = 0;
+        st.good[i] = ParseCore(st.blob.as<uint8_t>() + st.core_at[i], st.core_size[i], P, &f, st.high.as<uint8_t>() + i * P,
+                               st.low.as<uint8_t>() + i * P) ? 1 : 0;
+        st.flags.as<uint8_t>()[i] = f;
+      }
+      k = 0;
+      while (k < st.n && st.good[k]) k++;
+      if (k == 0) return 0;
+    }
     if (fpv_decode(ctx, st.high.as<uint8_t>(), st.low.as<uint8_t>(), st.flags.as<uint8_t>(), (uint32_t)k, options,
                    out.as<uint8_t>()) != FPV_OK) {
       FPV_FAIL(std::string("fpv_decode: ") + fpv_last_error(ctx));

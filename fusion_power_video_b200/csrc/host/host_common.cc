@@ -77,6 +77,34 @@ void AppendCore(uint8_t flags, const uint8_t* high, const uint8_t* low, size_t p
   BrotliPlane(high, plane_bytes, scratch, out);
 }
 
+bool ScanCodedPlane(const uint8_t* in, size_t avail, size_t plane_bytes, std::vector<uint64_t>* chunk_offsets,
+                    size_t* stream_bytes) {
+  constexpr size_t kChunk = 65536, kDirBlock = 236;
+  const size_t chunks = (plane_bytes + kChunk - 1) / kChunk;
+  const size_t first = chunk_offsets->size();
+  size_t pos = 0;
+  for (size_t k = 0; k < chunks; k++) {
+    // 2 header bytes of the metadata meta-block, then 'F' 'D' version 1 | kind | chunk bytes u24 ...
+    if (pos + kDirBlock > avail || in[pos + 2] != 0x46 || in[pos + 3] != 0x44 || in[pos + 4] != 1) {
+      chunk_offsets->resize(first);
+      return false;
+    }
+    const size_t cb = (size_t)in[pos + 6] | ((size_t)in[pos + 7] << 8) | ((size_t)in[pos + 8] << 16);
+    if (cb < kDirBlock || cb > avail - pos) {
+      chunk_offsets->resize(first);
+      return false;
+    }
+    chunk_offsets->push_back(pos);
+    pos += cb;
+  }
+  if (chunks == 0 || pos >= avail || in[pos] != 0x03) {     // ISLAST, ISLASTEMPTY ends the stream
+    chunk_offsets->resize(first);
+    return false;
+  }
+  *stream_bytes = pos + 1;
+  return true;
+}
+
 bool ParseCore(const uint8_t* in, size_t size, size_t plane_bytes, uint8_t* flags, uint8_t* high, uint8_t* low) {
   if (size == 0) return FPV_FAIL("out of bounds");
   size_t pos = 0;

@@ -61,6 +61,14 @@ bool BrotliPlane(const uint8_t* plane, size_t size, std::vector<uint8_t>* scratc
 // reference .cc:186-214).  Fails if the stream is malformed or its size differs.
 bool BrotliUnplane(const uint8_t* in, size_t size, size_t* pos, uint8_t* out, size_t expect);
 
+// Walks the directory meta-blocks of ONE plane stream written by the GPU entropy coder (csrc/fpv_entropy.cu: every
+// 64 KiB chunk starts with a metadata meta-block holding, among other things, the chunk's size).  On success the
+// offsets of the stream's chunks (relative to `in`) are appended to *chunk_offsets and *stream_bytes is the
+// length of the whole stream, final 0x03 included.  false: not such a stream (libbrotli's output carries no
+// directory) or a truncated one -- the caller then takes the brotli path.
+bool ScanCodedPlane(const uint8_t* in, size_t avail, size_t plane_bytes, std::vector<uint64_t>* chunk_offsets,
+                    size_t* stream_bytes);
+
 // core := flags | brotli(low)? | brotli(high)
 void AppendCore(uint8_t flags, const uint8_t* high, const uint8_t* low, size_t plane_bytes,
                 std::vector<uint8_t>* scratch, std::vector<uint8_t>* out);

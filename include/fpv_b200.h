@@ -233,6 +233,32 @@ int fpv_decode_submit(fpv_ctx* ctx, uint32_t slot, const uint8_t* high_host,
                       const uint8_t* low_host, const uint8_t* flags_host, uint32_t n,
                       uint32_t options, void* out_host);
 
+/* Frames whose plane streams were written by this library's GPU entropy coder
+ * (fpv_encode_stream_submit / fpv_entropy_device): every 64 KiB chunk of such a
+ * stream starts with a metadata meta-block -- skipped by brotli decoders, the
+ * reference's included -- that carries a directory (chunk size, code lengths,
+ * bit positions of 2048-byte spans; layout in csrc/fpv_internal.h).  This call
+ * replaces BrotliDecompress (.cc:186-214) + the post-brotli part of
+ * DecompressImage (.cc:326-344) for n frames: the coded bytes are uploaded as
+ * they are (about half the plane bytes), decoded by one warp per chunk into
+ * the context's plane buffers and inverted like fpv_decode.  `blob_host` holds
+ * the coded bytes of all frames; `chunks_host` names every chunk of every plane
+ * a frame needs (no low-plane chunks for frames with flags & 4): its offset in
+ * the blob, the frame, the plane (0 = high, 1 = low) and its index inside the
+ * plane (plane bytes [index * 65536, ...)).  The host side finds the offsets by
+ * walking the directories (each holds its chunk's size).  Synchronous.
+ * Streams libbrotli wrote carry no directory and go through fpv_decode. */
+typedef struct fpv_coded_chunk {
+  uint64_t offset;
+  uint32_t frame;
+  uint32_t plane;
+  uint32_t index;
+  uint32_t reserved;
+} fpv_coded_chunk;
+int fpv_decode_coded(fpv_ctx* ctx, const uint8_t* blob_host, size_t blob_bytes,
+                     const fpv_coded_chunk* chunks_host, uint32_t n_chunks,
+                     const uint8_t* flags_host, uint32_t n, uint32_t options, void* out_host);
+
 /* Plane-level inverse, replacing Frame::Uncompress's prediction undo
  * (.cc:773-774 -> :612-641, :595-610): inverse CG on high and preview, delta
  * add on both byte planes; planes are rewritten in place (host buffers).

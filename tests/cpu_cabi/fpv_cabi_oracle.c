@@ -171,6 +171,11 @@ int fpv_decode_device(fpv_ctx* c, const void* high, const void* low, const void*
   (void)stream;
   return fpv_decode(c, (const uint8_t*)high, (const uint8_t*)low, (const uint8_t*)flags, n, options, out);
 }
+int fpv_decode_coded(fpv_ctx* c, const uint8_t* blob, size_t blob_bytes, const fpv_coded_chunk* chunks, uint32_t n_chunks,
+                     const uint8_t* flags, uint32_t n, uint32_t options, void* out) {
+  (void)c; (void)blob; (void)blob_bytes; (void)chunks; (void)n_chunks; (void)flags; (void)n; (void)options; (void)out;
+  return fail(FPV_ERR_UNSUPPORTED, "the GPU entropy decoder has no CPU stand-in");
+}
 int fpv_decode_submit(fpv_ctx* c, uint32_t slot, const uint8_t* high, const uint8_t* low, const uint8_t* flags, uint32_t n,
                       uint32_t options, void* out) {
   if (slot >= FPV_NUM_SLOTS) return fail(FPV_ERR_INVALID_ARG, "slot out of range");

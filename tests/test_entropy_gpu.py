@@ -173,3 +173,92 @@ def test_more_frames_than_layout_threads():
         assert int.from_bytes(chunks[i][:4], "little") == len(chunks[i]), f"frame {i}: container size field"
     for i in (0, 1, 511, 1023, 1024, 1025, n - 1):
         assert chunks[i] == expected_chunk(int(flags[i]), high[i], low[i], preview[i]), f"frame {i}"
+
+
+def _chunk_table(chunks, P):
+    """Container chunks of encode_stream -> (blob, chunk table, flags) for fpv_decode_coded, walking the directories
+    with the CPU restatement's scanner."""
+    blob, table, flags = bytearray(), [], []
+    for f, ch in enumerate(chunks):
+        total, kind, bp1 = struct.unpack_from("<IBI", ch)
+        assert total == len(ch) and kind == 0
+        core = ch[10 + bp1 - 1:]
+        fl = core[0]
+        flags.append(fl)
+        pos = 1
+        for plane in ([1, 0] if not fl & 4 else [0]):
+            offs, length = href.scan_plane(core[pos:], P)
+            table += [(len(blob) + pos + o, f, plane, k) for k, o in enumerate(offs)]
+            pos += length
+        assert pos == len(core)
+        blob += core
+        blob += bytes(-len(blob) % 16)
+    return bytes(blob), table, np.array(flags, np.uint8)
+
+
+@pytest.mark.parametrize("W,H,bits,shift,n", [(1280, 160, 12, 4, 6), (1024, 136, 16, 0, 5), (320, 48, 8, 8, 4), (2048, 72, 16, 0, 3),
+                                              (100, 100, 16, 0, 3)])
+def test_gpu_entropy_decoder_round_trip(W, H, bits, shift, n):
+    """fpv_decode_coded: coded container chunks -> (k_entropy_decode: one warp per chunk from the directories) ->
+    inverse transform == the raw input; same images as the planes through fpv_decode."""
+    import fusion_power_video_b200 as fpv
+    from fusion_power_video_b200 import synth
+
+    frames = synth.plasma_frames(n, W, H, bits=bits, seed=W + n).reshape(n, -1)
+    frames[n - 1] = frames[0]                  # planes of zeros: constant chunks
+    with fpv.Context(W, H, shift, False, max_batch=8) as ctx:
+        ctx.set_delta_raw(frames[0])
+        flags, chunks = ctx.encode_stream(frames)
+        pf, high, low, _ = ctx.encode(frames)
+        want = ctx.decode(high, low, pf)
+        blob, table, fl = _chunk_table(chunks, W * H)
+        assert np.array_equal(fl, flags)
+        got = ctx.decode_coded(blob, table, fl)
+        assert np.array_equal(got, want)
+        raw = ctx.decode_coded(blob, table, fl, fpv.DEC_UNEXTRACT)
+        assert np.array_equal(raw, frames)
+
+
+def test_gpu_entropy_decoder_crafted_planes():
+    """Planes straight into the coder (deep trees: codes longer than the 10-bit table; incompressible: raw chunks;
+    constant; a ragged last chunk), decoded again by k_entropy_decode; flags 0 keeps the inverse transform out of it."""
+    import torch
+
+    import fusion_power_video_b200 as fpv
+
+    W, H, n = 1024, 68, 6            # 69632 bytes per plane: one full chunk and a ragged one
+    P, PP = W * H, (W // 4) * (H // 4)
+    rng = np.random.default_rng(3)
+    wts = 1.7 ** -np.arange(40)
+    planes = [rng.choice(40, P, p=wts / wts.sum()).astype(np.uint8),                      # depth-limited deep tree
+              rng.integers(0, 256, P).astype(np.uint8),                                 # raw chunks
+              np.full(P, 9, np.uint8),                                                  # constant
+              np.minimum(rng.geometric(0.05, P) - 1, 255).astype(np.uint8),
+              (np.cumsum(rng.integers(-2, 3, P)) & 255).astype(np.uint8),
+              rng.integers(0, 2, P).astype(np.uint8)]
+    high = np.stack(planes)
+    low = np.stack(planes[::-1])
+    prev = np.zeros((n, PP), np.uint8)
+    flags = np.zeros(n, np.uint8)
+    dev = torch.device("cuda", 0)
+    th, tl, tp, tf = (torch.from_numpy(a).to(dev) for a in (high, low, prev, flags))
+    with fpv.Context(W, H, 0, False, max_batch=n) as ctx:
+        cap = ctx.stream_bound(n)
+        out = torch.zeros(cap, dtype=torch.uint8, device=dev)
+        off = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+        ctx.entropy_device(tf.data_ptr(), th.data_ptr(), tl.data_ptr(), tp.data_ptr(), n, out.data_ptr(), cap, off.data_ptr())
+        torch.cuda.synchronize()
+        off, out = off.cpu().numpy(), out.cpu().numpy()
+        chunks = [out[off[i]:off[i + 1]].tobytes() for i in range(n)]
+        blob, table, fl = _chunk_table(chunks, P)
+        img = ctx.decode_coded(blob, table, fl)
+        assert np.array_equal(img, (high.astype(np.uint16) << 8) | low)
+        # a damaged directory is refused, not decoded to garbage: span 1's bit position of the first chunk
+        bad = bytearray(blob)
+        at = table[0][0] + 2 + 138 + 3
+        bad[at] ^= 0x10
+        with pytest.raises(fpv.FpvError):
+            ctx.decode_coded(bytes(bad), table, fl)
+        # and a chunk table that misses a chunk is refused on the host
+        with pytest.raises(fpv.FpvError):
+            ctx.decode_coded(blob, table[:-1], fl)

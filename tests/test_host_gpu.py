@@ -147,3 +147,21 @@ def test_gpu_entropy_full_size_round_trip(W, H, bits, shift, n):
         nd, dec_ref, wo, ho = Ref().decode_stream(np.frombuffer(stream, np.uint8), n, W, H)
         assert nd == n
         assert np.array_equal(dec_ref[:n] >> shift if shift else dec_ref[:n], frames)
+
+
+def test_gpu_coded_stream_both_decoder_paths(monkeypatch):
+    """A GPU-coded stream through StreamingDecoder twice: coded bytes decoded on the GPU from the chunk directories
+    (the default for such streams), and through libbrotlidec on host threads (FPV_HOST_BROTLI_DECODE) -- the same
+    images either way; a truncated stream yields the same leading frames on both paths."""
+    W, H, shift, n = 1280, 160, 4, 21
+    frames = synth.plasma_frames(n, W, H, bits=12, seed=5).reshape(n, -1)
+    stream = host.encode_stream(frames, W, H, shift, False, threads=4, batch=8, gpu_entropy=True)
+    gpu = host.decode_stream(stream, n, W, H, batch=8, raw_shift=shift)
+    assert np.array_equal(gpu, frames)
+    cut = stream[: len(stream) * 2 // 3]
+    gpu_cut = host.decode_stream(cut, n, W, H, batch=8, raw_shift=shift)
+    monkeypatch.setenv("FPV_HOST_BROTLI_DECODE", "1")
+    cpu = host.decode_stream(stream, n, W, H, batch=8, raw_shift=shift)
+    cpu_cut = host.decode_stream(cut, n, W, H, batch=8, raw_shift=shift)
+    assert np.array_equal(cpu, frames)
+    assert 0 < gpu_cut.shape[0] < n and np.array_equal(gpu_cut, cpu_cut)
