@@ -797,7 +797,7 @@ def main():
         # decode side of the codec: StreamingDecoder (host brotli decode on all cores + GPU inverse transform +
         # UnextractFrame on the GPU) on the stream just described, both entropy variants (rank 0, N = 1)
         if world == 1:
-            nd = min(ns, 256 if not big else 32)
+            nd = min(ns, 1024 if not big else 32)
             dec = {}
             for name, ge in (("brotli_stream", False), ("gpu_entropy_stream", True)):
                 st = fpv_host.encode_stream(fr[:nd], W, H, shift, False, threads=ncpu, batch=32, gpu_entropy=ge)

@@ -9,6 +9,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <future>
 #include <thread>
 
 #include "fusion_power_video.h"
@@ -41,8 +42,10 @@ struct GpuDecoder {
     std::vector<size_t> core_at, core_size;    // where each frame's core sits in the blob (for the fallback)
   } sets[2];
   bool coded_ok = true;        // false once the C ABI said it cannot decode coded chunks (CPU stand-in)
-  Pinned out;
+  Pinned out, out1;             // decoded frames of set 0 / set 1
   std::unique_ptr<Pool> pool;
+
+  Pinned& outbuf(int which) { return which ? out1 : out; }
 
   ~GpuDecoder() { close(); }
 
@@ -58,6 +61,7 @@ struct GpuDecoder {
       st.blob.reset();
     }
     out.reset();
+    out1.reset();
   }
 
   bool alloc_set(Set& st) {
@@ -132,6 +136,7 @@ struct GpuDecoder {
   bool start(int which, const uint8_t* const* cores, const size_t* sizes, size_t n, bool allow_delta) {
     Set& st = sets[which];
     if (!alloc_set(st)) return false;
+    if (which == 1 && !out1.bytes() && !out1.alloc((size_t)B * P * 2)) return FPV_FAIL("pinned allocation failed");
     st.coded = scan_coded(st, cores, sizes, n, allow_delta);
     if (st.coded) return true;
     st.good.assign(n, 0);
@@ -168,7 +173,7 @@ struct GpuDecoder {
     if (k == 0) return 0;
     if (st.coded) {
       const int rc = fpv_decode_coded(ctx, st.blob.as<uint8_t>(), st.blob_bytes, st.chunks.data(), (uint32_t)st.chunks.size(),
-                                      st.flags.as<uint8_t>(), (uint32_t)k, options, out.as<uint8_t>());
+                                      st.flags.as<uint8_t>(), (uint32_t)k, options, outbuf(which).as<uint8_t>());
       if (rc == FPV_OK) return k;
       // A chunk the GPU decoder refused (or a C ABI without one): the same bytes through libbrotlidec, frame by
       // frame, so that malformed streams fail exactly like libbrotli-coded ones
@@ -185,7 +190,7 @@ struct GpuDecoder {
       if (k == 0) return 0;
     }
     if (fpv_decode(ctx, st.high.as<uint8_t>(), st.low.as<uint8_t>(), st.flags.as<uint8_t>(), (uint32_t)k, options,
-                   out.as<uint8_t>()) != FPV_OK) {
+                   outbuf(which).as<uint8_t>()) != FPV_OK) {
       FPV_FAIL(std::string("fpv_decode: ") + fpv_last_error(ctx));
       return 0;
     }
@@ -300,22 +305,24 @@ void StreamingDecoder::Decode(
   };
   int cur = 0;
   bool have = s.have_delta && gather(cur);
+  size_t good = have ? s.gpu.finish(cur, options) : 0;
   while (have) {
     const size_t end_of_cur = scan;
-    // batch k + 1 is brotli-decoded on the pool while the GPU inverts batch k and the callbacks consume it
+    // While the callbacks consume batch k, batch k + 1 is entropy-decoded (pool threads, or the GPU for streams that
+    // carry chunk directories) and inverted on the GPU by a helper thread; each batch has its own output buffer.
     const bool have_next = !stream_bad && gather(cur ^ 1);
-    const size_t good = s.gpu.finish(cur, options);
+    std::future<size_t> next_good;
+    if (have_next) next_good = std::async(std::launch::async, [&s, cur, options] { return s.gpu.finish(cur ^ 1, options); });
     for (size_t i = 0; i < good; i++) {
-      callback(true, s.gpu.out.as<uint16_t>() + i * s.gpu.P, s.gpu.W, s.gpu.H, payload);
+      callback(true, s.gpu.outbuf(cur).as<uint16_t>() + i * s.gpu.P, s.gpu.W, s.gpu.H, payload);
       s.id++;
     }
-    if (good != cores[cur].size()) {
-      if (have_next) s.gpu.finish(cur ^ 1, options);   // let the started tasks drain before the buffers go away
-      return fail("decompressing frame failed");
-    }
+    const size_t good_of_next = have_next ? next_good.get() : 0;   // (also drains the started tasks before any return)
+    if (good != cores[cur].size()) return fail("decompressing frame failed");
     pos = end_of_cur;
     cur ^= 1;
     have = have_next;
+    good = good_of_next;
   }
   if (stream_bad) return fail(bad_what);
 
