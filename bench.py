@@ -801,15 +801,21 @@ def main():
             dec = {}
             for name, ge in (("brotli_stream", False), ("gpu_entropy_stream", True)):
                 st = fpv_host.encode_stream(fr[:nd], W, H, shift, False, threads=ncpu, batch=32, gpu_entropy=ge)
-                fpv_host.decode_stream(st, nd, W, H, block=0, batch=32, raw_shift=shift)
+                out = fpv_host.decode_stream(st, nd, W, H, block=0, batch=32, raw_shift=shift)
+                okd = bool(np.array_equal(out, fr[:nd]))
+                del out
                 t_a = time.perf_counter()
-                bestd, okd = None, False
+                bestd = bestc = None
                 for _ in range(2):
-                    out, sec = fpv_host.decode_stream(st, nd, W, H, block=0, batch=32, raw_shift=shift, return_time=True)
+                    # the decoder alone (the callback counts frames) and with a consumer that copies every frame out
+                    cnt, sec = fpv_host.decode_stream(st, nd, W, H, block=0, batch=32, raw_shift=shift, return_time=True, keep=False)
+                    okd = okd and cnt.shape[0] == nd
                     bestd = sec if bestd is None else min(bestd, sec)
-                    okd = bool(np.array_equal(out, fr[:nd]))
+                    _, sec = fpv_host.decode_stream(st, nd, W, H, block=0, batch=32, raw_shift=shift, return_time=True)
+                    bestc = sec if bestc is None else min(bestc, sec)
                 windows.append((t_a, time.perf_counter()))
                 dec[name] = {"value": nd * P * 2 / bestd / 1e9, "unit": "GB/s", "frames_per_s": nd / bestd, "frames": nd,
+                             "with_consumer_copy": nd * P * 2 / bestc / 1e9,
                              "round_trip_exact": okd, "stream_bytes": len(st)}
             stream_leg["decode"] = dec
 

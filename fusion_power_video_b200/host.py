@@ -166,19 +166,23 @@ def time_encode(frames, xsize, ysize, shift=0, big_endian=False, threads=4, batc
 
 
 def decode_stream(stream, max_frames, xsize, ysize, block=0, batch=32, raw_shift=-1, big_endian=False, device=0,
-                  return_time=False):
+                  return_time=False, keep=True):
     """Decodes with StreamingDecoder in `block`-byte pieces.  Returns uint16 [n, ysize*xsize] (images, or the raw
-    file words when raw_shift >= 0)."""
+    file words when raw_shift >= 0).  keep=False: the callback only counts the frames (timing the decoder without a
+    consumer's copy of every frame); the returned array then has the right length and no contents."""
     L = lib()
     buf = np.frombuffer(stream, np.uint8)
-    out = np.zeros((max_frames, xsize * ysize), np.uint16)
+    out = np.empty((max_frames if keep else 0, xsize * ysize), np.uint16)
+    out[...] = 0            # touched before the timed call: the callback's memcpy must not pay the page faults
     W, H, sec = C.c_size_t(0), C.c_size_t(0), C.c_double(0)
-    n = L.fpvh_decode_stream(_p(buf), buf.size, block, batch, device, raw_shift, int(big_endian), _p(out), max_frames,
-                             C.byref(W), C.byref(H), C.byref(sec))
+    n = L.fpvh_decode_stream(_p(buf), buf.size, block, batch, device, raw_shift, int(big_endian), _p(out) if keep else None,
+                             max_frames, C.byref(W), C.byref(H), C.byref(sec))
     if n < 0:
         raise HostError(f"decode failed: {last_error()}")
     if n and (W.value, H.value) != (xsize, ysize):
         raise HostError(f"stream is {W.value}x{H.value}, expected {xsize}x{ysize}")
+    if not keep:
+        out = np.empty((n, 0), np.uint16)
     return (out[:n], sec.value) if return_time else out[:n]
 
 
