@@ -100,7 +100,7 @@ def launches_md(tag):
     tot = sum(sum(v) for v in per.values())
     lines = [f"# Launch list ({tag})", "",
              "`ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k_... -c 120 python bench.py --steps 3 --warmup 3 "
-             "--no-e2e --no-cpu --no-stream` on one B200 (the bench's default workload, C2: 12-bit 1280x800, 1184 frames per step; "
+             "--no-e2e --no-cpu --no-stream` on one B200 (the bench's default workload, C2: 12-bit 1280x800, one full wave of frames per step; "
              "encode steps, then decode steps, then the entropy coder on 256 frames).  Per-launch times are cold-cache and "
              "serialised: compare shares, not absolutes.", "",
              "| kernel | launches | avg us | min us | max us | share of all listed time |", "|---|---|---|---|---|---|"]
@@ -111,15 +111,17 @@ def launches_md(tag):
     main = [x for k, v in enc.items() if "k_encode_fast" in k for x in v if x > 100]
     lines += ["", f"Within the encode steps, the main pass of `k_encode_fast` (the {len(main)} launches > 100 us) is "
               f"{100 * sum(main) / etot:.1f} % of the listed encode time; bench.py's event timing of the same share "
-              "(`roofline.kernel_share_of_step`) is 0.89-0.91."]
+              "(`roofline.kernel_share_of_step`) is in the bench line."]
     open(os.path.join(ROOT, "profiles", f"{tag}_launches.md"), "w").write("\n".join(lines) + "\n")
 
 
 def main():
     tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
     P = 1280 * 800
-    launches_md(tag)
     import json
+    if tag != "r01":
+        return main_r02(tag)
+    launches_md(tag)
     traffic = {}
     F = 1184
     traffic["encode"] = kernel_md(f"{tag}_encode", f"k_encode_fast, main pass (C2, {F} frames)", os.path.join(OUT, "prof_encode_main.ncu-rep"),
@@ -130,27 +132,61 @@ def main():
               F * 800, "frame row (1280 px)", F * P * 4.0,
               "`ncu --set full --clock-control none --import-source on -k regex:k_decode_pair -s 1 -c 1 python bench.py --steps 3 "
               "--warmup 3 --no-e2e --no-cpu --no-stream --no-entropy`.")
-    if os.path.exists(os.path.join(OUT, "prof_entropy.ncu-rep")):
+    json.dump(traffic, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
+
+
+def main_r02(tag):
+    """Round 2: the bench's default step is 2368 frames of C2 (one wave of k_decode_fused: 16 frames per SM); the
+    captures come from scripts/gpu_profile_r2.sh.  Missing reports are skipped."""
+    import json
+    P, F = 1280 * 800, 2368
+    cmd = "python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu --no-stream --no-configs --no-ingest"
+    if os.path.exists(os.path.join(OUT, "launches.csv")):
+        launches_md(tag)
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    traffic = json.load(open(tpath)) if os.path.exists(tpath) else {}
+
+    def have(name):
+        return os.path.exists(os.path.join(OUT, name))
+
+    if have("prof_encode_main.ncu-rep"):
+        traffic["encode"] = kernel_md(f"{tag}_encode", f"k_encode_fast, main pass (C2, {F} frames)", os.path.join(OUT, "prof_encode_main.ncu-rep"),
+              F * P / 256, "warp-row (256 px)", F * P * 4.0625,
+              f"`ncu --set full --clock-control none --import-source on -k regex:k_encode_fast -s 9 -c 1 {cmd} --no-decode --no-entropy` "
+              "(a main pass of a timed step; decisions, flags and preview prediction are fused into this kernel since round 2).")
+    if have("prof_decode.ncu-rep"):
+        traffic["decode"] = kernel_md(f"{tag}_decode", f"k_decode_fused (C2: 12-bit 1280x800, L = 40, bulk-store output, {F} frames = one wave)",
+              os.path.join(OUT, "prof_decode.ncu-rep"), F * 800 / 2, "pair row (2 x 1280 px)", F * P * 4.0,
+              f"`ncu --set full --clock-control none --import-source on -k regex:k_decode_fused -s 2 -c 1 {cmd} --no-entropy`.")
+    if have("prof_decode_c1.ncu-rep"):
+        P1 = 1024 * 1024
+        traffic["decode_c1"] = kernel_md(f"{tag}_decode_c1", f"k_decode_fused (C1 geometry: 16-bit 1024x1024, L = 32, 256-bit direct stores, {F} frames)",
+              os.path.join(OUT, "prof_decode_c1.ncu-rep"), F * 1024 / 2, "pair row (2 x 1024 px)", F * P1 * 4.0,
+              f"`ncu ... -k regex:k_decode_fused -s 2 -c 1 {cmd} --workload c1 --no-entropy`.")
+    if have("prof_decode_c3.ncu-rep"):
+        F3, P3 = 1184, 2048 * 2048
+        traffic["decode_c3"] = kernel_md(f"{tag}_decode_c3", f"k_decode_fused in split mode (C3: 16-bit 2048x2048, {F3} frames = one wave)",
+              os.path.join(OUT, "prof_decode_c3.ncu-rep"), F3 * 2048, "frame row (2048 px)", F3 * P3 * 4.0,
+              f"`ncu ... -k regex:k_decode_fused -s 2 -c 1 {cmd} --workload c3 --no-entropy`.")
+    if have("prof_encode_c3.ncu-rep"):
+        F3, P3 = 1184, 2048 * 2048
+        traffic["encode_c3"] = kernel_md(f"{tag}_encode_c3", f"k_encode_fast, main pass (C3: 16-bit 2048x2048, {F3} frames)",
+              os.path.join(OUT, "prof_encode_c3.ncu-rep"), F3 * P3 / 256, "warp-row (256 px)", F3 * P3 * 4.0625,
+              f"`ncu ... -k regex:k_encode_fast -s 9 -c 1 {cmd} --workload c3 --no-decode --no-entropy`.")
+    if have("prof_entropy.ncu-rep"):
         Fe = 256
         traffic["entropy"] = kernel_md(f"{tag}_entropy", f"k_entropy_chunk (C2 planes, {Fe} frames = {Fe * 33} chunks of 64 KiB)",
               os.path.join(OUT, "prof_entropy.ncu-rep"), Fe * 33, "chunk (<= 64 KiB)", Fe * P * (2 + 1 / 16) * 1.5,
-              "`ncu --set full --clock-control none --import-source on -k regex:k_entropy_chunk -s 1 -c 1 python bench.py --steps 3 "
-              "--warmup 3 --no-e2e --no-cpu --no-stream --no-decode`.  Algorithmic bytes here = planes read once + coded bytes "
-              "written to the scratch (about half the plane bytes); the kernel reads each chunk three times (histogram, sizes, "
-              "packing), the second and third time from L1/L2.  It is not HBM bound: the serial Huffman construction per chunk dominates.")
-    if os.path.exists(os.path.join(OUT, "prof_decode_c3.ncu-rep")):
-        F3, P3 = 592, 2048 * 2048
-        traffic["decode_c3"] = kernel_md(f"{tag}_decode_c3", f"k_decode_pair in split mode (C3: 16-bit 2048x2048, {F3} frames = one wave)",
-              os.path.join(OUT, "prof_decode_c3.ncu-rep"), F3 * 2048, "frame row (2048 px)", F3 * P3 * 4.0,
-              "`ncu --set full --clock-control none --import-source on -k regex:k_decode_pair -s 1 -c 1 python bench.py --workload c3 "
-              "--frames 592 --steps 3 --warmup 3 --no-e2e --no-cpu --no-stream --no-entropy`.")
-    if os.path.exists(os.path.join(OUT, "prof_encode_c3.ncu-rep")):
-        F3, P3 = 592, 2048 * 2048
-        traffic["encode_c3"] = kernel_md(f"{tag}_encode_c3", f"k_encode_fast, main pass (C3: 16-bit 2048x2048, {F3} frames)",
-              os.path.join(OUT, "prof_encode_c3.ncu-rep"), F3 * P3 / 256, "warp-row (256 px)", F3 * P3 * 4.0625,
-              "`ncu ... -k regex:k_encode_fast -s 3 -c 1 python bench.py --workload c3 --frames 592 --steps 3 --warmup 3 --no-e2e "
-              "--no-cpu --no-stream --no-entropy --no-decode`.")
-    json.dump(traffic, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
+              f"`ncu ... -k regex:k_entropy_chunk -s 1 -c 1 {cmd} --no-decode`.  Algorithmic bytes here = planes read once + coded "
+              "bytes written to the scratch (about half the plane bytes).  Not HBM bound: the serial Huffman construction per "
+              "chunk dominates.")
+    if have("prof_entropy_decode.ncu-rep"):
+        Fd = 64
+        traffic["entropy_decode"] = kernel_md(f"{tag}_entropy_decode", f"k_entropy_decode (C2, {Fd} frames = {Fd * 32} chunks, one warp each)",
+              os.path.join(OUT, "prof_entropy_decode.ncu-rep"), Fd * 32, "chunk (<= 64 KiB)", Fd * P * 2 * 1.5,
+              "`ncu ... -k regex:k_entropy_decode -s 2 -c 1 python scripts/gpu_entdec.py 64`.  Algorithmic bytes = coded bytes "
+              "read (about half the plane bytes) + plane bytes written.")
+    json.dump(traffic, open(tpath, "w"), indent=1)
 
 
 if __name__ == "__main__":
