@@ -801,21 +801,27 @@ def main():
             dec = {}
             for name, ge in (("brotli_stream", False), ("gpu_entropy_stream", True)):
                 st = fpv_host.encode_stream(fr[:nd], W, H, shift, False, threads=ncpu, batch=32, gpu_entropy=ge)
-                out = fpv_host.decode_stream(st, nd, W, H, block=0, batch=32, raw_shift=shift)
+                db = 64 if not big else 16       # frames per GPU call of the decoder (GpuOptions::batch)
+                out = fpv_host.decode_stream(st, nd, W, H, block=0, batch=db, raw_shift=shift)
                 okd = bool(np.array_equal(out, fr[:nd]))
                 del out
                 t_a = time.perf_counter()
                 bestd = bestc = None
                 for _ in range(2):
                     # the decoder alone (the callback counts frames) and with a consumer that copies every frame out
-                    cnt, sec = fpv_host.decode_stream(st, nd, W, H, block=0, batch=32, raw_shift=shift, return_time=True, keep=False)
+                    cnt, sec, first = fpv_host.decode_stream(st, nd, W, H, block=0, batch=db, raw_shift=shift, return_time="both",
+                                                             keep=False)
                     okd = okd and cnt.shape[0] == nd
-                    bestd = sec if bestd is None else min(bestd, sec)
-                    _, sec = fpv_host.decode_stream(st, nd, W, H, block=0, batch=32, raw_shift=shift, return_time=True)
+                    if bestd is None or sec < bestd:
+                        bestd, steady = sec, (nd - db) / max(sec - first, 1e-9)
+                    _, sec = fpv_host.decode_stream(st, nd, W, H, block=0, batch=db, raw_shift=shift, return_time=True)
                     bestc = sec if bestc is None else min(bestc, sec)
                 windows.append((t_a, time.perf_counter()))
                 dec[name] = {"value": nd * P * 2 / bestd / 1e9, "unit": "GB/s", "frames_per_s": nd / bestd, "frames": nd,
-                             "with_consumer_copy": nd * P * 2 / bestc / 1e9,
+                             "with_consumer_copy": nd * P * 2 / bestc / 1e9, "batch": db,
+                             "steady_frames_per_s": steady, "steady_gbs": steady * P * 2 / 1e9,
+                             "what": "value: the whole call, decoder construction (GPU context, pinned staging) included; steady: "
+                                     "frames after the first batch / time after the first frame came out",
                              "round_trip_exact": okd, "stream_bytes": len(st)}
             stream_leg["decode"] = dec
 

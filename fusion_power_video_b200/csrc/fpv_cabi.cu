@@ -44,6 +44,7 @@ struct Slot {
   CodedChunk* d_chunks = nullptr;
   size_t chunks_cap = 0;
   uint32_t* d_dec_err = nullptr;
+  uint32_t* h_dec_err = nullptr;   // pinned: a pageable destination would make the download synchronous
   bool allocated = false;
   // a pending fpv_encode_stream_submit: fpv_wait fetches the coded bytes once their number is known
   uint8_t* stream_out_host = nullptr;
@@ -339,6 +340,7 @@ void fpv_destroy(fpv_ctx* c) {
     if (s.d_coded) cudaFree(s.d_coded);
     if (s.d_chunks) cudaFree(s.d_chunks);
     if (s.d_dec_err) cudaFree(s.d_dec_err);
+    if (s.h_dec_err) cudaFreeHost(s.h_dec_err);
     if (s.done) cudaEventDestroy(s.done);
     if (s.stream) cudaStreamDestroy(s.stream);
   }
@@ -825,42 +827,92 @@ int fpv_decode_coded(fpv_ctx* c, const uint8_t* blob_host, size_t blob_bytes, co
   FPV_CUDA(cudaSetDevice(c->device));
   int rc = ensure_slot(c, 0);
   if (rc != FPV_OK) return rc;
-  Slot& s = c->slots[0];
-  if (s.coded_cap < blob_bytes + 16) {
-    if (s.d_coded) cudaFree(s.d_coded);
-    s.d_coded = nullptr;
-    s.coded_cap = 0;
+  Slot& s0 = c->slots[0];
+  if (s0.coded_cap < blob_bytes + 16) {
+    if (s0.d_coded) cudaFree(s0.d_coded);
+    s0.d_coded = nullptr;
+    s0.coded_cap = 0;
     const size_t want = std::max(blob_bytes + 16, stream_bound(c, c->max_batch));
-    FPV_CUDA(cudaMalloc(&s.d_coded, want));
-    s.coded_cap = want;
+    FPV_CUDA(cudaMalloc(&s0.d_coded, want));
+    s0.coded_cap = want;
   }
-  if (s.chunks_cap < n_chunks) {
-    if (s.d_chunks) cudaFree(s.d_chunks);
-    s.d_chunks = nullptr;
-    s.chunks_cap = 0;
+  if (s0.chunks_cap < n_chunks) {
+    if (s0.d_chunks) cudaFree(s0.d_chunks);
+    s0.d_chunks = nullptr;
+    s0.chunks_cap = 0;
     const size_t want = std::max<size_t>(n_chunks, (size_t)c->max_batch * 2 * cpl);
-    FPV_CUDA(cudaMalloc(&s.d_chunks, want * sizeof(CodedChunk)));
-    s.chunks_cap = want;
+    FPV_CUDA(cudaMalloc(&s0.d_chunks, want * sizeof(CodedChunk)));
+    s0.chunks_cap = want;
   }
-  if (!s.d_dec_err) FPV_CUDA(cudaMalloc(&s.d_dec_err, sizeof(uint32_t)));
-  FPV_CUDA(cudaMemcpyAsync(s.d_coded, blob_host, blob_bytes, cudaMemcpyHostToDevice, s.stream));
-  FPV_CUDA(cudaMemcpyAsync(s.d_chunks, chunks_host, (size_t)n_chunks * sizeof(CodedChunk), cudaMemcpyHostToDevice, s.stream));
-  FPV_CUDA(cudaMemcpyAsync(s.d_flags, flags_host, (size_t)n, cudaMemcpyHostToDevice, s.stream));
-  FPV_CUDA(cudaMemsetAsync(s.d_dec_err, 0, sizeof(uint32_t), s.stream));
-  EntropyDecodeParams p;
-  p.blob = s.d_coded; p.blob_bytes = blob_bytes; p.chunks = s.d_chunks; p.n_chunks = n_chunks; p.n_frames = n;
-  p.high = s.d_high; p.low = s.d_low; p.P = P; p.err = s.d_dec_err;
-  cudaError_t e = cudaSuccess;
-  const int l = enqueue_entropy_decode(p, s.stream, &e);
-  if (l < 0) return cuda_fail(c, e, "entropy decode kernel launch");
-  c->launches += (uint64_t)l;
-  rc = decode_device_impl(c, s.d_high, s.d_low, s.d_flags, n, options, s.d_frames, s.stream, true);
-  if (rc != FPV_OK) return rc;
-  uint32_t dec_err = 0;
-  FPV_CUDA(cudaMemcpyAsync(&dec_err, s.d_dec_err, sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream));
-  FPV_CUDA(cudaMemcpyAsync(out_host, s.d_frames, (size_t)n * P * 2, cudaMemcpyDeviceToHost, s.stream));
-  FPV_CUDA(cudaStreamSynchronize(s.stream));
-  if (dec_err) return fail(c, FPV_ERR_INVALID_ARG, "malformed coded chunk (entropy decoder reason " + std::to_string(dec_err) + ")");
+  if (!s0.d_dec_err) {
+    FPV_CUDA(cudaMalloc(&s0.d_dec_err, kNumSlots * sizeof(uint32_t)));
+    FPV_CUDA(cudaMemset(s0.d_dec_err, 0, kNumSlots * sizeof(uint32_t)));
+    FPV_CUDA(cudaMallocHost(&s0.h_dec_err, kNumSlots * sizeof(uint32_t)));
+  }
+  // The batch is cut into up to kNumSlots pieces of whole frames, each on its own slot (stream + plane buffers):
+  // the upload of one piece overlaps the kernels of another and the download of a third.  That needs the chunk
+  // table grouped by frame (the host decoders build it that way); otherwise the batch goes as one piece.
+  bool grouped = true;
+  for (uint32_t i = 1; i < n_chunks && grouped; i++) grouped = chunks_host[i].frame >= chunks_host[i - 1].frame;
+  uint32_t pieces = grouped ? std::min<uint32_t>(kNumSlots, (n + 15) / 16) : 1;
+  if (pieces < 1) pieces = 1;
+  uint32_t* dec_err = s0.h_dec_err;
+  for (int i = 0; i < kNumSlots; i++) dec_err[i] = 0;
+  uint32_t c0 = 0;
+  for (uint32_t pc = 0; pc < pieces; pc++) {
+    const uint32_t f0 = (uint32_t)((uint64_t)n * pc / pieces), f1 = (uint32_t)((uint64_t)n * (pc + 1) / pieces);
+    if (f1 == f0) continue;
+    rc = ensure_slot(c, (int)pc);
+    if (rc != FPV_OK) return rc;
+    Slot& s = c->slots[pc];
+    uint32_t c1 = c0;
+    uint64_t lo = blob_bytes, hi = 0;
+    if (grouped) {
+      while (c1 < n_chunks && chunks_host[c1].frame < f1) c1++;
+    } else {
+      c1 = n_chunks;
+    }
+    for (uint32_t i = c0; i < c1; i++) {
+      // the chunk's size sits in its directory (bytes 6..8); a chunk that claims more than the blob holds is
+      // cut off here and refused by the kernel
+      const uint64_t o = chunks_host[i].offset;
+      uint64_t len = blob_bytes - o;
+      if (len >= 9) {
+        const uint64_t cb = (uint64_t)blob_host[o + 6] | ((uint64_t)blob_host[o + 7] << 8) | ((uint64_t)blob_host[o + 8] << 16);
+        if (cb + 1 < len) len = cb + 1;            // + the stream's final 0x03 after a plane's last chunk
+      }
+      lo = std::min(lo, o);
+      hi = std::max(hi, o + len);
+    }
+    if (hi > lo) {
+      lo &= ~(uint64_t)15;
+      FPV_CUDA(cudaMemcpyAsync(s0.d_coded + lo, blob_host + lo, hi - lo, cudaMemcpyHostToDevice, s.stream));
+    }
+    if (c1 > c0)
+      FPV_CUDA(cudaMemcpyAsync(s0.d_chunks + c0, chunks_host + c0, (size_t)(c1 - c0) * sizeof(CodedChunk), cudaMemcpyHostToDevice,
+                               s.stream));
+    FPV_CUDA(cudaMemcpyAsync(s.d_flags, flags_host + f0, (size_t)(f1 - f0), cudaMemcpyHostToDevice, s.stream));
+    FPV_CUDA(cudaMemsetAsync(s0.d_dec_err + pc, 0, sizeof(uint32_t), s.stream));
+    EntropyDecodeParams p;
+    p.blob = s0.d_coded; p.blob_bytes = blob_bytes; p.chunks = s0.d_chunks + c0; p.n_chunks = c1 - c0;
+    p.n_frames = f1 - f0; p.frame0 = f0;
+    p.high = s.d_high; p.low = s.d_low; p.P = P; p.err = s0.d_dec_err + pc;
+    cudaError_t e = cudaSuccess;
+    const int l = enqueue_entropy_decode(p, s.stream, &e);
+    if (l < 0) return cuda_fail(c, e, "entropy decode kernel launch");
+    c->launches += (uint64_t)l;
+    rc = decode_device_impl(c, s.d_high, s.d_low, s.d_flags, f1 - f0, options, s.d_frames, s.stream, true);
+    if (rc != FPV_OK) return rc;
+    FPV_CUDA(cudaMemcpyAsync(&dec_err[pc], s0.d_dec_err + pc, sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream));
+    FPV_CUDA(cudaMemcpyAsync(static_cast<uint8_t*>(out_host) + (size_t)f0 * P * 2, s.d_frames, (size_t)(f1 - f0) * P * 2,
+                             cudaMemcpyDeviceToHost, s.stream));
+    c0 = c1;
+  }
+  for (uint32_t pc = 0; pc < pieces; pc++)
+    if (c->slots[pc].allocated) FPV_CUDA(cudaStreamSynchronize(c->slots[pc].stream));
+  for (uint32_t pc = 0; pc < pieces; pc++)
+    if (dec_err[pc])
+      return fail(c, FPV_ERR_INVALID_ARG, "malformed coded chunk (entropy decoder reason " + std::to_string(dec_err[pc]) + ")");
   return FPV_OK;
 }
 

@@ -583,11 +583,11 @@ __global__ void __launch_bounds__(32 * kDecWarps) k_entropy_decode(const Entropy
   if (dir[0] != 0x46 || dir[1] != 0x44 || dir[2] != 1) { bad(2); return; }
   const uint32_t kind = dir[3], cb = load_u24(dir + 4), n = ((uint32_t)dir[7] | ((uint32_t)dir[8] << 8)) + 1u;
   const uint64_t plane_off = (uint64_t)ch.index * kEntropyChunk;
-  if (cb < kDirBlock || cb > p.blob_bytes - ch.offset || ch.frame >= p.n_frames || ch.plane > 1 ||
+  if (cb < kDirBlock || cb > p.blob_bytes - ch.offset || ch.frame < p.frame0 || ch.frame - p.frame0 >= p.n_frames || ch.plane > 1 ||
       plane_off + n > p.P || (plane_off + n != p.P && n != kEntropyChunk)) { bad(3); return; }
   uint8_t* plane = ch.plane ? p.low : p.high;
   if (plane == nullptr) { bad(4); return; }
-  uint8_t* dst = plane + (uint64_t)ch.frame * p.P + plane_off;
+  uint8_t* dst = plane + (uint64_t)(ch.frame - p.frame0) * p.P + plane_off;
   const bool dst4 = (reinterpret_cast<uintptr_t>(dst) & 3u) == 0;
 
   if (kind == kKindConstant) {

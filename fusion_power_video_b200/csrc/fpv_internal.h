@@ -99,6 +99,7 @@ struct EntropyDecodeParams {
   uint64_t blob_bytes;
   const CodedChunk* chunks;
   uint32_t n_chunks, n_frames;
+  uint32_t frame0;   // chunk frame indices are relative to the whole batch: this launch covers [frame0, frame0 + n_frames)
   uint8_t* high;     // [n_frames][P]
   uint8_t* low;      // [n_frames][P] or nullptr
   uint64_t P;

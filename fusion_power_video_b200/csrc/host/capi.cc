@@ -103,6 +103,7 @@ double fpvh_time_encode(size_t xsize, size_t ysize, int shift, int big_endian, s
 // Decodes a stream with fpvc::StreamingDecoder fed in `block`-byte pieces
 // (0 = all at once).  raw_shift < 0: frames are 16-bit images; otherwise raw
 // file bytes (UnextractFrame on the GPU) with that shift / endianness.
+// seconds: [0] the whole call, [1] the time until the first frame came out.
 // Returns the number of frames, -1 on a decoder failure.
 long fpvh_decode_stream(const uint8_t* bytes, size_t size, size_t block, uint32_t batch, int device, int raw_shift,
                         int big_endian, uint16_t* frames, size_t max_frames, size_t* xsize_out, size_t* ysize_out,
@@ -111,6 +112,7 @@ long fpvh_decode_stream(const uint8_t* bytes, size_t size, size_t block, uint32_
     uint16_t* frames;
     size_t max_frames, count = 0, W = 0, H = 0;
     bool failed = false;
+    double first = 0;          // when the first frame came out
   } st;
   st.frames = frames;
   st.max_frames = max_frames;
@@ -127,6 +129,7 @@ long fpvh_decode_stream(const uint8_t* bytes, size_t size, size_t block, uint32_
       dec.Decode(bytes + pos, n,
                  [&st](bool ok, uint16_t* frame, size_t xs, size_t ys, void*) {
                    if (!ok) { st.failed = true; return; }
+                   if (st.count == 0) st.first = Now();
                    st.W = xs;
                    st.H = ys;
                    if (st.frames && st.count < st.max_frames) memcpy(st.frames + st.count * xs * ys, frame, xs * ys * 2);
@@ -135,7 +138,10 @@ long fpvh_decode_stream(const uint8_t* bytes, size_t size, size_t block, uint32_
                  nullptr);
     }
   }
-  if (seconds) *seconds = Now() - t0;
+  if (seconds) {
+    seconds[0] = Now() - t0;                          // decoder construction (GPU context, pinned staging) .. destruction
+    seconds[1] = st.count ? st.first - t0 : 0.0;      // until the first frame came out (set-up + the first batch)
+  }
   if (xsize_out) *xsize_out = st.W;
   if (ysize_out) *ysize_out = st.H;
   return st.failed ? -1 : (long)st.count;

@@ -40,12 +40,12 @@ struct GpuDecoder {
     size_t blob_bytes = 0;
     std::vector<fpv_coded_chunk> chunks;
     std::vector<size_t> core_at, core_size;    // where each frame's core sits in the blob (for the fallback)
-  } sets[2];
+  } sets[3];
   bool coded_ok = true;        // false once the C ABI said it cannot decode coded chunks (CPU stand-in)
-  Pinned out, out1;             // decoded frames of set 0 / set 1
+  Pinned out, out1, out2;       // decoded frames of set 0 / 1 / 2
   std::unique_ptr<Pool> pool;
 
-  Pinned& outbuf(int which) { return which ? out1 : out; }
+  Pinned& outbuf(int which) { return which == 0 ? out : which == 1 ? out1 : out2; }
 
   ~GpuDecoder() { close(); }
 
@@ -62,6 +62,7 @@ struct GpuDecoder {
     }
     out.reset();
     out1.reset();
+    out2.reset();
   }
 
   bool alloc_set(Set& st) {
@@ -136,7 +137,7 @@ struct GpuDecoder {
   bool start(int which, const uint8_t* const* cores, const size_t* sizes, size_t n, bool allow_delta) {
     Set& st = sets[which];
     if (!alloc_set(st)) return false;
-    if (which == 1 && !out1.bytes() && !out1.alloc((size_t)B * P * 2)) return FPV_FAIL("pinned allocation failed");
+    if (which != 0 && !outbuf(which).bytes() && !outbuf(which).alloc((size_t)B * P * 2)) return FPV_FAIL("pinned allocation failed");
     st.coded = scan_coded(st, cores, sizes, n, allow_delta);
     if (st.coded) return true;
     st.good.assign(n, 0);
@@ -273,8 +274,8 @@ void StreamingDecoder::Decode(
   }
 
   const uint32_t options = s.raw_output ? FPV_DEC_UNEXTRACT : FPV_DEC_DEFAULT;
-  std::vector<const uint8_t*> cores[2];
-  std::vector<size_t> sizes[2];
+  std::vector<const uint8_t*> cores[3];
+  std::vector<size_t> sizes[3];
   bool stream_bad = false;
   const char* bad_what = nullptr;
   size_t scan = pos;
@@ -303,26 +304,32 @@ void StreamingDecoder::Decode(
       cores[set].clear();
     return !cores[set].empty();
   };
+  // Three batches are in flight, each in its own buffer set: while the callbacks consume batch k, a helper thread
+  // entropy-decodes (waits for the pool, or uploads the coded bytes of directory-carrying streams) and inverts batch
+  // k + 1 on the GPU, and the pool already copies / brotli-decodes batch k + 2.
   int cur = 0;
+  size_t end_of[3] = {pos, pos, pos};
   bool have = s.have_delta && gather(cur);
-  size_t good = have ? s.gpu.finish(cur, options) : 0;
+  end_of[cur] = scan;
+  std::future<size_t> inflight;
+  if (have) inflight = std::async(std::launch::async, [&s, cur, options] { return s.gpu.finish(cur, options); });
   while (have) {
-    const size_t end_of_cur = scan;
-    // While the callbacks consume batch k, batch k + 1 is entropy-decoded (pool threads, or the GPU for streams that
-    // carry chunk directories) and inverted on the GPU by a helper thread; each batch has its own output buffer.
-    const bool have_next = !stream_bad && gather(cur ^ 1);
-    std::future<size_t> next_good;
-    if (have_next) next_good = std::async(std::launch::async, [&s, cur, options] { return s.gpu.finish(cur ^ 1, options); });
+    const int nxt = (cur + 1) % 3;
+    const bool have_next = !stream_bad && gather(nxt);     // its pool tasks run while the GPU works on `cur`
+    end_of[nxt] = scan;
+    const size_t good = inflight.get();
+    if (have_next) inflight = std::async(std::launch::async, [&s, nxt, options] { return s.gpu.finish(nxt, options); });
     for (size_t i = 0; i < good; i++) {
       callback(true, s.gpu.outbuf(cur).as<uint16_t>() + i * s.gpu.P, s.gpu.W, s.gpu.H, payload);
       s.id++;
     }
-    const size_t good_of_next = have_next ? next_good.get() : 0;   // (also drains the started tasks before any return)
-    if (good != cores[cur].size()) return fail("decompressing frame failed");
-    pos = end_of_cur;
-    cur ^= 1;
+    if (good != cores[cur].size()) {
+      if (have_next) inflight.get();      // let the started work drain before the buffers go away
+      return fail("decompressing frame failed");
+    }
+    pos = end_of[cur];
+    cur = nxt;
     have = have_next;
-    good = good_of_next;
   }
   if (stream_bad) return fail(bad_what);
 

@@ -174,16 +174,18 @@ def decode_stream(stream, max_frames, xsize, ysize, block=0, batch=32, raw_shift
     buf = np.frombuffer(stream, np.uint8)
     out = np.empty((max_frames if keep else 0, xsize * ysize), np.uint16)
     out[...] = 0            # touched before the timed call: the callback's memcpy must not pay the page faults
-    W, H, sec = C.c_size_t(0), C.c_size_t(0), C.c_double(0)
+    W, H, sec = C.c_size_t(0), C.c_size_t(0), (C.c_double * 2)()
     n = L.fpvh_decode_stream(_p(buf), buf.size, block, batch, device, raw_shift, int(big_endian), _p(out) if keep else None,
-                             max_frames, C.byref(W), C.byref(H), C.byref(sec))
+                             max_frames, C.byref(W), C.byref(H), sec)
     if n < 0:
         raise HostError(f"decode failed: {last_error()}")
     if n and (W.value, H.value) != (xsize, ysize):
         raise HostError(f"stream is {W.value}x{H.value}, expected {xsize}x{ysize}")
     if not keep:
         out = np.empty((n, 0), np.uint16)
-    return (out[:n], sec.value) if return_time else out[:n]
+    if return_time == "both":
+        return out[:n], sec[0], sec[1]      # whole call, time until the first frame came out
+    return (out[:n], sec[0]) if return_time else out[:n]
 
 
 def random_access(stream, first, count, xsize, ysize, batch=32, device=0, want_preview=True):

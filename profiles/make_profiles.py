@@ -169,7 +169,7 @@ def main_r02(tag):
               os.path.join(OUT, "prof_decode_c3.ncu-rep"), F3 * 2048, "frame row (2048 px)", F3 * P3 * 4.0,
               f"`ncu ... -k regex:k_decode_fused -s 2 -c 1 {cmd} --workload c3 --no-entropy`.")
     if have("prof_encode_c3.ncu-rep"):
-        F3, P3 = 1184, 2048 * 2048
+        F3, P3 = 2368, 2048 * 2048          # the encode leg of `--workload c3` keeps the default 2368 frames per step
         traffic["encode_c3"] = kernel_md(f"{tag}_encode_c3", f"k_encode_fast, main pass (C3: 16-bit 2048x2048, {F3} frames)",
               os.path.join(OUT, "prof_encode_c3.ncu-rep"), F3 * P3 / 256, "warp-row (256 px)", F3 * P3 * 4.0625,
               f"`ncu ... -k regex:k_encode_fast -s 9 -c 1 {cmd} --workload c3 --no-decode --no-entropy`.")
