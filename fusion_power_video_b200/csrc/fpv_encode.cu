@@ -574,34 +574,59 @@ int enqueue_encode(const Geom& g, const EncodeTuning& t, EncodeScratch& s,
     if (t.max_ctas > 0 && ctas_per_sm > t.max_ctas) ctas_per_sm = t.max_ctas;
     int grid = t.num_sms * ctas_per_sm;
     // A task is a WHOLE FRAME whenever that keeps the CTAs evenly loaded: the frame's statistics then never leave
-    // the CTA's shared memory (the decision is taken there, task_done), and no halo row is read twice.
+    // the CTA's shared memory (the decision is taken there, task_done), and no halo row is read twice.  A batch
+    // that does not fill its last wave of frame tasks (2500 frames on 296 CTAs) is cut in two launches: whole waves of
+    // frame tasks, then the remaining frames as band tasks (band tasks for everything cost 15 % at 2048x2048).
+    uint32_t n_whole = 0;             // frames [0, n_whole) go as frame tasks in a launch of their own
     if ((uint64_t)n >= (uint64_t)grid && g.P / 480 < 60000 && !getenv("FPV_NO_FRAME_TASKS")) {
       const uint64_t waves = ((uint64_t)n + grid - 1) / grid;
       if ((double)n / (double)(waves * grid) >= 0.94) band = g.H;
+      else if (!getenv("FPV_NO_SPLIT_LAUNCH")) n_whole = (n / (uint32_t)grid) * (uint32_t)grid;
+    }
+    if (n_whole) {
+      // band height of the remaining frames (same rule as above)
+      const uint32_t rest = n - n_whole;
+      band = ((uint32_t)t.band_rows / 4) * 4; if (band < 4) band = 4;
+      if (band > 1024) band = 1024;
+      while (band > 8 && (uint64_t)rest * ((g.H + band - 1) / band) < (uint64_t)t.num_sms * 4) band = ((band / 2) / 4) * 4;
+      if (band > g.H) band = g.H;
     }
     fp.band_rows = band;
     fp.bands = (g.H + band - 1) / band;
-    uint64_t max_tasks = (uint64_t)n * fp.bands;
+    fp.f0 = n_whole; fp.nf = n - n_whole;
+    const int grid_all = grid;
+    uint64_t max_tasks = (uint64_t)fp.nf * fp.bands;
     if ((uint64_t)grid > max_tasks) grid = (int)max_tasks;
     const bool full = g.W % kStripPx == 0;
-    for (int pass = 0; pass < 3; pass++) {
-      fp.list = pass == 0 ? nullptr : s.lists + (size_t)pass * s.cap;
-      fp.count = pass == 0 ? nullptr : s.counts + pass;
-      fp.next_list = pass < 2 ? s.lists + (size_t)(pass + 1) * s.cap : nullptr;
-      fp.next_count = pass < 2 ? s.counts + pass + 1 : nullptr;
+    for (int pass = (n_whole ? -1 : 0); pass < 3; pass++) {
+      // pass -1: the whole waves of frame tasks of a batch cut in two (see above)
+      FastParams fw = fp;
+      if (pass == -1) { fw.band_rows = g.H; fw.bands = 1; fw.f0 = 0; fw.nf = n_whole; }
+      const FastParams& fq = pass == -1 ? fw : fp;
+      const bool first_launch = pass == (n_whole ? -1 : 0);
+      if (pass >= 0) {
+        fp.list = pass == 0 ? nullptr : s.lists + (size_t)pass * s.cap;
+        fp.count = pass == 0 ? nullptr : s.counts + pass;
+        fp.next_list = pass < 2 ? s.lists + (size_t)(pass + 1) * s.cap : nullptr;
+        fp.next_count = pass < 2 ? s.counts + pass + 1 : nullptr;
+      } else {
+        fw.list = nullptr; fw.count = nullptr;
+        fw.next_list = s.lists + (size_t)1 * s.cap; fw.next_count = s.counts + 1;
+      }
       // redo passes are almost always empty: a small grid is enough
-      int gpass = pass == 0 ? grid : (grid < 2 * t.num_sms ? grid : 2 * t.num_sms);
+      int gpass = pass == -1 ? grid_all : pass == 0 ? grid : (grid < 2 * t.num_sms ? grid : 2 * t.num_sms);
+      if (pass > 0 && gpass < 1) gpass = 1;
       cudaError_t e = cudaSuccess;
-      if (hook && pass == 0) cudaEventRecord(hook->start, stream);
+      if (hook && first_launch) cudaEventRecord(hook->start, stream);
 #define FPV_LAUNCH_FAST(F, R)                                                                                       \
   do {                                                                                                              \
-    if (pass == 0) { FPV_DISPATCH_MODE(g.mode, (e = launch_fast<M, F, R, true>(fp, gpass, threads, smem, stream))); } \
-    else { FPV_DISPATCH_MODE(g.mode, (e = launch_fast<M, F, R, false>(fp, gpass, threads, smem, stream))); }         \
+    if (pass <= 0) { FPV_DISPATCH_MODE(g.mode, (e = launch_fast<M, F, R, true>(fq, gpass, threads, smem, stream))); } \
+    else { FPV_DISPATCH_MODE(g.mode, (e = launch_fast<M, F, R, false>(fq, gpass, threads, smem, stream))); }         \
   } while (0)
       if (rps == 4) { if (full) FPV_LAUNCH_FAST(true, 4); else FPV_LAUNCH_FAST(false, 4); }
       else { if (full) FPV_LAUNCH_FAST(true, 2); else FPV_LAUNCH_FAST(false, 2); }
 #undef FPV_LAUNCH_FAST
-      if (hook && pass == 0) cudaEventRecord(hook->stop, stream);
+      if (hook && pass == 0) cudaEventRecord(hook->stop, stream);   // (covers both pass-0 launches of a batch cut in two)
       launches++;
       if (e != cudaSuccess) { *err = e; return -1; }
     }

@@ -61,6 +61,7 @@ struct FastParams {
   const uint32_t* list;         // redo passes: the frames to redo; nullptr in pass 0 (all n frames, assumed = *guess)
   const uint32_t* count;        // redo passes: length of list
   uint32_t n;                   // frames of the batch
+  uint32_t f0, nf;              // pass 0: this launch covers the frames [f0, f0 + nf) (a batch may be cut in two launches)
   uint32_t* next_list;          // where frame_decide puts frames whose assumption was wrong (nullptr: last pass)
   uint32_t* next_count;
   const uint32_t* guess_in;     // flags (bit 0 delta, bit 1 cg) pass 0 assumes for every frame ...
@@ -93,7 +94,7 @@ struct StageCursor {
   uint32_t band_rows, bands;    // of this launch (short frame lists use shorter bands, see the kernel)
   __device__ __forceinline__ bool load_task(const FastParams& p, uint32_t total) {
     if (t >= total) return false;
-    f = p.list ? p.list[t / bands] : t / bands;
+    f = p.list ? p.list[t / bands] : p.f0 + t / bands;
     const uint32_t b = t % bands;
     y0 = b * band_rows;
     y1 = min(p.H, y0 + band_rows);
@@ -466,7 +467,7 @@ __global__ void __maxnreg__(FPV_FAST_MAXNREG) k_encode_fast(const FastParams p) 
 
   // A short frame list (the redo passes: the few frames whose flags were guessed wrong) would leave
   // most CTAs without a task and the rest with one long one; it is cut into 32-row bands instead.
-  const uint32_t nframes = PASS0 ? p.n : *p.count;
+  const uint32_t nframes = PASS0 ? p.nf : *p.count;
   const bool short_list = nframes * p.bands < gridDim.x && p.band_rows > 32;
   StageCursor cur;
   cur.band_rows = short_list ? 32u : p.band_rows;

@@ -111,6 +111,26 @@ def test_no_delta_option_matches_empty_delta(oracle):
         check_planes(ctx.encode(frames), *exp)
 
 
+@pytest.mark.parametrize("n", [2368, 2500, 3100, 700])
+def test_large_batches_frame_tasks_and_split_launch(oracle, n):
+    """Batches of more frames than persistent CTAs: whole-frame tasks (the decision taken in shared memory), and a
+    batch that does not fill its last wave cut in two launches (whole waves as frame tasks, the rest as band tasks) --
+    flags, planes and previews of EVERY frame against the oracle; the mixed content forces redo passes in both parts."""
+    W, H = 256, 16
+    base = mixed_batch(W, H)
+    rng = np.random.default_rng(n)
+    pick = rng.integers(0, base.shape[0], n)
+    frames = base[pick].copy()
+    frames[:, 0] ^= (np.arange(n) & 0xFF).astype(np.uint16)        # no two frames exactly alike
+    delta = synth.plasma_frames(1, W, H, bits=16, seed=77).reshape(-1)
+    exp = oracle_batch(oracle, frames, W, H, 0, 0, delta)
+    assert len(set(exp[0])) >= 3
+    with fpv.Context(W, H, 0, 0, max_batch=n) as ctx:
+        ctx.set_delta_raw(delta)
+        check_planes(ctx.encode(frames), *exp, what=f"{n} frames")
+        check_planes(ctx.encode(frames[::-1]), *tuple(e[::-1] if e is not None else None for e in exp), what="reversed")
+
+
 @pytest.mark.parametrize("stages", ["2", "5"])
 def test_ring_depths(oracle, stages, monkeypatch):
     monkeypatch.setenv("FPV_STAGES", stages)
