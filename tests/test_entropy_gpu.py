@@ -197,7 +197,7 @@ def _chunk_table(chunks, P):
 
 
 @pytest.mark.parametrize("W,H,bits,shift,n", [(1280, 160, 12, 4, 6), (1024, 136, 16, 0, 5), (320, 48, 8, 8, 4), (2048, 72, 16, 0, 3),
-                                              (100, 100, 16, 0, 3)])
+                                              (100, 100, 16, 0, 3), (512, 132, 12, 4, 50), (256, 64, 16, 0, 17)])
 def test_gpu_entropy_decoder_round_trip(W, H, bits, shift, n):
     """fpv_decode_coded: coded container chunks -> (k_entropy_decode: one warp per chunk from the directories) ->
     inverse transform == the raw input; same images as the planes through fpv_decode."""
@@ -206,7 +206,8 @@ def test_gpu_entropy_decoder_round_trip(W, H, bits, shift, n):
 
     frames = synth.plasma_frames(n, W, H, bits=bits, seed=W + n).reshape(n, -1)
     frames[n - 1] = frames[0]                  # planes of zeros: constant chunks
-    with fpv.Context(W, H, shift, False, max_batch=8) as ctx:
+    # (batches of 17 and 50 frames are cut into 2 and 4 pieces that run on the context's slots side by side)
+    with fpv.Context(W, H, shift, False, max_batch=max(8, n)) as ctx:
         ctx.set_delta_raw(frames[0])
         flags, chunks = ctx.encode_stream(frames)
         pf, high, low, _ = ctx.encode(frames)
