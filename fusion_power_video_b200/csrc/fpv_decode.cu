@@ -860,6 +860,16 @@ int enqueue_unpredict_planes(const Geom& g, int num_sms, uint8_t* high, uint8_t*
 
 }  // namespace fpv
 
+#ifdef FPV_FUSED_PROF
+// Profiling builds only: reads and clears k_decode_fused's histogram of repair rounds per row.
+extern "C" int fpv_debug_fused_rounds(unsigned long long* out8) {
+  cudaDeviceSynchronize();
+  if (cudaMemcpyFromSymbol(out8, fpv::g_fused_rounds, 8 * sizeof(unsigned long long)) != cudaSuccess) return 1;
+  unsigned long long zero[8] = {};
+  return cudaMemcpyToSymbol(fpv::g_fused_rounds, zero, sizeof zero) == cudaSuccess ? 0 : 1;
+}
+#endif
+
 #ifdef FPV_PAIR_PROF
 // Profiling builds only: reads and clears the per-role cycle counters of k_decode_pair.
 extern "C" int fpv_debug_pair_prof(unsigned long long* out16) {

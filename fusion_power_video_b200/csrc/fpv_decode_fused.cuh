@@ -36,6 +36,12 @@
 
 namespace fpv {
 
+// -DFPV_FUSED_PROF (profiling builds only, scripts/gpu_fused_rounds.py): histogram of repair rounds per row of a pair,
+// [0..6] rounds, [7] = 7 or more.
+#ifdef FPV_FUSED_PROF
+__device__ unsigned long long g_fused_rounds[8];
+#endif
+
 constexpr int kFusedWarps = 4;          // warps (pairs of frames) per CTA; two CTAs per SM
 constexpr int kFusedR1 = 2, kFusedLow = 3, kFusedDel = 2;
 
@@ -332,6 +338,9 @@ __device__ __forceinline__ void fused_chain_row(FusedCtx<LW2, DIRECT>& cx, const
     }
   }
   // repair: re-run segments whose incoming value was wrong until nothing changes
+#ifdef FPV_FUSED_PROF
+  uint32_t prof_rounds = 0;
+#endif
   for (;;) {
     uint32_t w_new = __shfl_up_sync(0xffffffffu, x[L - 1] & kHiBytes, 1);
     if (SPLIT) {
@@ -348,6 +357,9 @@ __device__ __forceinline__ void fused_chain_row(FusedCtx<LW2, DIRECT>& cx, const
     }
     const bool changed = ((w_new ^ w_in) & vmask) != 0;
     if (!__any_sync(0xffffffffu, changed)) break;
+#ifdef FPV_FUSED_PROF
+    prof_rounds++;
+#endif
     w_in = w_new;
     uint32_t w = w_in, nw = nw_in;
     bool settled = false;     // the chains met their old values before the segment ends: no end changed
@@ -373,6 +385,9 @@ __device__ __forceinline__ void fused_chain_row(FusedCtx<LW2, DIRECT>& cx, const
     // again and may have changed.
     if (settled && !(SPLIT && !FULL)) break;
   }
+#ifdef FPV_FUSED_PROF
+  if (lane == 0) atomicAdd(&g_fused_rounds[prof_rounds < 7 ? prof_rounds : 7], 1ull);
+#endif
   if (cgmask == 0xffffffffu) {
     // clean the guard bytes: this row is the next row's n / nw and the next write-out's input
 #pragma unroll
