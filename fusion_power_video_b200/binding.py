@@ -106,6 +106,12 @@ def lib() -> C.CDLL:
     L.fpv_decode_device.restype = i32
     L.fpv_decode_submit.argtypes = [vp, u32, vp, vp, vp, u32, u32, vp]
     L.fpv_decode_submit.restype = i32
+    L.fpv_encode_submit_v.argtypes = [vp, u32, vp, u32, u32, vp, vp, vp, vp]
+    L.fpv_encode_submit_v.restype = i32
+    L.fpv_encode_stream_submit_v.argtypes = [vp, u32, vp, u32, u32, vp, vp, vp, sz]
+    L.fpv_encode_stream_submit_v.restype = i32
+    L.fpv_host_is_pinned.argtypes = [vp]
+    L.fpv_host_is_pinned.restype = i32
     L.fpv_decode_coded.argtypes = [vp, vp, sz, vp, u32, vp, u32, u32, vp]
     L.fpv_decode_coded.restype = i32
     L.fpv_unpredict_planes.argtypes = [vp, vp, vp, vp, vp, u32]

@@ -559,14 +559,33 @@ int fpv_encode_device(fpv_ctx* c, const void* frames_dev, uint32_t n, uint32_t o
                                static_cast<cudaStream_t>(stream));
 }
 
-int fpv_encode_submit(fpv_ctx* c, uint32_t slot, const uint16_t* frames_host, uint32_t n, uint32_t options,
-                      uint8_t* flags_host, uint8_t* high_host, uint8_t* low_host, uint8_t* preview_host) {
+// frames_host (n frames back to back) or frame_ptrs (n pointers to one frame each) -> the slot's device frames
+static int upload_frames(fpv_ctx* c, Slot& s, const uint16_t* frames_host, const uint16_t* const* frame_ptrs, uint32_t n) {
+  const size_t P = c->g.P;
+  if (frames_host) {
+    FPV_CUDA(cudaMemcpyAsync(s.d_frames, frames_host, (size_t)n * P * 2, cudaMemcpyHostToDevice, s.stream));
+    return FPV_OK;
+  }
+  // neighbouring frames that are also neighbours in host memory go as one copy
+  for (uint32_t i = 0; i < n;) {
+    uint32_t j = i + 1;
+    while (j < n && frame_ptrs[j] == frame_ptrs[j - 1] + P) j++;
+    if (!frame_ptrs[i]) return fail(c, FPV_ERR_INVALID_ARG, "NULL frame pointer");
+    FPV_CUDA(cudaMemcpyAsync(s.d_frames + (size_t)i * P, frame_ptrs[i], (size_t)(j - i) * P * 2, cudaMemcpyHostToDevice, s.stream));
+    i = j;
+  }
+  return FPV_OK;
+}
+
+static int encode_submit_impl(fpv_ctx* c, uint32_t slot, const uint16_t* frames_host, const uint16_t* const* frame_ptrs,
+                              uint32_t n, uint32_t options, uint8_t* flags_host, uint8_t* high_host, uint8_t* low_host,
+                              uint8_t* preview_host) {
   if (!c) return FPV_ERR_INVALID_ARG;
   FPV_LOCK(c);
   if (slot >= kNumSlots) return fail(c, FPV_ERR_INVALID_ARG, "slot out of range");
   if (n == 0) return FPV_OK;
   if (n > c->max_batch) return fail(c, FPV_ERR_INVALID_ARG, "n exceeds max_batch");
-  if (!frames_host || !flags_host || !high_host || !preview_host)
+  if ((!frames_host && !frame_ptrs) || !flags_host || !high_host || !preview_host)
     return fail(c, FPV_ERR_INVALID_ARG, "NULL host buffer");
   const bool has_low = mode_has_low(c->g.mode);
   if (has_low && !low_host) return fail(c, FPV_ERR_INVALID_ARG, "low plane buffer is NULL");
@@ -575,7 +594,8 @@ int fpv_encode_submit(fpv_ctx* c, uint32_t slot, const uint16_t* frames_host, ui
   if (rc != FPV_OK) return rc;
   Slot& s = c->slots[slot];
   const size_t P = c->g.P, PP = c->g.PP;
-  FPV_CUDA(cudaMemcpyAsync(s.d_frames, frames_host, (size_t)n * P * 2, cudaMemcpyHostToDevice, s.stream));
+  rc = upload_frames(c, s, frames_host, frame_ptrs, n);
+  if (rc != FPV_OK) return rc;
   rc = encode_device_chunked(c, (int)slot, s.d_frames, n, options, s.d_flags, s.d_high, s.d_low,
                              s.d_preview, s.stream);
   if (rc != FPV_OK) return rc;
@@ -586,6 +606,25 @@ int fpv_encode_submit(fpv_ctx* c, uint32_t slot, const uint16_t* frames_host, ui
   FPV_CUDA(cudaMemcpyAsync(flags_host, s.d_flags, (size_t)n, cudaMemcpyDeviceToHost, s.stream));
   FPV_CUDA(cudaEventRecord(s.done, s.stream));
   return FPV_OK;
+}
+
+int fpv_encode_submit(fpv_ctx* c, uint32_t slot, const uint16_t* frames_host, uint32_t n, uint32_t options,
+                      uint8_t* flags_host, uint8_t* high_host, uint8_t* low_host, uint8_t* preview_host) {
+  return encode_submit_impl(c, slot, frames_host, nullptr, n, options, flags_host, high_host, low_host, preview_host);
+}
+
+int fpv_encode_submit_v(fpv_ctx* c, uint32_t slot, const uint16_t* const* frame_ptrs, uint32_t n, uint32_t options,
+                        uint8_t* flags_host, uint8_t* high_host, uint8_t* low_host, uint8_t* preview_host) {
+  return encode_submit_impl(c, slot, nullptr, frame_ptrs, n, options, flags_host, high_host, low_host, preview_host);
+}
+
+int fpv_host_is_pinned(const void* p) {
+  cudaPointerAttributes a;
+  if (!p || cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return a.type == cudaMemoryTypeHost ? 1 : 0;
 }
 
 int fpv_wait(fpv_ctx* c, uint32_t slot) {
@@ -697,14 +736,15 @@ int fpv_entropy_device(fpv_ctx* c, const void* flags_dev, const void* high_dev, 
                              static_cast<uint64_t*>(frame_off_dev), static_cast<cudaStream_t>(stream));
 }
 
-int fpv_encode_stream_submit(fpv_ctx* c, uint32_t slot, const uint16_t* frames_host, uint32_t n, uint32_t options,
-                             uint8_t* flags_host, uint64_t* frame_off_host, uint8_t* out_host, size_t capacity) {
+static int encode_stream_submit_impl(fpv_ctx* c, uint32_t slot, const uint16_t* frames_host, const uint16_t* const* frame_ptrs,
+                                     uint32_t n, uint32_t options, uint8_t* flags_host, uint64_t* frame_off_host,
+                                     uint8_t* out_host, size_t capacity) {
   if (!c) return FPV_ERR_INVALID_ARG;
   FPV_LOCK(c);
   if (slot >= kNumSlots) return fail(c, FPV_ERR_INVALID_ARG, "slot out of range");
   if (n == 0) return FPV_OK;
   if (n > c->max_batch) return fail(c, FPV_ERR_INVALID_ARG, "n exceeds max_batch");
-  if (!frames_host || !flags_host || !frame_off_host || !out_host)
+  if ((!frames_host && !frame_ptrs) || !flags_host || !frame_off_host || !out_host)
     return fail(c, FPV_ERR_INVALID_ARG, "NULL host buffer");
   if (capacity < stream_bound(c, n)) return fail(c, FPV_ERR_INVALID_ARG, "capacity below fpv_stream_bound(n)");
   FPV_CUDA(cudaSetDevice(c->device));
@@ -714,8 +754,8 @@ int fpv_encode_stream_submit(fpv_ctx* c, uint32_t slot, const uint16_t* frames_h
   Slot& s = c->slots[slot];
   if (s.stream_n) return fail(c, FPV_ERR_INVALID_ARG, "slot has an unfinished stream submit: call fpv_wait first");
   EntropyBuf& e = c->entropy[slot];
-  const size_t P = c->g.P;
-  FPV_CUDA(cudaMemcpyAsync(s.d_frames, frames_host, (size_t)n * P * 2, cudaMemcpyHostToDevice, s.stream));
+  rc = upload_frames(c, s, frames_host, frame_ptrs, n);
+  if (rc != FPV_OK) return rc;
   rc = encode_device_chunked(c, (int)slot, s.d_frames, n, options, s.d_flags, s.d_high, s.d_low, s.d_preview,
                              s.stream);
   if (rc != FPV_OK) return rc;
@@ -730,6 +770,16 @@ int fpv_encode_stream_submit(fpv_ctx* c, uint32_t slot, const uint16_t* frames_h
   s.stream_off_host = frame_off_host;
   s.stream_n = n;
   return FPV_OK;
+}
+
+int fpv_encode_stream_submit(fpv_ctx* c, uint32_t slot, const uint16_t* frames_host, uint32_t n, uint32_t options,
+                             uint8_t* flags_host, uint64_t* frame_off_host, uint8_t* out_host, size_t capacity) {
+  return encode_stream_submit_impl(c, slot, frames_host, nullptr, n, options, flags_host, frame_off_host, out_host, capacity);
+}
+
+int fpv_encode_stream_submit_v(fpv_ctx* c, uint32_t slot, const uint16_t* const* frame_ptrs, uint32_t n, uint32_t options,
+                               uint8_t* flags_host, uint64_t* frame_off_host, uint8_t* out_host, size_t capacity) {
+  return encode_stream_submit_impl(c, slot, nullptr, frame_ptrs, n, options, flags_host, frame_off_host, out_host, capacity);
 }
 
 // ---- decode -------------------------------------------------------------------

@@ -53,6 +53,7 @@ struct Encoder::Impl {
   bool has_low = true;
   uint32_t B = 1;
   bool gpu_entropy = false;           // planes are entropy-coded and framed on the GPU (fpv_encode_stream_submit)
+  bool zero_copy = getenv("FPV_NO_ZERO_COPY") == nullptr;   // frames in page-locked memory are uploaded from where they are
   size_t stream_cap = 0;              // fpv_stream_bound(B)
 
   // Compressed pieces of one frame, filled by its two brotli tasks.
@@ -70,6 +71,8 @@ struct Encoder::Impl {
     uint64_t seq = 0;                 // batch number in submission order (device = seq % G; emission order of coded batches)
     std::vector<Callback> callbacks;
     std::vector<void*> payloads;
+    std::vector<const uint16_t*> src;   // where frame i is uploaded from: its place in `frames`, or the caller's own
+                                        // buffer when that is page-locked memory (no host copy at all)
     std::vector<Pieces> pieces;
     std::atomic<uint32_t> pending{0};
     uint32_t slot = 0;
@@ -225,6 +228,7 @@ struct Encoder::Impl {
       b->n = 0;
       b->callbacks.clear();
       b->payloads.clear();
+      b->src.clear();
       free_.push_back(b);
     }
     cv_free.notify_all();
@@ -327,12 +331,12 @@ struct Encoder::Impl {
         next_slot ^= 1u;
         int rc = !ok.load() ? FPV_ERR_INVALID_ARG
                  : gpu_entropy
-                     ? fpv_encode_stream_submit(lane.ctx, b->slot, b->frames.as<uint16_t>(), b->n, FPV_ENC_DEFAULT,
-                                                b->flags.as<uint8_t>(), b->offs.as<uint64_t>(),
-                                                b->coded.as<uint8_t>(), stream_cap)
-                     : fpv_encode_submit(lane.ctx, b->slot, b->frames.as<uint16_t>(), b->n, FPV_ENC_DEFAULT,
-                                         b->flags.as<uint8_t>(), b->high.as<uint8_t>(),
-                                         has_low ? b->low.as<uint8_t>() : nullptr, b->preview.as<uint8_t>());
+                     ? fpv_encode_stream_submit_v(lane.ctx, b->slot, b->src.data(), b->n, FPV_ENC_DEFAULT,
+                                                  b->flags.as<uint8_t>(), b->offs.as<uint64_t>(),
+                                                  b->coded.as<uint8_t>(), stream_cap)
+                     : fpv_encode_submit_v(lane.ctx, b->slot, b->src.data(), b->n, FPV_ENC_DEFAULT,
+                                           b->flags.as<uint8_t>(), b->high.as<uint8_t>(),
+                                           has_low ? b->low.as<uint8_t>() : nullptr, b->preview.as<uint8_t>());
         if (rc != FPV_OK) {
           if (ok.load()) fail("fpv_encode_submit");
           {
@@ -523,7 +527,13 @@ void Encoder::CompressFrame(const uint16_t* img, Callback callback, void* payloa
     if (!s.alloc_batch(b)) return;
   }
   // only this (the submitting) thread touches a filling batch
-  if (s.copy_pool) {
+  uint16_t* slot_in_batch = b->frames.as<uint16_t>() + (size_t)b->n * s.P;
+  if (s.zero_copy && fpv_host_is_pinned(img)) {
+    // The caller's buffer is page-locked memory: the GPU reads it where it is.  The reference's contract covers this
+    // ("img ... must exist until the callback for this frame is called", fusion_power_video.h:197-199).
+    b->src.push_back(img);
+  } else if (s.copy_pool) {
+    b->src.push_back(slot_in_batch);
     const size_t parts = s.copy_pool->size() + 1, bytes = s.P * 2, step = ((bytes + parts - 1) / parts + 4095) & ~(size_t)4095;
     uint8_t* dst = reinterpret_cast<uint8_t*>(b->frames.as<uint16_t>() + (size_t)b->n * s.P);
     const uint8_t* src = reinterpret_cast<const uint8_t*>(img);
@@ -540,7 +550,8 @@ void Encoder::CompressFrame(const uint16_t* img, Callback callback, void* payloa
     copy_part(0);                                   // the caller copies its share too
     while (left.load(std::memory_order_acquire)) std::this_thread::yield();
   } else {
-    memcpy(b->frames.as<uint16_t>() + (size_t)b->n * s.P, img, s.P * 2);
+    b->src.push_back(slot_in_batch);
+    memcpy(slot_in_batch, img, s.P * 2);
   }
   b->callbacks.push_back(callback);
   b->payloads.push_back(payload);

@@ -209,6 +209,23 @@ int fpv_encode_stream_submit(fpv_ctx* ctx, uint32_t slot, const uint16_t* frames
                              uint32_t options, uint8_t* flags_host, uint64_t* frame_off_host,
                              uint8_t* out_host, size_t capacity);
 
+/* Scatter forms of the two submit calls: frame_ptrs[i] points at frame i (each
+ * xsize * ysize uint16 in host memory).  For callers whose frames already sit in
+ * pinned memory of their own (camera DMA buffers registered with
+ * cudaHostRegister, or fpv_host_alloc blocks): nothing is copied on the host, each
+ * frame goes to the device straight from where it is, and -- as the reference's
+ * CompressFrame requires of its callers (fusion_power_video.h:197-199) -- it must
+ * stay valid until fpv_wait(slot) returns.  Frames that are neighbours in memory
+ * are uploaded with one copy.  fpv_host_is_pinned tells whether a host pointer is
+ * page-locked memory CUDA knows about. */
+int fpv_encode_submit_v(fpv_ctx* ctx, uint32_t slot, const uint16_t* const* frame_ptrs, uint32_t n,
+                        uint32_t options, uint8_t* flags_host, uint8_t* high_host, uint8_t* low_host,
+                        uint8_t* preview_host);
+int fpv_encode_stream_submit_v(fpv_ctx* ctx, uint32_t slot, const uint16_t* const* frame_ptrs, uint32_t n,
+                               uint32_t options, uint8_t* flags_host, uint64_t* frame_off_host,
+                               uint8_t* out_host, size_t capacity);
+int fpv_host_is_pinned(const void* p);
+
 /* ---- decode (inverse) transform ---------------------------------------- */
 
 /* Replaces the post-brotli part of DecompressImage (.cc:326-344) for n frames

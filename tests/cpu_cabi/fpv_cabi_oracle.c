@@ -132,6 +132,19 @@ int fpv_encode_submit(fpv_ctx* c, uint32_t slot, const uint16_t* frames, uint32_
   if (c && n > c->max_batch) return fail(FPV_ERR_INVALID_ARG, "n exceeds max_batch");
   return fpv_encode(c, frames, n, options, flags, high, low, preview);
 }
+int fpv_encode_submit_v(fpv_ctx* c, uint32_t slot, const uint16_t* const* frame_ptrs, uint32_t n, uint32_t options,
+                        uint8_t* flags, uint8_t* high, uint8_t* low, uint8_t* preview) {
+  if (slot >= FPV_NUM_SLOTS) return fail(FPV_ERR_INVALID_ARG, "slot out of range");
+  if (!c || !frame_ptrs) return fail(FPV_ERR_INVALID_ARG, "NULL");
+  if (n > c->max_batch) return fail(FPV_ERR_INVALID_ARG, "n exceeds max_batch");
+  for (uint32_t i = 0; i < n; i++) {
+    int rc = fpv_encode(c, frame_ptrs[i], 1, options, flags + i, high + (size_t)i * c->P, low ? low + (size_t)i * c->P : NULL,
+                        preview + (size_t)i * ((c->W / 4) * (size_t)(c->H / 4)));
+    if (rc != FPV_OK) return rc;
+  }
+  return FPV_OK;
+}
+int fpv_host_is_pinned(const void* p) { (void)p; return 0; }
 int fpv_wait(fpv_ctx* c, uint32_t slot) { return c && slot < FPV_NUM_SLOTS ? FPV_OK : FPV_ERR_INVALID_ARG; }
 
 size_t fpv_stream_bound(const fpv_ctx* c, uint32_t n) { return c ? (size_t)n * (3 * c->P + 4096) : 0; }
@@ -141,6 +154,11 @@ int fpv_entropy_device(fpv_ctx* c, const void* a, const void* b, const void* d, 
   return fail(FPV_ERR_UNSUPPORTED, "the GPU entropy coder has no CPU stand-in");
 }
 int fpv_encode_stream_submit(fpv_ctx* c, uint32_t slot, const uint16_t* f, uint32_t n, uint32_t o, uint8_t* fl,
+                             uint64_t* off, uint8_t* out, size_t cap) {
+  (void)c; (void)slot; (void)f; (void)n; (void)o; (void)fl; (void)off; (void)out; (void)cap;
+  return fail(FPV_ERR_UNSUPPORTED, "the GPU entropy coder has no CPU stand-in");
+}
+int fpv_encode_stream_submit_v(fpv_ctx* c, uint32_t slot, const uint16_t* const* f, uint32_t n, uint32_t o, uint8_t* fl,
                              uint64_t* off, uint8_t* out, size_t cap) {
   (void)c; (void)slot; (void)f; (void)n; (void)o; (void)fl; (void)off; (void)out; (void)cap;
   return fail(FPV_ERR_UNSUPPORTED, "the GPU entropy coder has no CPU stand-in");

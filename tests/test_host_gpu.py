@@ -165,3 +165,29 @@ def test_gpu_coded_stream_both_decoder_paths(monkeypatch):
     cpu_cut = host.decode_stream(cut, n, W, H, batch=8, raw_shift=shift)
     assert np.array_equal(cpu, frames)
     assert 0 < gpu_cut.shape[0] < n and np.array_equal(gpu_cut, cpu_cut)
+
+
+@pytest.mark.parametrize("gpu_entropy", [False, True])
+def test_pinned_input_is_uploaded_in_place_and_gives_the_same_stream(gpu_entropy):
+    """Frames handed to CompressFrame in page-locked memory are not copied on the host (fpv_*_submit_v from the
+    caller's buffers); the stream is byte for byte the one pageable input gives."""
+    import ctypes as C
+
+    import fusion_power_video_b200 as fpv
+
+    W, H, shift, n = 640, 96, 4, 37
+    frames = synth.plasma_frames(n, W, H, bits=12, seed=15).reshape(n, -1)
+    L = fpv.lib()
+    nbytes = frames.nbytes
+    p = L.fpv_host_alloc(nbytes)
+    assert p and L.fpv_host_is_pinned(C.c_void_p(p)) == 1
+    assert L.fpv_host_is_pinned(C.c_void_p(frames.ctypes.data)) == 0
+    try:
+        pinned = np.frombuffer((C.c_uint8 * nbytes).from_address(p), np.uint16).reshape(n, -1)
+        pinned[:] = frames
+        a = host.encode_stream(frames, W, H, shift, False, threads=4, batch=8, gpu_entropy=gpu_entropy)
+        b = host.encode_stream(pinned, W, H, shift, False, threads=4, batch=8, gpu_entropy=gpu_entropy)
+        assert a == b
+        assert np.array_equal(host.decode_stream(b, n, W, H, batch=8, raw_shift=shift), frames)
+    finally:
+        L.fpv_host_free(C.c_void_p(p))
