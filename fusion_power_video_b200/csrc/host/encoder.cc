@@ -54,6 +54,24 @@ struct Encoder::Impl {
   uint32_t B = 1;
   bool gpu_entropy = false;           // planes are entropy-coded and framed on the GPU (fpv_encode_stream_submit)
   bool zero_copy = getenv("FPV_NO_ZERO_COPY") == nullptr;   // frames in page-locked memory are uploaded from where they are
+  // cudaPointerGetAttributes costs ~15 us on pageable memory: frames that follow each other in memory (the usual
+  // case: one big array, a ring of camera buffers) reuse the last answer, which is asked again every 64 frames.
+  // Either answer is safe -- a wrong "pinned" only makes the upload a staged copy, a wrong "pageable" only a host copy.
+  const uint16_t* pin_last = nullptr;
+  bool pin_answer = false;
+  uint32_t pin_age = 0;
+  bool is_pinned(const uint16_t* img) {
+    const ptrdiff_t d = img - pin_last;
+    const ptrdiff_t near_by = (ptrdiff_t)(4 * P);
+    if (pin_last && d >= -near_by && d <= near_by && ++pin_age < 64) {
+      pin_last = img;
+      return pin_answer;
+    }
+    pin_last = img;
+    pin_age = 0;
+    pin_answer = fpv_host_is_pinned(img) != 0;
+    return pin_answer;
+  }
   size_t stream_cap = 0;              // fpv_stream_bound(B)
 
   // Compressed pieces of one frame, filled by its two brotli tasks.
@@ -528,7 +546,7 @@ void Encoder::CompressFrame(const uint16_t* img, Callback callback, void* payloa
   }
   // only this (the submitting) thread touches a filling batch
   uint16_t* slot_in_batch = b->frames.as<uint16_t>() + (size_t)b->n * s.P;
-  if (s.zero_copy && fpv_host_is_pinned(img)) {
+  if (s.zero_copy && s.is_pinned(img)) {
     // The caller's buffer is page-locked memory: the GPU reads it where it is.  The reference's contract covers this
     // ("img ... must exist until the callback for this frame is called", fusion_power_video.h:197-199).
     b->src.push_back(img);
