@@ -33,7 +33,13 @@ namespace fpv {
 namespace {
 
 constexpr int kET = 256;                       // threads per CTA
-constexpr uint32_t kOutWords = kEntropyChunkCap / 4;
+// The chunk's bit buffer in shared memory is a WINDOW of 32 KiB of the coded chunk: the directory, the prefix-code
+// header and -- for chunks that compress to less than half, the usual case -- all literal bits sit in window 0; larger
+// chunks are packed window by window (a thread walks its span once per window it touches).  A buffer for the whole
+// chunk (66 KB) left room for three CTAs per SM only, and the kernel's time goes into barriers around its serial
+// sections (one thread merges the Huffman tree, writes the header): more resident CTAs hide exactly that.
+constexpr uint32_t kWinWords = 8192;
+constexpr uint32_t kOutWords = kWinWords + 8;
 
 // RFC 7932 section 5: insert length code -> base, extra bits
 __constant__ uint32_t kInsBase[24] = {0, 1, 2, 3, 4, 5, 6, 8, 10, 14, 18, 26, 34, 50, 66, 98, 130, 194, 322, 578, 1090, 2114, 6210, 22594};
@@ -380,54 +386,66 @@ __global__ void __launch_bounds__(kET) k_entropy_chunk(const EntropyParams p) {
     }
     uint32_t total;
     const uint32_t o = block_excl_scan(s, mybits, &total);
-    {
-      const uint32_t bitpos = lit_start + o;
-      if (b0 < n && b0 % kEntropySpan == 0) dir_put(s, kDirSpans + 3 * (b0 / kEntropySpan), bitpos, 3);
-      uint32_t wi = bitpos >> 5, nb = bitpos & 31u;
-      unsigned long long acc = 0;
-      auto emit = [&](uint32_t byte) {
-        const uint32_t e = s.lc[byte];
-        acc |= (unsigned long long)(e & 0xffffu) << nb;
-        nb += e >> 16;
-        if (nb >= 32) {
-          atomicOr(&s.out[wi], (uint32_t)acc);
-          wi++;
-          acc >>= 32;
-          nb -= 32;
-        }
+    const uint32_t bitpos = lit_start + o;
+    if (b0 < n && b0 % kEntropySpan == 0) dir_put(s, kDirSpans + 3 * (b0 / kEntropySpan), bitpos, 3);
+    // after the literals: an empty metadata meta-block (ISLAST = 0, MNIBBLES = 0 coded 3, reserved 0, MSKIPBYTES = 0)
+    // pads to a byte; then, for a plane's last chunk, 0x03 (ISLAST, ISLASTEMPTY)
+    const uint32_t pad_pos = lit_start + lit_bits;
+    const uint32_t nbytes = (pad_pos + 6 + 7) / 8;
+    bytes = nbytes + (last ? 1u : 0u);
+    if (tid == 0) dir_put(s, 4, nbytes, 3);                 // chunk bytes (without the stream's final 0x03)
+    const uint32_t my_w0 = bitpos >> 5, my_w1 = (bitpos + mybits + 31) >> 5;   // words this thread's bits touch
+    for (uint32_t lo = 0; lo * 4 < bytes; lo += kWinWords) {
+      const uint32_t hi = lo + kWinWords;
+      if (lo > 0) {
+        for (uint32_t i = tid; i < kWinWords; i += kET) s.out[i] = 0;
+        __syncthreads();
+      }
+      auto or_word = [&](uint32_t w, uint32_t v) {
+        if (w >= lo && w < hi) atomicOr(&s.out[w - lo], v);
       };
-      if (aligned) {
-        uint32_t i = b0;
-        for (; i + 16 <= b1; i += 16) {
-          const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + i));
-          const uint32_t ww[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-          for (int k = 0; k < 4; k++) {
-            emit(ww[k] & 255u); emit((ww[k] >> 8) & 255u); emit((ww[k] >> 16) & 255u); emit(ww[k] >> 24);
+      if (mybits && my_w0 < hi && my_w1 > lo) {
+        uint32_t wi = bitpos >> 5, nb = bitpos & 31u;
+        unsigned long long acc = 0;
+        auto emit = [&](uint32_t byte) {
+          const uint32_t e = s.lc[byte];
+          acc |= (unsigned long long)(e & 0xffffu) << nb;
+          nb += e >> 16;
+          if (nb >= 32) {
+            or_word(wi, (uint32_t)acc);
+            wi++;
+            acc >>= 32;
+            nb -= 32;
           }
+        };
+        if (aligned) {
+          uint32_t i = b0;
+          for (; i + 16 <= b1; i += 16) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + i));
+            const uint32_t ww[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+              emit(ww[k] & 255u); emit((ww[k] >> 8) & 255u); emit((ww[k] >> 16) & 255u); emit(ww[k] >> 24);
+            }
+          }
+          for (; i < b1; i++) emit(src[i]);
+        } else {
+          for (uint32_t i = b0; i < b1; i++) emit(src[i]);
         }
-        for (; i < b1; i++) emit(src[i]);
-      } else {
-        for (uint32_t i = b0; i < b1; i++) emit(src[i]);
+        if (nb) or_word(wi, (uint32_t)acc);
       }
-      if (nb) atomicOr(&s.out[wi], (uint32_t)acc);
-    }
-    __syncthreads();
-    if (tid == 0) {
-      uint32_t pos = lit_start + lit_bits;
-      // empty metadata meta-block: ISLAST = 0, MNIBBLES = 0 (coded 3), reserved 0, MSKIPBYTES = 0; pads to a byte
-      put_bits(s, pos, 0, 1); put_bits(s, pos, 3, 2); put_bits(s, pos, 0, 1); put_bits(s, pos, 0, 2);
-      uint32_t nbytes = (pos + 7) / 8;
-      dir_put(s, 4, nbytes, 3);                          // chunk bytes (without the stream's final 0x03)
-      if (last) {
-        reinterpret_cast<uint8_t*>(s.out)[nbytes] = 0x03;    // ISLAST, ISLASTEMPTY
-        nbytes++;
+      if (tid == 0) {
+        // the six bits of the empty metadata block: 0, 11, 0, 00 = value 6 at pad_pos (may straddle two words)
+        const uint32_t w = pad_pos >> 5, sh = pad_pos & 31u;
+        or_word(w, 6u << sh);
+        if (sh + 6 > 32) or_word(w + 1, 6u >> (32 - sh));
+        if (last) or_word(nbytes >> 2, 0x03u << (8 * (nbytes & 3u)));
       }
-      s.misc = nbytes;
+      __syncthreads();
+      const uint32_t w_end = (bytes + 3) / 4 < hi ? (bytes + 3) / 4 : hi;
+      for (uint32_t i = lo + tid; i < w_end; i += kET) reinterpret_cast<uint32_t*>(dst)[i] = s.out[i - lo];
+      __syncthreads();
     }
-    __syncthreads();
-    bytes = s.misc;
-    for (uint32_t i = tid; i < (bytes + 3) / 4; i += kET) reinterpret_cast<uint32_t*>(dst)[i] = s.out[i];
   } else {
     // ---- uncompressed meta-block: header up to ISUNCOMPRESSED = 1, pad, raw bytes -------------
     const uint32_t hdr_bits = s.misc + 1 - kDirBits;   // bits of the meta-block header up to ISUNCOMPRESSED
