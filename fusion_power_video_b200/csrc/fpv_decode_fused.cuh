@@ -45,11 +45,20 @@ __device__ unsigned long long g_fused_rounds[8];
 constexpr int kFusedWarps = 4;          // warps (pairs of frames) per CTA; two CTAs per SM
 constexpr int kFusedR1 = 2, kFusedLow = 3, kFusedDel = 2;
 
-static inline size_t fused_warp_bytes(int LW2) {
+// (no OUT row when the output goes out with 256-bit stores straight from registers: DIRECT)
+static inline size_t fused_warp_bytes(int LW2, bool direct) {
   const size_t RB = 32 * 8 * (size_t)LW2;
-  return RB * (2 * kFusedR1 + 2 * kFusedLow + 4 * kFusedDel + 4) + 64;
+  return RB * (2 * kFusedR1 + 2 * kFusedLow + 4 * kFusedDel + (direct ? 0 : 4)) + 64;
 }
-static inline size_t fused_smem_bytes(int LW2) { return kFusedWarps * fused_warp_bytes(LW2); }
+static inline size_t fused_smem_bytes(int LW2, bool direct) { return kFusedWarps * fused_warp_bytes(LW2, direct); }
+// Resident CTAs per SM: two.  Three fit for L <= 32 with direct stores (shared memory: no OUT row) if the kernel is
+// held to 168 registers, but that build is slower although it spills almost nothing (1024x1024: 0.77 at 2368 frames,
+// 0.85 at 3552 against 0.88 with two CTAs of 216-254 registers; 2048x2048 0.76 against 0.89): with fewer registers the
+// compiler can no longer keep the write-out's operands in flight beside the chain.  -DFPV_FUSED_CTAS3=1 builds it.
+#ifndef FPV_FUSED_CTAS3
+#define FPV_FUSED_CTAS3 0
+#endif
+constexpr int fused_min_ctas(int LW2, bool direct) { return (FPV_FUSED_CTAS3 && direct && LW2 <= 4) ? 3 : 2; }
 
 // Per-warp state of the TMA rings and the write-out.  Everything is warp-uniform.
 // DIRECT: the output row does not go through shared memory: every lane stores its own 2 L bytes per frame with
@@ -62,7 +71,8 @@ template <int LW2, bool DIRECT = false>
 struct FusedCtx {
   static constexpr uint32_t L = 8 * LW2, RB = 32 * L;
   static constexpr uint32_t kR1 = 0, kLow = kR1 + kFusedR1 * 2 * RB, kDel = kLow + kFusedLow * 2 * RB;
-  static constexpr uint32_t kOut = kDel + kFusedDel * 4 * RB, kBars = kOut + 4 * RB;
+  static constexpr uint32_t kOut = kDel + kFusedDel * 4 * RB, kBars = kOut + (DIRECT ? 0u : 4 * RB);
+  static constexpr uint32_t kBytes = kBars + 64;     // one warp's region
   uint32_t sm0;                       // this warp's region
   uint32_t W, H, stride;
   const uint8_t *s1A, *s1B;           // next residual row to fetch
@@ -419,7 +429,7 @@ __device__ __forceinline__ void fused_chain_row(FusedCtx<LW2, DIRECT>& cx, const
 // SPLIT: the two 16-bit lanes are the left and the right half of ONE frame (widths 1281..2560).
 template <int LW2, bool FULL, bool SHIFT, bool SPLIT = false, bool DIRECT = false, int K0T = FPV_PAIR_K0,
           int G = (FPV_PAIR_G ? FPV_PAIR_G : (LW2 == 4 ? 16 : 8))>
-__global__ void __launch_bounds__(32 * kFusedWarps, 2) k_decode_fused(const PairParams p) {
+__global__ void __launch_bounds__(32 * kFusedWarps, fused_min_ctas(LW2, DIRECT)) k_decode_fused(const PairParams p) {
   extern __shared__ __align__(128) uint8_t fsm[];
   constexpr int L = 8 * LW2;
   constexpr uint32_t RB = 32 * L;
@@ -436,7 +446,7 @@ __global__ void __launch_bounds__(32 * kFusedWarps, 2) k_decode_fused(const Pair
   const uint32_t W = p.W, H = p.H;
 
   C cx;
-  cx.sm0 = smem_u32(fsm) + (uint32_t)warp * (uint32_t)(RB * (2 * kFusedR1 + 2 * kFusedLow + 4 * kFusedDel + 4) + 64);
+  cx.sm0 = smem_u32(fsm) + (uint32_t)warp * C::kBytes;
   cx.W = W; cx.H = H; cx.stride = p.stride; cx.lane = lane;
   cx.lowA = !(flA & kFlagNoLow) && p.low != nullptr;
   cx.lowB = !(flB & kFlagNoLow) && p.low != nullptr;
@@ -538,12 +548,12 @@ __global__ void __launch_bounds__(32 * kFusedWarps, 2) k_decode_fused(const Pair
 
 template <int LW2, bool SPLIT = false>
 static cudaError_t launch_fused(const PairParams& p, bool full, cudaStream_t stream) {
-  const size_t smem = fused_smem_bytes(LW2);
   const bool shift = p.unextract && p.shift != 0;
   const uint32_t units = SPLIT ? p.n : (p.n + 1) / 2;
   const int blocks = (int)((units + kFusedWarps - 1) / kFusedWarps);
   // 256-bit stores straight from registers where a lane's piece of the row is a whole number of 32-byte sectors
   const bool direct = LW2 % 2 == 0 && reinterpret_cast<uintptr_t>(p.out) % 32 == 0 && getenv("FPV_FUSED_NO_DIRECT") == nullptr;
+  const size_t smem = fused_smem_bytes(LW2, direct);
   cudaError_t e = cudaSuccess;
 #define FPV_LAUNCH_FUSED(F, S, D)                                                                                            \
   do {                                                                                                                       \
