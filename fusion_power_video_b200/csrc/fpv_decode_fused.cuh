@@ -125,6 +125,48 @@ struct FusedCtx {
     if (++id_slot == kFusedDel) id_slot = 0;
   }
 
+  // Everything lane 0 has to issue at the end of a row, in ONE divergent region (six separate `if (lane == 0)` blocks
+  // per row cost 11 % of the kernel's stall samples in branches and reconvergence): the bulk stores of the row just
+  // written out (`store`: not for direct-store variants), then the refills of the three rings.
+  // with_r1: the residual ring is refilled here too (direct-store variants); the bulk-store variants (L = 40) refill
+  // it right after the slot is consumed at the start of the row -- a lead of one row instead of two measured 0.847
+  // against 0.862 there, while the direct-store variants gain a point from the single region.
+  __device__ __forceinline__ void refill(bool store, bool with_r1) {
+    const bool do1 = with_r1 && i1_row < H, dol = (lowA || lowB) && il_row < H, dod = dmask != 0 && id_row < H;
+    if (lane == 0) {
+      if (store) {
+        bulk_s2g(oA, sm0 + kOut, 2 * W);
+        if (store_b) bulk_s2g(oB, sm0 + kOut + 2 * RB, 2 * W);
+        bulk_commit();
+      }
+      if (do1) {
+        const uint32_t dst = sm0 + kR1 + i1_slot * 2 * RB, bar = bar_r1(i1_slot);
+        mbar_arrive_expect_tx(bar, 2 * W);
+        bulk_g2s(dst, s1A, W, bar);
+        bulk_g2s(dst + RB, s1B, W, bar);
+      }
+      if (dol) {
+        const uint32_t dst = sm0 + kLow + il_slot * 2 * RB, bar = bar_low(il_slot);
+        mbar_arrive_expect_tx(bar, (lowA ? W : 0u) + (lowB ? W : 0u));
+        if (lowA) bulk_g2s(dst, s2A, W, bar);
+        if (lowB) bulk_g2s(dst + RB, s2B, W, bar);
+      }
+      if (dod) {
+        const uint32_t dst = sm0 + kDel + id_slot * 4 * RB, bar = bar_del(id_slot);
+        mbar_arrive_expect_tx(bar, 4 * RB);
+        bulk_g2s(dst, s2D, 4 * RB, bar);             // a whole permuted row: 32 L words (pair_ddup_word)
+      }
+    }
+    if (with_r1) {
+      s1A += stride; s1B += stride; i1_row++;
+      if (++i1_slot == kFusedR1) i1_slot = 0;
+    }
+    s2A += stride; s2B += stride; il_row++;
+    if (++il_slot == kFusedLow) il_slot = 0;
+    s2D += RB; id_row++;
+    if (++id_slot == kFusedDel) id_slot = 0;
+  }
+
   // ---- residual bytes of the next row -> S form [0, a, 0, b] per register ----------------------
   __device__ __forceinline__ void load_residuals(uint32_t (&r)[8 * LW2]) {
     mbar_wait(bar_r1(c1_slot), c1_par);
@@ -154,8 +196,10 @@ struct FusedCtx {
       r[8 * k + 4] = __byte_perm(A[k].y, t, 0x6404); r[8 * k + 5] = __byte_perm(A[k].y, t, 0x7414);
       r[8 * k + 6] = __byte_perm(A[k].y, u, 0x4626); r[8 * k + 7] = __byte_perm(A[k].y, u, 0x5636);
     }
-    __syncwarp();            // every lane has read the slot: refill it (row + kFusedR1)
-    issue_r1();
+    if constexpr (!DIRECT) {
+      __syncwarp();            // every lane has read the slot: refill it (row + kFusedR1)
+      issue_r1();
+    }                          // (direct-store variants: refill() at the end of the row)
   }
 };
 
@@ -248,20 +292,10 @@ template <int LW2, bool DIRECT>
 __device__ __forceinline__ void fused_out_store(FusedCtx<LW2, DIRECT>& cx) {
   constexpr uint32_t L = 8 * LW2, RB = 32 * L;
   using C = FusedCtx<LW2, DIRECT>;
-  if constexpr (!DIRECT) {
-    fence_proxy_async();
-    __syncwarp();
-    if (cx.lane == 0) {
-      bulk_s2g(cx.oA, cx.sm0 + C::kOut, 2 * cx.W);
-      if (cx.store_b) bulk_s2g(cx.oB, cx.sm0 + C::kOut + 2 * RB, 2 * cx.W);
-      bulk_commit();
-    }
-  } else {
-    __syncwarp();          // every lane has read its LOW / DEL slots: they may be refilled
-  }
+  if constexpr (!DIRECT) fence_proxy_async();
+  __syncwarp();            // every lane has read its R1 / LOW / DEL slots and written its piece of the OUT row
+  cx.refill(!DIRECT, DIRECT);
   cx.oA += cx.stride; cx.oB += cx.stride;
-  cx.issue_low();
-  cx.issue_del();
 }
 
 // The write-out of a whole row at once (first / last rows and frames without ClampedGradient).
@@ -510,10 +544,9 @@ __global__ void __launch_bounds__(32 * kFusedWarps, fused_min_ctas(LW2, DIRECT))
     }
     last_prev = __shfl_sync(0xffffffffu, v, (int)last_lane);
   }
-  // after its first row a refill of the LOW / DEL rings follows every write-out; the first one has no
-  // write-out before it
-  cx.issue_low();
-  cx.issue_del();
+  // a refill of the three rings follows every write-out; row 0 has no write-out before it
+  __syncwarp();
+  cx.refill(false, DIRECT);
 
   if (cx.cgmask == 0) {
     // neither frame is ClampedGradient-predicted: rows are the residual rows
