@@ -288,8 +288,9 @@ int fpvh_ingest(size_t xsize, size_t ysize, int shift, int big_endian, size_t th
     };
     enc.Init(frames, xsize, ysize, sink, (void*)(uintptr_t)(size_t)-1);
     if (!enc.ok()) return -1;
-    // warm the pipeline (contexts, pinned batches, worker threads) before the camera starts
-    for (size_t i = 0; i < std::min<size_t>(npool, 2 * (batch ? batch : 8)); i++)
+    // warm the pipeline (contexts, EVERY pinned batch buffer -- the first use of one is a page-locked allocation of
+    // tens of milliseconds --, worker threads) before the camera starts
+    for (size_t i = 0; i < 8 * (size_t)(batch ? batch : 8); i++)
       enc.CompressFrame(frames + (i % npool) * P, sink, (void*)(uintptr_t)(size_t)-1);
     std::this_thread::sleep_for(std::chrono::milliseconds(300));
     const double period = 1.0 / fps, patience = (double)ring_frames / fps;

@@ -437,8 +437,7 @@ void Encoder::Init(const uint16_t* delta_frame, size_t xsize, size_t ysize, Call
     s.stream_cap = fpv_stream_bound(s.ctx, s.B);
   }
   // enough batches that the brotli workers always have about two frames each queued
-  // behind the (up to) three batches that are filling / on the GPU; pinned memory is
-  // only allocated when a batch is first used
+  // behind the (up to) three batches that are filling / on the GPU
   // (GPU entropy stage: one filling, two on the GPU, one being emitted)
   // (several GPUs: two more in flight per additional device)
   const size_t extra = 2 * (s.lanes.size() - 1);
@@ -446,7 +445,13 @@ void Encoder::Init(const uint16_t* delta_frame, size_t xsize, size_t ysize, Call
                   : s.gpu_entropy ? (int)std::min<size_t>(kMaxBatches, 4 + extra)
                                   : (int)std::min<size_t>(kMaxBatches, 3 + extra + (2 * s.threads + s.B - 1) / s.B);
   for (int i = 0; i < s.num_batches; i++) s.free_.push_back(&s.batches[i]);
-  if (!s.alloc_batch(&s.batches[0])) return;
+  // Every batch buffer now, not on first use: a page-locked allocation takes tens of milliseconds, which a camera
+  // feeding CompressFrame at a few thousand frames per second sees as dropped frames (the paced-ingest harness found
+  // 20-130 drops at 2000 fps, all in the moments a batch buffer was used for the first time).  FPV_LAZY_BATCHES=1
+  // restores allocation on first use.
+  const int eager = getenv("FPV_LAZY_BATCHES") ? 1 : s.num_batches;
+  for (int i = 0; i < eager; i++)
+    if (!s.alloc_batch(&s.batches[i])) return;
   if (fpv_set_delta_raw(s.ctx, delta_frame) != FPV_OK) {
     s.fail("fpv_set_delta_raw");
     return;
