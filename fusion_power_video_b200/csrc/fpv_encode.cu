@@ -499,6 +499,15 @@ template <int MODE, bool FULL, int RPS, bool PASS0>
 static cudaError_t launch_fast(const FastParams& fp, int grid, int threads, size_t smem,
                                cudaStream_t stream) {
   // per launch: the attribute is per device and is lost by cudaDeviceReset; the call costs about a microsecond
+  static const bool wide72 = getenv("FPV_FAST_NO_R72") == nullptr;
+  if (threads > 224 && RPS == 4 && wide72) {
+    // nine (or more) warps per CTA: the 72-register build, three CTAs per SM
+    cudaError_t ea = cudaFuncSetAttribute(k_encode_fast<MODE, FULL, RPS, PASS0, 72>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          232448 - 1024);
+    if (ea != cudaSuccess) return ea;
+    k_encode_fast<MODE, FULL, RPS, PASS0, 72><<<grid, threads, smem, stream>>>(fp);
+    return cudaGetLastError();
+  }
   cudaError_t ea = cudaFuncSetAttribute(k_encode_fast<MODE, FULL, RPS, PASS0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         232448 - 1024);
   if (ea != cudaSuccess) return ea;

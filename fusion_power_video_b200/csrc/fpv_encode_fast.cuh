@@ -429,22 +429,22 @@ __device__ __forceinline__ void task_done(const FastParams& p, const uint32_t f,
   decide_core<MODE>(p, f, assumed, lane, dbit, va, vb, low_or);
 }
 
-// Shared memory: [ring: stages x {raw stage, delta stage}] [per consumer warp: hist_a | hist_b]
-// [two CTA-level task tables] [full barriers] [empty barriers]
+// Shared memory: [ring: stages x {raw stage, delta stage}] [two CTA-level task tables] [full barriers] [empty barriers]
 // FULL: xsize is a multiple of 256, every lane of every consumer warp owns pixels.
 // PASS0: all n frames of the batch under the guessed flags; otherwise the frames of p.list under their own.
 #ifndef FPV_FAST_MAXNREG
 #define FPV_FAST_MAXNREG 80
 #endif
-template <int MODE, bool FULL, int RPS, bool PASS0>
-__global__ void __maxnreg__(FPV_FAST_MAXNREG) k_encode_fast(const FastParams p) {
+// MAXR: register cap.  80 keeps four CTAs of up to six warps on an SM (widths up to 1280); frames of more than 1792
+// columns (nine warps per CTA) get 72 so that THREE of their CTAs fit (288 threads x 72 registers).
+template <int MODE, bool FULL, int RPS, bool PASS0, int MAXR = FPV_FAST_MAXNREG>
+__global__ void __maxnreg__(MAXR) k_encode_fast(const FastParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   if (!PASS0 && *p.count == 0) return;   // a redo pass with nothing to redo (the normal case): gone in a microsecond
   const uint32_t S = p.stages;
   const uint32_t slot_bytes = 2 * p.stage_bytes;
   const int NW = (int)p.compute_warps;
-  uint8_t* scratch = smem + (size_t)S * slot_bytes;
-  uint8_t* ctabs = scratch + (size_t)NW * kWarpScratchBytes;
+  uint8_t* ctabs = smem + (size_t)S * slot_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(ctabs + 2 * kCtaStatWords * 4);
   const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + S);
   const uint32_t ring0 = smem_u32(smem);
@@ -454,8 +454,8 @@ __global__ void __maxnreg__(FPV_FAST_MAXNREG) k_encode_fast(const FastParams p) 
   const uint32_t W = p.W;
   const QConst qc = p.qc;   // from the host: each mask is a constant-bank operand of its LOP3, not a derived register
 
-  for (uint32_t i = threadIdx.x; i < ((uint32_t)NW * kWarpScratchBytes + 2 * kCtaStatWords * 4) / 4; i += blockDim.x)
-    reinterpret_cast<uint32_t*>(scratch)[i] = 0;
+  for (uint32_t i = threadIdx.x; i < (2 * kCtaStatWords * 4) / 4; i += blockDim.x)
+    reinterpret_cast<uint32_t*>(ctabs)[i] = 0;
   if (threadIdx.x == 0) {
     for (uint32_t i = 0; i < S; i++) {
       mbar_init(full0 + 8 * i, 1);
@@ -557,8 +557,6 @@ __global__ void __maxnreg__(FPV_FAST_MAXNREG) k_encode_fast(const FastParams p) 
   const bool active = c0 < W;
   const uint32_t w31 = W % 31;
   const uint32_t rowb = W * 2;                            // bytes per row in a stage
-  uint32_t hist_a = smem_u32(scratch + (size_t)warp * kWarpScratchBytes);
-  asm volatile("" : "+r"(hist_a));  // keep it in a register instead of recomputing it per row
 
   while (more) {
     // ---- start of a task ---------------------------------------------------------
@@ -566,7 +564,12 @@ __global__ void __maxnreg__(FPV_FAST_MAXNREG) k_encode_fast(const FastParams p) 
     const uint32_t assumed = PASS0 ? guess : p.stats[f].assumed;
     const bool use_delta = p.delta != nullptr && (assumed & 1u);
     const bool use_cg = (assumed & 2u) != 0;
-    const uint32_t ctab = ctab0 + (cur.tseq & 1u) * (kCtaStatWords * 4);
+    // The ClampedGradient decision samples (at most one per lane and row: 8 of a warp's 32 lanes) go straight into the
+    // CTA-level table of the task: no warp-private histograms (round 1 / 2 kept 2 KB per warp and flushed them per
+    // task; at 2048 columns that was the 16 KB that kept a third CTA off the SM).
+    uint32_t ctab = ctab0 + (cur.tseq & 1u) * (kCtaStatWords * 4);
+    asm volatile("" : "+r"(ctab));  // keep it in a register instead of recomputing it per row
+    const uint32_t hist_a = ctab;
     const uint32_t bands = cur.bands;
     StripState st;
 #pragma unroll
@@ -640,13 +643,6 @@ __global__ void __maxnreg__(FPV_FAST_MAXNREG) k_encode_fast(const FastParams p) 
       const uint32_t orl = __reduce_or_sync(0xffffffffu, (FULL || active) ? (st.orl & kLoBytes) : 0u);
       if (lane == 0 && orl) atoms_or(ctab + 4 * (512 + 8), orl);
     }
-    for (uint32_t i = lane; i < kWarpHistWords; i += 32) {
-      const uint32_t v = lds32(hist_a + 4 * i);
-      if (v) {
-        sts32(hist_a + 4 * i, 0);
-        atoms_add(ctab + 4 * i, v);
-      }
-    }
     task_done<MODE>(p, f, assumed, bands, ctab, (uint32_t)NW + 1, lane);
   }
 }
@@ -654,7 +650,8 @@ __global__ void __maxnreg__(FPV_FAST_MAXNREG) k_encode_fast(const FastParams p) 
 static inline size_t fast_smem_bytes(uint32_t W, int stages, int rows_per_stage) {
   const size_t stage_bytes = ((size_t)rows_per_stage * W + kHaloPx) * 2;
   const size_t warps = (W + kStripPx - 1) / kStripPx;
-  return (size_t)stages * 2 * stage_bytes + warps * kWarpScratchBytes + 2 * kCtaStatWords * 4 + 2 * (size_t)stages * 8;
+  (void)warps;
+  return (size_t)stages * 2 * stage_bytes + 2 * kCtaStatWords * 4 + 2 * (size_t)stages * 8;
 }
 
 }  // namespace fpv
