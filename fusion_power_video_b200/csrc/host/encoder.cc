@@ -445,11 +445,12 @@ void Encoder::Init(const uint16_t* delta_frame, size_t xsize, size_t ysize, Call
                   : s.gpu_entropy ? (int)std::min<size_t>(kMaxBatches, 4 + extra)
                                   : (int)std::min<size_t>(kMaxBatches, 3 + extra + (2 * s.threads + s.B - 1) / s.B);
   for (int i = 0; i < s.num_batches; i++) s.free_.push_back(&s.batches[i]);
-  // Every batch buffer now, not on first use: a page-locked allocation takes tens of milliseconds, which a camera
+  // Batch buffers are allocated on first use; a page-locked allocation takes tens of milliseconds, which a camera
   // feeding CompressFrame at a few thousand frames per second sees as dropped frames (the paced-ingest harness found
-  // 20-130 drops at 2000 fps, all in the moments a batch buffer was used for the first time).  FPV_LAZY_BATCHES=1
-  // restores allocation on first use.
-  const int eager = getenv("FPV_LAZY_BATCHES") ? 1 : s.num_batches;
+  // 20-130 drops at 2000 fps, all in the moments a batch buffer was used for the first time): real-time callers set
+  // FPV_EAGER_BATCHES=1 (every buffer allocated here, a longer Init) or push 8 batches of frames before the camera
+  // starts, as the harness does.
+  const int eager = getenv("FPV_EAGER_BATCHES") ? s.num_batches : 1;
   for (int i = 0; i < eager; i++)
     if (!s.alloc_batch(&s.batches[i])) return;
   if (fpv_set_delta_raw(s.ctx, delta_frame) != FPV_OK) {
