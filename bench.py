@@ -27,6 +27,17 @@ host-buffer C-ABI calls (pinned H2D + kernels + D2H inside the timed region);
 `roofline` is the fused encode kernel against the measured HBM peak;
 `cpu_baseline` is the reference's own CPU code (oracle/_ref) on this box's
 host cores.  `--impl reference` times only that CPU code.
+
+Further entries of the line: `e2e.pcie_ceiling` (the box's own host <-> device
+copy ceiling with every rank copying at once, measured in the same run) and
+`e2e.frac_of_pcie_ceiling`; `decode` (inverse transform, one full wave of the
+decode kernel, bit-exact round trip); `decode_e2e`, `e2e_stream`; `entropy`
+(GPU entropy coder on resident planes); `stream` (whole codec: host brotli,
+GPU entropy stage from pageable and from page-locked frames, the decoders on
+both kinds of stream incl. the GPU entropy decoder, next to the reference's
+Encoder / StreamingDecoder); `configs` (configs[0] / configs[2] geometries);
+`ingest` (configs[4]: paced real-time ingest); `multi_gpu` (N > 1: delta halo
+by CUDA IPC, merged-stream check).
 """
 from __future__ import annotations
 
