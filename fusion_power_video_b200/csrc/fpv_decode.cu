@@ -20,6 +20,13 @@
 // Rows are staged with cp.async (residual row, low row, delta row) a few rows
 // ahead so that the chain never waits on HBM; the delta add, the high/low
 // recombination and UnextractFrame are fused into the row write-out.
+//
+// Kernels, in the order pick_decode_kernel prefers them:
+//   k_decode_fused (fpv_decode_fused.cuh)  one warp per pair of frames, TMA rings, write-out interleaved with the chain
+//   k_decode_pair  (fpv_decode_pair.cuh)   round 1's three-warps-per-pair kernel (FPV_DECODE_KERNEL=pair)
+//   k_decode_simd  (below)                 widths the two above do not take (W % 4 == 0, W <= 2048)
+//   k_decode_spec  (below)                 everything else; in planes mode also fpv_unpredict_planes
+//   k_cg_inverse_serial                    rows too wide for shared memory only
 #include <stdlib.h>
 #include <string.h>
 

@@ -1,4 +1,6 @@
-// fpv_decode_pair.cuh -- the warp-specialised decode kernel (k_decode_pair).
+// fpv_decode_pair.cuh -- the warp-specialised decode kernel (k_decode_pair): round 1's default, since round 2 the
+// fallback behind k_decode_fused (fpv_decode_fused.cuh), which reuses this file's chain_step, pair_ddup_word and
+// PairParams.  FPV_DECODE_KERNEL=pair selects it; the parity tests run it on every geometry.
 //
 // Same job as the rest of fpv_decode.cu: the post-brotli part of DecompressImage
 // (fusion_power_video.cc:326-344) fused with UnextractFrame (.cc:850-862).
