@@ -252,6 +252,20 @@ long fpvh_columnar_planes(size_t xsize, size_t ysize, int shift, int big_endian,
   return (failed || !enc->ok()) ? -1 : (long)count;
 }
 
+// The host decoders' directory walk (ScanCodedPlane) on one plane stream, for tests: chunk offsets into offs[cap],
+// their number into *n, the stream's length into *stream_bytes.  Returns 1 if the stream carries the GPU coder's
+// directories, 0 if not (a libbrotli stream, a truncated or damaged one).
+int fpvh_scan_coded_plane(const uint8_t* stream, size_t avail, size_t plane_bytes, uint64_t* offs, size_t cap, size_t* n,
+                          size_t* stream_bytes) {
+  std::vector<uint64_t> v;
+  size_t len = 0;
+  if (!fpvc::internal::ScanCodedPlane(stream, avail, plane_bytes, &v, &len)) return 0;
+  for (size_t i = 0; i < v.size() && i < cap; i++) offs[i] = v[i];
+  if (n) *n = v.size();
+  if (stream_bytes) *stream_bytes = len;
+  return 1;
+}
+
 // Real-time ingest (BASELINE configs[4]; the loop of reference encode.cc:63-96 driven by a camera clock instead of
 // stdin): frames ARRIVE at `fps` for `seconds`, whether or not the encoder keeps up.  The camera side owns a ring of
 // `ring_frames` buffers; the feeder thread hands arrived frames to Encoder::CompressFrame in order, and a frame whose

@@ -42,6 +42,8 @@ def lib() -> C.CDLL:
     L.fpvh_columnar_roundtrip.restype = C.c_long
     L.fpvh_columnar_planes.argtypes = [sz, sz, i32, i32, i32, vp, vp, sz, vp, vp, vp, vp]
     L.fpvh_columnar_planes.restype = C.c_long
+    L.fpvh_scan_coded_plane.argtypes = [vp, sz, sz, vp, sz, C.POINTER(sz), C.POINTER(sz)]
+    L.fpvh_scan_coded_plane.restype = i32
     L.fpvh_encode_stream_multi.argtypes = [sz, sz, i32, i32, sz, u32, vp, i32, i32, vp, vp, sz, vp, sz, C.POINTER(C.c_double)]
     L.fpvh_encode_stream_multi.restype = sz
     L.fpvh_ingest.argtypes = [sz, sz, i32, i32, sz, u32, i32, i32, vp, sz, C.c_double, C.c_double, sz, C.POINTER(C.c_double)]
@@ -251,3 +253,16 @@ def columnar_planes(frames, timestamps, xsize, ysize, shift=0, big_endian=False,
     if cnt != n:
         raise HostError(f"columnar planes probe failed ({cnt} of {n} frames): {last_error()}")
     return flags, high, low, preview
+
+
+def scan_coded_plane(stream, plane_bytes):
+    """The host decoders' walk over the chunk directories of one plane stream (GPU entropy coder): (chunk offsets,
+    stream length), or None if the stream carries none."""
+    L = lib()
+    buf = np.frombuffer(bytes(stream), np.uint8)
+    cap = (plane_bytes + 65535) // 65536 + 1
+    offs = np.zeros(cap, np.uint64)
+    n, length = C.c_size_t(0), C.c_size_t(0)
+    if not L.fpvh_scan_coded_plane(_p(buf), buf.size, plane_bytes, _p(offs), cap, C.byref(n), C.byref(length)):
+        return None
+    return [int(x) for x in offs[:n.value]], length.value

@@ -70,3 +70,31 @@ def test_encoder_pipeline_is_race_free_under_thread_sanitizer():
         pytest.skip("libtsan not installed")
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "all runs identical" in r.stdout and "ThreadSanitizer" not in r.stdout + r.stderr
+
+
+def test_directory_walk_of_the_host_decoders_matches_the_restatement(host):
+    """ScanCodedPlane (csrc/host/host_common.cc): what StreamingDecoder / RandomAccessDecoder use to find the chunks of a
+    GPU-coded plane stream -- same offsets and length as the CPU restatement's scanner; libbrotli streams, truncated
+    streams and damaged directories are not mistaken for one (the decoders then take the libbrotlidec path)."""
+    import huffcoder_ref as href
+
+    rng = np.random.default_rng(8)
+    for size, kind in ((1, 0), (70000, 1), (65536, 2), (200000, 3), (131073, 1)):
+        data = [np.full(size, 3, np.uint8), np.minimum(rng.geometric(0.2, size) - 1, 255).astype(np.uint8),
+                rng.integers(0, 4, size).astype(np.uint8), rng.integers(0, 256, size).astype(np.uint8)][kind]
+        stream = href.encode_plane(data)
+        want = href.scan_plane(stream + b"\x11\x22\x33", size)
+        assert want is not None
+        got = host.scan_coded_plane(stream + b"\x11\x22\x33", size)
+        assert got is not None and got[0] == want[0] and got[1] == want[1] == len(stream)
+        assert host.scan_coded_plane(stream[:-1], size) is None                 # the final 0x03 is missing
+        assert host.scan_coded_plane(stream[: len(stream) // 2], size) is None   # truncated
+        assert host.scan_coded_plane(stream, size + 65536) is None               # one chunk short for this plane size
+        bad = bytearray(stream)
+        bad[2] ^= 0xFF                                                           # the directory's 'F'
+        assert host.scan_coded_plane(bytes(bad), size) is None
+    # libbrotli's own output (quality 1) carries no directory
+    W, H, n = 64, 64, 2
+    frames = synth.plasma_frames(n, W, H, bits=16, seed=2).reshape(n, -1)
+    s = host.encode_stream(frames, W, H, 0, threads=0, batch=1)
+    assert host.scan_coded_plane(s[24:], W * H) is None
